@@ -1,0 +1,221 @@
+/*
+ * uhsdr_b200.h -- C ABI of the B200-native batched UHSDR receiver/transmitter DSP engine.
+ *
+ * This is the drop-in boundary for UHSDR's audio/RF block path.  The reference has no plugin
+ * or FFI layer: its boundary is three C functions plus global state:
+ *
+ *   void AudioDriver_I2SCallback(AudioSample_t *audio, IqSample_t *iq, AudioSample_t *audioDst,
+ *                                int16_t blockSize);            mchf-eclipse/drivers/audio/audio_driver.h:651
+ *   static void AudioDriver_RxProcessor(IqSample_t*, AudioSample_t*, uint16_t, bool external_mute)
+ *                                                               mchf-eclipse/drivers/audio/audio_driver.c:2603
+ *   void TxProcessor_Run(AudioSample_t*, IqSample_t*, AudioSample_t*, uint16_t, bool)
+ *                                                               mchf-eclipse/drivers/audio/tx_processor.h:24
+ *   void AudioDriver_SetProcessingChain(uint8_t dmod_mode, bool reset_dsp_nr)
+ *                                                               mchf-eclipse/drivers/audio/audio_driver.c:1093
+ *
+ * The engine keeps that block contract (32 IqSample_t in -> 32 AudioSample_t out per channel and
+ * block, 48 ksps, int32 words with the signal left-justified by 16 bits) but processes many
+ * independent channels and many consecutive blocks per call.  All per-channel parameters the
+ * reference reads from its globals (ts, ads, agc_wdsp_conf, nr_params, sd) travel in
+ * uhsdr_chan_cfg_t.  The coefficient tables (FilterPathInfo[], filters/ *.c) are NOT embedded:
+ * the host hands them over once as a table blob (uhsdr_tables.h), exactly as the firmware links
+ * its own filters/ *.c.
+ *
+ * Plain C, plain pointers and sizes, integer return codes, no exceptions, no CPU fallback:
+ * every entry point fails with UHSDR_ERR_CUDA / UHSDR_ERR_NO_DEVICE when no B200 is usable.
+ */
+#ifndef UHSDR_B200_H
+#define UHSDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UHSDR_BLOCK_SIZE 32        /* IQ_BLOCK_SIZE, uhsdr_board_config.h:217 */
+#define UHSDR_SAMPLE_RATE 48000    /* IQ_SAMPLE_RATE, uhsdr_board_config.h:207 */
+#define UHSDR_NUM_FILTER_PATHS 87  /* AUDIO_FILTER_PATH_NUM, audio_filter.h:141 */
+#define UHSDR_SPECTRUM_FFT_LEN 512 /* sd.fft_iq_len/2 on 480x320 displays, ui_spectrum.c:975-979 */
+
+/* IqSample_t / AudioSample_t, audio_driver.h:44-52: two int32 words, l then r.
+ * RX in:  l = I, r = Q (audio_driver.c:2677-2678).  RX out: l = main audio, r = copy
+ * (audio_driver.c:2911-2912).  TX in: microphone in l (tx_processor.c:394).  TX out: l = I, r = Q. */
+typedef struct { int32_t l; int32_t r; } uhsdr_iq_sample_t;
+typedef struct { int32_t l; int32_t r; } uhsdr_audio_sample_t;
+
+/* DemodModes_t, uhsdr_board.h:72-84 (same numeric values). */
+enum {
+    UHSDR_DEMOD_USB = 0, UHSDR_DEMOD_LSB = 1, UHSDR_DEMOD_CW = 2, UHSDR_DEMOD_AM = 3,
+    UHSDR_DEMOD_SAM = 4, UHSDR_DEMOD_FM = 5, UHSDR_DEMOD_DIGI = 6
+};
+/* sam_sideband_t, audio_driver.h:181-190. */
+enum { UHSDR_SAM_SIDEBAND_BOTH = 0, UHSDR_SAM_SIDEBAND_LSB = 1, UHSDR_SAM_SIDEBAND_USB = 2 };
+/* ts.iq_freq_mode, audio_driver.h:520-526. */
+enum {
+    UHSDR_FREQ_IQ_CONV_OFF = 0, UHSDR_FREQ_IQ_CONV_P6KHZ = 1, UHSDR_FREQ_IQ_CONV_M6KHZ = 2,
+    UHSDR_FREQ_IQ_CONV_P12KHZ = 3, UHSDR_FREQ_IQ_CONV_M12KHZ = 4
+};
+/* ts.dsp.active bits, audio_driver.h:195-200. */
+enum {
+    UHSDR_DSP_NR_ENABLE = 0x01, UHSDR_DSP_NR_POSTAGC_ENABLE = 0x02, UHSDR_DSP_NOTCH_ENABLE = 0x04,
+    UHSDR_DSP_NB_ENABLE = 0x08, UHSDR_DSP_MNOTCH_ENABLE = 0x10, UHSDR_DSP_MPEAK_ENABLE = 0x20
+};
+/* ts.tx_filter, tx_processor.c:92-102. */
+enum { UHSDR_TX_FILTER_SOPRANO = 1, UHSDR_TX_FILTER_TENOR = 2, UHSDR_TX_FILTER_BASS = 3 };
+
+/* Return codes. */
+enum {
+    UHSDR_OK = 0,
+    UHSDR_ERR_ARG = -1,        /* NULL pointer, channel/path out of range, nblocks <= 0 ...       */
+    UHSDR_ERR_NO_DEVICE = -2,  /* no CUDA device / not an sm_100 part                              */
+    UHSDR_ERR_CUDA = -3,       /* a CUDA runtime call failed; see uhsdr_last_error()               */
+    UHSDR_ERR_TABLES = -4,     /* table blob missing, wrong magic/version or truncated             */
+    UHSDR_ERR_UNSUPPORTED = -5,/* configuration the engine does not implement (fails loudly)       */
+    UHSDR_ERR_STATE = -6       /* channel not configured                                           */
+};
+
+/* Per-channel configuration: exactly the fields the reference's block path reads from its globals.
+ * Defaults (uhsdr_default_chan_cfg) are the reference's ui_configuration.c:60-220 values. */
+typedef struct {
+    uint32_t struct_size;        /* sizeof(uhsdr_chan_cfg_t), for ABI evolution                     */
+    /* mode / path selection */
+    int32_t dmod_mode;           /* ts.dmod_mode                                                    */
+    int32_t filter_path;         /* ts.filter_path: index into FilterPathInfo[87], audio_filter.c:147 */
+    int32_t cw_lsb;              /* ts.cw_lsb, radio_management.c:1676                              */
+    int32_t digi_lsb;            /* ts.digi_lsb                                                     */
+    int32_t iq_freq_mode;        /* ts.iq_freq_mode, default FREQ_IQ_CONV_M12KHZ                    */
+    /* IQ correction, audio_driver.c:2254-2316 */
+    int32_t iq_auto_correction;  /* ts.iq_auto_correction (default 1)                               */
+    float   rx_adj_gain_i;       /* ts.rx_adj_gain_var.i (manual mode)                              */
+    float   rx_adj_gain_q;       /* ts.rx_adj_gain_var.q                                            */
+    float   iq_phase_balance_rx; /* ads.iq_phase_balance_rx                                         */
+    /* DSP switches and EQ, audio_driver.c:994-1050 */
+    int32_t dsp_active;          /* ts.dsp.active bit mask                                          */
+    int32_t notch_frequency;     /* ts.dsp.notch_frequency (Hz)                                     */
+    int32_t peak_frequency;      /* ts.dsp.peak_frequency (Hz)                                      */
+    int32_t bass_gain;           /* ts.dsp.bass_gain (dB), default 2                                */
+    int32_t treble_gain;         /* ts.dsp.treble_gain (dB), default 0                              */
+    int32_t nr_strength;         /* ts.dsp.nr_strength, default 160                                 */
+    int32_t nb_setting;          /* ts.dsp.nb_setting                                               */
+    /* WDSP AGC, agc_wdsp_params_t audio_agc.h:23-36 */
+    int32_t agc_mode;            /* 0..5 (5 = off), default 2                                       */
+    int32_t agc_slope;           /* default 70                                                      */
+    int32_t agc_hang_enable;     /* default 0                                                       */
+    int32_t agc_thresh;          /* default 20                                                      */
+    int32_t agc_hang_thresh;     /* 45, audio_agc.c:113                                             */
+    int32_t agc_hang_time;       /* 500, audio_agc.c:112                                            */
+    int32_t agc_tau_decay[6];    /* {4000,2000,500,250,50,1}                                        */
+    int32_t agc_tau_hang_decay;  /* 500                                                             */
+    /* SAM, audio_driver.c:709-745 */
+    int32_t sam_sideband;        /* ads.sam_sideband                                                */
+    int32_t sam_fade_leveler;    /* ads.fade_leveler, default 1                                     */
+    int32_t sam_pll_fmax;        /* ads.pll_fmax_int, default 2500                                  */
+    int32_t sam_zeta;            /* ads.zeta_int (x100), default 65                                 */
+    int32_t sam_omegaN;          /* ads.omegaN_int, default 250                                     */
+    /* FM, audio_driver.c:1544-1737 */
+    int32_t fm_sql_threshold;    /* ts.fm_sql_threshold, default 12                                 */
+    int32_t fm_dev_5khz;         /* ts.flags2 & FLAGS2_FM_MODE_DEVIATION_5KHZ                       */
+    float   fm_subaudible_tone_det_freq; /* ads.fm_conf.subaudible_tone_det_freq, 0 = off           */
+    /* spectral NR, audio_nr.c:1841-2195 */
+    int32_t nr_decimation_enable;/* nr_params.NR_decimation_enable (default 1)                      */
+    /* spectrum display, ui_spectrum.c:1350-1390 */
+    int32_t spectrum_enable;     /* 0 = no spectrum ring / FFT for this channel                     */
+    int32_t spectrum_magnify;    /* sd.magnify (only 0 implemented)                                 */
+    float   codec_gain_calc;     /* ads.codec_gain_calc (spectrum scaling), default 1               */
+    /* TX, tx_processor.c */
+    int32_t tx_filter;           /* ts.tx_filter, default SOPRANO                                   */
+    int32_t tx_bass_gain;        /* ts.dsp.tx_bass_gain, default 4                                  */
+    int32_t tx_treble_gain;      /* ts.dsp.tx_treble_gain, default 4                                */
+    int32_t tx_mic_gain;         /* ts.tx_gain[TX_AUDIO_MIC], default 15                            */
+    int32_t tx_comp_level;       /* ts.tx_comp_level, default 2                                     */
+    int32_t tx_alc_decay;        /* ts.alc_decay, default 10                                        */
+    int32_t tx_alc_postfilt_gain;/* ts.alc_tx_postfilt_gain, default 1                              */
+    float   tx_power_factor;     /* ts.tx_power_factor                                              */
+    float   tx_adj_gain_i;       /* ts.tx_adj_gain_var[trans_idx].i                                 */
+    float   tx_adj_gain_q;       /* ts.tx_adj_gain_var[trans_idx].q                                 */
+    float   iq_phase_balance_tx; /* ads.iq_phase_balance_tx[trans_idx]                              */
+} uhsdr_chan_cfg_t;
+
+/* Per-channel side outputs (SURVEY.md section 5 "metrics"); none is on the parity-critical path. */
+typedef struct {
+    int32_t adc_clip;            /* ads.adc_clip / half / quarter, audio_driver.c:2662-2675         */
+    int32_t adc_half_clip;
+    int32_t adc_quarter_clip;
+    int32_t agc_action;          /* agc_wdsp_conf.action, audio_agc.c:552-561                       */
+    int32_t agc_hang_action;     /* agc_wdsp_conf.hang_action, audio_agc.c:400-407                  */
+    int32_t fm_squelched;        /* ads.fm_conf.squelched                                           */
+    float   fm_sql_avg;          /* ads.fm_conf.sql_avg                                             */
+    int32_t sam_carrier_freq_offset; /* ads.carrier_freq_offset, audio_driver.c:2150-2162           */
+    float   iq_corr_c1;          /* adb.iq_corr.M_c1, M_c2                                          */
+    float   iq_corr_c2;
+    float   tx_peak_audio;       /* ads.peak_audio, tx_processor.c:403                              */
+    float   tx_alc_val;          /* ads.alc_val                                                     */
+    int64_t blocks_processed;
+} uhsdr_chan_status_t;
+
+typedef struct uhsdr_engine uhsdr_engine_t;
+
+/* Library identity.  uhsdr_b200_backend() returns "cuda-sm100a". */
+int         uhsdr_b200_abi_version(void);
+const char *uhsdr_b200_backend(void);
+const char *uhsdr_strerror(int code);
+/* Text of the last CUDA failure on this engine (or of engine creation when e == NULL). */
+const char *uhsdr_last_error(const uhsdr_engine_t *e);
+
+/* Reference defaults (ui_configuration.c:60-220; USB, path 35, -12 kHz translate, AGC mode 2). */
+int uhsdr_default_chan_cfg(uhsdr_chan_cfg_t *cfg);
+
+/* Engine for num_channels channels on CUDA device `device`.  `tables` is the blob described in
+ * uhsdr_tables.h (the reference's FilterPathInfo[] + coefficient arrays); it is copied.
+ * Replaces AudioDriver_Init (audio_driver.c:677). */
+int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device,
+                        const void *tables, size_t tables_bytes);
+int uhsdr_engine_destroy(uhsdr_engine_t *e);
+int uhsdr_engine_num_channels(const uhsdr_engine_t *e);
+
+/* AudioDriver_SetProcessingChain (audio_driver.c:1093) + TxProcessor_Set (tx_processor.c:72) for
+ * channels [first, first+count).  reset != 0: fresh-process semantics (all DSP state zeroed to the
+ * boot values, SURVEY.md 8a "state inventory"); reset == 0: the reference's reconfigure semantics
+ * (FIR/decimator/interpolator histories and lattice states cleared, the rest kept). */
+int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count,
+                             const uhsdr_chan_cfg_t *cfg, int reset);
+int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg_t *cfg, int reset);
+
+/* AudioDriver_RxProcessor for every channel and nblocks consecutive blocks.
+ * iq / audio: channel-major, [num_channels][nblocks*32] elements, HOST memory (pinned or pageable).
+ * mute: optional [num_channels][nblocks] bytes = external_mute per block (NULL = never muted).
+ * Copies in, runs the CUDA chain, copies out, returns when the audio is in `audio`. */
+int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio_sample_t *audio,
+                     int nblocks, const uint8_t *mute);
+/* Same with DEVICE pointers on the engine's device; asynchronous on the engine's stream
+ * (uhsdr_engine_sync to wait).  audio_f (optional, device) receives the float audio before the
+ * int32 formatting, [num_channels][nblocks*32] floats (adb.a_buffer[1], audio_driver.c:2911). */
+int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev,
+                            uhsdr_audio_sample_t *audio_dev, float *audio_f_dev,
+                            int nblocks, const uint8_t *mute_dev);
+/* TxProcessor_Run, SSB voice branch (tx_processor.c:891, :989-995): mic audio in, I/Q out. */
+int uhsdr_tx_process(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio, uhsdr_iq_sample_t *iq,
+                     int nblocks, const uint8_t *mute);
+int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio_dev,
+                            uhsdr_iq_sample_t *iq_dev, float *iq_f_dev, int nblocks,
+                            const uint8_t *mute_dev);
+int uhsdr_engine_sync(uhsdr_engine_t *e);
+/* The engine's CUDA stream as a void* (cudaStream_t), for callers that time with CUDA events. */
+void *uhsdr_engine_stream(uhsdr_engine_t *e);
+
+/* UiSpectrum_RedrawSpectrum states 0-2 (ui_spectrum.c:1362-1390): snapshot of the channel's
+ * spectrum ring, Hann window, 512-point complex FFT, magnitudes.  mags: [count][512] floats (host). */
+int uhsdr_get_spectrum(uhsdr_engine_t *e, int first, int count, float *mags);
+int uhsdr_get_spectrum_device(uhsdr_engine_t *e, int first, int count, float *mags_dev);
+
+int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_t *status);
+
+/* Number of kernel launches issued by this engine so far (bench.py "gpu_launches"). */
+int64_t uhsdr_engine_launch_count(const uhsdr_engine_t *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UHSDR_B200_H */

@@ -1,0 +1,164 @@
+/*
+ * ref_harness.c -- ORACLE / TEST INFRASTRUCTURE ONLY (never linked into the product library).
+ *
+ * Drives the reference's own RX/TX block processors, compiled unmodified from /root/reference,
+ * for ONE channel per loaded copy of the shared object (the reference keeps all DSP state in
+ * file-scope and function-local statics, e.g. audio_driver.c:1915-1916,1976,1531,
+ * audio_agc.c:88,579, freq_shift.c:277-283).  A fresh channel == a freshly loaded copy.
+ *
+ * The reference translation unit is #included so that its static entry point
+ * AudioDriver_RxProcessor (audio_driver.c:2603) and static coefficient arrays are reachable;
+ * nothing of it is copied into this repository.
+ */
+#include "audio_driver.c"   /* from /root/reference via -I, see oracle/Makefile */
+
+#include "uhsdr_b200.h"
+#include "ui_configuration.h"
+
+static uhsdr_chan_cfg_t g_cfg;
+static int g_inited = 0;
+
+static void ref_apply_cfg(const uhsdr_chan_cfg_t *c)
+{
+    ts.dmod_mode = c->dmod_mode;
+    ts.cw_lsb = c->cw_lsb;
+    ts.digi_lsb = c->digi_lsb;
+    ts.iq_freq_mode = c->iq_freq_mode;
+    ts.iq_auto_correction = c->iq_auto_correction;
+    ts.rx_adj_gain_var.i = c->rx_adj_gain_i;
+    ts.rx_adj_gain_var.q = c->rx_adj_gain_q;
+    ads.iq_phase_balance_rx = c->iq_phase_balance_rx;
+    ts.dsp.active = (uint8_t)c->dsp_active;
+    ts.dsp.notch_frequency = c->notch_frequency;
+    ts.dsp.peak_frequency = c->peak_frequency;
+    ts.dsp.bass_gain = c->bass_gain;
+    ts.dsp.treble_gain = c->treble_gain;
+    ts.dsp.nr_strength = (uint8_t)c->nr_strength;
+    ts.dsp.nb_setting = (uint8_t)c->nb_setting;
+    ts.dsp.notch_numtaps = DSP_NOTCH_NUMTAPS_DEFAULT;
+    ts.dsp.notch_mu = DSP_NOTCH_MU_DEFAULT;
+    ts.dsp.notch_delaybuf_len = DSP_NOTCH_DELAYBUF_DEFAULT;
+
+    agc_wdsp_conf.mode = (uint8_t)c->agc_mode;
+    agc_wdsp_conf.slope = (uint8_t)c->agc_slope;
+    agc_wdsp_conf.hang_enable = (uint8_t)c->agc_hang_enable;
+    agc_wdsp_conf.thresh = c->agc_thresh;
+    agc_wdsp_conf.hang_thresh = c->agc_hang_thresh;
+    agc_wdsp_conf.hang_time = c->agc_hang_time;
+    for (int i = 0; i < 6; i++) agc_wdsp_conf.tau_decay[i] = c->agc_tau_decay[i];
+    agc_wdsp_conf.tau_hang_decay = c->agc_tau_hang_decay;
+    agc_wdsp_conf.switch_mode = 1;
+
+    ads.sam_sideband = (sam_sideband_t)c->sam_sideband;
+    ads.fade_leveler = (uint8_t)c->sam_fade_leveler;
+    ads.pll_fmax_int = c->sam_pll_fmax;
+    ads.zeta_int = c->sam_zeta;
+    ads.omegaN_int = c->sam_omegaN;
+
+    ts.fm_sql_threshold = (uint8_t)c->fm_sql_threshold;
+    if (c->fm_dev_5khz) ts.flags2 |= FLAGS2_FM_MODE_DEVIATION_5KHZ; else ts.flags2 &= ~FLAGS2_FM_MODE_DEVIATION_5KHZ;
+
+    nr_params.NR_decimation_enable = c->nr_decimation_enable;
+
+    sd.magnify = (uint8_t)c->spectrum_magnify;
+    sd.fft_iq_len = c->spectrum_enable ? 1024 : 0;   /* 480x320 layout: 512-point FFT, ui_spectrum.c:975-979 */
+    ads.codec_gain_calc = c->codec_gain_calc;
+
+    ts.tx_filter = (uint8_t)c->tx_filter;
+    ts.dsp.tx_bass_gain = c->tx_bass_gain;
+    ts.dsp.tx_treble_gain = c->tx_treble_gain;
+    ts.tx_comp_level = (int16_t)c->tx_comp_level;
+    ts.alc_decay = c->tx_alc_decay;
+    ts.alc_tx_postfilt_gain = c->tx_alc_postfilt_gain;
+    ts.tx_gain[TX_AUDIO_MIC] = (uint8_t)c->tx_mic_gain;
+    ts.tx_mic_gain_mult = ts.tx_gain[TX_AUDIO_MIC];   /* ui_driver.c / radio_management: mic gain multiplier == setting */
+    ts.tx_power_factor = c->tx_power_factor;
+    for (int t = 0; t < IQ_TRANS_NUM; t++) {
+        ts.tx_adj_gain_var[t].i = c->tx_adj_gain_i;
+        ts.tx_adj_gain_var[t].q = c->tx_adj_gain_q;
+        ads.iq_phase_balance_tx[t] = c->iq_phase_balance_tx;
+    }
+}
+
+static void ref_select_path(int path)
+{
+    /* AudioDriver_SetProcessingChain re-reads the "last used in mode" memory (audio_driver.c:1105,
+     * audio_filter.c:1032-1035); pin every mode's memory to the requested path. */
+    uint16_t fm = AudioFilter_GetFilterModeFromDemodMode(ts.dmod_mode);
+    ts.filter_path = (uint8_t)path;
+    ts.filter_path_mem[fm][0] = (uint8_t)path;
+}
+
+/* One-time init for this copy of the library == firmware boot: configuration load
+ * (ui_configuration.c defaults, overridden by cfg), AudioDriver_Init (uhsdr_main.c:444), then
+ * AudioDriver_SetProcessingChain (audio_driver.c:1093). */
+int ref_init(const uhsdr_chan_cfg_t *cfg)
+{
+    if (cfg == NULL || cfg->struct_size != sizeof(uhsdr_chan_cfg_t)) return -1;
+    if (g_inited) return -2;        /* statics cannot be re-zeroed: load a fresh copy instead */
+    g_cfg = *cfg;
+    memset((void *)&ts, 0, sizeof(ts));
+    ts.samp_rate = 48000;
+    ts.txrx_mode = TRX_MODE_RX;
+    ts.tx_audio_source = TX_AUDIO_MIC;
+    ts.rx_iq_source = RX_IQ_CODEC;
+    ts.rx_gain[RX_AUDIO_SPKR].value = 10;
+    ts.rx_gain[RX_AUDIO_DIG].value = 31;
+    ts.beep_frequency = DEFAULT_BEEP_FREQUENCY;
+    ref_apply_cfg(cfg);
+    AudioDriver_Init();
+    if (cfg->fm_subaudible_tone_det_freq > 0.0f) AudioManagement_CalcSubaudibleDetFreq(cfg->fm_subaudible_tone_det_freq);
+    ref_select_path(cfg->filter_path);
+    AudioDriver_SetProcessingChain(ts.dmod_mode, true);
+    if (ts.filter_path != cfg->filter_path) return -3;
+    g_inited = 1;
+    return 0;
+}
+
+/* Reconfigure an initialised channel (reference semantics: AudioDriver_SetProcessingChain again). */
+int ref_reconfigure(const uhsdr_chan_cfg_t *cfg)
+{
+    if (!g_inited || cfg == NULL || cfg->struct_size != sizeof(uhsdr_chan_cfg_t)) return -1;
+    g_cfg = *cfg;
+    ref_apply_cfg(cfg);
+    if (cfg->fm_subaudible_tone_det_freq > 0.0f) AudioManagement_CalcSubaudibleDetFreq(cfg->fm_subaudible_tone_det_freq);
+    ref_select_path(cfg->filter_path);
+    AudioDriver_SetProcessingChain(ts.dmod_mode, false);
+    return ts.filter_path == cfg->filter_path ? 0 : -3;
+}
+
+/* nblocks calls of AudioDriver_RxProcessor (audio_driver.c:2603).  iq/audio: nblocks*32 samples of
+ * {int32 l, int32 r}.  audio_f (optional): adb.a_buffer[1] before the int conversion
+ * (audio_driver.c:2911).  mute (optional): external_mute per block.  The deferred noise-reduction
+ * task (PendSV, ui_driver.c:7157-7178) is run once after every block: the oracle's fixed schedule. */
+int ref_rx(const int32_t *iq, int32_t *audio, float *audio_f, int nblocks, const uint8_t *mute)
+{
+    if (!g_inited) return -1;
+    for (int b = 0; b < nblocks; b++) {
+        IqSample_t src[IQ_BLOCK_SIZE];
+        AudioSample_t dst[IQ_BLOCK_SIZE];
+        memcpy(src, iq + (size_t)b * 2 * IQ_BLOCK_SIZE, sizeof(src));
+        AudioDriver_RxProcessor(src, dst, IQ_BLOCK_SIZE, mute ? (mute[b] != 0) : false);
+        memcpy(audio + (size_t)b * 2 * IQ_BLOCK_SIZE, dst, sizeof(dst));
+        if (audio_f) memcpy(audio_f + (size_t)b * IQ_BLOCK_SIZE, adb.a_buffer[1], sizeof(float) * IQ_BLOCK_SIZE);
+        AudioNr_HandleNoiseReduction();
+    }
+    return 0;
+}
+
+int ref_get_status(uhsdr_chan_status_t *st)
+{
+    memset(st, 0, sizeof(*st));
+    st->adc_clip = ads.adc_clip; st->adc_half_clip = ads.adc_half_clip; st->adc_quarter_clip = ads.adc_quarter_clip;
+    st->agc_action = agc_wdsp_conf.action; st->agc_hang_action = agc_wdsp_conf.hang_action;
+    st->fm_squelched = ads.fm_conf.squelched; st->fm_sql_avg = ads.fm_conf.sql_avg;
+    st->sam_carrier_freq_offset = ads.carrier_freq_offset;
+    st->iq_corr_c1 = adb.iq_corr.M_c1; st->iq_corr_c2 = adb.iq_corr.M_c2;
+    st->tx_peak_audio = ads.peak_audio; st->tx_alc_val = ads.alc_val;
+    return 0;
+}
+
+/* Debug taps for the restatement's development: current I/Q scratch and audio scratch. */
+const float *ref_tap_iq_i(void) { return adb.iq_buf.i_buffer; }
+const float *ref_tap_iq_q(void) { return adb.iq_buf.q_buffer; }
+const float *ref_tap_a0(void) { return adb.a_buffer[0]; }
