@@ -1,0 +1,105 @@
+// configure.cu -- device side of uhsdr_configure_channels: stores the new parameter record and
+// applies the reference's state rules.
+//   reset != 0 : fresh-process state (SURVEY.md 8a "state inventory": everything zero except
+//                agc out_index = -1, FM squelched, NCO vector (0,1), M_c2 = 1, ALC = 1, NR Hk = 1 ...).
+//   always     : what AudioDriver_SetProcessingChain does (audio_driver.c:1093-1251): lattice
+//                states, FIR / decimator / interpolator histories and the IQ-correction averages
+//                are cleared; the AGC ring is re-initialised only when the decimated rate changed
+//                (audio_agc.c:138-142) and in_index is re-derived from out_index (:292-293);
+//                biquad, SAM, FM, fade-leveler and NR state are kept.
+#include "kernels.h"
+
+namespace uhsdr {
+
+__device__ void nr_boot_state(NrState &n)
+{
+    // NR_Init (audio_nr.c:78-103) + first_time==1 branch (:1920-1935) happens lazily in the kernel
+    n.first_time = 1; n.init_counter = 0; n.was_here = 0; n.out_buffer = -1;
+}
+
+__global__ void nr_boot_kernel(NrState *nr, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nr_boot_state(nr[i]);
+}
+
+__global__ void tx_boot_kernel(TxState *tx, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tx[i].alc_val = 1.0f;      // tx_processor.c:137
+}
+
+__global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
+                                 TxParams *txparams, const __grid_constant__ ChanParams newp,
+                                 const __grid_constant__ TxParams newtx, int first, int count, int reset)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int ch = first + i;
+    params[ch] = newp;
+    if (txparams) txparams[ch] = newtx;
+    ChanState &s = state[ch];
+    if (reset) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(&s);
+        for (int k = 0; k < (int)(sizeof(ChanState) / 4); k++) w[k] = 0u;
+        s.osc_vect_q = 1.0f;            // freq_shift.c:45-46
+        s.fm_squelched = 1;             // audio_driver.c:475
+        s.agc_out_index = -1;           // audio_agc.c:190
+        s.agc_sample_rate = 0.0f;
+        if (nr) {
+            uint32_t *wn = reinterpret_cast<uint32_t *>(&nr[ch]);
+            for (int k = 0; k < (int)(sizeof(NrState) / 4); k++) wn[k] = 0u;
+            nr_boot_state(nr[ch]);
+        }
+        if (spec_ring) for (int k = 0; k < 1024; k++) spec_ring[(size_t)ch * 1024 + k] = 0.0f;
+        if (tx) {
+            uint32_t *wt = reinterpret_cast<uint32_t *>(&tx[ch]);
+            for (int k = 0; k < (int)(sizeof(TxState) / 4); k++) wt[k] = 0u;
+            tx[ch].alc_val = 1.0f;
+        }
+    }
+    // AudioDriver_SetProcessingChain
+    for (int k = 0; k < MAX_LAT; k++) { s.pre_s[k] = 0.0f; s.aa_s[k] = 0.0f; }
+    s.M_c1 = 0.0f; s.M_c2 = 1.0f; s.teta1_old = 0.0f; s.teta2_old = 0.0f; s.teta3_old = 0.0f;
+    for (int k = 0; k < H1; k++) { s.s1_hist_i[k] = 0.0f; s.s1_hist_q[k] = 0.0f; }
+    for (int k = 0; k < H2; k++) { s.s2_hist_i[k] = 0.0f; s.s2_hist_q[k] = 0.0f; }
+    for (int k = 0; k < INTERP_HIST; k++) s.interp_hist[k] = 0.0f;
+    if (s.agc_sample_rate != newp.agc.sample_rate) {
+        s.agc_sample_rate = newp.agc.sample_rate;
+        for (int k = 0; k < AGC_RB; k++) s.agc_ring[k] = 0.0f;
+        s.agc_out_index = -1;
+        s.agc_ring_max = 0.0f; s.agc_volts = 0.0f; s.agc_save_volts = 0.0f;
+        s.agc_fast_backaverage = 0.0f; s.agc_hang_backaverage = 0.0f;
+        s.agc_hang_counter = 0; s.agc_decay_type = 0; s.agc_state = 0;
+    }
+    s.agc_in_index = (int)((uint32_t)(newp.agc.attack_buffsize + s.agc_out_index) % (uint32_t)AGC_RB);
+    if (tx) {
+        // TxProcessor_Set (tx_processor.c:72-119): lattice state and Hilbert histories cleared
+        for (int k = 0; k < MAX_LAT; k++) tx[ch].lat_s[k] = 0.0f;
+        for (int k = 0; k < H2; k++) tx[ch].hist[k] = 0.0f;
+    }
+}
+
+cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
+                             TxParams *txparams, const ChanParams &newp, const TxParams &newtx, int first, int count,
+                             int reset, cudaStream_t stream)
+{
+    const int threads = 64;
+    configure_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(params, state, nr, spec_ring, tx, txparams,
+                                                                               newp, newtx, first, count, reset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nr_boot(NrState *nr, int n, cudaStream_t stream)
+{
+    nr_boot_kernel<<<(n + 127) / 128, 128, 0, stream>>>(nr, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tx_boot(TxState *tx, int n, cudaStream_t stream)
+{
+    tx_boot_kernel<<<(n + 127) / 128, 128, 0, stream>>>(tx, n);
+    return cudaGetLastError();
+}
+
+}  // namespace uhsdr

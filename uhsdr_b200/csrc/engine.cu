@@ -1,0 +1,373 @@
+// engine.cu -- the C ABI of include/uhsdr_b200.h: engine lifetime, channel configuration, and the
+// host-buffer / device-buffer entry points that stand in for AudioDriver_I2SCallback ->
+// AudioDriver_RxProcessor / TxProcessor_Run (mchf-eclipse/drivers/audio/audio_driver.c:2962,2603;
+// tx_processor.c:891).  There is no CPU path: every call needs a usable CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "host_tables.h"
+#include "kernels.h"
+#include "uhsdr_b200.h"
+
+using namespace uhsdr;
+
+struct uhsdr_engine {
+    int device = 0;
+    int nch = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream[2] = { nullptr, nullptr };
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    HostTables tables;
+    float *d_pool = nullptr;
+    ChanParams *d_params = nullptr;
+    ChanState *d_state = nullptr;
+    NrState *d_nr = nullptr;
+    float *d_spec = nullptr;
+    TxState *d_tx = nullptr;
+    TxParams *d_txp = nullptr;
+    std::vector<ChanParams> h_params;
+    // dispatch lists (rebuilt after configure)
+    bool lists_dirty = true;
+    std::vector<int> h_list_fused, h_list_generic;
+    int *d_list_fused = nullptr, *d_list_generic = nullptr;
+    FusedCoefs fused_coefs;
+    bool fused_coefs_valid = false;
+    int fused_s1_ci = -1, fused_s2_ci = -1, fused_s2_cq = -1;
+    // staging for the host-buffer entry points
+    void *d_in = nullptr, *d_out = nullptr;
+    uint8_t *d_mute = nullptr;
+    size_t d_in_bytes = 0, d_out_bytes = 0, d_mute_bytes = 0;
+    std::string last_error;
+    int64_t launches = 0;
+    int sm_count = 148;
+    int use_fused = 1;
+};
+
+static std::string g_create_error;
+
+#define CK(e, call)                                                                             \
+    do {                                                                                        \
+        cudaError_t _err = (call);                                                              \
+        if (_err != cudaSuccess) {                                                              \
+            (e)->last_error = std::string(#call) + ": " + cudaGetErrorString(_err);             \
+            return UHSDR_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+extern "C" {
+
+int uhsdr_b200_abi_version(void) { return 1; }
+
+const char *uhsdr_b200_backend(void)
+{
+#if UHSDR_EXACT
+    return "cuda-sm100a-exact";
+#else
+    return "cuda-sm100a";
+#endif
+}
+
+const char *uhsdr_strerror(int code)
+{
+    switch (code) {
+    case UHSDR_OK: return "ok";
+    case UHSDR_ERR_ARG: return "invalid argument";
+    case UHSDR_ERR_NO_DEVICE: return "no usable CUDA device";
+    case UHSDR_ERR_CUDA: return "CUDA runtime error";
+    case UHSDR_ERR_TABLES: return "bad coefficient-table blob";
+    case UHSDR_ERR_UNSUPPORTED: return "configuration not implemented";
+    case UHSDR_ERR_STATE: return "channel not configured";
+    default: return "unknown error";
+    }
+}
+
+const char *uhsdr_last_error(const uhsdr_engine_t *e) { return e ? e->last_error.c_str() : g_create_error.c_str(); }
+
+int uhsdr_default_chan_cfg(uhsdr_chan_cfg_t *cfg)
+{
+    if (!cfg) return UHSDR_ERR_ARG;
+    default_chan_cfg(cfg);
+    return UHSDR_OK;
+}
+
+int uhsdr_engine_destroy(uhsdr_engine_t *e)
+{
+    if (!e) return UHSDR_ERR_ARG;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec);
+    cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
+    cudaFree(e->d_list_fused); cudaFree(e->d_list_generic);
+    for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
+    for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return UHSDR_OK;
+}
+
+int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, const void *tables, size_t tables_bytes)
+{
+    if (!out || num_channels <= 0) { g_create_error = "bad arguments"; return UHSDR_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        g_create_error = std::string("cudaGetDeviceCount: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "no device / bad index");
+        return UHSDR_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "device is not an sm_100-class (Blackwell) GPU; the library carries sm_100a code only";
+        return UHSDR_ERR_NO_DEVICE;
+    }
+    uhsdr_engine *e = new (std::nothrow) uhsdr_engine();
+    if (!e) { g_create_error = "out of memory"; return UHSDR_ERR_ARG; }
+    e->device = device; e->nch = num_channels; e->sm_count = prop.multiProcessorCount;
+    std::string err;
+    if (!e->tables.load(tables, tables_bytes, &err)) { g_create_error = err; delete e; return UHSDR_ERR_TABLES; }
+    const char *nf = getenv("UHSDR_B200_NO_FUSED");
+    if (nf && nf[0] == '1') e->use_fused = 0;
+    auto fail = [&](const char *what, cudaError_t er) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(er);
+        uhsdr_engine_destroy(e);
+        return UHSDR_ERR_CUDA;
+    };
+    cudaError_t er;
+    if ((er = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", er);
+    if ((er = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", er);
+    for (auto &s : e->copy_stream) if ((er = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", er);
+    for (auto &v : e->ev) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    const size_t n = (size_t)num_channels;
+    if ((er = cudaMalloc(&e->d_pool, e->tables.pool.size() * sizeof(float))) != cudaSuccess) return fail("cudaMalloc pool", er);
+    if ((er = cudaMemcpy(e->d_pool, e->tables.pool.data(), e->tables.pool.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy pool", er);
+    if ((er = cudaMalloc(&e->d_params, n * sizeof(ChanParams))) != cudaSuccess) return fail("cudaMalloc params", er);
+    if ((er = cudaMemset(e->d_params, 0, n * sizeof(ChanParams))) != cudaSuccess) return fail("cudaMemset params", er);
+    if ((er = cudaMalloc(&e->d_state, n * sizeof(ChanState))) != cudaSuccess) return fail("cudaMalloc state", er);
+    if ((er = cudaMemset(e->d_state, 0, n * sizeof(ChanState))) != cudaSuccess) return fail("cudaMemset state", er);
+    if ((er = cudaMalloc(&e->d_list_fused, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_list_generic, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    e->h_params.assign(n, ChanParams{});
+    *out = e;
+    return UHSDR_OK;
+}
+
+int uhsdr_engine_num_channels(const uhsdr_engine_t *e) { return e ? e->nch : UHSDR_ERR_ARG; }
+void *uhsdr_engine_stream(uhsdr_engine_t *e) { return e ? (void *)e->stream : nullptr; }
+int64_t uhsdr_engine_launch_count(const uhsdr_engine_t *e) { return e ? e->launches : 0; }
+
+int uhsdr_engine_sync(uhsdr_engine_t *e)
+{
+    if (!e) return UHSDR_ERR_ARG;
+    CK(e, cudaSetDevice(e->device));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return UHSDR_OK;
+}
+
+int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count, const uhsdr_chan_cfg_t *cfg, int reset)
+{
+    if (!e || !cfg || first < 0 || count <= 0 || first + count > e->nch) { if (e) e->last_error = "configure: bad channel range or NULL cfg"; return UHSDR_ERR_ARG; }
+    ChanParams p;
+    std::string err;
+    int rc = build_chan_params(e->tables, *cfg, &p, &err);
+    if (rc != UHSDR_OK) { e->last_error = err; return rc; }
+    TxParams tp;
+    rc = build_tx_params(e->tables, *cfg, &tp, &err);
+    if (rc != UHSDR_OK) { e->last_error = err; return rc; }
+    CK(e, cudaSetDevice(e->device));
+    const size_t n = (size_t)e->nch;
+    if (p.nr_enable && !e->d_nr) {
+        CK(e, cudaMalloc(&e->d_nr, n * sizeof(NrState)));
+        CK(e, cudaMemsetAsync(e->d_nr, 0, n * sizeof(NrState), e->stream));
+        CK(e, launch_nr_boot(e->d_nr, e->nch, e->stream));
+        e->launches++;
+    }
+    if (p.spectrum_enable && !e->d_spec) {
+        CK(e, cudaMalloc(&e->d_spec, n * 1024 * sizeof(float)));
+        CK(e, cudaMemsetAsync(e->d_spec, 0, n * 1024 * sizeof(float), e->stream));
+    }
+    if (!e->d_tx) {
+        CK(e, cudaMalloc(&e->d_tx, n * sizeof(TxState)));
+        CK(e, cudaMemsetAsync(e->d_tx, 0, n * sizeof(TxState), e->stream));
+        CK(e, launch_tx_boot(e->d_tx, e->nch, e->stream));
+        e->launches++;
+        CK(e, cudaMalloc(&e->d_txp, n * sizeof(TxParams)));
+        CK(e, cudaMemsetAsync(e->d_txp, 0, n * sizeof(TxParams), e->stream));
+    }
+    CK(e, launch_configure(e->d_params, e->d_state, e->d_nr, e->d_spec, e->d_tx, e->d_txp, p, tp, first, count, reset, e->stream));
+    e->launches++;
+    for (int c = first; c < first + count; c++) e->h_params[c] = p;
+    e->lists_dirty = true;
+    return UHSDR_OK;
+}
+
+int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg_t *cfg, int reset)
+{
+    return uhsdr_configure_channels(e, channel, 1, cfg, reset);
+}
+
+// Channels whose chain is the narrow-SSB topology with one shared coefficient set run on the
+// fused kernel (rx_ssb_fused.cu); everything else runs on the general kernel.
+static int rebuild_lists(uhsdr_engine *e)
+{
+    e->h_list_fused.clear(); e->h_list_generic.clear();
+    e->fused_s1_ci = -1;
+    for (int c = 0; c < e->nch; c++) {
+        const ChanParams &p = e->h_params[c];
+        if (!p.configured) { e->last_error = "rx/tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
+        bool fused = e->use_fused && fused_eligible(p);
+        if (fused) {
+            if (e->fused_s1_ci < 0) { e->fused_s1_ci = p.s1_ci; e->fused_s2_ci = p.s2_ci; e->fused_s2_cq = p.s2_cq; }
+            else if (p.s1_ci != e->fused_s1_ci || p.s2_ci != e->fused_s2_ci || p.s2_cq != e->fused_s2_cq) fused = false;
+        }
+        (fused ? e->h_list_fused : e->h_list_generic).push_back(c);
+    }
+    if (!e->h_list_fused.empty()) {
+        CK(e, cudaMemcpyAsync(e->d_list_fused, e->h_list_fused.data(), e->h_list_fused.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        const float *pool = e->tables.pool.data();
+        fill_fused_coefs(&e->fused_coefs, pool + e->fused_s1_ci, pool + e->fused_s2_ci, pool + e->fused_s2_cq);
+    }
+    if (!e->h_list_generic.empty())
+        CK(e, cudaMemcpyAsync(e->d_list_generic, e->h_list_generic.data(), e->h_list_generic.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));   // the host vectors may be rebuilt before the copies run
+    e->lists_dirty = false;
+    return UHSDR_OK;
+}
+
+int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_audio_sample_t *audio_dev,
+                            float *audio_f_dev, int nblocks, const uint8_t *mute_dev)
+{
+    if (!e || !iq_dev || !audio_dev || nblocks <= 0) { if (e) e->last_error = "rx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    if (e->lists_dirty) { int rc = rebuild_lists(e); if (rc != UHSDR_OK) return rc; }
+    RxArgs a;
+    a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
+    a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
+    if (!e->h_list_fused.empty()) {
+        a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
+        CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, e->stream));
+        e->launches++;
+    }
+    if (!e->h_list_generic.empty()) {
+        a.chan_list = e->d_list_generic; a.num_items = (int)e->h_list_generic.size();
+        CK(e, launch_rx_generic(a, e->stream));
+        e->launches++;
+    }
+    return UHSDR_OK;
+}
+
+static int ensure_staging(uhsdr_engine *e, size_t in_bytes, size_t out_bytes, size_t mute_bytes)
+{
+    if (in_bytes > e->d_in_bytes) { cudaFree(e->d_in); e->d_in = nullptr; e->d_in_bytes = 0; CK(e, cudaMalloc(&e->d_in, in_bytes)); e->d_in_bytes = in_bytes; }
+    if (out_bytes > e->d_out_bytes) { cudaFree(e->d_out); e->d_out = nullptr; e->d_out_bytes = 0; CK(e, cudaMalloc(&e->d_out, out_bytes)); e->d_out_bytes = out_bytes; }
+    if (mute_bytes > e->d_mute_bytes) { cudaFree(e->d_mute); e->d_mute = nullptr; e->d_mute_bytes = 0; CK(e, cudaMalloc(&e->d_mute, mute_bytes)); e->d_mute_bytes = mute_bytes; }
+    return UHSDR_OK;
+}
+
+int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio_sample_t *audio, int nblocks, const uint8_t *mute)
+{
+    if (!e || !iq || !audio || nblocks <= 0) { if (e) e->last_error = "rx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)e->nch * (size_t)nblocks * BLK * sizeof(uhsdr_iq_sample_t);
+    const size_t mbytes = mute ? (size_t)e->nch * (size_t)nblocks : 0;
+    int rc = ensure_staging(e, bytes, bytes, mbytes);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(e->d_in, iq, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (mute) CK(e, cudaMemcpyAsync(e->d_mute, mute, mbytes, cudaMemcpyHostToDevice, e->stream));
+    rc = uhsdr_rx_process_device(e, (const uhsdr_iq_sample_t *)e->d_in, (uhsdr_audio_sample_t *)e->d_out, nullptr, nblocks, mute ? e->d_mute : nullptr);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(audio, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return UHSDR_OK;
+}
+
+int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio_dev, uhsdr_iq_sample_t *iq_dev,
+                            float *iq_f_dev, int nblocks, const uint8_t *mute_dev)
+{
+    if (!e || !audio_dev || !iq_dev || nblocks <= 0) { if (e) e->last_error = "tx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    for (int c = 0; c < e->nch; c++)
+        if (!e->h_params[c].configured) { e->last_error = "tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
+    TxArgs a;
+    a.params = e->d_params; a.state = e->d_state; a.tx = e->d_tx; a.txp = e->d_txp; a.pool = e->d_pool;
+    a.audio = audio_dev; a.iq = iq_dev; a.iq_f = iq_f_dev; a.mute = mute_dev; a.nblocks = nblocks; a.num_items = e->nch;
+    CK(e, launch_tx_ssb(a, e->stream));
+    e->launches++;
+    return UHSDR_OK;
+}
+
+int uhsdr_tx_process(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio, uhsdr_iq_sample_t *iq, int nblocks, const uint8_t *mute)
+{
+    if (!e || !iq || !audio || nblocks <= 0) { if (e) e->last_error = "tx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)e->nch * (size_t)nblocks * BLK * sizeof(uhsdr_iq_sample_t);
+    const size_t mbytes = mute ? (size_t)e->nch * (size_t)nblocks : 0;
+    int rc = ensure_staging(e, bytes, bytes, mbytes);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(e->d_in, audio, bytes, cudaMemcpyHostToDevice, e->stream));
+    if (mute) CK(e, cudaMemcpyAsync(e->d_mute, mute, mbytes, cudaMemcpyHostToDevice, e->stream));
+    rc = uhsdr_tx_process_device(e, (const uhsdr_audio_sample_t *)e->d_in, (uhsdr_iq_sample_t *)e->d_out, nullptr, nblocks, mute ? e->d_mute : nullptr);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(iq, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return UHSDR_OK;
+}
+
+int uhsdr_get_spectrum_device(uhsdr_engine_t *e, int first, int count, float *mags_dev)
+{
+    if (!e || !mags_dev || first < 0 || count <= 0 || first + count > e->nch) { if (e) e->last_error = "get_spectrum: bad arguments"; return UHSDR_ERR_ARG; }
+    if (!e->d_spec) { e->last_error = "get_spectrum: no channel has spectrum_enable set"; return UHSDR_ERR_STATE; }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, launch_spectrum(e->d_params, e->d_state, e->d_spec, e->d_pool, e->tables.off(e->tables.ex->spectrum_window_array),
+                          e->tables.tw512_off, first, count, mags_dev, e->stream));
+    e->launches++;
+    return UHSDR_OK;
+}
+
+int uhsdr_get_spectrum(uhsdr_engine_t *e, int first, int count, float *mags)
+{
+    if (!e || !mags || count <= 0) { if (e) e->last_error = "get_spectrum: bad arguments"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)count * UHSDR_SPECTRUM_FFT_LEN * sizeof(float);
+    int rc = ensure_staging(e, 0, bytes, 0);
+    if (rc != UHSDR_OK) return rc;
+    rc = uhsdr_get_spectrum_device(e, first, count, (float *)e->d_out);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(mags, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return UHSDR_OK;
+}
+
+int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_t *status)
+{
+    if (!e || !status || first < 0 || count <= 0 || first + count > e->nch) { if (e) e->last_error = "get_status: bad arguments"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    std::vector<ChanState> hs((size_t)count);
+    CK(e, cudaMemcpyAsync(hs.data(), e->d_state + first, (size_t)count * sizeof(ChanState), cudaMemcpyDeviceToHost, e->stream));
+    std::vector<TxState> ht;
+    if (e->d_tx) {
+        ht.resize((size_t)count);
+        CK(e, cudaMemcpyAsync(ht.data(), e->d_tx + first, (size_t)count * sizeof(TxState), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(e, cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < count; i++) {
+        const ChanState &s = hs[i];
+        uhsdr_chan_status_t &o = status[i];
+        memset(&o, 0, sizeof(o));
+        o.adc_clip = s.adc_clip; o.adc_half_clip = s.adc_half_clip; o.adc_quarter_clip = s.adc_quarter_clip;
+        o.agc_action = s.agc_action; o.agc_hang_action = s.agc_hang_action;
+        o.fm_squelched = s.fm_squelched; o.fm_sql_avg = s.fm_sql_avg;
+        o.sam_carrier_freq_offset = s.carrier_freq_offset;
+        o.iq_corr_c1 = s.M_c1; o.iq_corr_c2 = s.M_c2;
+        o.blocks_processed = s.blocks;
+        if (!ht.empty()) { o.tx_peak_audio = ht[i].peak_audio; o.tx_alc_val = ht[i].alc_val; }
+    }
+    return UHSDR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// kernels.h -- launch interfaces of the CUDA kernels (host side sees only these).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "uhsdr_dev.h"
+
+namespace uhsdr {
+
+struct RxArgs {
+    const ChanParams *params;   // [num_channels]
+    ChanState *state;           // [num_channels]
+    NrState *nr;                // [num_channels] or nullptr
+    float *spec_ring;           // [num_channels][1024] or nullptr
+    const float *pool;          // coefficient pool
+    const void *iq;             // [num_channels][nblocks*32] {int32 l, int32 r}
+    void *audio;                // same shape
+    float *audio_f;             // optional [num_channels][nblocks*32]
+    const uint8_t *mute;        // optional [num_channels][nblocks]
+    const int *chan_list;       // optional: channels handled by this launch (nullptr = 0..num_items-1)
+    int num_items;
+    int nblocks;
+};
+
+cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);
+
+// fused narrow-SSB receiver (rx_ssb_fused.cu)
+bool fused_eligible(const ChanParams &p);
+void fill_fused_coefs(FusedCoefs *fc, const float *dec83, const float *hil_i199, const float *hil_q199);
+cudaError_t launch_rx_ssb_fused(const RxArgs &a, const FusedCoefs &fc, int sm_count, cudaStream_t stream);
+
+struct TxArgs {
+    const ChanParams *params;
+    ChanState *state;           // shares the FreqShift NCO with RX (freq_shift.c:277-283 statics)
+    TxState *tx;
+    const TxParams *txp;
+    const float *pool;
+    const void *audio;          // [num_channels][nblocks*32] {int32 l, int32 r}, microphone in l
+    void *iq;                   // [num_channels][nblocks*32] {int32 I, int32 Q}
+    float *iq_f;                // optional [num_channels][nblocks*32][2]
+    const uint8_t *mute;
+    int num_items;
+    int nblocks;
+};
+cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream);
+cudaError_t launch_tx_boot(TxState *tx, int n, cudaStream_t stream);
+cudaError_t launch_nr_boot(NrState *nr, int n, cudaStream_t stream);
+
+// UiSpectrum_RedrawSpectrum states 0-2
+cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, const float *spec_ring, const float *pool,
+                            int window_off, int twiddle_off, int first, int count, float *mags, cudaStream_t stream);
+
+// configure: write params for channels [first, first+count) and apply the reference's state
+// reset rules (reset != 0: boot state; 0: AudioDriver_SetProcessingChain semantics)
+cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
+                             TxParams *txparams, const ChanParams &newp, const TxParams &newtx, int first, int count,
+                             int reset, cudaStream_t stream);
+
+}  // namespace uhsdr
