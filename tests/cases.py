@@ -1,0 +1,43 @@
+"""Shared parity cases: (label, cfg kwargs, nblocks).  Every distinct signal-flow topology, every
+demodulator and the configuration switches the reference reads on the block path."""
+from uhsdr_b200.config import (DEMOD_AM, DEMOD_CW, DEMOD_DIGI, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, DSP_MNOTCH_ENABLE,
+                               DSP_MPEAK_ENABLE, DSP_NR_ENABLE, FREQ_IQ_CONV_M6KHZ, FREQ_IQ_CONV_OFF, FREQ_IQ_CONV_P12KHZ,
+                               FREQ_IQ_CONV_P6KHZ, SAM_SIDEBAND_LSB, SAM_SIDEBAND_USB)
+
+RX_CASES = [
+    ("usb_p35", dict(), 96),
+    ("lsb_p38", dict(dmod_mode=DEMOD_LSB, filter_path=38), 96),
+    ("usb_p44_antialias", dict(filter_path=44), 96),
+    ("usb_p48_hilbert_first", dict(filter_path=48), 96),
+    ("usb_p55_dec2", dict(filter_path=55), 96),
+    ("lsb_p65_dec2_antialias", dict(dmod_mode=DEMOD_LSB, filter_path=65), 96),
+    ("cw_p8", dict(dmod_mode=DEMOD_CW, filter_path=8), 96),
+    ("cw_lsb_p16", dict(dmod_mode=DEMOD_CW, filter_path=16, cw_lsb=1), 96),
+    ("digi_lsb_p38", dict(dmod_mode=DEMOD_DIGI, filter_path=38, digi_lsb=1), 96),
+    ("am_p70", dict(dmod_mode=DEMOD_AM, filter_path=70), 96),
+    ("am_p84_nofade", dict(dmod_mode=DEMOD_AM, filter_path=84, sam_fade_leveler=0), 96),
+    ("sam_p72_both", dict(dmod_mode=DEMOD_SAM, filter_path=72), 96),
+    ("sam_p72_usb", dict(dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=SAM_SIDEBAND_USB), 96),
+    ("sam_p84_lsb", dict(dmod_mode=DEMOD_SAM, filter_path=84, sam_sideband=SAM_SIDEBAND_LSB), 96),
+    ("fm_p2", dict(dmod_mode=DEMOD_FM, filter_path=2), 480),
+    ("fm_p1_sql0_5k", dict(dmod_mode=DEMOD_FM, filter_path=1, fm_sql_threshold=0, fm_dev_5khz=1), 320),
+    ("usb_p6k", dict(iq_freq_mode=FREQ_IQ_CONV_P6KHZ), 96),
+    ("usb_m6k", dict(iq_freq_mode=FREQ_IQ_CONV_M6KHZ), 96),
+    ("usb_p12k", dict(iq_freq_mode=FREQ_IQ_CONV_P12KHZ), 96),
+    ("usb_no_translate", dict(iq_freq_mode=FREQ_IQ_CONV_OFF), 96),
+    ("usb_manual_iq", dict(iq_auto_correction=0, rx_adj_gain_i=1.01, rx_adj_gain_q=0.99, iq_phase_balance_rx=-0.01), 96),
+    ("usb_manual_iq_pos", dict(iq_auto_correction=0, rx_adj_gain_i=0.98, rx_adj_gain_q=1.02, iq_phase_balance_rx=0.02), 96),
+    ("usb_agc_off", dict(agc_mode=5), 96),
+    ("usb_agc_fast_hang", dict(agc_mode=4, agc_hang_enable=1), 192),
+    ("usb_agc_long_hang", dict(agc_mode=0, agc_hang_enable=1, agc_thresh=40, agc_slope=40), 192),
+    ("usb_notch_peak_eq", dict(dsp_active=DSP_MNOTCH_ENABLE | DSP_MPEAK_ENABLE, treble_gain=3, bass_gain=-4), 96),
+]
+
+NR_CASES = [
+    ("usb_p35_nr_dec", dict(dsp_active=DSP_NR_ENABLE), 320),
+    ("usb_p44_nr_nodec", dict(filter_path=44, dsp_active=DSP_NR_ENABLE), 224),
+    ("usb_p35_nr_decoff", dict(dsp_active=DSP_NR_ENABLE, nr_decimation_enable=0, nr_strength=100), 224),
+]
+
+# float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these
+LIBM_CASES = {"sam_p72_both", "sam_p72_usb", "sam_p84_lsb", "fm_p2", "fm_p1_sql0_5k"}

@@ -1,0 +1,92 @@
+"""Host-side logic that needs no GPU: table blob parsing, filter-path lookup, synthetic signals,
+channel partitioning across ranks (world_size 2 over gloo)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from uhsdr_b200 import synth
+from uhsdr_b200.config import DEMOD_LSB, default_cfg
+from uhsdr_b200.tables import FILTER_MODE_AM, FILTER_MODE_CW, FILTER_MODE_FM, FILTER_MODE_SSB, Tables
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tables_blob_matches_reference_layout():
+    t = Tables()
+    assert len(t.paths) == 87 and len(t.filters) == 31          # AUDIO_FILTER_PATH_NUM, AUDIO_FILTER_NUM
+    p35 = t.paths[35]
+    assert (p35.fir_numtaps, p35.dec_numtaps, p35.sample_rate_dec, p35.fir_is_new_coeffs) == (199, 83, 4, 1)
+    assert t.width(35) == 2300 and t.width(38) == 2700
+    assert t.lattices[p35.pre_lattice][0] == 10
+    assert t.paths[48].fir_numtaps == 89 and t.paths[48].dec_numtaps == 43 and not t.paths[48].fir_is_new_coeffs
+    assert t.paths[55].sample_rate_dec == 2 and t.paths[55].pre_lattice == -1
+    assert t.paths[2].sample_rate_dec == 1 and t.paths[2].interpolate == -1
+    assert set(t.paths_for_mode(FILTER_MODE_FM)) == {1, 2, 3}
+    assert min(t.paths_for_mode(FILTER_MODE_AM)) == 66 and 35 in t.paths_for_mode(FILTER_MODE_CW)
+    assert 36 in t.paths_for_mode(FILTER_MODE_SSB) and 36 not in t.paths_for_mode(FILTER_MODE_CW)
+    assert t.arrays[t.extras["tx_hilbert_i_array"]].size == 201
+    assert t.arrays[t.extras["spectrum_window_array"]].size == 1024
+    with pytest.raises(ValueError):
+        Tables(blob=t.blob[:-4])
+
+
+def test_hilbert_pair_sideband_convention():
+    """SURVEY.md 8d sanity numbers: with the CMSIS tap order, +f passes USB = I+Q with gain 2 and -f
+    is rejected by >= 70 dB (199-tap pair at 12 ksps)."""
+    t = Tables()
+    p = t.paths[35]
+    hi, hq = t.arrays[p.fir_i_array][::-1].astype(np.float64), t.arrays[p.fir_q_array][::-1].astype(np.float64)
+    n = np.arange(199)
+    for f, lo, hi_lim in ((1500.0, 1.95, 2.05), (-1500.0, 0.0, 2e-4)):
+        w = np.exp(-2j * np.pi * f / 12000.0 * n)
+        g = abs(np.sum(hi * w) * 1.0 + np.sum(hq * w) * (-1j if True else 1j) * 1.0)   # I=cos, Q=sin
+        g = abs(np.sum(hi * w) + (-1j) * np.sum(hq * w))
+        assert lo <= g <= hi_lim, (f, g)
+
+
+def test_synth_is_deterministic_and_sliceable():
+    cfg = default_cfg()
+    a = synth.rx_iq(cfg, 7, 4096)
+    b = synth.rx_iq(cfg, 7, 4096)
+    assert np.array_equal(a, b) and a.dtype == np.int32 and a.shape == (4096, 2)
+    assert not np.array_equal(a, synth.rx_iq(cfg, 8, 4096))
+    assert np.max(np.abs(a)) < 2**31 - 1
+    lsb = synth.rx_iq(default_cfg(dmod_mode=DEMOD_LSB), 7, 4096)
+    assert not np.array_equal(a, lsb)
+
+
+def test_rank_partition_gloo_world2(tmp_path):
+    """bench.py's sharding rule: rank r owns global channels [r*C, (r+1)*C); ranks agree on the
+    max-over-ranks time through one all_reduce.  Exercised with 2 CPU processes over gloo."""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, torch, torch.distributed as dist\n"
+        "dist.init_process_group('gloo')\n"
+        "r, w = dist.get_rank(), dist.get_world_size()\n"
+        "C = 6\n"
+        "mine = torch.arange(r * C, (r + 1) * C)\n"
+        "allc = [torch.empty_like(mine) for _ in range(w)]\n"
+        "dist.all_gather(allc, mine)\n"
+        "got = torch.cat(allc)\n"
+        "assert torch.equal(got, torch.arange(w * C)), got\n"
+        "t = torch.tensor([10.0 + r], dtype=torch.float64)\n"
+        "dist.all_reduce(t, op=dist.ReduceOp.MAX)\n"
+        "assert t.item() == 10.0 + w - 1\n"
+        "dist.barrier()\n"
+        "print('rank', r, 'ok')\n")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_bench_reference_arm_exits_cleanly_on_nonzero_rank():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == ""
