@@ -250,7 +250,9 @@ int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev, 
     a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
     if (!e->h_list_fused.empty()) {
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
-        CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, e->stream));
+        // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
+        if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, e->stream));
+        else CK(e, launch_rx_generic(a, e->stream));
         e->launches++;
     }
     if (!e->h_list_generic.empty()) {

@@ -35,6 +35,17 @@ __device__ __forceinline__ float fir_dot(const float *x, const float *__restrict
     return acc;
 }
 
+// Reference-order arithmetic in both builds.  Used for AM / synchronous AM: their post-AGC DC
+// remover (audio_agc.c:577-594, pole 0.9999) holds a state ~1e4 x the carrier level, so the
+// rounding of that state -- and with it the output at the 1e-4 level -- follows every last bit of
+// its input; only bit-identical inputs reproduce the reference's output within tolerance.
+__device__ __forceinline__ float fir_dot_exact(const float *x, const float *__restrict__ c, int ntaps)
+{
+    float acc = 0.0f;
+    for (int k = 0; k < ntaps; k++) acc = __fadd_rn(acc, __fmul_rn(x[k], __ldg(c + k)));
+    return acc;
+}
+
 __device__ __forceinline__ void shift_history(float *buf, int H, int nnew, int lane)
 {
     // keep the newest H samples: buf[0..H) = buf[nnew..nnew+H)
@@ -110,20 +121,20 @@ rx_generic_kernel(RxArgs a)
                 // audio_driver.c:2274-2313 (Moseley & Slump): block statistics, EMA in double
                 float t1 = __fmul_rn(sign_new(fi), fq), t2 = __fmul_rn(sign_new(fi), fi), t3 = __fmul_rn(sign_new(fq), fq);
                 float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#if UHSDR_EXACT
-                for (int j = 0; j < 32; j++) {
-                    s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, t1, j));
-                    s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, t2, j));
-                    s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, t3, j));
+                if (UHSDR_EXACT || p.topo == TOPO_AM_SAM) {
+                    for (int j = 0; j < 32; j++) {
+                        s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, t1, j));
+                        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, t2, j));
+                        s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, t3, j));
+                    }
+                } else {
+                    s1 = t1; s2 = t2; s3 = t3;
+                    for (int d = 16; d > 0; d >>= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+                        s3 += __shfl_xor_sync(0xffffffffu, s3, d);
+                    }
                 }
-#else
-                s1 = t1; s2 = t2; s3 = t3;
-                for (int d = 16; d > 0; d >>= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-                    s3 += __shfl_xor_sync(0xffffffffu, s3, d);
-                }
-#endif
                 const float te1 = (float)(-0.003 * (double)__fdiv_rn(s1, 32.0f) + 0.997 * (double)st.teta1_old);
                 const float te2 = (float)(0.003 * (double)__fdiv_rn(s2, 32.0f) + 0.997 * (double)st.teta2_old);
                 const float te3 = (float)(0.003 * (double)__fdiv_rn(s3, 32.0f) + 0.997 * (double)st.teta3_old);
@@ -197,10 +208,16 @@ rx_generic_kernel(RxArgs a)
             const int nout = ns / M1;
             const float *ci = pool + p.s1_ci, *cq = pool + p.s1_cq;
             const int base = H1 - (N - 1);
-            for (int m = lane; m < nout; m += 32) {
-                const float yi = fir_dot(w.xi + base + m * M1, ci, N);
-                const float yq = fir_dot(w.xq + base + m * M1, cq, N);
-                w.bi[H2 + m] = yi; w.bq[H2 + m] = yq;
+            if (p.topo == TOPO_AM_SAM) {
+                for (int m = lane; m < nout; m += 32) {
+                    w.bi[H2 + m] = fir_dot_exact(w.xi + base + m * M1, ci, N);
+                    w.bq[H2 + m] = fir_dot_exact(w.xq + base + m * M1, cq, N);
+                }
+            } else {
+                for (int m = lane; m < nout; m += 32) {
+                    w.bi[H2 + m] = fir_dot(w.xi + base + m * M1, ci, N);
+                    w.bq[H2 + m] = fir_dot(w.xq + base + m * M1, cq, N);
+                }
             }
         }
         __syncwarp();

@@ -1,13 +1,668 @@
-// rx_ssb_fused.cu -- fused narrow-SSB receiver kernel (placeholder: not yet eligible for any channel).
+// rx_ssb_fused.cu -- fused narrow-SSB/CW receiver kernel (BASELINE.json configs[1]).
+//
+// One persistent CTA owns up to 32 channels for the whole launch and every sample crosses HBM
+// once: int32 I/Q in, int32 audio out.  The reference chain for these filter paths
+// (FilterPathInfo[4..47], mchf-eclipse/drivers/audio/audio_filter.c:147-922; flow in
+// audio_driver.c:2603-2942) is
+//
+//   format + IQ correction + Fs/4 translate -> 83-tap /4 decimator on I and Q
+//   -> 199-tap Hilbert pair @12 ksps -> I +/- Q -> 10-stage lattice IIR -> WDSP AGC -> gain
+//   -> 4-stage biquad -> x4 polyphase interpolator -> (6-stage anti-alias lattice) -> treble
+//   biquad -> x10 -> int32 << 16.
+//
+// The time-parallel part (front end + both FIR pairs, 282 of the 346 FLOP per sample) runs on
+// "FIR warps": 8 lanes per channel, 4 decimated outputs per lane, coefficients as immediate
+// constant-bank operands (the taps travel as a __grid_constant__ kernel parameter), samples staged
+// in shared memory (polyphase layout for the decimator, so every LDS is a conflict-free 128-bit
+// load) and streamed once through 4 FMAs each.  The sample-serial recurrences run one channel per
+// lane on four specialised warps (lattice | AGC | EQ + interpolator | anti-alias + treble) that
+// form a software pipeline with the FIR warps through double-buffered, channel-minor shared-memory
+// queues; one __syncthreads per 128-sample chunk advances the pipeline.  The AGC's sliding
+// 49-sample maximum (audio_agc.c:409-429 rescans on demand, divergent) is computed with the
+// van Herk / Gil-Werman block decomposition, which yields the same exact maximum with uniform
+// control flow.
 #include "dsp_device.cuh"
 #include "kernels.h"
+#include "uhsdr_b200.h"
 
 namespace uhsdr {
-bool fused_eligible(const ChanParams &p) { (void)p; return false; }
-void fill_fused_coefs(FusedCoefs *fc, const float *d, const float *hi, const float *hq) { (void)fc; (void)d; (void)hi; (void)hq; }
+
+namespace {
+
+constexpr int FG = 32;             // channel slots per CTA
+constexpr int CH4 = 128;           // input samples per chunk (4 blocks)
+constexpr int ND = 32;             // decimated samples per chunk
+constexpr int XP = 56;             // per-phase slots: 21 history + 32 new + 3 pad
+constexpr int XCH = 2 * 4 * XP + 4;   // floats per channel (I phases, Q phases) + 4 -> bank stagger
+constexpr int DL = 200 + ND;       // Hilbert input: 200 history slots + 32 new
+constexpr int DCH = 2 * DL;
+constexpr int SMS = 33;            // channel-minor stride of the pipeline queues
+constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
+constexpr int RING = 64;
+constexpr int NWARP_FIR = FG / 4;
+constexpr int W_LAT = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_EQ = NWARP_FIR + 2, W_POST = NWARP_FIR + 3;
+constexpr int NTHREADS = 32 * (NWARP_FIR + 4);
+constexpr int PIPE_DEPTH = 5;      // FIR t | LAT t-1 | AGC t-2 | EQ t-3 | POST t-4 | WRITE t-5
+
+struct Smem {
+    float x[FG * XCH];
+    float d[FG * DCH];
+    float aud[2][ND * SMS];
+    float lat[2][ND * SMS];
+    float agc[2][ND * SMS];
+    float out[3][CH4 * SMS];
+    float ring[RING * SMS];
+    float smax[AGC_W * SMS];
+};
+
+template <int N> struct IC { static constexpr int value = N; };
+template <int I, int N, typename F> __device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) { f(IC<I>{}); static_for<I + 1, N>(f); }
+}
+
+__device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+// ---------------------------------------------------------------------------------------------
+// FIR warps
+// ---------------------------------------------------------------------------------------------
+struct FirLaneState {
+    float te1, te2, te3;     // teta*_old
+    float c1, c2;            // M_c1, M_c2
+    int clip;                // bit0 quarter, bit1 half, bit2 full
+};
+
+// Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 84 history
+// samples in front, buffer position b = 4m + k + 2; phase = b & 3, idx = b >> 2.  Elements are
+// consumed in ascending b, which is ascending k for every output: the reference's summation order.
+template <typename Coefs>
+__device__ __forceinline__ void decimate4(const float *xp /* [4][XP] of this channel */, int m0, const Coefs &fc, float acc[4])
+{
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+    static_for<0, 7>([&](auto q) {
+        constexpr int Q = decltype(q)::value;
+        float4 v[4];
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) v[ph] = lds128(xp + ph * XP + m0 + 4 * Q);
+        static_for<0, 4>([&](auto e) {
+            constexpr int E = decltype(e)::value;            // element within the float4
+            constexpr int U = 4 * Q + E;                     // idx - m0
+            // order of positions b for fixed idx: phase 0,1,2,3
+            static_for<0, 4>([&](auto phv) {
+                constexpr int PH = decltype(phv)::value;
+                const float xv = (E == 0) ? v[PH].x : (E == 1) ? v[PH].y : (E == 2) ? v[PH].z : v[PH].w;
+                static_for<0, 4>([&](auto jv) {
+                    constexpr int J = decltype(jv)::value;
+                    constexpr int K = 4 * (U - J) + PH - 2;  // tap index
+                    if constexpr (K >= 0 && K <= 82) acc[J] = mad(fc.dec[K], xv, acc[J]);
+                });
+            });
+        });
+    });
+}
+
+// Hilbert pair at 12 ksps: y[n] = sum_k c[k] d[n - 198 + k] (arm_fir_f32.c:522-529).  With 200
+// history slots, position = n + k + 2; elements are streamed in ascending position.
+template <bool IS_Q, typename Coefs>
+__device__ __forceinline__ void hilbert4(const float *dp /* [DL] */, int n0, const Coefs &fc, float acc[4])
+{
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
+    static_for<0, 51>([&](auto q) {
+        constexpr int Q = decltype(q)::value;
+        const float4 v = lds128(dp + n0 + 4 * Q);
+        static_for<0, 4>([&](auto e) {
+            constexpr int E = decltype(e)::value;
+            constexpr int P = 4 * Q + E;                     // position - n0
+            const float xv = (E == 0) ? v.x : (E == 1) ? v.y : (E == 2) ? v.z : v.w;
+            static_for<0, 4>([&](auto jv) {
+                constexpr int J = decltype(jv)::value;
+                constexpr int K = P - J - 2;
+                if constexpr (K >= 0 && K <= 198) acc[J] = mad(IS_Q ? fc.hil_q[K] : fc.hil_i[K], xv, acc[J]);
+            });
+        });
+    });
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ FusedCoefs fc, int chans_per_cta)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cta_first = blockIdx.x * chans_per_cta;
+    const int n_here = min(chans_per_cta, a.num_items - cta_first);
+    const int nchunks = a.nblocks / 4;
+    const float *__restrict__ pool = a.pool;
+
+    if (warp < NWARP_FIR) {
+        // ======================= FIR warp: 4 channels x 8 lanes =================================
+        const int cl = lane >> 3, r = lane & 7;
+        const int g = warp * 4 + cl;                   // channel slot in the CTA
+        const bool active = g < n_here;
+        const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
+        const ChanParams &p = a.params[ch];
+        ChanState *st = a.state + ch;
+        float *xi = sm.x + g * XCH, *xq = xi + 4 * XP;
+        float *di = sm.d + g * DCH, *dq = di + DL;
+        const unsigned gmask = 0xffu << (8 * cl);
+
+        // ---- load histories and IQ-correction state ----
+        FirLaneState ls;
+        ls.te1 = st->teta1_old; ls.te2 = st->teta2_old; ls.te3 = st->teta3_old; ls.c1 = st->M_c1; ls.c2 = st->M_c2; ls.clip = 0;
+        // s1_hist[H1=96]: sample s (-84..-1) at [96 + s] -> position b = s + 84 -> phase b&3, idx b>>2
+        for (int b = r; b < 84; b += 8) {
+            xi[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_i[H1 - 84 + b] : 0.0f;
+            xq[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_q[H1 - 84 + b] : 0.0f;
+        }
+        for (int i = r; i < 200; i += 8) {
+            di[i] = active ? st->s2_hist_i[i] : 0.0f;
+            dq[i] = active ? st->s2_hist_q[i] : 0.0f;
+        }
+        const int iq_auto = p.iq_auto, shift_kind = p.shift_kind, shift_down = p.shift_down, lsb = p.lsb;
+        const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
+        const size_t chan_base = (size_t)ch * (size_t)a.nblocks * BLK;
+        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base);
+        int4 *__restrict__ dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(a.audio) + chan_base);
+        float2 *__restrict__ dst_f = a.audio_f ? reinterpret_cast<float2 *>(a.audio_f + chan_base) : nullptr;
+        const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+        __syncwarp();
+
+        for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
+            if (t < nchunks) {
+                // ---- front end: 16 samples per lane (pairs p = r + 8i, samples 2p, 2p+1) ----
+                float fi[16], fq[16];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    int4 v = make_int4(0, 0, 0, 0);
+                    if (active) v = __ldg(src + (size_t)t * 64 + r + 8 * i);
+                    const int l0 = abs(v.x) >> 16, l1 = abs(v.z) >> 16;
+                    const int lv = max(l0, l1);
+                    ls.clip |= (lv > 1024 ? 1 : 0) | (lv > 2048 ? 2 : 0) | (lv > 4096 ? 4 : 0);
+                    fi[2 * i] = __fmul_rn((float)v.x, 0.0000152587890625f);
+                    fq[2 * i] = __fmul_rn((float)v.y, 0.0000152587890625f);
+                    fi[2 * i + 1] = __fmul_rn((float)v.z, 0.0000152587890625f);
+                    fq[2 * i + 1] = __fmul_rn((float)v.w, 0.0000152587890625f);
+                }
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    // block b holds this lane's samples 4b .. 4b+3 (pairs i = 2b, 2b+1)
+                    if (iq_auto) {
+                        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#if UHSDR_EXACT
+                        // reference order: sample n of the block lives in lane (n/2)&7, slot 4b + 2*((n/2)>>3) + (n&1)
+#pragma unroll
+                        for (int n = 0; n < 32; n++) {
+                            const int slot = 4 * b + 2 * ((n >> 1) >> 3) + (n & 1);
+                            const float vi = __shfl_sync(gmask, fi[slot], (n >> 1) & 7, 8);
+                            const float vq = __shfl_sync(gmask, fq[slot], (n >> 1) & 7, 8);
+                            s1 = __fadd_rn(s1, __fmul_rn(sign_new(vi), vq));
+                            s2 = __fadd_rn(s2, __fmul_rn(sign_new(vi), vi));
+                            s3 = __fadd_rn(s3, __fmul_rn(sign_new(vq), vq));
+                        }
+#else
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float vi = fi[4 * b + k], vq = fq[4 * b + k];
+                            s1 += __fmul_rn(sign_new(vi), vq);
+                            s2 += fabsf(vi);
+                            s3 += fabsf(vq);
+                        }
+#pragma unroll
+                        for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                            s1 += __shfl_xor_sync(gmask, s1, dlt, 8);
+                            s2 += __shfl_xor_sync(gmask, s2, dlt, 8);
+                            s3 += __shfl_xor_sync(gmask, s3, dlt, 8);
+                        }
+#endif
+                        // teta = -/+0.003*(sum/32) + 0.997*teta_old, evaluated in double (:2281-2283)
+                        ls.te1 = (float)(-0.003 * (double)__fdiv_rn(s1, 32.0f) + 0.997 * (double)ls.te1);
+                        ls.te2 = (float)(0.003 * (double)__fdiv_rn(s2, 32.0f) + 0.997 * (double)ls.te2);
+                        ls.te3 = (float)(0.003 * (double)__fdiv_rn(s3, 32.0f) + 0.997 * (double)ls.te3);
+                        ls.c1 = (ls.te2 != 0.0f) ? __fdiv_rn(ls.te1, ls.te2) : 0.0f;
+                        float help = __fmul_rn(ls.te2, ls.te2);
+                        if (help > 0.0f) help = __fdiv_rn(__fsub_rn(__fmul_rn(ls.te3, ls.te3), __fmul_rn(ls.te1, ls.te1)), help);
+                        ls.c2 = (help > 0.0f) ? __fsqrt_rn(help) : 1.0f;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            fq[4 * b + k] = __fadd_rn(fq[4 * b + k], __fmul_rn(ls.c1, fi[4 * b + k]));
+                            fi[4 * b + k] = __fmul_rn(fi[4 * b + k], ls.c2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            float vi = __fmul_rn(fi[4 * b + k], adj_i), vq = __fmul_rn(fq[4 * b + k], adj_q);
+                            if (phase_bal < 0.0f) vq = __fadd_rn(vq, __fmul_rn(vi, phase_bal));
+                            else if (phase_bal > 0.0f) vi = __fadd_rn(vi, __fmul_rn(vq, phase_bal));
+                            fi[4 * b + k] = vi; fq[4 * b + k] = vq;
+                        }
+                    }
+                }
+                // ---- Fs/4 translate (freq_shift.c:219-262) + store in polyphase layout ----
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int n = 2 * (r + 8 * i) + e;        // sample index in the chunk
+                        float vi = fi[2 * i + e], vq = fq[2 * i + e];
+                        if (shift_kind == 1) {
+                            float ib = shift_down ? vq : vi, qb = shift_down ? vi : vq;
+                            const int ph = n & 3;
+                            float ni = ib, nq = qb;
+                            if (ph == 1) { ni = qb; nq = -ib; }
+                            else if (ph == 2) { ni = -ib; nq = -qb; }
+                            else if (ph == 3) { ni = -qb; nq = ib; }
+                            if (shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
+                        }
+                        const int pos = n + 84;
+                        xi[(pos & 3) * XP + (pos >> 2)] = vi;
+                        xq[(pos & 3) * XP + (pos >> 2)] = vq;
+                    }
+                }
+                __syncwarp();
+                // ---- decimate: outputs m0 .. m0+3 for I and Q ----
+                {
+                    float ai[4], aq[4];
+                    decimate4(xi, 4 * r, fc, ai);
+                    decimate4(xq, 4 * r, fc, aq);
+                    *reinterpret_cast<float4 *>(di + 200 + 4 * r) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+                    *reinterpret_cast<float4 *>(dq + 200 + 4 * r) = make_float4(aq[0], aq[1], aq[2], aq[3]);
+                }
+                __syncwarp();
+                // keep the newest 21 entries of every phase: idx 32..52 -> 0..20
+                {
+                    float ki[11], kq[11];
+#pragma unroll
+                    for (int u = 0; u < 11; u++) {
+                        const int e = r + 8 * u;             // 0..83 -> (phase, idx)
+                        if (e < 84) { ki[u] = xi[(e / 21) * XP + 32 + (e % 21)]; kq[u] = xq[(e / 21) * XP + 32 + (e % 21)]; }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 11; u++) {
+                        const int e = r + 8 * u;
+                        if (e < 84) { xi[(e / 21) * XP + (e % 21)] = ki[u]; xq[(e / 21) * XP + (e % 21)] = kq[u]; }
+                    }
+                }
+                // ---- Hilbert pair + sideband combine ----
+                {
+                    float hi[4], hq[4];
+                    hilbert4<false>(di, 4 * r, fc, hi);
+                    hilbert4<true>(dq, 4 * r, fc, hq);
+                    float *aud = sm.aud[t & 1];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        aud[(4 * r + j) * SMS + g] = lsb ? __fsub_rn(hi[j], hq[j]) : __fadd_rn(hi[j], hq[j]);
+                }
+                __syncwarp();
+                // slide the Hilbert input: d[0..200) = d[32..232)
+                {
+                    float4 ki[7], kq[7];
+#pragma unroll
+                    for (int u = 0; u < 7; u++) {
+                        const int e = r + 8 * u;             // float4 index 0..49
+                        if (e < 50) { ki[u] = lds128(di + 32 + 4 * e); kq[u] = lds128(dq + 32 + 4 * e); }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 7; u++) {
+                        const int e = r + 8 * u;
+                        if (e < 50) { *reinterpret_cast<float4 *>(di + 4 * e) = ki[u]; *reinterpret_cast<float4 *>(dq + 4 * e) = kq[u]; }
+                    }
+                }
+            }
+            // ---- write out chunk t-5 (output stage, audio_driver.c:2845-2941) ----
+            if (t >= PIPE_DEPTH && active) {
+                const int c = t - PIPE_DEPTH;
+                const float *o = sm.out[c % 3];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int pr = r + 8 * i;
+                    const int n = 2 * pr;
+                    const bool muted = mute && mute[c * 4 + (i >> 1)];
+                    const float v0 = muted ? 0.0f : o[n * SMS + g], v1 = muted ? 0.0f : o[(n + 1) * SMS + g];
+                    const int w0 = muted ? 0 : format_audio_word(v0), w1 = muted ? 0 : format_audio_word(v1);
+                    dst[(size_t)c * 64 + pr] = make_int4(w0, w0, w1, w1);
+                    if (dst_f) dst_f[(size_t)c * 64 + pr] = make_float2(v0, v1);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- store state ----
+        if (active) {
+            for (int b = r; b < 84; b += 8) {
+                st->s1_hist_i[H1 - 84 + b] = xi[(b & 3) * XP + (b >> 2)];
+                st->s1_hist_q[H1 - 84 + b] = xq[(b & 3) * XP + (b >> 2)];
+            }
+            for (int i = r; i < 200; i += 8) { st->s2_hist_i[i] = di[i]; st->s2_hist_q[i] = dq[i]; }
+            int clip = ls.clip;
+            clip |= __shfl_xor_sync(gmask, clip, 1, 8); clip |= __shfl_xor_sync(gmask, clip, 2, 8); clip |= __shfl_xor_sync(gmask, clip, 4, 8);
+            if (r == 0) {
+                st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
+                if (clip & 1) st->adc_quarter_clip = 1;
+                if (clip & 2) st->adc_half_clip = 1;
+                if (clip & 4) st->adc_clip = 1;
+                st->blocks += a.nblocks;
+                if (shift_kind != 0 && st->conversion_freq != p.shift_freq) { st->conversion_freq = p.shift_freq; st->osc_vect_i = 0.0f; st->osc_vect_q = 1.0f; }
+            }
+        }
+        return;
+    }
+
+    // ======================= serial warps: one channel per lane =================================
+    const int g = lane;
+    const bool active = g < n_here;
+    const int ch = a.chan_list[cta_first + (active ? g : 0)];
+    const ChanParams &p = a.params[ch];
+    ChanState *st = a.state + ch;
+
+    if (warp == W_LAT) {
+        // ---- 10-stage lattice pre-filter (arm_iir_lattice_f32.c:348-440), front-padded ----
+        float k[10], v[11], s[10];
+        const int n = p.pre.n, pad = 10 - n;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            k[j] = (j >= pad) ? __ldg(pool + p.pre.k_off + (j - pad)) : 0.0f;
+            v[j] = (j >= pad) ? __ldg(pool + p.pre.v_off + (j - pad)) : 0.0f;
+            s[j] = (j >= pad) ? st->pre_s[j - pad] : 0.0f;
+        }
+        v[10] = (n > 0) ? __ldg(pool + p.pre.v_off + n) : 1.0f;
+        for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
+            const int c = t - 1;
+            if (c >= 0 && c < nchunks) {
+                const float *in = sm.aud[c & 1];
+                float *out = sm.lat[c & 1];
+#pragma unroll 4
+                for (int i = 0; i < ND; i++) {
+                    float f = in[i * SMS + g], acc = 0.0f, fn = f;
+#pragma unroll
+                    for (int j = 0; j < 10; j++) {
+                        const float gg = s[j];
+                        fn = __fsub_rn(f, __fmul_rn(k[j], gg));
+                        const float gn = __fadd_rn(__fmul_rn(fn, k[j]), gg);
+                        acc = __fadd_rn(acc, __fmul_rn(gn, v[j]));
+                        if (j > 0) s[j - 1] = gn;
+                        f = fn;
+                    }
+                    acc = __fadd_rn(acc, __fmul_rn(fn, v[10]));
+                    s[9] = fn;
+                    out[i * SMS + g] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 10; j++) if (j >= pad) st->pre_s[j - pad] = s[j];
+        }
+        return;
+    }
+
+    if (warp == W_AGC) {
+        // ---- WDSP AGC (audio_agc.c:349-595), mono, 12 ksps: 49-sample look-ahead ----
+        const AgcP ap = p.agc;
+        AgcRun ar = { 0, 0, st->agc_ring_max, st->agc_volts, st->agc_save_volts, st->agc_fast_backaverage,
+                      st->agc_hang_backaverage, st->agc_hang_counter, st->agc_decay_type, st->agc_state,
+                      st->agc_action, st->agc_hang_action };
+        // compact ring: slot (wp - k) & 63 holds x[t-k]; history x[-49..-1] from the 192-slot state ring
+        const int in_index = st->agc_in_index;
+        for (int kk = 1; kk <= AGC_W; kk++) {
+            int idx = in_index - (kk - 1);
+            idx %= AGC_RB; if (idx < 0) idx += AGC_RB;
+            sm.ring[((RING - kk) & (RING - 1)) * SMS + g] = st->agc_ring[idx];
+        }
+        // suffix maxima of the "previous block" = history x[-48..-1] at offsets 1..48
+        {
+            float m = 0.0f;
+            for (int o = AGC_W - 1; o >= 1; o--) {
+                const int kk = AGC_W - o;             // offset o holds x[-(49-o)]
+                m = fmaxf(m, fabsf(sm.ring[((RING - kk) & (RING - 1)) * SMS + g]));
+                sm.smax[o * SMS + g] = m;
+            }
+        }
+        int wp = 0;          // slot of the sample being written (uniform across lanes)
+        int off = 0;         // offset inside the current van Herk block (uniform)
+        float pmax = 0.0f;   // prefix maximum of the current block
+        for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
+            const int c = t - 2;
+            if (c >= 0 && c < nchunks) {
+                const float *in = sm.lat[c & 1];
+                float *out = sm.agc[c & 1];
+                for (int i = 0; i < ND; i++) {
+                    const float x = in[i * SMS + g];
+                    float y;
+                    if (ap.mode == 5) {
+                        y = __fmul_rn(x, ap.fixed_gain);          // AGC off (audio_agc.c:354-365)
+                    } else {
+                        const float out_sample = sm.ring[((wp - AGC_W) & (RING - 1)) * SMS + g];
+                        const float abs_out = fabsf(out_sample), abs_in = fabsf(x);
+                        sm.ring[wp * SMS + g] = x;
+                        pmax = (off == 0) ? abs_in : fmaxf(pmax, abs_in);
+                        float ring_max = pmax;
+                        if (off < AGC_W - 1) ring_max = fmaxf(ring_max, sm.smax[(off + 1) * SMS + g]);
+                        // ---- identical to agc_step from here on, with ring_max supplied ----
+                        ar.fast_backaverage = __fadd_rn(__fmul_rn(ap.fast_backmult, abs_out), __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
+                        ar.hang_backaverage = __fadd_rn(__fmul_rn(ap.hang_backmult, abs_out), __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
+                        ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
+                        ar.ring_max = ring_max;
+                        if (ar.hang_counter > 0) --ar.hang_counter;
+                        const float dv = __fsub_rn(ar.ring_max, ar.volts);
+                        const bool attack = ar.ring_max >= ar.volts;
+                        float mult_sel = ap.attack_mult;
+                        bool upd = true;
+                        int nstate = ar.state;
+                        if (attack) {
+                            if (ar.state >= 2) ar.save_volts = ar.volts;
+                            nstate = 0;
+                        } else {
+                            switch (ar.state) {
+                            case 0:
+                                if (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage)) { nstate = 1; mult_sel = ap.fast_decay_mult; }
+                                else if (ap.hang_enable && (ar.hang_backaverage > ap.hang_level)) {
+                                    nstate = 2; ar.hang_counter = (int)__fmul_rn(ap.hangtime, ap.sample_rate); ar.decay_type = 1; upd = false;
+                                } else { nstate = 3; mult_sel = ap.decay_mult; ar.decay_type = 0; }
+                                break;
+                            case 1:
+                                if (ar.volts > ar.save_volts) mult_sel = ap.fast_decay_mult;
+                                else if (ar.hang_counter > 0) { nstate = 2; upd = false; }
+                                else if (ar.decay_type == 0) { nstate = 3; mult_sel = ap.decay_mult; }
+                                else { nstate = 4; mult_sel = ap.hang_decay_mult; }
+                                break;
+                            case 2:
+                                if (ar.hang_counter == 0) { nstate = 4; mult_sel = ap.hang_decay_mult; } else upd = false;
+                                break;
+                            case 3: mult_sel = ap.decay_mult; break;
+                            default: mult_sel = ap.hang_decay_mult; break;
+                            }
+                        }
+                        ar.state = nstate;
+                        if (upd) ar.volts = __fadd_rn(ar.volts, __fmul_rn(dv, mult_sel));
+                        if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
+                        float vo = log10f_fast(__fmul_rn(ap.inv_max_input, ar.volts));
+                        if (vo > 0.0f) vo = 0.0f;
+                        const float mult = __fdiv_rn(__fsub_rn(ap.out_target, __fmul_rn(ap.slope_constant, vo)), ar.volts);
+                        y = __fmul_rn(out_sample, mult);
+                    }
+                    out[i * SMS + g] = y;
+                    // ---- advance the sliding-maximum bookkeeping (uniform control flow) ----
+                    if (off == AGC_W - 1) {
+                        float m = 0.0f;
+                        for (int o = AGC_W - 1; o >= 0; o--) {
+                            m = fmaxf(m, fabsf(sm.ring[((wp - (AGC_W - 1 - o)) & (RING - 1)) * SMS + g]));
+                            sm.smax[o * SMS + g] = m;
+                        }
+                        off = 0;
+                    } else {
+                        off++;
+                    }
+                    wp = (wp + 1) & (RING - 1);
+                }
+            }
+            __syncthreads();
+        }
+        if (active && ap.mode != 5) {
+            const long long T = (long long)nchunks * ND;
+            int new_in = (int)(((long long)st->agc_in_index + T) % AGC_RB);
+            int new_out = (int)((((long long)st->agc_out_index + T) % AGC_RB + AGC_RB) % AGC_RB);
+            for (int kk = 1; kk <= AGC_W; kk++) {
+                int idx = new_in - (kk - 1);
+                idx %= AGC_RB; if (idx < 0) idx += AGC_RB;
+                st->agc_ring[idx] = sm.ring[((wp - kk) & (RING - 1)) * SMS + g];
+            }
+            st->agc_in_index = new_in; st->agc_out_index = new_out;
+            st->agc_ring_max = ar.ring_max; st->agc_volts = ar.volts; st->agc_save_volts = ar.save_volts;
+            st->agc_fast_backaverage = ar.fast_backaverage; st->agc_hang_backaverage = ar.hang_backaverage;
+            st->agc_hang_counter = ar.hang_counter; st->agc_decay_type = ar.decay_type; st->agc_state = ar.state;
+            st->agc_action = ar.action; st->agc_hang_action = ar.hang_action;
+        }
+        return;
+    }
+
+    if (warp == W_EQ) {
+        // ---- fixed gain (:2513-2524), biquad_1 (:2527), x4 interpolator (:2560-2577) ----
+        float bc[4][5]; BiquadS bs[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+#pragma unroll
+            for (int q = 0; q < 5; q++) bc[s][q] = p.bq1[s][q];
+            bs[s] = st->bq1[s];
+        }
+        const float scale_gain = p.scale_gain;
+        // interpolator taps as [phase j][k] with phase length padded to 4 (leading zeros)
+        float ic[4][4], ih[3];
+        const int P = p.interp_plen;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int kq = 0; kq < 4; kq++) {
+                const int kk = kq - (4 - P);
+                ic[j][kq] = (kk >= 0) ? __ldg(pool + p.interp_c + (3 - j) + 4 * kk) : 0.0f;
+            }
+#pragma unroll
+        for (int q = 0; q < 3; q++) ih[q] = st->interp_hist[INTERP_HIST - 3 + q];
+        for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
+            const int c = t - 3;
+            if (c >= 0 && c < nchunks) {
+                const float *in = sm.agc[c & 1];
+                float *out = sm.out[c % 3];
+#pragma unroll 2
+                for (int i = 0; i < ND; i++) {
+                    float x = __fmul_rn(in[i * SMS + g], scale_gain);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) x = biquad_step(x, bc[s], bs[s]);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float sum = 0.0f;
+                        sum = mad(ih[0], ic[j][0], sum); sum = mad(ih[1], ic[j][1], sum);
+                        sum = mad(ih[2], ic[j][2], sum); sum = mad(x, ic[j][3], sum);
+                        out[(4 * i + j) * SMS + g] = sum;
+                    }
+                    ih[0] = ih[1]; ih[1] = ih[2]; ih[2] = x;
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) st->bq1[s] = bs[s];
+            // the generic kernel keeps the newest 8 decimated samples; older slots are only read
+            // by interpolators with longer phases than this kernel is eligible for
+            for (int q = 0; q < INTERP_HIST - 3; q++) st->interp_hist[q] = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; q++) st->interp_hist[INTERP_HIST - 3 + q] = ih[q];
+        }
+        return;
+    }
+
+    // warp == W_POST
+    {
+        // ---- anti-alias lattice (:2581-2583, 6 stages, some paths), treble biquad (:2832), x10 ----
+        float k[6], v[7], s[6];
+        const int n = p.aa.n;
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            k[j] = (n == 6) ? __ldg(pool + p.aa.k_off + j) : 0.0f;
+            v[j] = (n == 6) ? __ldg(pool + p.aa.v_off + j) : 0.0f;
+            s[j] = (n == 6) ? st->aa_s[j] : 0.0f;
+        }
+        v[6] = (n == 6) ? __ldg(pool + p.aa.v_off + 6) : 1.0f;
+        const bool any_aa = __any_sync(0xffffffffu, active && n == 6);
+        float bc[5];
+#pragma unroll
+        for (int q = 0; q < 5; q++) bc[q] = p.bq2[q];
+        BiquadS bs = st->bq2;
+        for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
+            const int c = t - 4;
+            if (c >= 0 && c < nchunks) {
+                float *buf = sm.out[c % 3];
+#pragma unroll 4
+                for (int i = 0; i < CH4; i++) {
+                    float x = buf[i * SMS + g];
+                    if (any_aa) {
+                        float f = x, acc = 0.0f, fn = x;
+#pragma unroll
+                        for (int j = 0; j < 6; j++) {
+                            const float gg = s[j];
+                            fn = __fsub_rn(f, __fmul_rn(k[j], gg));
+                            const float gn = __fadd_rn(__fmul_rn(fn, k[j]), gg);
+                            acc = __fadd_rn(acc, __fmul_rn(gn, v[j]));
+                            if (j > 0) s[j - 1] = gn;
+                            f = fn;
+                        }
+                        acc = __fadd_rn(acc, __fmul_rn(fn, v[6]));
+                        s[5] = fn;
+                        x = (n == 6) ? acc : x;
+                    }
+                    x = biquad_step(x, bc, bs);
+                    buf[i * SMS + g] = __fmul_rn(x, 10.0f);       // LINE_OUT_SCALING_FACTOR (:2860)
+                }
+            }
+            __syncthreads();
+        }
+        if (active) {
+            if (n == 6) {
+#pragma unroll
+                for (int j = 0; j < 6; j++) st->aa_s[j] = s[j];
+            }
+            st->bq2 = bs;
+        }
+    }
+}
+
+// A channel runs on the fused kernel when its chain is the narrow-SSB/CW topology with the stock
+// 83-tap decimator and 199-tap Hilbert pair, Fs/4 (or no) translation, a x4 interpolator with at
+// most 4 taps per phase, and no deferred consumer (spectral NR, spectrum ring).
+bool fused_eligible(const ChanParams &p)
+{
+    return p.configured && p.topo == TOPO_SSB_DEC_FIRST && p.M == 4 && p.s1_ntaps == 83 && p.s2_ntaps == 199 &&
+           p.shift_kind != 2 && !p.nr_enable && !p.spectrum_enable && p.pre.n <= 10 && (p.aa.n == 0 || p.aa.n == 6) &&
+           p.interp_L == 4 && p.interp_plen >= 1 && p.interp_plen <= 4 && p.agc.attack_buffsize == AGC_W;
+}
+
+void fill_fused_coefs(FusedCoefs *fc, const float *dec83, const float *hil_i199, const float *hil_q199)
+{
+    memset(fc, 0, sizeof(*fc));
+    memcpy(fc->dec, dec83, 83 * sizeof(float));
+    memcpy(fc->hil_i, hil_i199, 199 * sizeof(float));
+    memcpy(fc->hil_q, hil_q199, 199 * sizeof(float));
+}
+
 cudaError_t launch_rx_ssb_fused(const RxArgs &a, const FusedCoefs &fc, int sm_count, cudaStream_t stream)
 {
-    (void)a; (void)fc; (void)sm_count; (void)stream;
-    return cudaErrorNotSupported;
+    if (a.num_items <= 0) return cudaSuccess;
+    if (a.nblocks % 4 != 0 || a.chan_list == nullptr) return cudaErrorInvalidValue;
+    // channels per CTA: fill every SM once, in multiples of 4 (one FIR warp = 4 channels)
+    int per = (a.num_items + sm_count - 1) / sm_count;
+    per = ((per + 3) / 4) * 4;
+    if (per > FG) per = FG;
+    if (per < 4) per = 4;
+    const int grid = (a.num_items + per - 1) / per;
+    cudaError_t e = cudaFuncSetAttribute(rx_ssb_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    rx_ssb_fused_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, fc, per);
+    return cudaGetLastError();
 }
+
 }  // namespace uhsdr
