@@ -35,11 +35,13 @@ constexpr int ND = 32;             // decimated samples per chunk
 constexpr int XP = 56;             // per-phase slots: 21 history + 32 new + 3 pad
 constexpr int XCH = 2 * 4 * XP + 4;   // floats per channel (I phases, Q phases) + 4 -> bank stagger
 constexpr int DL = 200 + ND;       // Hilbert input: 200 history slots + 32 new
-constexpr int DCH = 2 * DL;
+constexpr int DCH = 2 * DL + 4;     // + 4 -> neighbouring channels land on disjoint banks
 constexpr int SMS = 33;            // channel-minor stride of the pipeline queues
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int RING = 64;
-constexpr int NWARP_FIR = FG / 4;
+constexpr int NWARP_FIR = FG / 8;   // one FIR warp = 8 channels x 4 lanes, 8 decimated outputs per lane
+constexpr int DEC_PAD = 32;        // zero padding in front of the decimator taps (FusedCoefs::dec)
+constexpr int HIL_PAD = 12;        // zero padding in front of the Hilbert taps
 constexpr int W_LAT = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_EQ = NWARP_FIR + 2, W_POST = NWARP_FIR + 3;
 constexpr int NTHREADS = 32 * (NWARP_FIR + 4);
 constexpr int PIPE_DEPTH = 5;      // FIR t | LAT t-1 | AGC t-2 | EQ t-3 | POST t-4 | WRITE t-5
@@ -73,54 +75,64 @@ struct FirLaneState {
 };
 
 // Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 84 history
-// samples in front, buffer position b = 4m + k + 2; phase = b & 3, idx = b >> 2.  Elements are
-// consumed in ascending b, which is ascending k for every output: the reference's summation order.
-template <typename Coefs>
-__device__ __forceinline__ void decimate4(const float *xp /* [4][XP] of this channel */, int m0, const Coefs &fc, float acc[4])
+// samples in front, buffer position b = 4m + k + 2; phase = b & 3, idx = b >> 2.  Each lane makes 8
+// consecutive outputs m0..m0+7.  Elements are consumed in ascending b, which is ascending k for
+// every output (the reference's summation order).  The loop is rolled (instruction-cache
+// footprint); taps outside [0, 82] hit the zero padding of FusedCoefs::dec and add +-0.
+__device__ __forceinline__ void decimate8(const float *xpi, const float *xpq, int m0, const FusedCoefs &fc,
+                                          float ai[8], float aq[8])
 {
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
-    static_for<0, 7>([&](auto q) {
-        constexpr int Q = decltype(q)::value;
-        float4 v[4];
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) v[ph] = lds128(xp + ph * XP + m0 + 4 * Q);
-        static_for<0, 4>([&](auto e) {
-            constexpr int E = decltype(e)::value;            // element within the float4
-            constexpr int U = 4 * Q + E;                     // idx - m0
-            // order of positions b for fixed idx: phase 0,1,2,3
-            static_for<0, 4>([&](auto phv) {
-                constexpr int PH = decltype(phv)::value;
-                const float xv = (E == 0) ? v[PH].x : (E == 1) ? v[PH].y : (E == 2) ? v[PH].z : v[PH].w;
-                static_for<0, 4>([&](auto jv) {
-                    constexpr int J = decltype(jv)::value;
-                    constexpr int K = 4 * (U - J) + PH - 2;  // tap index
-                    if constexpr (K >= 0 && K <= 82) acc[J] = mad(fc.dec[K], xv, acc[J]);
-                });
-            });
-        });
-    });
+    for (int j = 0; j < 8; j++) { ai[j] = 0.0f; aq[j] = 0.0f; }
+#pragma unroll 1
+    for (int q = 0; q < 7; q++) {
+        float4 vi[4], vq[4];
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) { vi[ph] = lds128(xpi + ph * XP + m0 + 4 * q); vq[ph] = lds128(xpq + ph * XP + m0 + 4 * q); }
+        const float *cq = fc.dec + DEC_PAD + 16 * q - 2;      // tap index K = 16q + 4(E - J) + PH - 2
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+#pragma unroll
+            for (int ph = 0; ph < 4; ph++) {
+                const float xi = (e == 0) ? vi[ph].x : (e == 1) ? vi[ph].y : (e == 2) ? vi[ph].z : vi[ph].w;
+                const float xq = (e == 0) ? vq[ph].x : (e == 1) ? vq[ph].y : (e == 2) ? vq[ph].z : vq[ph].w;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float c = cq[4 * (e - j) + ph];
+                    ai[j] = mad(c, xi, ai[j]);
+                    aq[j] = mad(c, xq, aq[j]);
+                }
+            }
+        }
+    }
+    // the one contribution outside the rolled range: idx m0+28, phase 0 -> tap 82 of output 7
+    ai[7] = mad(fc.dec[DEC_PAD + 82], xpi[m0 + 28], ai[7]);
+    aq[7] = mad(fc.dec[DEC_PAD + 82], xpq[m0 + 28], aq[7]);
 }
 
 // Hilbert pair at 12 ksps: y[n] = sum_k c[k] d[n - 198 + k] (arm_fir_f32.c:522-529).  With 200
-// history slots, position = n + k + 2; elements are streamed in ascending position.
-template <bool IS_Q, typename Coefs>
-__device__ __forceinline__ void hilbert4(const float *dp /* [DL] */, int n0, const Coefs &fc, float acc[4])
+// history slots, position = n + k + 2; 8 outputs per lane, elements streamed in ascending position.
+__device__ __forceinline__ void hilbert8(const float *dpi, const float *dpq, int n0, const FusedCoefs &fc,
+                                         float hi[8], float hq[8])
 {
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.0f;
-    static_for<0, 51>([&](auto q) {
-        constexpr int Q = decltype(q)::value;
-        const float4 v = lds128(dp + n0 + 4 * Q);
-        static_for<0, 4>([&](auto e) {
-            constexpr int E = decltype(e)::value;
-            constexpr int P = 4 * Q + E;                     // position - n0
-            const float xv = (E == 0) ? v.x : (E == 1) ? v.y : (E == 2) ? v.z : v.w;
-            static_for<0, 4>([&](auto jv) {
-                constexpr int J = decltype(jv)::value;
-                constexpr int K = P - J - 2;
-                if constexpr (K >= 0 && K <= 198) acc[J] = mad(IS_Q ? fc.hil_q[K] : fc.hil_i[K], xv, acc[J]);
-            });
-        });
-    });
+#pragma unroll
+    for (int j = 0; j < 8; j++) { hi[j] = 0.0f; hq[j] = 0.0f; }
+#pragma unroll 4
+    for (int q = 0; q < 52; q++) {
+        const float4 vi = lds128(dpi + n0 + 4 * q), vq = lds128(dpq + n0 + 4 * q);
+        const float *ci = fc.hil_i + HIL_PAD + 4 * q - 2;     // tap index K = 4q + E - J - 2
+        const float *cq = fc.hil_q + HIL_PAD + 4 * q - 2;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float xi = (e == 0) ? vi.x : (e == 1) ? vi.y : (e == 2) ? vi.z : vi.w;
+            const float xq = (e == 0) ? vq.x : (e == 1) ? vq.y : (e == 2) ? vq.z : vq.w;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                hi[j] = mad(ci[e - j], xi, hi[j]);
+                hq[j] = mad(cq[e - j], xq, hq[j]);
+            }
+        }
+    }
 }
 
 }  // namespace
@@ -138,26 +150,26 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
     const float *__restrict__ pool = a.pool;
 
     if (warp < NWARP_FIR) {
-        // ======================= FIR warp: 4 channels x 8 lanes =================================
-        const int cl = lane >> 3, r = lane & 7;
-        const int g = warp * 4 + cl;                   // channel slot in the CTA
+        // ======================= FIR warp: 8 channels x 4 lanes ==================================
+        const int cl = lane >> 2, r = lane & 3;
+        const int g = warp * 8 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
         const ChanParams &p = a.params[ch];
         ChanState *st = a.state + ch;
         float *xi = sm.x + g * XCH, *xq = xi + 4 * XP;
         float *di = sm.d + g * DCH, *dq = di + DL;
-        const unsigned gmask = 0xffu << (8 * cl);
+        const unsigned gmask = 0xfu << (4 * cl);
 
         // ---- load histories and IQ-correction state ----
         FirLaneState ls;
         ls.te1 = st->teta1_old; ls.te2 = st->teta2_old; ls.te3 = st->teta3_old; ls.c1 = st->M_c1; ls.c2 = st->M_c2; ls.clip = 0;
         // s1_hist[H1=96]: sample s (-84..-1) at [96 + s] -> position b = s + 84 -> phase b&3, idx b>>2
-        for (int b = r; b < 84; b += 8) {
+        for (int b = r; b < 84; b += 4) {
             xi[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_i[H1 - 84 + b] : 0.0f;
             xq[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_q[H1 - 84 + b] : 0.0f;
         }
-        for (int i = r; i < 200; i += 8) {
+        for (int i = r; i < 200; i += 4) {
             di[i] = active ? st->s2_hist_i[i] : 0.0f;
             dq[i] = active ? st->s2_hist_q[i] : 0.0f;
         }
@@ -172,49 +184,47 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
 
         for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
             if (t < nchunks) {
-                // ---- front end: 16 samples per lane (pairs p = r + 8i, samples 2p, 2p+1) ----
-                float fi[16], fq[16];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    int4 v = make_int4(0, 0, 0, 0);
-                    if (active) v = __ldg(src + (size_t)t * 64 + r + 8 * i);
-                    const int l0 = abs(v.x) >> 16, l1 = abs(v.z) >> 16;
-                    const int lv = max(l0, l1);
-                    ls.clip |= (lv > 1024 ? 1 : 0) | (lv > 2048 ? 2 : 0) | (lv > 4096 ? 4 : 0);
-                    fi[2 * i] = __fmul_rn((float)v.x, 0.0000152587890625f);
-                    fq[2 * i] = __fmul_rn((float)v.y, 0.0000152587890625f);
-                    fi[2 * i + 1] = __fmul_rn((float)v.z, 0.0000152587890625f);
-                    fq[2 * i + 1] = __fmul_rn((float)v.w, 0.0000152587890625f);
-                }
-#pragma unroll
+                // ---- front end, one 32-sample block at a time: pairs p = r + 4i (samples 2p, 2p+1) ----
+#pragma unroll 1
                 for (int b = 0; b < 4; b++) {
-                    // block b holds this lane's samples 4b .. 4b+3 (pairs i = 2b, 2b+1)
+                    float fi[8], fq[8];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        int4 v = make_int4(0, 0, 0, 0);
+                        if (active) v = __ldg(src + (size_t)t * 64 + b * 16 + r + 4 * i);
+                        const int lv = max(abs(v.x) >> 16, abs(v.z) >> 16);     // audio_driver.c:2662-2675
+                        ls.clip |= (lv > 1024 ? 1 : 0) | (lv > 2048 ? 2 : 0) | (lv > 4096 ? 4 : 0);
+                        fi[2 * i] = __fmul_rn((float)v.x, 0.0000152587890625f);
+                        fq[2 * i] = __fmul_rn((float)v.y, 0.0000152587890625f);
+                        fi[2 * i + 1] = __fmul_rn((float)v.z, 0.0000152587890625f);
+                        fq[2 * i + 1] = __fmul_rn((float)v.w, 0.0000152587890625f);
+                    }
                     if (iq_auto) {
+                        // Moseley & Slump statistics of the block (audio_driver.c:2274-2279)
                         float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #if UHSDR_EXACT
-                        // reference order: sample n of the block lives in lane (n/2)&7, slot 4b + 2*((n/2)>>3) + (n&1)
+                        // reference order: sample n lives in lane (n/2)&3, slot 2*((n/2)>>2) + (n&1)
 #pragma unroll
                         for (int n = 0; n < 32; n++) {
-                            const int slot = 4 * b + 2 * ((n >> 1) >> 3) + (n & 1);
-                            const float vi = __shfl_sync(gmask, fi[slot], (n >> 1) & 7, 8);
-                            const float vq = __shfl_sync(gmask, fq[slot], (n >> 1) & 7, 8);
+                            const int slot = 2 * ((n >> 1) >> 2) + (n & 1);
+                            const float vi = __shfl_sync(gmask, fi[slot], (n >> 1) & 3, 4);
+                            const float vq = __shfl_sync(gmask, fq[slot], (n >> 1) & 3, 4);
                             s1 = __fadd_rn(s1, __fmul_rn(sign_new(vi), vq));
                             s2 = __fadd_rn(s2, __fmul_rn(sign_new(vi), vi));
                             s3 = __fadd_rn(s3, __fmul_rn(sign_new(vq), vq));
                         }
 #else
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const float vi = fi[4 * b + k], vq = fq[4 * b + k];
-                            s1 += __fmul_rn(sign_new(vi), vq);
-                            s2 += fabsf(vi);
-                            s3 += fabsf(vq);
+                        for (int k = 0; k < 8; k++) {
+                            s1 += __fmul_rn(sign_new(fi[k]), fq[k]);
+                            s2 += fabsf(fi[k]);
+                            s3 += fabsf(fq[k]);
                         }
 #pragma unroll
-                        for (int dlt = 1; dlt < 8; dlt <<= 1) {
-                            s1 += __shfl_xor_sync(gmask, s1, dlt, 8);
-                            s2 += __shfl_xor_sync(gmask, s2, dlt, 8);
-                            s3 += __shfl_xor_sync(gmask, s3, dlt, 8);
+                        for (int dlt = 1; dlt < 4; dlt <<= 1) {
+                            s1 += __shfl_xor_sync(gmask, s1, dlt, 4);
+                            s2 += __shfl_xor_sync(gmask, s2, dlt, 4);
+                            s3 += __shfl_xor_sync(gmask, s3, dlt, 4);
                         }
 #endif
                         // teta = -/+0.003*(sum/32) + 0.997*teta_old, evaluated in double (:2281-2283)
@@ -226,89 +236,89 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                         if (help > 0.0f) help = __fdiv_rn(__fsub_rn(__fmul_rn(ls.te3, ls.te3), __fmul_rn(ls.te1, ls.te1)), help);
                         ls.c2 = (help > 0.0f) ? __fsqrt_rn(help) : 1.0f;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            fq[4 * b + k] = __fadd_rn(fq[4 * b + k], __fmul_rn(ls.c1, fi[4 * b + k]));
-                            fi[4 * b + k] = __fmul_rn(fi[4 * b + k], ls.c2);
+                        for (int k = 0; k < 8; k++) {
+                            fq[k] = __fadd_rn(fq[k], __fmul_rn(ls.c1, fi[k]));
+                            fi[k] = __fmul_rn(fi[k], ls.c2);
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            float vi = __fmul_rn(fi[4 * b + k], adj_i), vq = __fmul_rn(fq[4 * b + k], adj_q);
+                        for (int k = 0; k < 8; k++) {
+                            float vi = __fmul_rn(fi[k], adj_i), vq = __fmul_rn(fq[k], adj_q);
                             if (phase_bal < 0.0f) vq = __fadd_rn(vq, __fmul_rn(vi, phase_bal));
                             else if (phase_bal > 0.0f) vi = __fadd_rn(vi, __fmul_rn(vq, phase_bal));
-                            fi[4 * b + k] = vi; fq[4 * b + k] = vq;
+                            fi[k] = vi; fq[k] = vq;
                         }
                     }
-                }
-                // ---- Fs/4 translate (freq_shift.c:219-262) + store in polyphase layout ----
+                    // ---- Fs/4 translate (freq_shift.c:219-262) + store in polyphase layout ----
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < 4; i++) {
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const int n = 2 * (r + 8 * i) + e;        // sample index in the chunk
-                        float vi = fi[2 * i + e], vq = fq[2 * i + e];
-                        if (shift_kind == 1) {
-                            float ib = shift_down ? vq : vi, qb = shift_down ? vi : vq;
-                            const int ph = n & 3;
-                            float ni = ib, nq = qb;
-                            if (ph == 1) { ni = qb; nq = -ib; }
-                            else if (ph == 2) { ni = -ib; nq = -qb; }
-                            else if (ph == 3) { ni = -qb; nq = ib; }
-                            if (shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
+                        for (int e = 0; e < 2; e++) {
+                            const int n = 32 * b + 2 * (r + 4 * i) + e;      // sample index in the chunk
+                            float vi = fi[2 * i + e], vq = fq[2 * i + e];
+                            if (shift_kind == 1) {
+                                float ib = shift_down ? vq : vi, qb = shift_down ? vi : vq;
+                                const int ph = n & 3;
+                                float ni = ib, nq = qb;
+                                if (ph == 1) { ni = qb; nq = -ib; }
+                                else if (ph == 2) { ni = -ib; nq = -qb; }
+                                else if (ph == 3) { ni = -qb; nq = ib; }
+                                if (shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
+                            }
+                            const int pos = n + 84;
+                            xi[(pos & 3) * XP + (pos >> 2)] = vi;
+                            xq[(pos & 3) * XP + (pos >> 2)] = vq;
                         }
-                        const int pos = n + 84;
-                        xi[(pos & 3) * XP + (pos >> 2)] = vi;
-                        xq[(pos & 3) * XP + (pos >> 2)] = vq;
                     }
                 }
                 __syncwarp();
-                // ---- decimate: outputs m0 .. m0+3 for I and Q ----
+                // ---- decimate: outputs 8r .. 8r+7 for I and Q ----
                 {
-                    float ai[4], aq[4];
-                    decimate4(xi, 4 * r, fc, ai);
-                    decimate4(xq, 4 * r, fc, aq);
-                    *reinterpret_cast<float4 *>(di + 200 + 4 * r) = make_float4(ai[0], ai[1], ai[2], ai[3]);
-                    *reinterpret_cast<float4 *>(dq + 200 + 4 * r) = make_float4(aq[0], aq[1], aq[2], aq[3]);
+                    float ai[8], aq[8];
+                    decimate8(xi, xq, 8 * r, fc, ai, aq);
+                    *reinterpret_cast<float4 *>(di + 200 + 8 * r) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+                    *reinterpret_cast<float4 *>(di + 204 + 8 * r) = make_float4(ai[4], ai[5], ai[6], ai[7]);
+                    *reinterpret_cast<float4 *>(dq + 200 + 8 * r) = make_float4(aq[0], aq[1], aq[2], aq[3]);
+                    *reinterpret_cast<float4 *>(dq + 204 + 8 * r) = make_float4(aq[4], aq[5], aq[6], aq[7]);
                 }
                 __syncwarp();
                 // keep the newest 21 entries of every phase: idx 32..52 -> 0..20
                 {
-                    float ki[11], kq[11];
+                    float ki[21], kq[21];
 #pragma unroll
-                    for (int u = 0; u < 11; u++) {
-                        const int e = r + 8 * u;             // 0..83 -> (phase, idx)
-                        if (e < 84) { ki[u] = xi[(e / 21) * XP + 32 + (e % 21)]; kq[u] = xq[(e / 21) * XP + 32 + (e % 21)]; }
+                    for (int u = 0; u < 21; u++) {
+                        const int e = r + 4 * u;             // 0..83 -> (phase, idx)
+                        ki[u] = xi[(e / 21) * XP + 32 + (e % 21)]; kq[u] = xq[(e / 21) * XP + 32 + (e % 21)];
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 11; u++) {
-                        const int e = r + 8 * u;
-                        if (e < 84) { xi[(e / 21) * XP + (e % 21)] = ki[u]; xq[(e / 21) * XP + (e % 21)] = kq[u]; }
+                    for (int u = 0; u < 21; u++) {
+                        const int e = r + 4 * u;
+                        xi[(e / 21) * XP + (e % 21)] = ki[u]; xq[(e / 21) * XP + (e % 21)] = kq[u];
                     }
                 }
                 // ---- Hilbert pair + sideband combine ----
                 {
-                    float hi[4], hq[4];
-                    hilbert4<false>(di, 4 * r, fc, hi);
-                    hilbert4<true>(dq, 4 * r, fc, hq);
+                    float hi[8], hq[8];
+                    hilbert8(di, dq, 8 * r, fc, hi, hq);
                     float *aud = sm.aud[t & 1];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        aud[(4 * r + j) * SMS + g] = lsb ? __fsub_rn(hi[j], hq[j]) : __fadd_rn(hi[j], hq[j]);
+                    for (int j = 0; j < 8; j++)
+                        aud[(8 * r + j) * SMS + g] = lsb ? __fsub_rn(hi[j], hq[j]) : __fadd_rn(hi[j], hq[j]);
                 }
                 __syncwarp();
                 // slide the Hilbert input: d[0..200) = d[32..232)
                 {
-                    float4 ki[7], kq[7];
+                    float4 ki[13], kq[13];
 #pragma unroll
-                    for (int u = 0; u < 7; u++) {
-                        const int e = r + 8 * u;             // float4 index 0..49
+                    for (int u = 0; u < 13; u++) {
+                        const int e = r + 4 * u;             // float4 index 0..49
                         if (e < 50) { ki[u] = lds128(di + 32 + 4 * e); kq[u] = lds128(dq + 32 + 4 * e); }
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 7; u++) {
-                        const int e = r + 8 * u;
+                    for (int u = 0; u < 13; u++) {
+                        const int e = r + 4 * u;
                         if (e < 50) { *reinterpret_cast<float4 *>(di + 4 * e) = ki[u]; *reinterpret_cast<float4 *>(dq + 4 * e) = kq[u]; }
                     }
                 }
@@ -317,11 +327,11 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
             if (t >= PIPE_DEPTH && active) {
                 const int c = t - PIPE_DEPTH;
                 const float *o = sm.out[c % 3];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int pr = r + 8 * i;
+#pragma unroll 4
+                for (int i = 0; i < 16; i++) {
+                    const int pr = r + 4 * i;
                     const int n = 2 * pr;
-                    const bool muted = mute && mute[c * 4 + (i >> 1)];
+                    const bool muted = mute && mute[c * 4 + (i >> 2)];
                     const float v0 = muted ? 0.0f : o[n * SMS + g], v1 = muted ? 0.0f : o[(n + 1) * SMS + g];
                     const int w0 = muted ? 0 : format_audio_word(v0), w1 = muted ? 0 : format_audio_word(v1);
                     dst[(size_t)c * 64 + pr] = make_int4(w0, w0, w1, w1);
@@ -332,13 +342,13 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
         }
         // ---- store state ----
         if (active) {
-            for (int b = r; b < 84; b += 8) {
+            for (int b = r; b < 84; b += 4) {
                 st->s1_hist_i[H1 - 84 + b] = xi[(b & 3) * XP + (b >> 2)];
                 st->s1_hist_q[H1 - 84 + b] = xq[(b & 3) * XP + (b >> 2)];
             }
-            for (int i = r; i < 200; i += 8) { st->s2_hist_i[i] = di[i]; st->s2_hist_q[i] = dq[i]; }
+            for (int i = r; i < 200; i += 4) { st->s2_hist_i[i] = di[i]; st->s2_hist_q[i] = dq[i]; }
             int clip = ls.clip;
-            clip |= __shfl_xor_sync(gmask, clip, 1, 8); clip |= __shfl_xor_sync(gmask, clip, 2, 8); clip |= __shfl_xor_sync(gmask, clip, 4, 8);
+            clip |= __shfl_xor_sync(gmask, clip, 1, 4); clip |= __shfl_xor_sync(gmask, clip, 2, 4);
             if (r == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
                 if (clip & 1) st->adc_quarter_clip = 1;
@@ -644,16 +654,16 @@ bool fused_eligible(const ChanParams &p)
 void fill_fused_coefs(FusedCoefs *fc, const float *dec83, const float *hil_i199, const float *hil_q199)
 {
     memset(fc, 0, sizeof(*fc));
-    memcpy(fc->dec, dec83, 83 * sizeof(float));
-    memcpy(fc->hil_i, hil_i199, 199 * sizeof(float));
-    memcpy(fc->hil_q, hil_q199, 199 * sizeof(float));
+    memcpy(fc->dec + DEC_PAD, dec83, 83 * sizeof(float));
+    memcpy(fc->hil_i + HIL_PAD, hil_i199, 199 * sizeof(float));
+    memcpy(fc->hil_q + HIL_PAD, hil_q199, 199 * sizeof(float));
 }
 
 cudaError_t launch_rx_ssb_fused(const RxArgs &a, const FusedCoefs &fc, int sm_count, cudaStream_t stream)
 {
     if (a.num_items <= 0) return cudaSuccess;
     if (a.nblocks % 4 != 0 || a.chan_list == nullptr) return cudaErrorInvalidValue;
-    // channels per CTA: fill every SM once, in multiples of 4 (one FIR warp = 4 channels)
+    // channels per CTA: fill every SM once, in multiples of 4
     int per = (a.num_items + sm_count - 1) / sm_count;
     per = ((per + 3) / 4) * 4;
     if (per > FG) per = FG;

@@ -158,9 +158,9 @@ struct TxState {
 // Coefficients of the fused narrow-SSB kernel, passed by value as a kernel parameter so that
 // every tap is an immediate constant-bank operand of its FFMA.
 struct FusedCoefs {
-    float dec[84];           // 83-tap sideband-suppression decimator (fir_rx_decimate_4.c:81), padded
-    float hil_i[200];        // 199-tap i_rx_new_coeffs (iq_rx_filter.c:589), padded
-    float hil_q[200];        // 199-tap q_rx_new_coeffs (iq_rx_filter.c:591), padded
+    float dec[144];          // 83-tap sideband-suppression decimator (fir_rx_decimate_4.c:81) at [32, 115), zero padded
+    float hil_i[224];        // 199-tap i_rx_new_coeffs (iq_rx_filter.c:589) at [12, 211), zero padded
+    float hil_q[224];        // 199-tap q_rx_new_coeffs (iq_rx_filter.c:591) at [12, 211), zero padded
 };
 
 }  // namespace uhsdr
