@@ -14,6 +14,8 @@
 
 #include "uhsdr_b200.h"
 #include "ui_configuration.h"
+#include "tx_processor.h"
+#include "arm_const_structs.h"
 
 static uhsdr_chan_cfg_t g_cfg;
 static int g_inited = 0;
@@ -73,6 +75,8 @@ static void ref_apply_cfg(const uhsdr_chan_cfg_t *c)
     ts.tx_gain[TX_AUDIO_MIC] = (uint8_t)c->tx_mic_gain;
     ts.tx_mic_gain_mult = ts.tx_gain[TX_AUDIO_MIC];   /* ui_driver.c / radio_management: mic gain multiplier == setting */
     ts.tx_power_factor = c->tx_power_factor;
+    ts.flags1 &= ~FLAGS1_SSB_TX_FILTER_DISABLE;
+    if (g_inited) AudioManagement_CalcTxCompLevel();   /* the UI re-derives ALC decay / post-filter gain on change */
     for (int t = 0; t < IQ_TRANS_NUM; t++) {
         ts.tx_adj_gain_var[t].i = c->tx_adj_gain_i;
         ts.tx_adj_gain_var[t].q = c->tx_adj_gain_q;
@@ -107,6 +111,7 @@ int ref_init(const uhsdr_chan_cfg_t *cfg)
     ts.beep_frequency = DEFAULT_BEEP_FREQUENCY;
     ref_apply_cfg(cfg);
     AudioDriver_Init();
+    nr_params.NR_decimation_enable = cfg->nr_decimation_enable;   /* NR_Init (audio_nr.c:88) forces it to true */
     if (cfg->fm_subaudible_tone_det_freq > 0.0f) AudioManagement_CalcSubaudibleDetFreq(cfg->fm_subaudible_tone_det_freq);
     ref_select_path(cfg->filter_path);
     AudioDriver_SetProcessingChain(ts.dmod_mode, true);
@@ -143,6 +148,50 @@ int ref_rx(const int32_t *iq, int32_t *audio, float *audio_f, int nblocks, const
         if (audio_f) memcpy(audio_f + (size_t)b * IQ_BLOCK_SIZE, adb.a_buffer[1], sizeof(float) * IQ_BLOCK_SIZE);
         AudioNr_HandleNoiseReduction();
     }
+    return 0;
+}
+
+/* nblocks calls of TxProcessor_Run (tx_processor.c:891), SSB voice branch.  mic: nblocks*32 x
+ * {int32 l, int32 r} (microphone in l); iq: same shape (l = I, r = Q); iq_f (optional): the float
+ * I/Q after TxProcessor_IqFinalProcessing's scaling and phase mix, before the int conversion. */
+int ref_tx(const int32_t *mic, int32_t *iq, float *iq_f, int nblocks, const uint8_t *mute)
+{
+    if (!g_inited) return -1;
+    if (ts.txrx_mode != TRX_MODE_TX) {
+        ts.txrx_mode = TRX_MODE_TX;
+        TxProcessor_PrepareRun();           /* audio_driver.c:3012-3015 */
+    }
+    for (int b = 0; b < nblocks; b++) {
+        AudioSample_t src[IQ_BLOCK_SIZE], side[IQ_BLOCK_SIZE];
+        IqSample_t dst[IQ_BLOCK_SIZE];
+        memcpy(src, mic + (size_t)b * 2 * IQ_BLOCK_SIZE, sizeof(src));
+        TxProcessor_Run(src, dst, side, IQ_BLOCK_SIZE, mute ? (mute[b] != 0) : false);
+        memcpy(iq + (size_t)b * 2 * IQ_BLOCK_SIZE, dst, sizeof(dst));
+        if (iq_f) {
+            for (int i = 0; i < IQ_BLOCK_SIZE; i++) {
+                iq_f[((size_t)b * IQ_BLOCK_SIZE + i) * 2] = adb.iq_buf.i_buffer[i];
+                iq_f[((size_t)b * IQ_BLOCK_SIZE + i) * 2 + 1] = adb.iq_buf.q_buffer[i];
+            }
+        }
+    }
+    return 0;
+}
+
+/* UiSpectrum_RedrawSpectrum states 0-2 (ui_spectrum.c:1362-1390) for the 480x320 layout
+ * (fft_iq_len 1024, 512-point FFT, ui_spectrum.c:975-979), restated around the reference's own
+ * CMSIS routines because ui_spectrum.c itself drags in the LCD stack.  `window` is von_Hann_1024
+ * (ui_spectrum.c:362, a function-local constant; the caller passes it from the table blob). */
+int ref_spectrum(const float *window, float *mags)
+{
+    static float samples[1024];
+    if (!g_inited || sd.fft_iq_len != 1024) return -1;
+    arm_copy_f32(&sd.FFT_RingBuffer[sd.samp_ptr], &samples[0], sd.fft_iq_len - sd.samp_ptr);
+    arm_copy_f32(&sd.FFT_RingBuffer[0], &samples[sd.fft_iq_len - sd.samp_ptr], sd.samp_ptr);
+    for (int i = 0; i < 1024; i++) samples[i] *= window[i];                 /* :409-413 */
+    float32_t gcalc = 1.0 / ads.codec_gain_calc;                            /* :438-439 */
+    arm_scale_f32(samples, gcalc, samples, 1024);
+    arm_cfft_f32(&arm_cfft_sR_f32_len512, samples, 0, 1);                   /* :1383 */
+    arm_cmplx_mag_f32(samples, mags, 512);                                  /* :1389 */
     return 0;
 }
 

@@ -83,6 +83,18 @@ class RefChannel:
             raise RuntimeError(f"ref_tx failed: {rc}")
         return iq, iq_f
 
+    def spectrum(self) -> np.ndarray:
+        """UiSpectrum_RedrawSpectrum states 0-2: 512 magnitudes of the current spectrum ring."""
+        from uhsdr_b200.tables import Tables
+        t = Tables()
+        win = np.ascontiguousarray(t.arrays[t.extras["spectrum_window_array"]], dtype=np.float32)
+        mags = np.empty(512, dtype=np.float32)
+        self._lib.ref_spectrum.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        rc = self._lib.ref_spectrum(win.ctypes.data, mags.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"ref_spectrum failed: {rc}")
+        return mags
+
     def status(self) -> ChanStatus:
         st = ChanStatus()
         self._lib.ref_get_status(ctypes.byref(st))

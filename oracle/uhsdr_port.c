@@ -468,12 +468,14 @@ static void agc_run(agc_t *a, float *buf, int n)
 /* spectral noise reduction state (audio_nr.c), filled in below                                */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
-    /* ISR-side packing, audio_driver.c:2328-2434 */
-    float in_buf[4][NR_FFT];        /* mmb.nr_audio_buff[k]: [0..127] input half, [128..255] output half */
+    /* ISR-side packing, audio_driver.c:2328-2434; mmb.nr_audio_buff[k] (freedv_uhsdr.h:44-55) folded
+     * to 256 floats: [0..127] packed input half, [128..255] processed output half */
+    float in_buf[4][NR_FFT];
     int trans_count_in, outbuff_count, fill_in_pt;
     int out_buffer;                  /* index of buffer being drained, -1 = none */
-    int in_fifo[4], in_head, in_tail;   /* NR_in_buffer FIFO, audio_nr.c:174-236 */
-    int out_fifo[4], out_head, out_tail;
+    int in_fifo[5], in_head, in_tail;   /* NR_in_buffer FIFO, audio_nr.c:174-236 */
+    int out_fifo[5], out_head, out_tail;
+    int current_buffer_idx, was_here;   /* NR.current_buffer_idx / NR.was_here, audio_nr.c:314-349 */
     firdec_t dec;                    /* DECIMATE_NR */
     firint_t interp;                 /* INTERPOLATE_NR */
     /* spectral_noise_reduction_3 state, audio_nr.c:1841-2195 */

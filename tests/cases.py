@@ -39,5 +39,18 @@ NR_CASES = [
     ("usb_p35_nr_decoff", dict(dsp_active=DSP_NR_ENABLE, nr_decimation_enable=0, nr_strength=100), 224),
 ]
 
+SPECTRUM_CASES = [
+    ("spec_usb_p35", dict(spectrum_enable=1)),
+    ("spec_fm_gain", dict(spectrum_enable=1, codec_gain_calc=2.5, dmod_mode=DEMOD_FM, filter_path=2)),
+]
+
+TX_CASES = [
+    ("tx_usb", dict(), 160),
+    ("tx_lsb", dict(dmod_mode=DEMOD_LSB), 160),
+    ("tx_usb_p6k_bass_comp8", dict(iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_filter=3, tx_comp_level=8, iq_phase_balance_tx=0.01, tx_adj_gain_i=0.97), 160),
+    ("tx_lsb_notrans_tenor_nocomp", dict(dmod_mode=DEMOD_LSB, iq_freq_mode=FREQ_IQ_CONV_OFF, tx_filter=2, tx_comp_level=-1, iq_phase_balance_tx=-0.02, tx_power_factor=0.05), 160),
+    ("tx_usb_custom_comp", dict(tx_comp_level=13, tx_alc_decay=3, tx_alc_postfilt_gain=9, tx_mic_gain=40, iq_freq_mode=FREQ_IQ_CONV_P12KHZ), 160),
+]
+
 # float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these
 LIBM_CASES = {"sam_p72_both", "sam_p72_usb", "sam_p84_lsb", "fm_p2", "fm_p1_sql0_5k"}

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from cases import NR_CASES, RX_CASES  # noqa: E402
+from cases import NR_CASES, RX_CASES, SPECTRUM_CASES, TX_CASES  # noqa: E402
 from oracle.refchain import RefChannel  # noqa: E402
 from uhsdr_b200 import synth  # noqa: E402
 from uhsdr_b200.config import default_cfg  # noqa: E402
@@ -45,6 +45,32 @@ def main():
     out["seq_mute_reconf/mute"] = mute
     out["seq_mute_reconf/audio_l"] = np.concatenate([a1[:, 0], a2[:, 0]])
     out["seq_mute_reconf/audio_f"] = np.concatenate([f1, f2])
+    # spectrum-display FFT (UiSpectrum_RedrawSpectrum states 0-2) after 37 and after 100 blocks
+    for label, kw in SPECTRUM_CASES:
+        cfg = default_cfg(**kw)
+        iq = synth.rx_iq(cfg, 4, 100 * 32, seed=55)
+        with RefChannel(cfg) as r:
+            r.rx(iq[: 37 * 32])
+            m1 = r.spectrum()
+            r.rx(iq[37 * 32:])
+            m2 = r.spectrum()
+        out[f"{label}/iq"] = iq
+        out[f"{label}/mags37"] = m1
+        out[f"{label}/mags100"] = m2
+    # SSB transmit chain
+    for label, kw, nblocks in TX_CASES:
+        cfg = default_cfg(**kw)
+        mic = synth.tx_mic(6, nblocks * 32, seed=99)
+        mute = np.zeros(nblocks, dtype=np.uint8)
+        mute[nblocks // 2: nblocks // 2 + 5] = 1
+        with RefChannel(cfg) as r:
+            iqw, iqf = r.tx(mic, mute)
+            st = r.status()
+        out[f"{label}/mic"] = mic[:, 0].copy()
+        out[f"{label}/mute"] = mute
+        out[f"{label}/iq"] = iqw
+        out[f"{label}/iq_f"] = iqf
+        out[f"{label}/status"] = np.array([st.tx_alc_val, st.tx_peak_audio], dtype=np.float32)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "rx_golden.npz"), **out)
     print("wrote rx_golden.npz with", len(out), "arrays")
 

@@ -1,0 +1,131 @@
+"""GPU parity: spectral noise reduction, spectrum-display FFT and the SSB transmit chain."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import NR_CASES, SPECTRUM_CASES, TX_CASES
+from conftest import oracle_channel
+from test_rx_parity_gpu import check_tolerance, run_engine_float
+from uhsdr_b200 import synth
+from uhsdr_b200.config import DEMOD_AM, default_cfg
+from uhsdr_b200.engine import Engine, UhsdrError
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "rx_golden.npz")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,nblocks", NR_CASES, ids=[c[0] for c in NR_CASES])
+def test_spectral_nr_within_tolerance(built, label, kw, nblocks, exact):
+    cfg = default_cfg(**kw)
+    nb = 3 * nblocks
+    nch = 3
+    iq = np.stack([synth.rx_iq(cfg, 20 + c, nb * 32, seed=17) for c in range(nch)])
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        h = (nb // 3) * 32
+        w1, f1 = run_engine_float(eng, iq[:, :h])
+        w2, f2 = run_engine_float(eng, iq[:, h:])
+    words, fl = np.concatenate([w1, w2], axis=1), np.concatenate([f1, f2], axis=1)
+    for c in range(nch):
+        with oracle_channel(cfg) as o:
+            want_w, want_f = o.rx(iq[c])
+        # the FIFO rule fixes the latency exactly: same first non-zero sample
+        assert np.flatnonzero(fl[c])[0] == np.flatnonzero(want_f)[0], label
+        check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
+
+
+@pytest.mark.parametrize("label,kw", SPECTRUM_CASES, ids=[c[0] for c in SPECTRUM_CASES])
+def test_spectrum_fft(built, label, kw):
+    g = np.load(GOLDEN)
+    cfg = default_cfg(**kw)
+    iq = g[f"{label}/iq"]
+    nch = 4
+    batch = np.stack([iq] * nch)
+    with Engine(nch) as eng:
+        eng.configure(cfg)
+        eng.rx(batch[:, : 37 * 32])
+        m1 = eng.spectrum()
+        eng.rx(batch[:, 37 * 32:])
+        m2 = eng.spectrum(first=1, count=2)
+    for got, key in ((m1[0], "mags37"), (m1[3], "mags37"), (m2[0], "mags100"), (m2[1], "mags100")):
+        want = g[f"{label}/{key}"]
+        assert np.max(np.abs(got - want)) <= 1e-4 * np.max(want), label
+        assert int(np.argmax(got)) == int(np.argmax(want))
+
+
+def test_spectrum_requires_enable(built):
+    with Engine(2) as eng:
+        eng.configure(default_cfg())
+        with pytest.raises(UhsdrError):
+            eng.spectrum()
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,nblocks", TX_CASES, ids=[c[0] for c in TX_CASES])
+def test_tx_ssb(built, label, kw, nblocks, exact):
+    import torch
+    g = np.load(GOLDEN)
+    cfg = default_cfg(**kw)
+    mic = np.zeros((nblocks * 32, 2), dtype=np.int32)
+    mic[:, 0] = g[f"{label}/mic"]
+    mute = g[f"{label}/mute"]
+    nch = 3
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        dev = torch.device("cuda", 0)
+        d_mic = torch.from_numpy(np.stack([mic] * nch)).to(dev)
+        d_mute = torch.from_numpy(np.stack([mute] * nch)).to(dev)
+        d_iq = torch.empty_like(d_mic)
+        d_f = torch.empty(d_mic.shape, dtype=torch.float32, device=dev)
+        h = (nblocks // 2 + 3)
+        a, b = d_mic[:, : h * 32].contiguous(), d_mic[:, h * 32:].contiguous()
+        oa, ob = torch.empty_like(a), torch.empty_like(b)
+        fa, fb = torch.empty(a.shape, dtype=torch.float32, device=dev), torch.empty(b.shape, dtype=torch.float32, device=dev)
+        eng.tx_device(a, oa, h, iq_f_dev=fa, mute_dev=d_mute[:, :h].contiguous())
+        eng.tx_device(b, ob, nblocks - h, iq_f_dev=fb, mute_dev=d_mute[:, h:].contiguous())
+        eng.sync()
+        iq = torch.cat([oa, ob], dim=1).cpu().numpy()
+        iq_f = torch.cat([fa, fb], dim=1).cpu().numpy()
+        st = eng.status()
+    want, want_f = g[f"{label}/iq"], g[f"{label}/iq_f"]
+    for c in range(nch):
+        if exact:
+            assert np.array_equal(iq[c], want), (label, c)
+            assert np.array_equal(iq_f[c].view(np.uint32), want_f.view(np.uint32))
+        else:
+            err = iq_f[c].astype(np.float64) - want_f
+            assert np.max(np.abs(err)) <= 1e-4 * np.max(np.abs(want_f)), label
+            assert 10 * np.log10(np.mean(want_f.astype(np.float64) ** 2) / max(np.mean(err ** 2), 1e-300)) >= 90.0
+            assert np.max(np.abs(iq[c].astype(np.int64) - want.astype(np.int64))) <= max(1.0, 1e-4 * np.max(np.abs(want_f)))
+        assert abs(st[c].tx_alc_val - g[f"{label}/status"][0]) <= 1e-5
+    # host-buffer entry point
+    with Engine(1, exact=True) as eng:
+        eng.configure(cfg)
+        got = eng.tx(mic[None], mute[None])
+    assert np.array_equal(got[0], want)
+
+
+def test_tx_non_ssb_is_rejected(built):
+    with Engine(1) as eng:
+        eng.configure(default_cfg(dmod_mode=DEMOD_AM, filter_path=70))
+        with pytest.raises(UhsdrError) as ei:
+            eng.tx(np.zeros((1, 64, 2), dtype=np.int32))
+        assert ei.value.code == -5
+
+
+def test_rx_after_tx_shares_the_translate_oscillator(built):
+    """FreqShift keeps one NCO for RX and TX (freq_shift.c:277-283 statics): RX after TX at +6 kHz
+    continues the oscillator where TX left it."""
+    cfg = default_cfg(iq_freq_mode=1)       # FREQ_IQ_CONV_P6KHZ
+    mic = synth.tx_mic(1, 64 * 32)
+    iq = synth.rx_iq(cfg, 1, 96 * 32, seed=4)
+    with Engine(1, exact=True) as eng:
+        eng.configure(cfg)
+        eng.tx(mic[None])
+        got = eng.rx(iq[None])
+    with oracle_channel(cfg) as o:
+        o.tx(mic)
+        want, _ = o.rx(iq)
+    assert np.array_equal(got[0], want)

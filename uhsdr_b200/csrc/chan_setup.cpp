@@ -374,6 +374,8 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
         p->nr_dec_c = t.off(t.ex->nr_decimate_array);
         p->nr_int_c = t.off(t.ex->nr_interpolate_array);
         p->nr_win_c = t.off(t.ex->sqrt_hann_256_array);
+        p->tw256_off = t.tw256_off; p->tw512_off = t.tw512_off;
+        p->nr_xih1 = exp10f((float)30 / 10.0);     // NR2.asnr = 30 (audio_nr.c:95, :1886)
     }
     p->spectrum_enable = cfg.spectrum_enable ? 1 : 0;
     p->codec_gain_calc = cfg.codec_gain_calc;

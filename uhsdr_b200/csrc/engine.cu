@@ -32,6 +32,7 @@ struct uhsdr_engine {
     TxState *d_tx = nullptr;
     TxParams *d_txp = nullptr;
     std::vector<ChanParams> h_params;
+    std::vector<int> h_tx_enabled;
     // dispatch lists (rebuilt after configure)
     bool lists_dirty = true;
     std::vector<int> h_list_fused, h_list_generic;
@@ -153,6 +154,7 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if ((er = cudaMalloc(&e->d_list_fused, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_generic, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     e->h_params.assign(n, ChanParams{});
+    e->h_tx_enabled.assign(n, 0);
     *out = e;
     return UHSDR_OK;
 }
@@ -201,7 +203,7 @@ int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count, const uhsd
     }
     CK(e, launch_configure(e->d_params, e->d_state, e->d_nr, e->d_spec, e->d_tx, e->d_txp, p, tp, first, count, reset, e->stream));
     e->launches++;
-    for (int c = first; c < first + count; c++) e->h_params[c] = p;
+    for (int c = first; c < first + count; c++) { e->h_params[c] = p; e->h_tx_enabled[c] = tp.enabled; }
     e->lists_dirty = true;
     return UHSDR_OK;
 }
@@ -294,7 +296,13 @@ int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio
     if (!e || !audio_dev || !iq_dev || nblocks <= 0) { if (e) e->last_error = "tx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
     for (int c = 0; c < e->nch; c++)
+    {
         if (!e->h_params[c].configured) { e->last_error = "tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
+        if (!e->h_tx_enabled[c]) {
+            e->last_error = "tx: channel " + std::to_string(c) + " is not in USB/LSB; only the SSB voice modulator (TxProcessor_SSB) is implemented";
+            return UHSDR_ERR_UNSUPPORTED;
+        }
+    }
     TxArgs a;
     a.params = e->d_params; a.state = e->d_state; a.tx = e->d_tx; a.txp = e->d_txp; a.pool = e->d_pool;
     a.audio = audio_dev; a.iq = iq_dev; a.iq_f = iq_f_dev; a.mute = mute_dev; a.nblocks = nblocks; a.num_items = e->nch;

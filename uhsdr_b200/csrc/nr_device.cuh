@@ -1,11 +1,198 @@
-// nr_device.cuh -- spectral noise reduction (audio_nr.c), warp-cooperative. Filled in below.
+// nr_device.cuh -- spectral noise reduction, warp-cooperative (one warp = one channel).
+//   ISR side   AudioDriver_RxProcessorNoiseReduction   mchf-eclipse/drivers/audio/audio_driver.c:2328-2434
+//   FIFOs      NR_in/out_buffer_*                      audio_nr.c:174-299
+//   task side  AudioNr_HandleNoiseReduction            audio_nr.c:314-349 (run once after every block:
+//                                                      the oracle's fixed schedule of the PendSV task)
+//   algorithm  spectral_noise_reduction_3              audio_nr.c:1841-2195
 #pragma once
-#include "dsp_device.cuh"
 #include "demod_device.cuh"
+#include "fft_device.cuh"
 
 namespace uhsdr {
-__device__ inline void nr_block(const ChanParams &p, NrState &nr, const float *__restrict__ pool, float *buf, int n, float *scr, int lane)
+
+constexpr int NR_FIFO = 5;     // NR_BUFFER_FIFO_SIZE = NR_BUFFER_NUM + 1 (freedv_uhsdr.h:130)
+
+__device__ __forceinline__ int nr_fifo_count(int head, int tail) { int len = head - tail; return len < 0 ? len + NR_FIFO : len; }
+
+// One 128-sample frame in place in `frame` (global memory), using `fft` (512 floats of shared memory).
+__device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float *__restrict__ pool, float *frame, float *fft, int lane)
 {
-    (void)p; (void)nr; (void)pool; (void)buf; (void)n; (void)scr; (void)lane;
+    const float *win = pool + p.nr_win_c;
+    const float psthr = 0.99f, pnsaf = 0.01f, psini = 0.5f, pspri = 0.5f;
+    const float ax = 0.7405f, ap = 0.8691f;
+    const float xih1 = p.nr_xih1;
+    const float xih1r = (float)(1.0 / (1.0 + (double)xih1) - 1.0);
+    const float pfac = (float)((1.0 / (double)pspri - 1.0) * (1.0 + (double)xih1));
+    const float snr_prio_min = 0.001f;
+    const float alpha = p.nr_alpha;
+
+    if (nr.first_time == 1) {
+        for (int b = lane; b < 128; b += 32) {
+            nr.last_sample[b] = 0.0f; nr.Hk[b] = 1.0f; nr.Hk_old[b] = 1.0f; nr.Nest0[b] = 0.0f; nr.pslp[b] = 0.5f;
+        }
+        __syncwarp();
+        if (lane == 0) nr.first_time = 2;
+        __syncwarp();
+    }
+    for (int i = lane; i < 128; i += 32) {
+        const float prev = nr.last_sample[i], cur = frame[i];
+        fft[2 * i] = __fmul_rn(prev, __ldg(win + i)); fft[2 * i + 1] = 0.0f;
+        fft[256 + 2 * i] = __fmul_rn(cur, __ldg(win + 128 + i)); fft[256 + 2 * i + 1] = 0.0f;
+        nr.last_sample[i] = cur;
+    }
+    __syncwarp();
+    fft_inplace<256, 8, 32>(fft, pool + p.tw256_off, false, lane);
+
+    const int first_time = nr.first_time;
+    int vad_low = 0, vad_high = 63;                      // audio_nr.c:1863-1864 until first_time == 3
+    if (first_time == 3) { vad_low = p.nr_vad_low; vad_high = p.nr_vad_high; }
+    for (int b = lane; b < 128; b += 32) {
+        const float re = fft[2 * b], im = fft[2 * b + 1];
+        const float X = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
+        if (first_time == 2) {
+            const float nest = (float)((double)nr.Nest0[b] + 0.05 * (double)X);
+            nr.Nest0[b] = nest;
+            nr.xt[b] = __fmul_rn(psini, nest);
+        } else if (first_time == 3) {
+            float xt = nr.xt[b];
+            // MMSE speech-presence noise tracker (:2008-2024)
+            float ph1y = (float)(1.0 / (1.0 + (double)__fmul_rn(pfac, expf(__fdiv_rn(__fmul_rn(xih1r, X), xt)))));
+            const float pslp = (float)((double)__fmul_rn(ap, nr.pslp[b]) + (1.0 - (double)ap) * (double)ph1y);
+            nr.pslp[b] = pslp;
+            if (pslp > psthr) ph1y = (float)(1.0 - (double)pnsaf);
+            else ph1y = (float)fmin((double)ph1y, 1.0);
+            const float xtr = (float)((1.0 - (double)ph1y) * (double)X + (double)__fmul_rn(ph1y, xt));
+            xt = (float)((double)__fmul_rn(ax, xt) + (1.0 - (double)ax) * (double)xtr);
+            nr.xt[b] = xt;
+            // a-posteriori / a-priori SNR (:2027-2032)
+            const float post = (float)fmax(fmin((double)__fdiv_rn(X, xt), 1000.0), (double)snr_prio_min);
+            const float prio = (float)fmax((double)__fmul_rn(alpha, nr.Hk_old[b]) + (1.0 - (double)alpha) * fmax((double)post - 1.0, 0.0), 0.0);
+            if (b >= vad_low && b < vad_high) {
+                // gain (:2065-2078); musical-noise smoothing (:2080-2137) is the identity with the
+                // firmware's uninitialised power_threshold_int = 0 (NN == 1)
+                const float v = (float)((double)__fmul_rn(prio, post) / (1.0 + (double)prio));
+                const float rt = __fsqrt_rn((float)(0.7212 * (double)v + (double)__fmul_rn(v, v)));
+                const float hk = (float)fmax(1.0 / (double)post * (double)rt, 0.001);
+                nr.Hk[b] = hk;
+                nr.Hk_old[b] = __fmul_rn(__fmul_rn(post, hk), hk);
+            }
+        }
+    }
+    __syncwarp();
+    if (first_time == 2 && lane == 0) {
+        nr.init_counter++;
+        if (nr.init_counter > 19) { nr.init_counter = 0; nr.first_time = 3; }
+    }
+    // spectral weighting of the pass-band bins and their mirrors (:2146-2156)
+    for (int b = vad_low + lane; b < vad_high; b += 32) {
+        const float hk = nr.Hk[b];
+        fft[2 * b] = __fmul_rn(fft[2 * b], hk); fft[2 * b + 1] = __fmul_rn(fft[2 * b + 1], hk);
+        fft[512 - 2 * b - 2] = __fmul_rn(fft[512 - 2 * b - 2], hk); fft[512 - 2 * b - 1] = __fmul_rn(fft[512 - 2 * b - 1], hk);
+    }
+    __syncwarp();
+    fft_inplace<256, 8, 32>(fft, pool + p.tw256_off, true, lane);
+    // window on exit + overlap-add (:2165-2189)
+    for (int i = lane; i < 128; i += 32) {
+        const float a = __fmul_rn(fft[2 * i], __ldg(win + i));
+        const float bnext = __fmul_rn(fft[256 + 2 * i], __ldg(win + 128 + i));
+        frame[i] = __fadd_rn(a, nr.last_ifft[i]);
+        nr.last_ifft[i] = bnext;
+    }
+    __syncwarp();
 }
+
+// Per block: ISR side on lane 0, then the deferred task (warp-wide).  buf: the block's decimated
+// audio (n = 8 samples at 12 ksps) in shared memory, processed in place.
+__device__ inline void nr_block(const ChanParams &p, NrState &nr, const float *__restrict__ pool, float *buf, int n, float *fft, int lane)
+{
+    if (lane == 0) {
+        int no_dec = n;
+        float x[BLK];
+        for (int i = 0; i < n; i++) x[i] = buf[i];
+        if (p.nr_decim) {
+            // DECIMATE_NR: 4 taps, M = 2 (audio_driver.c:195, :649): y[m] = sum_k c[k] s[2m - 3 + k]
+            no_dec = n / 2;
+            const float *c = pool + p.nr_dec_c;
+            float s[3 + BLK];
+            for (int i = 0; i < 3; i++) s[i] = nr.dec_hist[i];
+            for (int i = 0; i < n; i++) s[3 + i] = x[i];
+            for (int m = 0; m < no_dec; m++) {
+                float acc = 0.0f;
+                for (int k = 0; k < 4; k++) acc = __fadd_rn(acc, __fmul_rn(s[2 * m + k], __ldg(c + k)));
+                x[m] = acc;
+            }
+            for (int i = 0; i < 3; i++) nr.dec_hist[i] = s[n + i];
+        }
+        float *inb = nr.bufs[nr.fill_in_pt];
+        for (int k = 0; k < no_dec; k += 2) {
+            inb[2 * nr.trans_count_in] = x[k];
+            inb[2 * nr.trans_count_in + 1] = x[k + 1];
+            nr.trans_count_in++;
+        }
+        if (nr.trans_count_in >= 64) {
+            const int next = (nr.in_head + 1) % NR_FIFO;
+            if (next != nr.in_tail) { nr.in_fifo[nr.in_head] = nr.fill_in_pt; nr.in_head = next; }
+            nr.trans_count_in = 0;
+            nr.fill_in_pt = (nr.fill_in_pt + 1) % 4;
+        }
+        if (nr.out_buffer < 0 && nr_fifo_count(nr.out_head, nr.out_tail) > 1) nr.out_buffer = nr.out_fifo[nr.out_tail];
+        float dec[BLK];
+        if (nr.out_buffer >= 0) {
+            const float *ob = nr.bufs[nr.out_buffer] + 128;
+            for (int j = 0; j < no_dec; j += 2) {
+                dec[j] = ob[2 * nr.outbuff_count];
+                dec[j + 1] = ob[2 * nr.outbuff_count + 1];
+                nr.outbuff_count++;
+            }
+            if (nr.outbuff_count >= 64) {
+                nr.outbuff_count = 0;
+                if (nr.out_head != nr.out_tail) nr.out_tail = (nr.out_tail + 1) % NR_FIFO;
+                nr.out_buffer = (nr.out_head != nr.out_tail) ? nr.out_fifo[nr.out_tail] : -1;
+            }
+        } else {
+            for (int j = 0; j < no_dec; j++) dec[j] = 0.0f;
+        }
+        if (p.nr_decim) {
+            // INTERPOLATE_NR: L = 2, 40 taps -> phase length 20 (audio_driver.c:198, :653), then x2.0
+            const float *c = pool + p.nr_int_c;
+            float s[19 + BLK];
+            for (int i = 0; i < 19; i++) s[i] = nr.int_hist[i];
+            for (int i = 0; i < no_dec; i++) s[19 + i] = dec[i];
+            for (int i = 0; i < no_dec; i++) {
+                for (int j = 0; j < 2; j++) {
+                    float sum = 0.0f;
+                    for (int k = 0; k < 20; k++) sum = __fadd_rn(sum, __fmul_rn(s[i + k], __ldg(c + (1 - j) + 2 * k)));
+                    buf[2 * i + j] = __fmul_rn(sum, 2.0f);
+                }
+            }
+            for (int i = 0; i < 19; i++) nr.int_hist[i] = s[no_dec + i];
+        } else {
+            for (int i = 0; i < n; i++) buf[i] = dec[i];
+        }
+        // deferred task bookkeeping (AudioNr_HandleNoiseReduction)
+        if (!nr.was_here) { nr.was_here = 1; nr.current_buffer_idx = 0; nr.in_tail = nr.in_head; nr.out_tail = nr.out_head; }
+    }
+    __syncwarp();
+    __threadfence_block();
+    const int pending = nr_fifo_count(nr.in_head, nr.in_tail) && (NR_FIFO - 1 - nr_fifo_count(nr.out_head, nr.out_tail));
+    if (pending) {
+        const int cur = nr.current_buffer_idx % 4;
+        const int k = nr.in_fifo[nr.in_tail];
+        __syncwarp();
+        nr_spectral(p, nr, pool, nr.bufs[k], fft, lane);
+        __threadfence_block();
+        __syncwarp();
+        for (int i = lane; i < 128; i += 32) nr.bufs[cur][128 + i] = nr.bufs[k][i];
+        __syncwarp();
+        if (lane == 0) {
+            nr.in_tail = (nr.in_tail + 1) % NR_FIFO;
+            const int next = (nr.out_head + 1) % NR_FIFO;
+            if (next != nr.out_tail) { nr.out_fifo[nr.out_head] = cur; nr.out_head = next; }
+            nr.current_buffer_idx = cur + 1;
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
 }  // namespace uhsdr

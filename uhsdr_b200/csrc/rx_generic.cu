@@ -23,6 +23,7 @@ struct WarpWork {
     float ip[INTERP_HIST + CHUNK];          // interpolator input [history | new]
     float out[CHUNK];                       // 48 ksps audio
     float scr[2 * BLK];                     // scratch (NCO values)
+    float fft[512];                         // spectral-NR FFT frame
     ChanState st;
 };
 
@@ -292,7 +293,7 @@ rx_generic_kernel(RxArgs a)
                     st.agc_decay_type = ar.decay_type; st.agc_state = ar.state; st.agc_action = ar.action; st.agc_hang_action = ar.hang_action;
                 }
                 __syncwarp();
-                if (nr) nr_block(p, *nr, pool, ad, ndec_blk, w.scr, lane);   // :2501-2509
+                if (nr) nr_block(p, *nr, pool, ad, ndec_blk, w.fft, lane);   // :2501-2509
                 if (lane == 0) {
                     // fixed gain :2513-2524, biquad_1 :2527
                     for (int i = 0; i < ndec_blk; i++) {

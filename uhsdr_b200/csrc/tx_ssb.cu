@@ -1,17 +1,273 @@
-// tx_ssb.cu -- SSB transmit modulator (TxProcessor_Run SSB branch, tx_processor.c:891-1078).
+// tx_ssb.cu -- SSB voice transmit modulator: TxProcessor_Run, SSB branch
+// (mchf-eclipse/drivers/audio/tx_processor.c:891-1078):
+//   AudioBufferFill (:339-405)  int32 mic x gain x 2^-16, peak_audio
+//   FilterAudio (:416-429)      10-stage lattice band-pass + 3-stage biquad (treble/bass shelves)
+//   VoiceCompressor (:173-242)  post-filter gain, per-sample ALC, 32-sample look-ahead delay line
+//   TxProcessor_SSB (:467-490)  201-tap Hilbert pair (I/Q filters swapped for LSB), FreqShift
+//   IqFinalProcessing (:282-330) x power factor x IQ gain x 1.133 x 65536, phase mix, float -> int32
+// One warp per channel: the recurrences (lattice, biquads, ALC) run on lane 0, the two 201-tap
+// FIRs, translation and output formatting on all 32 lanes.
 #include "dsp_device.cuh"
-#include "kernels.h"
 #include "host_tables.h"
+#include "kernels.h"
 
 namespace uhsdr {
 
-int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *out, std::string *err)
+// ---- host: TxProcessor_Set (:72-119), AudioManagement_CalcTxCompLevel (audio_management.c:240-291) ----
+static const float kPiTx = 3.14159265358979f;
+static void bq_scale_tx(float c[5], float sa, float sb) { c[3] = c[3] / sa; c[4] = c[4] / sa; c[0] = c[0] / sb; c[1] = c[1] / sb; c[2] = c[2] / sb; }
+static void shelf(float c[5], bool high, float f0, float S, float gain, float FS)     // audio_driver.c:906-964
 {
-    (void)t; (void)cfg; (void)err;
-    memset(out, 0, sizeof(*out));
+    float w0 = 2 * kPiTx * f0 / FS;
+    float A = exp10f(gain / 40.0);
+    float alpha = sinf(w0) / 2 * sqrtf((A + 1 / A) * (1 / S - 1) + 2);
+    float cosw0 = cosf(w0);
+    float twoAa = 2 * sqrtf(A) * alpha;
+    float scaling;
+    if (high) {
+        c[0] = A * ((A + 1) + (A - 1) * cosw0 + twoAa);
+        c[1] = -2 * A * ((A - 1) + (A + 1) * cosw0);
+        c[2] = A * ((A + 1) + (A - 1) * cosw0 - twoAa);
+        scaling = (A + 1) - (A - 1) * cosw0 + twoAa;
+        c[3] = -2 * ((A - 1) - (A + 1) * cosw0);
+        c[4] = twoAa - (A + 1) + (A - 1) * cosw0;
+    } else {
+        c[0] = A * ((A + 1) - (A - 1) * cosw0 + twoAa);
+        c[1] = 2 * A * ((A - 1) - (A + 1) * cosw0);
+        c[2] = A * ((A + 1) - (A - 1) * cosw0 - twoAa);
+        scaling = (A + 1) + (A - 1) * cosw0 + twoAa;
+        c[3] = 2 * ((A - 1) + (A + 1) * cosw0);
+        c[4] = twoAa - (A + 1) - (A - 1) * cosw0;
+    }
+    float DCgain = 1.0 * scaling;
+    bq_scale_tx(c, scaling, DCgain);
+}
+
+int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *tp, std::string *err)
+{
+    memset(tp, 0, sizeof(*tp));
+    const int mode = cfg.dmod_mode;
+    tp->enabled = (mode == UHSDR_DEMOD_USB || mode == UHSDR_DEMOD_LSB) ? 1 : 0;    // is_ssb(), uhsdr_board.h:809
+    tp->lsb = mode == UHSDR_DEMOD_LSB;
+    {
+        float gain_calc = (uint8_t)cfg.tx_mic_gain;      // ts.tx_mic_gain_mult (codec.c:321)
+        gain_calc /= 2;                                  // MIC_GAIN_RESCALE
+        gain_calc *= (0.0000152587890625);               // AUDIO_BIT_SCALE_DOWN
+        tp->gain_calc = gain_calc;
+    }
+    int li = t.ex->tx_lattice_soprano;
+    if (cfg.tx_filter == UHSDR_TX_FILTER_BASS) li = t.ex->tx_lattice_bass;
+    else if (cfg.tx_filter == UHSDR_TX_FILTER_TENOR) li = t.ex->tx_lattice_tenor;
+    if (li < 0 || li >= (int)t.h->num_lattices || t.lat[li].num_stages > MAX_LAT) { if (err) *err = "TX lattice missing from the table blob"; return UHSDR_ERR_TABLES; }
+    tp->lat.n = t.lat[li].num_stages; tp->lat.k_off = t.off(t.lat[li].k_array); tp->lat.v_off = t.off(t.lat[li].v_array);
+    shelf(tp->bq[0], true, 1700, 0.9, cfg.tx_treble_gain, 48000);
+    shelf(tp->bq[1], false, 300, 0.7, cfg.tx_bass_gain, 48000);
+    tp->bq[2][0] = 1.0f;
+    // speech-compressor settings
+    static const unsigned alc_params[13][2] = {
+        { 1, 15 }, { 2, 12 }, { 4, 10 }, { 6, 9 }, { 7, 8 }, { 8, 7 }, { 10, 6 }, { 12, 5 }, { 15, 4 }, { 17, 3 }, { 20, 2 }, { 25, 1 }, { 25, 0 } };
+    unsigned pg, dv;
+    const int lvl = (int16_t)cfg.tx_comp_level;
+    if (-1 < lvl && lvl < 13) { pg = alc_params[lvl][0]; dv = alc_params[lvl][1]; }
+    else if (lvl == 13) { pg = (unsigned)cfg.tx_alc_postfilt_gain; dv = (unsigned)cfg.tx_alc_decay; }
+    else { pg = 4; dv = 10; }
+    tp->comp_enabled = lvl > -1;
+    tp->postfilt_gain = ((float)(float)pg) / 2.0 + 0.5;
+    tp->alc_decay = exp10f(-((((float)dv) + 35.0) / 10.0));
+    tp->hil_ntaps = t.ex->tx_hilbert_numtaps;
+    tp->hil_ci = t.off(t.ex->tx_hilbert_i_array); tp->hil_cq = t.off(t.ex->tx_hilbert_q_array);
+    if (tp->hil_ntaps < 1 || tp->hil_ntaps - 1 > H2 || tp->hil_ci < 0 || tp->hil_cq < 0) { if (err) *err = "TX Hilbert pair missing from the table blob"; return UHSDR_ERR_TABLES; }
+    int shift = 0;
+    switch (cfg.iq_freq_mode) {
+    case UHSDR_FREQ_IQ_CONV_P6KHZ: shift = 6000; break;
+    case UHSDR_FREQ_IQ_CONV_M6KHZ: shift = -6000; break;
+    case UHSDR_FREQ_IQ_CONV_P12KHZ: shift = 12000; break;
+    case UHSDR_FREQ_IQ_CONV_M12KHZ: shift = -12000; break;
+    default: break;
+    }
+    tp->shift_freq = abs(shift); tp->shift_down = shift > 0;
+    tp->shift_kind = shift == 0 ? 0 : (tp->shift_freq == 12000 ? 1 : 2);
+    {
+        float nco_freq = (float)tp->shift_freq, sample_rate = 48000.0f;
+        double rate = (2 * M_PI * nco_freq) / sample_rate;
+        tp->osc_cos = cos(rate); tp->osc_sin = sin(rate);
+    }
+    {
+        float scaling = 1.133;                            // SSB_GAIN_COMP
+        scaling *= (1 << 16);                             // IQ_BIT_SCALE_UP
+        tp->final_gain_i = cfg.tx_power_factor * cfg.tx_adj_gain_i * scaling;
+        tp->final_gain_q = cfg.tx_power_factor * cfg.tx_adj_gain_q * scaling;
+    }
+    tp->phase_bal = cfg.iq_phase_balance_tx;
     return UHSDR_OK;
 }
 
-cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream) { (void)a; (void)stream; return cudaErrorNotSupported; }
+// ---- device ---------------------------------------------------------------------------------
+static constexpr int TX_WARPS = 4;
+
+struct TxWork {
+    float a[H2 + CHUNK];        // Hilbert input: [200 history | 128 new]
+    float scr[2 * BLK];
+    TxState st;
+};
+
+__global__ void __launch_bounds__(32 * TX_WARPS)
+tx_ssb_kernel(TxArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * TX_WARPS + warp;
+    if (ch >= a.num_items) return;
+    TxWork &w = reinterpret_cast<TxWork *>(smem_raw)[warp];
+    const TxParams &tp = a.txp[ch];
+    ChanState *rst = a.state + ch;
+    const float *__restrict__ pool = a.pool;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(a.tx + ch);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&w.st);
+        for (int i = lane; i < (int)(sizeof(TxState) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    for (int i = lane; i < H2; i += 32) w.a[i] = w.st.hist[i];
+    float osc_q = rst->osc_vect_q, osc_i = rst->osc_vect_i;
+    int conv = rst->conversion_freq;
+    if (tp.shift_kind != 0 && conv != tp.shift_freq) { conv = tp.shift_freq; osc_i = 0.0f; osc_q = 1.0f; }   // freq_shift.c:289-305
+    __syncwarp();
+    TxState &st = w.st;
+    const size_t base = (size_t)ch * (size_t)a.nblocks * BLK;
+    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + base;
+    int2 *__restrict__ iq = reinterpret_cast<int2 *>(a.iq) + base;
+    float2 *__restrict__ iq_f = a.iq_f ? reinterpret_cast<float2 *>(a.iq_f) + base : nullptr;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+    const int N = tp.hil_ntaps;
+    const float *ci = pool + (tp.lsb ? tp.hil_cq : tp.hil_ci), *cq = pool + (tp.lsb ? tp.hil_ci : tp.hil_cq);
+
+    for (int blk = 0; blk < a.nblocks; blk++) {
+        const bool muted = mute && mute[blk];
+        float vi = 0.0f, vq = 0.0f;
+        if (!muted && tp.enabled) {
+            // AudioBufferFill
+            const int2 s = mic[(size_t)blk * BLK + lane];
+            float x = (float)s.x;
+            if ((double)tp.gain_calc != 1.0) x = __fmul_rn(x, tp.gain_calc);
+            float mx = x, mn = x;
+            for (int d = 16; d > 0; d >>= 1) { mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d)); mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); }
+            w.scr[lane] = x;
+            __syncwarp();
+            if (lane == 0) {
+                st.peak_audio = (-mn > mx) ? -mn : mx;
+                for (int i = 0; i < BLK; i++) {
+                    float v = w.scr[i];
+                    v = lattice_step(v, st.lat_s, pool + tp.lat.k_off, pool + tp.lat.v_off, tp.lat.n);
+                    w.scr[i] = v;
+                }
+                // the reference runs the 3 biquad stages block-wise; per-sample order is equivalent
+                for (int i = 0; i < BLK; i++) {
+                    float v = w.scr[i];
+                    for (int sgi = 0; sgi < 3; sgi++) v = biquad_step(v, tp.bq[sgi], st.bq[sgi]);
+                    w.scr[i] = v;
+                }
+                if (tp.comp_enabled) {
+                    for (int i = 0; i < BLK; i++) {
+                        const float v = __fmul_rn(w.scr[i], tp.postfilt_gain);
+                        w.scr[i] = v;
+                        // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), :202
+                        const float alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(v, st.alc_val)), 30000.0f) - 1.0);
+                        if (alc_var < 0.0f) {
+                            st.alc_val = __fsub_rn(st.alc_val, __fmul_rn(__fmul_rn(st.alc_val, tp.alc_decay), alc_var));
+                        } else {
+                            st.alc_val = (float)((double)st.alc_val - (double)st.alc_val * 0.1 * (double)alc_var);
+                            if ((double)st.alc_val < 0.001) st.alc_val = (float)0.001;
+                        }
+                        if (st.alc_val > 1.0f) st.alc_val = 1.0f;
+                        w.scr[BLK + i] = __fmul_rn(st.alc_val, 1.00f);
+                    }
+                    st.alc_delay_inbuf += BLK;
+                }
+            }
+            __syncwarp();
+            float v = w.scr[lane];
+            if (tp.comp_enabled) {
+                // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
+                const uint32_t inb = st.alc_delay_inbuf % 320u, outb = (st.alc_delay_inbuf + BLK) % 320u;
+                __syncwarp();
+                st.delay[inb + lane] = v;
+                __syncwarp();
+                v = __fmul_rn(st.delay[outb + lane], w.scr[BLK + lane]);
+                if (lane == 0) st.alc_delay_inbuf = inb;
+            }
+            w.a[H2 + lane] = v;
+            __syncwarp();
+            // Hilbert pair, y[n] = sum_k c[k] a[n - (N-1) + k]
+            const float *xs = w.a + H2 + lane - (N - 1);
+            float yi = 0.0f, yq = 0.0f;
+            for (int k = 0; k < N; k++) { yi = mad(xs[k], __ldg(ci + k), yi); yq = mad(xs[k], __ldg(cq + k), yq); }
+            __syncwarp();
+            // slide the history by one block
+            float keep[(H2 + 31) / 32];
+            int cnt = 0;
+            for (int i = lane; i < H2; i += 32) keep[cnt++] = w.a[BLK + i];
+            __syncwarp();
+            cnt = 0;
+            for (int i = lane; i < H2; i += 32) w.a[i] = keep[cnt++];
+            __syncwarp();
+            vi = yi; vq = yq;
+            // FreqShift (:483-486)
+            if (tp.shift_kind == 1) {
+                float ib = tp.shift_down ? vq : vi, qb = tp.shift_down ? vi : vq;
+                const int ph = lane & 3;
+                float ni = ib, nq = qb;
+                if (ph == 1) { ni = qb; nq = -ib; } else if (ph == 2) { ni = -ib; nq = -qb; } else if (ph == 3) { ni = -qb; nq = ib; }
+                if (tp.shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
+            } else if (tp.shift_kind == 2) {
+                if (lane == 0) {
+                    float q0 = osc_q, i0 = osc_i;
+                    for (int n = 0; n < BLK; n++) {
+                        const float oq = __fsub_rn(__fmul_rn(q0, tp.osc_cos), __fmul_rn(i0, tp.osc_sin));
+                        const float oi = __fadd_rn(__fmul_rn(i0, tp.osc_cos), __fmul_rn(q0, tp.osc_sin));
+                        w.scr[n] = oq; w.scr[BLK + n] = oi; q0 = oq; i0 = oi;
+                    }
+                    const float g = __fdiv_rn(__fsub_rn(3.0f, __fadd_rn(__fmul_rn(q0, q0), __fmul_rn(i0, i0))), 2.0f);
+                    osc_q = __fmul_rn(g, q0); osc_i = __fmul_rn(g, i0);
+                }
+                __syncwarp();
+                const float oq = w.scr[lane], oi = w.scr[BLK + lane];
+                float ib = tp.shift_down ? vq : vi, qb = tp.shift_down ? vi : vq;
+                const float nq = __fsub_rn(__fmul_rn(qb, oq), __fmul_rn(ib, oi));
+                const float ni = __fadd_rn(__fmul_rn(ib, oq), __fmul_rn(qb, oi));
+                if (tp.shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
+                __syncwarp();
+            }
+        }
+        // IqFinalProcessing
+        vi = __fmul_rn(vi, tp.final_gain_i);
+        vq = __fmul_rn(vq, tp.final_gain_q);
+        if (tp.phase_bal < 0.0f) vq = __fadd_rn(vq, __fmul_rn(vi, tp.phase_bal));
+        else if (tp.phase_bal > 0.0f) vi = __fadd_rn(vi, __fmul_rn(vq, tp.phase_bal));
+        const size_t o = (size_t)blk * BLK + lane;
+        iq[o] = make_int2(__float2int_rz(vi), __float2int_rz(vq));
+        if (iq_f) iq_f[o] = make_float2(vi, vq);
+    }
+    __syncwarp();
+    for (int i = lane; i < H2; i += 32) w.st.hist[i] = w.a[i];
+    if (lane == 0) { st.blocks += a.nblocks; rst->osc_vect_q = osc_q; rst->osc_vect_i = osc_i; rst->conversion_freq = conv; }
+    __syncwarp();
+    {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.tx + ch);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&w.st);
+        for (int i = lane; i < (int)(sizeof(TxState) / 4); i += 32) dst[i] = src[i];
+    }
+}
+
+cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
+{
+    const size_t smem = sizeof(TxWork) * TX_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int grid = (a.num_items + TX_WARPS - 1) / TX_WARPS;
+    if (grid == 0) return cudaSuccess;
+    tx_ssb_kernel<<<grid, 32 * TX_WARPS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
 
 }  // namespace uhsdr

@@ -74,6 +74,8 @@ struct ChanParams {
     float nr_alpha;
     int nr_vad_low, nr_vad_high;
     int nr_dec_c, nr_int_c, nr_win_c;   // pool offsets
+    int tw256_off, tw512_off;           // FFT twiddle tables in the pool
+    float nr_xih1;                      // pow10f(NR2.asnr / 10), audio_nr.c:1886
     // spectrum
     int spectrum_enable;
     float codec_gain_calc;
@@ -122,7 +124,7 @@ struct NrState {
     int trans_count_in, outbuff_count, fill_in_pt, out_buffer;
     int in_fifo[5], in_head, in_tail, out_fifo[5], out_head, out_tail;
     int current_buffer_idx, was_here;
-    float dec_hist[4], int_hist[20];
+    float dec_hist[4], int_hist[20];    // DECIMATE_NR (3 used) / INTERPOLATE_NR (19 used) histories
     float last_sample[128], last_ifft[128], Hk[128], Hk_old[128], Nest0[128], xt[128], pslp[128];
     int first_time, init_counter;
 };
