@@ -31,8 +31,11 @@ def test_spectral_nr_within_tolerance(built, label, kw, nblocks, exact):
     for c in range(nch):
         with oracle_channel(cfg) as o:
             want_w, want_f = o.rx(iq[c])
-        # the FIFO rule fixes the latency exactly: same first non-zero sample
-        assert np.flatnonzero(fl[c])[0] == np.flatnonzero(want_f)[0], label
+        # the FIFO rule fixes the latency exactly (FFT round-off decides which of the first, nearly
+        # silent samples are non-zero, so compare where the output first rises above 1e-3 of peak)
+        thr = 1e-3 * np.max(np.abs(want_f))
+        assert np.flatnonzero(np.abs(fl[c]) > thr)[0] == np.flatnonzero(np.abs(want_f) > thr)[0], label
+        assert np.all(fl[c][: 32 * 32] == 0) and np.all(want_f[: 32 * 32] == 0)
         check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
 
 
@@ -83,8 +86,9 @@ def test_tx_ssb(built, label, kw, nblocks, exact):
         a, b = d_mic[:, : h * 32].contiguous(), d_mic[:, h * 32:].contiguous()
         oa, ob = torch.empty_like(a), torch.empty_like(b)
         fa, fb = torch.empty(a.shape, dtype=torch.float32, device=dev), torch.empty(b.shape, dtype=torch.float32, device=dev)
-        eng.tx_device(a, oa, h, iq_f_dev=fa, mute_dev=d_mute[:, :h].contiguous())
-        eng.tx_device(b, ob, nblocks - h, iq_f_dev=fb, mute_dev=d_mute[:, h:].contiguous())
+        ma, mb = d_mute[:, :h].contiguous(), d_mute[:, h:].contiguous()   # keep alive: the calls are asynchronous
+        eng.tx_device(a, oa, h, iq_f_dev=fa, mute_dev=ma)
+        eng.tx_device(b, ob, nblocks - h, iq_f_dev=fb, mute_dev=mb)
         eng.sync()
         iq = torch.cat([oa, ob], dim=1).cpu().numpy()
         iq_f = torch.cat([fa, fb], dim=1).cpu().numpy()

@@ -109,8 +109,9 @@ def test_port_nr_matches_golden_within_fft_rounding(golden, label, kw, nblocks):
         audio, audio_f = p.rx(golden[f"{label}/iq"])
     want = golden[f"{label}/audio_f"].astype(np.float64)
     # exact output latency: zeros until two processed frames are queued (audio_driver.c:2389-2417)
-    nz_want, nz_got = np.flatnonzero(want), np.flatnonzero(audio_f)
-    assert nz_want.size and nz_got[0] == nz_want[0]
+    thr = 1e-3 * np.max(np.abs(want))
+    assert np.flatnonzero(np.abs(audio_f) > thr)[0] == np.flatnonzero(np.abs(want) > thr)[0]
+    assert np.all(audio_f[: 32 * 32] == 0) and np.all(want[: 32 * 32] == 0)
     err = audio_f.astype(np.float64) - want
     assert np.max(np.abs(err)) <= 1e-5 * np.max(np.abs(want))
     assert 10 * np.log10(np.mean(want ** 2) / np.mean(err ** 2)) > 100.0

@@ -43,17 +43,22 @@ __device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float
     __syncwarp();
     fft_inplace<256, 8, 32>(fft, pool + p.tw256_off, false, lane);
 
-    const int first_time = nr.first_time;
+    // audio_nr.c:1989-2003: the 20th averaging frame switches first_time to 3 and the tracker
+    // below already runs on that same frame (two consecutive ifs in the reference)
+    const bool run2 = nr.first_time == 2;
+    const bool run3 = nr.first_time == 3 || (run2 && nr.init_counter + 1 > 19);
     int vad_low = 0, vad_high = 63;                      // audio_nr.c:1863-1864 until first_time == 3
-    if (first_time == 3) { vad_low = p.nr_vad_low; vad_high = p.nr_vad_high; }
+    if (run3) { vad_low = p.nr_vad_low; vad_high = p.nr_vad_high; }
+    __syncwarp();
     for (int b = lane; b < 128; b += 32) {
         const float re = fft[2 * b], im = fft[2 * b + 1];
         const float X = __fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im));
-        if (first_time == 2) {
+        if (run2) {
             const float nest = (float)((double)nr.Nest0[b] + 0.05 * (double)X);
             nr.Nest0[b] = nest;
             nr.xt[b] = __fmul_rn(psini, nest);
-        } else if (first_time == 3) {
+        }
+        if (run3) {
             float xt = nr.xt[b];
             // MMSE speech-presence noise tracker (:2008-2024)
             float ph1y = (float)(1.0 / (1.0 + (double)__fmul_rn(pfac, expf(__fdiv_rn(__fmul_rn(xih1r, X), xt)))));
@@ -79,7 +84,7 @@ __device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float
         }
     }
     __syncwarp();
-    if (first_time == 2 && lane == 0) {
+    if (run2 && lane == 0) {
         nr.init_counter++;
         if (nr.init_counter > 19) { nr.init_counter = 0; nr.first_time = 3; }
     }
