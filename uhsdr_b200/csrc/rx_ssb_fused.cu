@@ -29,17 +29,18 @@ namespace uhsdr {
 
 namespace {
 
-constexpr int FG = 32;             // channel slots per CTA
+constexpr int FG = 28;             // channel slots per CTA (7 FIR warps x 4 channels)
 constexpr int CH4 = 128;           // input samples per chunk (4 blocks)
 constexpr int ND = 32;             // decimated samples per chunk
-constexpr int XP = 56;             // per-phase slots: 21 history + 32 new + 3 pad
+constexpr int XP = 56;             // per-phase slots: 24 history (21 used) + 32 new
+constexpr int XH = 24;             // history slots per phase (multiple of 4: the slide is 6 float4)
 constexpr int XCH = 2 * 4 * XP + 4;   // floats per channel (I phases, Q phases) + 4 -> bank stagger
 constexpr int DL = 200 + ND;       // Hilbert input: 200 history slots + 32 new
 constexpr int DCH = 2 * DL + 4;     // + 4 -> neighbouring channels land on disjoint banks
 constexpr int SMS = 33;            // channel-minor stride of the pipeline queues
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
-constexpr int RING = 64;
-constexpr int NWARP_FIR = FG / 8;   // one FIR warp = 8 channels x 4 lanes, 8 decimated outputs per lane
+constexpr int RING = 128;           // AGC delay ring slots (>= 49 + one chunk, so pass 2 can re-read the delayed samples)
+constexpr int NWARP_FIR = FG / 4;   // one FIR warp = 4 channels x 8 lanes, 4 decimated outputs per lane
 constexpr int DEC_PAD = 32;        // zero padding in front of the decimator taps (FusedCoefs::dec)
 constexpr int HIL_PAD = 12;        // zero padding in front of the Hilbert taps
 constexpr int W_LAT = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_EQ = NWARP_FIR + 2, W_POST = NWARP_FIR + 3;
@@ -47,15 +48,44 @@ constexpr int NTHREADS = 32 * (NWARP_FIR + 4);
 constexpr int PIPE_DEPTH = 5;      // FIR t | LAT t-1 | AGC t-2 | EQ t-3 | POST t-4 | WRITE t-5
 
 struct Smem {
-    float x[FG * XCH];
-    float d[FG * DCH];
+    alignas(16) float x[FG * XCH];
+    alignas(16) float d[FG * DCH];
     float aud[2][ND * SMS];
     float lat[2][ND * SMS];
     float agc[2][ND * SMS];
     float out[3][CH4 * SMS];
     float ring[RING * SMS];
     float smax[AGC_W * SMS];
+    alignas(16) int2 raw[FG * CH4];     // staged input chunk: bulk-async copy target, 1 KB per channel
+    alignas(8) unsigned long long mbar[NWARP_FIR];   // one transaction barrier per FIR warp
 };
+
+// ---- bulk asynchronous copy (TMA, 1-D) + mbarrier, sm_90+/sm_100 PTX --------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int N> struct IC { static constexpr int value = N; };
 template <int I, int N, typename F> __device__ __forceinline__ void static_for(F &&f)
@@ -74,22 +104,23 @@ struct FirLaneState {
     int clip;                // bit0 quarter, bit1 half, bit2 full
 };
 
-// Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 84 history
-// samples in front, buffer position b = 4m + k + 2; phase = b & 3, idx = b >> 2.  Each lane makes 8
-// consecutive outputs m0..m0+7.  Elements are consumed in ascending b, which is ascending k for
-// every output (the reference's summation order).  The loop is rolled (instruction-cache
-// footprint); taps outside [0, 82] hit the zero padding of FusedCoefs::dec and add +-0.
-__device__ __forceinline__ void decimate8(const float *xpi, const float *xpq, int m0, const FusedCoefs &fc,
-                                          float ai[8], float aq[8])
+// Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 96 history
+// slots in front (24 per phase), buffer position b = 4m + k + 14; phase = b & 3, idx = b >> 2 =
+// m + 3 + ((k + 2) >> 2).  Each lane makes 4 consecutive outputs m0..m0+3 for I and for Q.
+// Elements are consumed in ascending b, which is ascending k for every output (the reference's
+// summation order).  The loop is rolled to keep the instruction-cache footprint small; taps outside
+// [0, 82] hit the zero padding of FusedCoefs::dec and add +-0.
+__device__ __forceinline__ void decimate4(const float *xpi, const float *xpq, int m0, const FusedCoefs &fc,
+                                          float ai[4], float aq[4])
 {
 #pragma unroll
-    for (int j = 0; j < 8; j++) { ai[j] = 0.0f; aq[j] = 0.0f; }
+    for (int j = 0; j < 4; j++) { ai[j] = 0.0f; aq[j] = 0.0f; }
 #pragma unroll 1
     for (int q = 0; q < 7; q++) {
         float4 vi[4], vq[4];
 #pragma unroll
         for (int ph = 0; ph < 4; ph++) { vi[ph] = lds128(xpi + ph * XP + m0 + 4 * q); vq[ph] = lds128(xpq + ph * XP + m0 + 4 * q); }
-        const float *cq = fc.dec + DEC_PAD + 16 * q - 2;      // tap index K = 16q + 4(E - J) + PH - 2
+        const float *cq = fc.dec + DEC_PAD + 16 * q - 14;     // tap index K = 16q + 4(E - 3 - J) + PH - 2
 #pragma unroll
         for (int e = 0; e < 4; e++) {
 #pragma unroll
@@ -97,7 +128,7 @@ __device__ __forceinline__ void decimate8(const float *xpi, const float *xpq, in
                 const float xi = (e == 0) ? vi[ph].x : (e == 1) ? vi[ph].y : (e == 2) ? vi[ph].z : vi[ph].w;
                 const float xq = (e == 0) ? vq[ph].x : (e == 1) ? vq[ph].y : (e == 2) ? vq[ph].z : vq[ph].w;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < 4; j++) {
                     const float c = cq[4 * (e - j) + ph];
                     ai[j] = mad(c, xi, ai[j]);
                     aq[j] = mad(c, xq, aq[j]);
@@ -105,20 +136,17 @@ __device__ __forceinline__ void decimate8(const float *xpi, const float *xpq, in
             }
         }
     }
-    // the one contribution outside the rolled range: idx m0+28, phase 0 -> tap 82 of output 7
-    ai[7] = mad(fc.dec[DEC_PAD + 82], xpi[m0 + 28], ai[7]);
-    aq[7] = mad(fc.dec[DEC_PAD + 82], xpq[m0 + 28], aq[7]);
 }
 
 // Hilbert pair at 12 ksps: y[n] = sum_k c[k] d[n - 198 + k] (arm_fir_f32.c:522-529).  With 200
-// history slots, position = n + k + 2; 8 outputs per lane, elements streamed in ascending position.
-__device__ __forceinline__ void hilbert8(const float *dpi, const float *dpq, int n0, const FusedCoefs &fc,
-                                         float hi[8], float hq[8])
+// history slots, position = n + k + 2; 4 outputs per lane, elements streamed in ascending position.
+__device__ __forceinline__ void hilbert4(const float *dpi, const float *dpq, int n0, const FusedCoefs &fc,
+                                         float hi[4], float hq[4])
 {
 #pragma unroll
-    for (int j = 0; j < 8; j++) { hi[j] = 0.0f; hq[j] = 0.0f; }
-#pragma unroll 4
-    for (int q = 0; q < 52; q++) {
+    for (int j = 0; j < 4; j++) { hi[j] = 0.0f; hq[j] = 0.0f; }
+#pragma unroll 3
+    for (int q = 0; q < 51; q++) {
         const float4 vi = lds128(dpi + n0 + 4 * q), vq = lds128(dpq + n0 + 4 * q);
         const float *ci = fc.hil_i + HIL_PAD + 4 * q - 2;     // tap index K = 4q + E - J - 2
         const float *cq = fc.hil_q + HIL_PAD + 4 * q - 2;
@@ -127,7 +155,7 @@ __device__ __forceinline__ void hilbert8(const float *dpi, const float *dpq, int
             const float xi = (e == 0) ? vi.x : (e == 1) ? vi.y : (e == 2) ? vi.z : vi.w;
             const float xq = (e == 0) ? vq.x : (e == 1) ? vq.y : (e == 2) ? vq.z : vq.w;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < 4; j++) {
                 hi[j] = mad(ci[e - j], xi, hi[j]);
                 hq[j] = mad(cq[e - j], xq, hq[j]);
             }
@@ -150,48 +178,61 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
     const float *__restrict__ pool = a.pool;
 
     if (warp < NWARP_FIR) {
-        // ======================= FIR warp: 8 channels x 4 lanes ==================================
-        const int cl = lane >> 2, r = lane & 3;
-        const int g = warp * 8 + cl;                   // channel slot in the CTA
+        // ======================= FIR warp: 4 channels x 8 lanes ==================================
+        const int cl = lane >> 3, r = lane & 7;
+        const int g = warp * 4 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
         const ChanParams &p = a.params[ch];
         ChanState *st = a.state + ch;
         float *xi = sm.x + g * XCH, *xq = xi + 4 * XP;
         float *di = sm.d + g * DCH, *dq = di + DL;
-        const unsigned gmask = 0xfu << (4 * cl);
+        const unsigned gmask = 0xffu << (8 * cl);
+        const int n_warp_ch = max(0, min(4, n_here - warp * 4));     // active channels of this warp
+        unsigned long long *bar = &sm.mbar[warp];
+        const int2 *raw = sm.raw + g * CH4;
 
         // ---- load histories and IQ-correction state ----
         FirLaneState ls;
         ls.te1 = st->teta1_old; ls.te2 = st->teta2_old; ls.te3 = st->teta3_old; ls.c1 = st->M_c1; ls.c2 = st->M_c2; ls.clip = 0;
-        // s1_hist[H1=96]: sample s (-84..-1) at [96 + s] -> position b = s + 84 -> phase b&3, idx b>>2
-        for (int b = r; b < 84; b += 4) {
-            xi[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_i[H1 - 84 + b] : 0.0f;
-            xq[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_q[H1 - 84 + b] : 0.0f;
+        // s1_hist[H1=96]: sample s (-96..-1) at [96 + s] = position b -> phase b&3, idx b>>2
+        for (int b = r; b < 4 * XH; b += 8) {
+            xi[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_i[b] : 0.0f;
+            xq[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_q[b] : 0.0f;
         }
-        for (int i = r; i < 200; i += 4) {
+        for (int i = r; i < 200; i += 8) {
             di[i] = active ? st->s2_hist_i[i] : 0.0f;
             dq[i] = active ? st->s2_hist_q[i] : 0.0f;
         }
         const int iq_auto = p.iq_auto, shift_kind = p.shift_kind, shift_down = p.shift_down, lsb = p.lsb;
         const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
         const size_t chan_base = (size_t)ch * (size_t)a.nblocks * BLK;
-        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base);
+        const int2 *__restrict__ src = reinterpret_cast<const int2 *>(a.iq) + chan_base;
         int4 *__restrict__ dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(a.audio) + chan_base);
         float2 *__restrict__ dst_f = a.audio_f ? reinterpret_cast<float2 *>(a.audio_f + chan_base) : nullptr;
         const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+
+        // ---- stage chunk 0: one bulk asynchronous copy of 1 KB per channel, tracked by the warp's mbarrier ----
+        if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncwarp();
+        if (nchunks > 0 && n_warp_ch > 0) {
+            if (lane == 0) mbar_expect_tx(bar, (unsigned)(n_warp_ch * CH4 * sizeof(int2)));
+            __syncwarp();
+            if (r == 0 && active) bulk_g2s(sm.raw + g * CH4, src, CH4 * sizeof(int2), bar);
+        }
         __syncwarp();
 
         for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
             if (t < nchunks) {
-                // ---- front end, one 32-sample block at a time: pairs p = r + 4i (samples 2p, 2p+1) ----
+                if (n_warp_ch > 0) mbar_wait(bar, (unsigned)(t & 1));
+#if UHSDR_EXACT
+                // ---- front end, one 32-sample block at a time: pairs p = r + 8i (samples 2p, 2p+1) ----
 #pragma unroll 1
                 for (int b = 0; b < 4; b++) {
-                    float fi[8], fq[8];
+                    float fi[4], fq[4];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        int4 v = make_int4(0, 0, 0, 0);
-                        if (active) v = __ldg(src + (size_t)t * 64 + b * 16 + r + 4 * i);
+                    for (int i = 0; i < 2; i++) {
+                        const int4 v = *reinterpret_cast<const int4 *>(raw + b * 32 + 2 * (r + 8 * i));
                         const int lv = max(abs(v.x) >> 16, abs(v.z) >> 16);     // audio_driver.c:2662-2675
                         ls.clip |= (lv > 1024 ? 1 : 0) | (lv > 2048 ? 2 : 0) | (lv > 4096 ? 4 : 0);
                         fi[2 * i] = __fmul_rn((float)v.x, 0.0000152587890625f);
@@ -203,28 +244,28 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                         // Moseley & Slump statistics of the block (audio_driver.c:2274-2279)
                         float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #if UHSDR_EXACT
-                        // reference order: sample n lives in lane (n/2)&3, slot 2*((n/2)>>2) + (n&1)
+                        // reference order: sample n lives in lane (n/2)&7, slot 2*((n/2)>>3) + (n&1)
 #pragma unroll
                         for (int n = 0; n < 32; n++) {
-                            const int slot = 2 * ((n >> 1) >> 2) + (n & 1);
-                            const float vi = __shfl_sync(gmask, fi[slot], (n >> 1) & 3, 4);
-                            const float vq = __shfl_sync(gmask, fq[slot], (n >> 1) & 3, 4);
+                            const int slot = 2 * ((n >> 1) >> 3) + (n & 1);
+                            const float vi = __shfl_sync(gmask, fi[slot], (n >> 1) & 7, 8);
+                            const float vq = __shfl_sync(gmask, fq[slot], (n >> 1) & 7, 8);
                             s1 = __fadd_rn(s1, __fmul_rn(sign_new(vi), vq));
                             s2 = __fadd_rn(s2, __fmul_rn(sign_new(vi), vi));
                             s3 = __fadd_rn(s3, __fmul_rn(sign_new(vq), vq));
                         }
 #else
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
+                        for (int k = 0; k < 4; k++) {
                             s1 += __fmul_rn(sign_new(fi[k]), fq[k]);
                             s2 += fabsf(fi[k]);
                             s3 += fabsf(fq[k]);
                         }
 #pragma unroll
-                        for (int dlt = 1; dlt < 4; dlt <<= 1) {
-                            s1 += __shfl_xor_sync(gmask, s1, dlt, 4);
-                            s2 += __shfl_xor_sync(gmask, s2, dlt, 4);
-                            s3 += __shfl_xor_sync(gmask, s3, dlt, 4);
+                        for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                            s1 += __shfl_xor_sync(gmask, s1, dlt, 8);
+                            s2 += __shfl_xor_sync(gmask, s2, dlt, 8);
+                            s3 += __shfl_xor_sync(gmask, s3, dlt, 8);
                         }
 #endif
                         // teta = -/+0.003*(sum/32) + 0.997*teta_old, evaluated in double (:2281-2283)
@@ -236,13 +277,13 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                         if (help > 0.0f) help = __fdiv_rn(__fsub_rn(__fmul_rn(ls.te3, ls.te3), __fmul_rn(ls.te1, ls.te1)), help);
                         ls.c2 = (help > 0.0f) ? __fsqrt_rn(help) : 1.0f;
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
+                        for (int k = 0; k < 4; k++) {
                             fq[k] = __fadd_rn(fq[k], __fmul_rn(ls.c1, fi[k]));
                             fi[k] = __fmul_rn(fi[k], ls.c2);
                         }
                     } else {
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
+                        for (int k = 0; k < 4; k++) {
                             float vi = __fmul_rn(fi[k], adj_i), vq = __fmul_rn(fq[k], adj_q);
                             if (phase_bal < 0.0f) vq = __fadd_rn(vq, __fmul_rn(vi, phase_bal));
                             else if (phase_bal > 0.0f) vi = __fadd_rn(vi, __fmul_rn(vq, phase_bal));
@@ -251,10 +292,10 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                     }
                     // ---- Fs/4 translate (freq_shift.c:219-262) + store in polyphase layout ----
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < 2; i++) {
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const int n = 32 * b + 2 * (r + 4 * i) + e;      // sample index in the chunk
+                            const int n = 32 * b + 2 * (r + 8 * i) + e;      // sample index in the chunk
                             float vi = fi[2 * i + e], vq = fq[2 * i + e];
                             if (shift_kind == 1) {
                                 float ib = shift_down ? vq : vi, qb = shift_down ? vi : vq;
@@ -265,60 +306,153 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                                 else if (ph == 3) { ni = -qb; nq = ib; }
                                 if (shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
                             }
-                            const int pos = n + 84;
+                            const int pos = n + 4 * XH;
                             xi[(pos & 3) * XP + (pos >> 2)] = vi;
                             xq[(pos & 3) * XP + (pos >> 2)] = vq;
                         }
                     }
                 }
-                __syncwarp();
-                // ---- decimate: outputs 8r .. 8r+7 for I and Q ----
+#else
+                // ---- front end (shipping build): the whole 128-sample chunk at once.  Pairs p = r + 8i
+                // (samples 2p, 2p+1), block b = i >> 1.  The 2^-16 input scaling (audio_driver.c:2680-2685)
+                // is exact, so it is folded into the correction factors; the Fs/4 translation
+                // (freq_shift.c:219-262) is a per-lane sign/swap pattern folded into the same factors.
                 {
-                    float ai[8], aq[8];
-                    decimate8(xi, xq, 8 * r, fc, ai, aq);
-                    *reinterpret_cast<float4 *>(di + 200 + 8 * r) = make_float4(ai[0], ai[1], ai[2], ai[3]);
-                    *reinterpret_cast<float4 *>(di + 204 + 8 * r) = make_float4(ai[4], ai[5], ai[6], ai[7]);
-                    *reinterpret_cast<float4 *>(dq + 200 + 8 * r) = make_float4(aq[0], aq[1], aq[2], aq[3]);
-                    *reinterpret_cast<float4 *>(dq + 204 + 8 * r) = make_float4(aq[4], aq[5], aq[6], aq[7]);
+                    float fi[16], fq[16];
+                    int lvmax = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int4 v = *reinterpret_cast<const int4 *>(raw + 2 * (r + 8 * i));
+                        lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
+                        fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
+                    }
+                    lvmax >>= 16;                                                // audio_driver.c:2662-2675
+                    ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
+                    const float kS = 0.0000152587890625f;                        // 2^-16
+                    float c1b[4], c2b[4];
+                    if (iq_auto) {
+                        // Moseley & Slump block statistics (:2274-2279) for the four blocks
+                        float s1[4], s2[4], s3[4];
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            s1[b] = 0.0f; s2[b] = 0.0f; s3[b] = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float vi = fi[4 * b + k], vq = fq[4 * b + k];
+                                s1[b] += __fmul_rn(sign_new(vi), vq); s2[b] += fabsf(vi); s3[b] += fabsf(vq);
+                            }
+                        }
+#pragma unroll
+                        for (int dlt = 1; dlt < 8; dlt <<= 1) {
+#pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                s1[b] += __shfl_xor_sync(gmask, s1[b], dlt, 8);
+                                s2[b] += __shfl_xor_sync(gmask, s2[b], dlt, 8);
+                                s3[b] += __shfl_xor_sync(gmask, s3[b], dlt, 8);
+                            }
+                        }
+                        // first-order low-pass over blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295):
+                        // lane r computes the pair of block r & 3, the group shares them by shuffle
+                        float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                        const float kE = 0.003f * 0.03125f * kS;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            t1 = fmaf(0.997f, t1, -kE * s1[b]); t2 = fmaf(0.997f, t2, kE * s2[b]); t3 = fmaf(0.997f, t3, kE * s3[b]);
+                            if ((r & 3) == b) { m1 = t1; m2 = t2; m3 = t3; }
+                        }
+                        ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
+                        const float den = m2 * m2;
+                        const float c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
+                        const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
+                        const float c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            c1b[b] = __shfl_sync(gmask, c1m, b, 8);
+                            c2b[b] = __shfl_sync(gmask, c2m, b, 8);
+                        }
+                        ls.c1 = c1b[3]; ls.c2 = c2b[3];
+                    }
+                    // per-lane Fs/4 pattern: sample 2p (e = 0) has phase (2r) & 3 in {0, 2}, sample 2p+1 phase +1
+                    const float sg0 = (shift_kind == 1 && (r & 1)) ? -1.0f : 1.0f;
+                    const float sg1 = (shift_kind == 1) ? (shift_down ? -sg0 : sg0) : 1.0f;
+                    float *pi0 = xi + ((2 * r) & 3) * XP + XH + (r >> 1), *pq0 = xq + ((2 * r) & 3) * XP + XH + (r >> 1);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int b = i >> 1;
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            float vi = fi[2 * i + e], vq = fq[2 * i + e];
+                            if (iq_auto) {
+                                vq = fmaf(c1b[b], vi, vq);            // q += M_c1 * i  (:2308-2311)
+                                vi = vi * c2b[b];                     // i *= M_c2      (:2313)
+                            } else {
+                                vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
+                                if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
+                                else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
+                            }
+                            float oi, oq;
+                            if (e == 0 || shift_kind != 1) { oi = vi * (kS * sg0); oq = vq * (kS * sg0); }
+                            else { oi = vq * (kS * sg1); oq = vi * (-kS * sg1); }
+                            pi0[e * XP + 4 * i] = oi;
+                            pq0[e * XP + 4 * i] = oq;
+                        }
+                    }
+                }
+#endif
+                __syncwarp();
+                // ---- the staging buffer is consumed: fetch the next chunk behind the FIR work ----
+                if (t + 1 < nchunks && n_warp_ch > 0) {
+                    fence_proxy_async();
+                    if (lane == 0) mbar_expect_tx(bar, (unsigned)(n_warp_ch * CH4 * sizeof(int2)));
+                    __syncwarp();
+                    if (r == 0 && active) bulk_g2s(sm.raw + g * CH4, src + (size_t)(t + 1) * CH4, CH4 * sizeof(int2), bar);
+                }
+                // ---- decimate: outputs 4r .. 4r+3 for I and Q ----
+                {
+                    float ai[4], aq[4];
+                    decimate4(xi, xq, 4 * r, fc, ai, aq);
+                    *reinterpret_cast<float4 *>(di + 200 + 4 * r) = make_float4(ai[0], ai[1], ai[2], ai[3]);
+                    *reinterpret_cast<float4 *>(dq + 200 + 4 * r) = make_float4(aq[0], aq[1], aq[2], aq[3]);
                 }
                 __syncwarp();
-                // keep the newest 21 entries of every phase: idx 32..52 -> 0..20
+                // keep the newest 24 entries of every phase: idx 32..55 -> 0..23 (6 float4 per phase)
                 {
-                    float ki[21], kq[21];
+                    float4 ki[3], kq[3];
 #pragma unroll
-                    for (int u = 0; u < 21; u++) {
-                        const int e = r + 4 * u;             // 0..83 -> (phase, idx)
-                        ki[u] = xi[(e / 21) * XP + 32 + (e % 21)]; kq[u] = xq[(e / 21) * XP + 32 + (e % 21)];
+                    for (int u = 0; u < 3; u++) {
+                        const int e = r + 8 * u;             // 0..23 -> (phase, float4)
+                        ki[u] = lds128(xi + (e / 6) * XP + 32 + 4 * (e % 6)); kq[u] = lds128(xq + (e / 6) * XP + 32 + 4 * (e % 6));
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 21; u++) {
-                        const int e = r + 4 * u;
-                        xi[(e / 21) * XP + (e % 21)] = ki[u]; xq[(e / 21) * XP + (e % 21)] = kq[u];
+                    for (int u = 0; u < 3; u++) {
+                        const int e = r + 8 * u;
+                        *reinterpret_cast<float4 *>(xi + (e / 6) * XP + 4 * (e % 6)) = ki[u];
+                        *reinterpret_cast<float4 *>(xq + (e / 6) * XP + 4 * (e % 6)) = kq[u];
                     }
                 }
                 // ---- Hilbert pair + sideband combine ----
                 {
-                    float hi[8], hq[8];
-                    hilbert8(di, dq, 8 * r, fc, hi, hq);
+                    float hi[4], hq[4];
+                    hilbert4(di, dq, 4 * r, fc, hi, hq);
                     float *aud = sm.aud[t & 1];
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        aud[(8 * r + j) * SMS + g] = lsb ? __fsub_rn(hi[j], hq[j]) : __fadd_rn(hi[j], hq[j]);
+                    for (int j = 0; j < 4; j++)
+                        aud[(4 * r + j) * SMS + g] = lsb ? __fsub_rn(hi[j], hq[j]) : __fadd_rn(hi[j], hq[j]);
                 }
                 __syncwarp();
                 // slide the Hilbert input: d[0..200) = d[32..232)
                 {
-                    float4 ki[13], kq[13];
+                    float4 ki[7], kq[7];
 #pragma unroll
-                    for (int u = 0; u < 13; u++) {
-                        const int e = r + 4 * u;             // float4 index 0..49
+                    for (int u = 0; u < 7; u++) {
+                        const int e = r + 8 * u;             // float4 index 0..49
                         if (e < 50) { ki[u] = lds128(di + 32 + 4 * e); kq[u] = lds128(dq + 32 + 4 * e); }
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < 13; u++) {
-                        const int e = r + 4 * u;
+                    for (int u = 0; u < 7; u++) {
+                        const int e = r + 8 * u;
                         if (e < 50) { *reinterpret_cast<float4 *>(di + 4 * e) = ki[u]; *reinterpret_cast<float4 *>(dq + 4 * e) = kq[u]; }
                     }
                 }
@@ -328,10 +462,10 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                 const int c = t - PIPE_DEPTH;
                 const float *o = sm.out[c % 3];
 #pragma unroll 4
-                for (int i = 0; i < 16; i++) {
-                    const int pr = r + 4 * i;
+                for (int i = 0; i < 8; i++) {
+                    const int pr = r + 8 * i;
                     const int n = 2 * pr;
-                    const bool muted = mute && mute[c * 4 + (i >> 2)];
+                    const bool muted = mute && mute[c * 4 + (i >> 1)];
                     const float v0 = muted ? 0.0f : o[n * SMS + g], v1 = muted ? 0.0f : o[(n + 1) * SMS + g];
                     const int w0 = muted ? 0 : format_audio_word(v0), w1 = muted ? 0 : format_audio_word(v1);
                     dst[(size_t)c * 64 + pr] = make_int4(w0, w0, w1, w1);
@@ -342,13 +476,13 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
         }
         // ---- store state ----
         if (active) {
-            for (int b = r; b < 84; b += 4) {
-                st->s1_hist_i[H1 - 84 + b] = xi[(b & 3) * XP + (b >> 2)];
-                st->s1_hist_q[H1 - 84 + b] = xq[(b & 3) * XP + (b >> 2)];
+            for (int b = r; b < 4 * XH; b += 8) {
+                st->s1_hist_i[b] = xi[(b & 3) * XP + (b >> 2)];
+                st->s1_hist_q[b] = xq[(b & 3) * XP + (b >> 2)];
             }
-            for (int i = r; i < 200; i += 4) { st->s2_hist_i[i] = di[i]; st->s2_hist_q[i] = dq[i]; }
+            for (int i = r; i < 200; i += 8) { st->s2_hist_i[i] = di[i]; st->s2_hist_q[i] = dq[i]; }
             int clip = ls.clip;
-            clip |= __shfl_xor_sync(gmask, clip, 1, 4); clip |= __shfl_xor_sync(gmask, clip, 2, 4);
+            clip |= __shfl_xor_sync(gmask, clip, 1, 8); clip |= __shfl_xor_sync(gmask, clip, 2, 8); clip |= __shfl_xor_sync(gmask, clip, 4, 8);
             if (r == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
                 if (clip & 1) st->adc_quarter_clip = 1;
@@ -440,19 +574,20 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
             if (c >= 0 && c < nchunks) {
                 const float *in = sm.lat[c & 1];
                 float *out = sm.agc[c & 1];
-                for (int i = 0; i < ND; i++) {
-                    const float x = in[i * SMS + g];
-                    float y;
-                    if (ap.mode == 5) {
-                        y = __fmul_rn(x, ap.fixed_gain);          // AGC off (audio_agc.c:354-365)
-                    } else {
-                        const float out_sample = sm.ring[((wp - AGC_W) & (RING - 1)) * SMS + g];
-                        const float abs_out = fabsf(out_sample), abs_in = fabsf(x);
+                if (ap.mode == 5) {
+                    for (int i = 0; i < ND; i++) out[i * SMS + g] = __fmul_rn(in[i * SMS + g], ap.fixed_gain);   // AGC off (audio_agc.c:354-365)
+                } else {
+                    // ---- pass 1 (sample-serial): delay ring, sliding maximum, 5-state detector -> volts[i] ----
+                    const int wp0 = wp;
+#pragma unroll 2
+                    for (int i = 0; i < ND; i++) {
+                        const float x = in[i * SMS + g];
+                        const float abs_out = fabsf(sm.ring[((wp - AGC_W) & (RING - 1)) * SMS + g]);
+                        const float abs_in = fabsf(x);
                         sm.ring[wp * SMS + g] = x;
                         pmax = (off == 0) ? abs_in : fmaxf(pmax, abs_in);
                         float ring_max = pmax;
                         if (off < AGC_W - 1) ring_max = fmaxf(ring_max, sm.smax[(off + 1) * SMS + g]);
-                        // ---- identical to agc_step from here on, with ring_max supplied ----
                         ar.fast_backaverage = __fadd_rn(__fmul_rn(ap.fast_backmult, abs_out), __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
                         ar.hang_backaverage = __fadd_rn(__fmul_rn(ap.hang_backmult, abs_out), __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
                         ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
@@ -490,24 +625,34 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                         ar.state = nstate;
                         if (upd) ar.volts = __fadd_rn(ar.volts, __fmul_rn(dv, mult_sel));
                         if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
-                        float vo = log10f_fast(__fmul_rn(ap.inv_max_input, ar.volts));
-                        if (vo > 0.0f) vo = 0.0f;
-                        const float mult = __fdiv_rn(__fsub_rn(ap.out_target, __fmul_rn(ap.slope_constant, vo)), ar.volts);
-                        y = __fmul_rn(out_sample, mult);
-                    }
-                    out[i * SMS + g] = y;
-                    // ---- advance the sliding-maximum bookkeeping (uniform control flow) ----
-                    if (off == AGC_W - 1) {
-                        float m = 0.0f;
-                        for (int o = AGC_W - 1; o >= 0; o--) {
-                            m = fmaxf(m, fabsf(sm.ring[((wp - (AGC_W - 1 - o)) & (RING - 1)) * SMS + g]));
-                            sm.smax[o * SMS + g] = m;
+                        out[i * SMS + g] = ar.volts;
+                        // ---- advance the sliding-maximum bookkeeping (uniform control flow) ----
+                        if (off == AGC_W - 1) {
+                            float m = 0.0f;
+                            for (int o = AGC_W - 1; o >= 0; o--) {
+                                m = fmaxf(m, fabsf(sm.ring[((wp - (AGC_W - 1 - o)) & (RING - 1)) * SMS + g]));
+                                sm.smax[o * SMS + g] = m;
+                            }
+                            off = 0;
+                        } else {
+                            off++;
                         }
-                        off = 0;
-                    } else {
-                        off++;
+                        wp = (wp + 1) & (RING - 1);
                     }
-                    wp = (wp + 1) & (RING - 1);
+                    // ---- pass 2 (independent per sample): log-slope gain applied to the delayed sample (:563-570) ----
+#pragma unroll 8
+                    for (int i = 0; i < ND; i++) {
+                        const float volts = out[i * SMS + g];
+                        const float out_sample = sm.ring[((wp0 + i - AGC_W) & (RING - 1)) * SMS + g];
+                        float vo = log10f_fast(__fmul_rn(ap.inv_max_input, volts));
+                        if (vo > 0.0f) vo = 0.0f;
+#if UHSDR_EXACT
+                        const float mult = __fdiv_rn(__fsub_rn(ap.out_target, __fmul_rn(ap.slope_constant, vo)), volts);
+#else
+                        const float mult = __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), volts);
+#endif
+                        out[i * SMS + g] = __fmul_rn(out_sample, mult);
+                    }
                 }
             }
             __syncthreads();
