@@ -569,6 +569,8 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
         int wp = 0;          // slot of the sample being written (uniform across lanes)
         int off = 0;         // offset inside the current van Herk block (uniform)
         float pmax = 0.0f;   // prefix maximum of the current block
+        // a channel can only be in the hang states (2, 4) or carry decay_type / hang_counter when hang was enabled
+        const bool any_hang = __any_sync(0xffffffffu, active && (ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0));
         for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
             const int c = t - 2;
             if (c >= 0 && c < nchunks) {
@@ -598,7 +600,16 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                         float mult_sel = ap.attack_mult;
                         bool upd = true;
                         int nstate = ar.state;
-                        if (attack) {
+                        if (!any_hang) {
+                            // hang AGC disabled on every channel of this warp (the default,
+                            // ui_configuration.c:81): only states 0 / 1 / 3 occur, decay_type stays 0 and
+                            // the hang counter stays 0 -- the 5-state machine reduces to selects
+                            const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
+                                                              : ((ar.state == 1) && (ar.volts > ar.save_volts));
+                            if (attack && ar.state >= 2) ar.save_volts = ar.volts;
+                            mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
+                            nstate = attack ? 0 : (fast ? 1 : 3);
+                        } else if (attack) {
                             if (ar.state >= 2) ar.save_volts = ar.volts;
                             nstate = 0;
                         } else {
