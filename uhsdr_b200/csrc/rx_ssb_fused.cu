@@ -39,7 +39,7 @@ constexpr int DL = 200 + ND;       // Hilbert input: 200 history slots + 32 new
 constexpr int DCH = 2 * DL + 4;     // + 4 -> neighbouring channels land on disjoint banks
 constexpr int SMS = 33;            // channel-minor stride of the pipeline queues
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
-constexpr int RING = 128;           // AGC delay ring slots (>= 49 + one chunk, so pass 2 can re-read the delayed samples)
+constexpr int RING = 64;            // AGC delay ring slots (>= 49 + one group of 8)
 constexpr int NWARP_FIR = FG / 4;   // one FIR warp = 4 channels x 8 lanes, 4 decimated outputs per lane
 constexpr int DEC_PAD = 32;        // zero padding in front of the decimator taps (FusedCoefs::dec)
 constexpr int HIL_PAD = 12;        // zero padding in front of the Hilbert taps
@@ -55,7 +55,7 @@ struct Smem {
     float agc[2][ND * SMS];
     float out[3][CH4 * SMS];
     float ring[RING * SMS];
-    float smax[AGC_W * SMS];
+    float smax[2][ND * SMS];            // suffix maxima of |x| over the previous two 32-sample chunks
     alignas(16) int2 raw[FG * CH4];     // staged input chunk: bulk-async copy target, 1 KB per channel
     alignas(8) unsigned long long mbar[NWARP_FIR];   // one transaction barrier per FIR warp
 };
@@ -557,18 +557,27 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
             idx %= AGC_RB; if (idx < 0) idx += AGC_RB;
             sm.ring[((RING - kk) & (RING - 1)) * SMS + g] = st->agc_ring[idx];
         }
-        // suffix maxima of the "previous block" = history x[-48..-1] at offsets 1..48
+        // Sliding maximum of |x| over the newest 49 samples (audio_agc.c:409-429 keeps it by rescanning
+        // the ring whenever the departing sample was the maximum -- data dependent and divergent).  The
+        // same exact maximum comes from the van Herk / Gil-Werman decomposition with blocks = chunks of
+        // 32: for the sample at offset o of the current chunk
+        //   ring_max = max( prefix_max(cur)[o],  o <= 16 ? max(M(prev), suffix(prev2)[16 + o]) : suffix(prev)[o - 16] )
+        // smax[s1] / smax[s2]: suffix maxima of the previous / second previous chunk.  History x[-48..-1]
+        // fills prev completely and prev2 from offset 16 on (the only part ever read).
+        int s1 = 0, s2 = 1;
         {
             float m = 0.0f;
-            for (int o = AGC_W - 1; o >= 1; o--) {
-                const int kk = AGC_W - o;             // offset o holds x[-(49-o)]
-                m = fmaxf(m, fabsf(sm.ring[((RING - kk) & (RING - 1)) * SMS + g]));
-                sm.smax[o * SMS + g] = m;
+            for (int o = ND - 1; o >= 0; o--) {        // prev: x[-32 + o]
+                m = fmaxf(m, fabsf(sm.ring[((RING - (ND - o)) & (RING - 1)) * SMS + g]));
+                sm.smax[s1][o * SMS + g] = m;
+            }
+            m = 0.0f;
+            for (int o = ND - 1; o >= 16; o--) {       // prev2: x[-64 + o], only x[-48..-33] exist in the window
+                m = fmaxf(m, fabsf(sm.ring[((RING - (2 * ND - o)) & (RING - 1)) * SMS + g]));
+                sm.smax[s2][o * SMS + g] = m;
             }
         }
         int wp = 0;          // slot of the sample being written (uniform across lanes)
-        int off = 0;         // offset inside the current van Herk block (uniform)
-        float pmax = 0.0f;   // prefix maximum of the current block
         // a channel can only be in the hang states (2, 4) or carry decay_type / hang_counter when hang was enabled
         const bool any_hang = __any_sync(0xffffffffu, active && (ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0));
         for (int t = 0; t < nchunks + PIPE_DEPTH; t++) {
@@ -579,90 +588,98 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                 if (ap.mode == 5) {
                     for (int i = 0; i < ND; i++) out[i * SMS + g] = __fmul_rn(in[i * SMS + g], ap.fixed_gain);   // AGC off (audio_agc.c:354-365)
                 } else {
-                    // ---- pass 1 (sample-serial): delay ring, sliding maximum, 5-state detector -> volts[i] ----
-                    const int wp0 = wp;
-#pragma unroll 2
-                    for (int i = 0; i < ND; i++) {
-                        const float x = in[i * SMS + g];
-                        const float abs_out = fabsf(sm.ring[((wp - AGC_W) & (RING - 1)) * SMS + g]);
-                        const float abs_in = fabsf(x);
-                        sm.ring[wp * SMS + g] = x;
-                        pmax = (off == 0) ? abs_in : fmaxf(pmax, abs_in);
-                        float ring_max = pmax;
-                        if (off < AGC_W - 1) ring_max = fmaxf(ring_max, sm.smax[(off + 1) * SMS + g]);
-                        ar.fast_backaverage = __fadd_rn(__fmul_rn(ap.fast_backmult, abs_out), __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
-                        ar.hang_backaverage = __fadd_rn(__fmul_rn(ap.hang_backmult, abs_out), __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
-                        ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
-                        ar.ring_max = ring_max;
-                        if (ar.hang_counter > 0) --ar.hang_counter;
-                        const float dv = __fsub_rn(ar.ring_max, ar.volts);
-                        const bool attack = ar.ring_max >= ar.volts;
-                        float mult_sel = ap.attack_mult;
-                        bool upd = true;
-                        int nstate = ar.state;
-                        if (!any_hang) {
-                            // hang AGC disabled on every channel of this warp (the default,
-                            // ui_configuration.c:81): only states 0 / 1 / 3 occur, decay_type stays 0 and
-                            // the hang counter stays 0 -- the 5-state machine reduces to selects
-                            const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
-                                                              : ((ar.state == 1) && (ar.volts > ar.save_volts));
-                            if (attack && ar.state >= 2) ar.save_volts = ar.volts;
-                            mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
-                            nstate = attack ? 0 : (fast ? 1 : 3);
-                        } else if (attack) {
-                            if (ar.state >= 2) ar.save_volts = ar.volts;
-                            nstate = 0;
-                        } else {
-                            switch (ar.state) {
-                            case 0:
-                                if (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage)) { nstate = 1; mult_sel = ap.fast_decay_mult; }
-                                else if (ap.hang_enable && (ar.hang_backaverage > ap.hang_level)) {
-                                    nstate = 2; ar.hang_counter = (int)__fmul_rn(ap.hangtime, ap.sample_rate); ar.decay_type = 1; upd = false;
-                                } else { nstate = 3; mult_sel = ap.decay_mult; ar.decay_type = 0; }
-                                break;
-                            case 1:
-                                if (ar.volts > ar.save_volts) mult_sel = ap.fast_decay_mult;
-                                else if (ar.hang_counter > 0) { nstate = 2; upd = false; }
-                                else if (ar.decay_type == 0) { nstate = 3; mult_sel = ap.decay_mult; }
-                                else { nstate = 4; mult_sel = ap.hang_decay_mult; }
-                                break;
-                            case 2:
-                                if (ar.hang_counter == 0) { nstate = 4; mult_sel = ap.hang_decay_mult; } else upd = false;
-                                break;
-                            case 3: mult_sel = ap.decay_mult; break;
-                            default: mult_sel = ap.hang_decay_mult; break;
-                            }
+                    const float *S1 = sm.smax[s1], *S2 = sm.smax[s2];
+                    const float mprev = S1[g];
+                    float pmax = 0.0f;       // prefix maximum inside the current chunk
+#pragma unroll 1
+                    for (int k8 = 0; k8 < ND; k8 += 8) {
+                        // ---- operands of 8 samples: all loads before any store of the group ----
+                        float x[8], dly[8], cmx[8], vv[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int o = k8 + j;
+                            x[j] = in[o * SMS + g];
+                            dly[j] = sm.ring[((wp + j - AGC_W) & (RING - 1)) * SMS + g];
+                            cmx[j] = (o <= 16) ? fmaxf(mprev, S2[(16 + o) * SMS + g]) : S1[(o - 16) * SMS + g];
                         }
-                        ar.state = nstate;
-                        if (upd) ar.volts = __fadd_rn(ar.volts, __fmul_rn(dv, mult_sel));
-                        if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
-                        out[i * SMS + g] = ar.volts;
-                        // ---- advance the sliding-maximum bookkeeping (uniform control flow) ----
-                        if (off == AGC_W - 1) {
-                            float m = 0.0f;
-                            for (int o = AGC_W - 1; o >= 0; o--) {
-                                m = fmaxf(m, fabsf(sm.ring[((wp - (AGC_W - 1 - o)) & (RING - 1)) * SMS + g]));
-                                sm.smax[o * SMS + g] = m;
+                        // ---- pass 1 (sample-serial): detector state -> volts ----
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
+                            pmax = fmaxf(pmax, abs_in);
+                            ar.fast_backaverage = __fadd_rn(__fmul_rn(ap.fast_backmult, abs_out), __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
+                            ar.hang_backaverage = __fadd_rn(__fmul_rn(ap.hang_backmult, abs_out), __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
+                            ar.ring_max = fmaxf(pmax, cmx[j]);
+                            if (ar.hang_counter > 0) --ar.hang_counter;
+                            const float dv = __fsub_rn(ar.ring_max, ar.volts);
+                            const bool attack = ar.ring_max >= ar.volts;
+                            float mult_sel = ap.attack_mult;
+                            bool upd = true;
+                            int nstate = ar.state;
+                            if (!any_hang) {
+                                // hang AGC disabled on every channel of this warp (the default,
+                                // ui_configuration.c:81): only states 0 / 1 / 3 occur, decay_type stays 0 and
+                                // the hang counter stays 0 -- the 5-state machine reduces to selects
+                                const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
+                                                                  : ((ar.state == 1) && (ar.volts > ar.save_volts));
+                                if (attack && ar.state >= 2) ar.save_volts = ar.volts;
+                                mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
+                                nstate = attack ? 0 : (fast ? 1 : 3);
+                            } else if (attack) {
+                                if (ar.state >= 2) ar.save_volts = ar.volts;
+                                nstate = 0;
+                            } else {
+                                switch (ar.state) {
+                                case 0:
+                                    if (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage)) { nstate = 1; mult_sel = ap.fast_decay_mult; }
+                                    else if (ap.hang_enable && (ar.hang_backaverage > ap.hang_level)) {
+                                        nstate = 2; ar.hang_counter = (int)__fmul_rn(ap.hangtime, ap.sample_rate); ar.decay_type = 1; upd = false;
+                                    } else { nstate = 3; mult_sel = ap.decay_mult; ar.decay_type = 0; }
+                                    break;
+                                case 1:
+                                    if (ar.volts > ar.save_volts) mult_sel = ap.fast_decay_mult;
+                                    else if (ar.hang_counter > 0) { nstate = 2; upd = false; }
+                                    else if (ar.decay_type == 0) { nstate = 3; mult_sel = ap.decay_mult; }
+                                    else { nstate = 4; mult_sel = ap.hang_decay_mult; }
+                                    break;
+                                case 2:
+                                    if (ar.hang_counter == 0) { nstate = 4; mult_sel = ap.hang_decay_mult; } else upd = false;
+                                    break;
+                                case 3: mult_sel = ap.decay_mult; break;
+                                default: mult_sel = ap.hang_decay_mult; break;
+                                }
                             }
-                            off = 0;
-                        } else {
-                            off++;
+                            ar.state = nstate;
+                            if (upd) ar.volts = __fadd_rn(ar.volts, __fmul_rn(dv, mult_sel));
+                            if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
+                            vv[j] = ar.volts;
                         }
-                        wp = (wp + 1) & (RING - 1);
-                    }
-                    // ---- pass 2 (independent per sample): log-slope gain applied to the delayed sample (:563-570) ----
-#pragma unroll 8
-                    for (int i = 0; i < ND; i++) {
-                        const float volts = out[i * SMS + g];
-                        const float out_sample = sm.ring[((wp0 + i - AGC_W) & (RING - 1)) * SMS + g];
-                        float vo = log10f_fast(__fmul_rn(ap.inv_max_input, volts));
-                        if (vo > 0.0f) vo = 0.0f;
+                        // ---- pass 2 (independent per sample): log-slope gain on the delayed sample (:563-570) ----
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float vo = log10f_fast(__fmul_rn(ap.inv_max_input, vv[j]));
+                            if (vo > 0.0f) vo = 0.0f;
 #if UHSDR_EXACT
-                        const float mult = __fdiv_rn(__fsub_rn(ap.out_target, __fmul_rn(ap.slope_constant, vo)), volts);
+                            const float mult = __fdiv_rn(__fsub_rn(ap.out_target, __fmul_rn(ap.slope_constant, vo)), vv[j]);
 #else
-                        const float mult = __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), volts);
+                            const float mult = __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), vv[j]);
 #endif
-                        out[i * SMS + g] = __fmul_rn(out_sample, mult);
+                            out[(k8 + j) * SMS + g] = __fmul_rn(dly[j], mult);
+                            sm.ring[((wp + j) & (RING - 1)) * SMS + g] = x[j];
+                        }
+                        wp = (wp + 8) & (RING - 1);
+                    }
+                    ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
+                    // suffix maxima of this chunk replace those of prev2; then the roles rotate
+                    {
+                        float *Sn = sm.smax[s2];
+                        float m = 0.0f;
+#pragma unroll 8
+                        for (int o = ND - 1; o >= 0; o--) {
+                            m = fmaxf(m, fabsf(sm.ring[((wp - (ND - o)) & (RING - 1)) * SMS + g]));
+                            Sn[o * SMS + g] = m;
+                        }
+                        const int tmp = s1; s1 = s2; s2 = tmp;
                     }
                 }
             }
