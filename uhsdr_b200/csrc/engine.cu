@@ -22,7 +22,9 @@ struct uhsdr_engine {
     int nch = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    static constexpr int kMaxSlices = 16;
+    cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
+    cudaEvent_t ev_done = nullptr;
     HostTables tables;
     float *d_pool = nullptr;
     ChanParams *d_params = nullptr;
@@ -106,7 +108,9 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
     cudaFree(e->d_list_fused); cudaFree(e->d_list_generic);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
-    for (auto &v : e->ev) if (v) cudaEventDestroy(v);
+    for (auto &v : e->ev_in) if (v) cudaEventDestroy(v);
+    for (auto &v : e->ev_k) if (v) cudaEventDestroy(v);
+    if (e->ev_done) cudaEventDestroy(e->ev_done);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return UHSDR_OK;
@@ -143,7 +147,9 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if ((er = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", er);
     if ((er = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", er);
     for (auto &s : e->copy_stream) if ((er = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", er);
-    for (auto &v : e->ev) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    for (auto &v : e->ev_in) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    for (auto &v : e->ev_k) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    if ((er = cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     const size_t n = (size_t)num_channels;
     if ((er = cudaMalloc(&e->d_pool, e->tables.pool.size() * sizeof(float))) != cudaSuccess) return fail("cudaMalloc pool", er);
     if ((er = cudaMemcpy(e->d_pool, e->tables.pool.data(), e->tables.pool.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy pool", er);
@@ -241,28 +247,37 @@ static int rebuild_lists(uhsdr_engine *e)
     return UHSDR_OK;
 }
 
+// Launches the receiver kernels for `nblocks` blocks of every channel; rows of the device buffers
+// are `chan_stride` samples apart (a time slice of a longer buffer has chan_stride > nblocks*32).
+static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_audio_sample_t *audio_dev, float *audio_f_dev,
+                     int nblocks, const uint8_t *mute_dev, long long chan_stride, long long mute_stride, cudaStream_t stream)
+{
+    RxArgs a;
+    a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
+    a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
+    a.chan_stride = chan_stride; a.mute_stride = mute_stride;
+    if (!e->h_list_fused.empty()) {
+        a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
+        // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
+        if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
+        else CK(e, launch_rx_generic(a, stream));
+        e->launches++;
+    }
+    if (!e->h_list_generic.empty()) {
+        a.chan_list = e->d_list_generic; a.num_items = (int)e->h_list_generic.size();
+        CK(e, launch_rx_generic(a, stream));
+        e->launches++;
+    }
+    return UHSDR_OK;
+}
+
 int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_audio_sample_t *audio_dev,
                             float *audio_f_dev, int nblocks, const uint8_t *mute_dev)
 {
     if (!e || !iq_dev || !audio_dev || nblocks <= 0) { if (e) e->last_error = "rx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
     if (e->lists_dirty) { int rc = rebuild_lists(e); if (rc != UHSDR_OK) return rc; }
-    RxArgs a;
-    a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
-    a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
-    if (!e->h_list_fused.empty()) {
-        a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
-        // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
-        if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, e->stream));
-        else CK(e, launch_rx_generic(a, e->stream));
-        e->launches++;
-    }
-    if (!e->h_list_generic.empty()) {
-        a.chan_list = e->d_list_generic; a.num_items = (int)e->h_list_generic.size();
-        CK(e, launch_rx_generic(a, e->stream));
-        e->launches++;
-    }
-    return UHSDR_OK;
+    return rx_launch(e, iq_dev, audio_dev, audio_f_dev, nblocks, mute_dev, (long long)nblocks * BLK, nblocks, e->stream);
 }
 
 static int ensure_staging(uhsdr_engine *e, size_t in_bytes, size_t out_bytes, size_t mute_bytes)
@@ -273,19 +288,49 @@ static int ensure_staging(uhsdr_engine *e, size_t in_bytes, size_t out_bytes, si
     return UHSDR_OK;
 }
 
+// Host-buffer entry point.  The call is cut into time slices (all channels, a range of blocks); the
+// H2D copy of slice s+1, the kernels of slice s and the D2H copy of slice s-1 run concurrently on
+// three streams, so with pinned host buffers the call is bound by one direction of the PCIe link.
 int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio_sample_t *audio, int nblocks, const uint8_t *mute)
 {
     if (!e || !iq || !audio || nblocks <= 0) { if (e) e->last_error = "rx_process: NULL buffer or nblocks <= 0"; return UHSDR_ERR_ARG; }
     CK(e, cudaSetDevice(e->device));
-    const size_t bytes = (size_t)e->nch * (size_t)nblocks * BLK * sizeof(uhsdr_iq_sample_t);
+    if (e->lists_dirty) { int rc = rebuild_lists(e); if (rc != UHSDR_OK) return rc; }
+    const size_t row = (size_t)nblocks * BLK * sizeof(uhsdr_iq_sample_t);
+    const size_t bytes = (size_t)e->nch * row;
     const size_t mbytes = mute ? (size_t)e->nch * (size_t)nblocks : 0;
     int rc = ensure_staging(e, bytes, bytes, mbytes);
     if (rc != UHSDR_OK) return rc;
-    CK(e, cudaMemcpyAsync(e->d_in, iq, bytes, cudaMemcpyHostToDevice, e->stream));
+    cudaStream_t s_in = e->copy_stream[0], s_out = e->copy_stream[1];
     if (mute) CK(e, cudaMemcpyAsync(e->d_mute, mute, mbytes, cudaMemcpyHostToDevice, e->stream));
-    rc = uhsdr_rx_process_device(e, (const uhsdr_iq_sample_t *)e->d_in, (uhsdr_audio_sample_t *)e->d_out, nullptr, nblocks, mute ? e->d_mute : nullptr);
-    if (rc != UHSDR_OK) return rc;
-    CK(e, cudaMemcpyAsync(audio, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    // slices: multiples of 4 blocks (the fused kernel's chunk) unless the call is small
+    int nsl = 1;
+    if (bytes >= ((size_t)32 << 20) && nblocks >= 64) nsl = std::min<int>(uhsdr_engine::kMaxSlices, 8);
+    int per = ((nblocks + nsl - 1) / nsl + 3) / 4 * 4;
+    if (per <= 0) per = nblocks;
+    // everything queued earlier on the compute stream (configure kernels, a previous device-side
+    // call) must be finished before the copy streams touch the staging buffers
+    CK(e, cudaEventRecord(e->ev_done, e->stream));
+    CK(e, cudaStreamWaitEvent(s_in, e->ev_done, 0));
+    CK(e, cudaStreamWaitEvent(s_out, e->ev_done, 0));
+    int si = 0;
+    for (int b0 = 0; b0 < nblocks; b0 += per, si++) {
+        const int nb = std::min(per, nblocks - b0);
+        const size_t off = (size_t)b0 * BLK * sizeof(uhsdr_iq_sample_t);
+        const size_t width = (size_t)nb * BLK * sizeof(uhsdr_iq_sample_t);
+        CK(e, cudaMemcpy2DAsync((char *)e->d_in + off, row, (const char *)iq + off, row, width, (size_t)e->nch, cudaMemcpyHostToDevice, s_in));
+        CK(e, cudaEventRecord(e->ev_in[si], s_in));
+        CK(e, cudaStreamWaitEvent(e->stream, e->ev_in[si], 0));
+        rc = rx_launch(e, (const uhsdr_iq_sample_t *)((char *)e->d_in + off), (uhsdr_audio_sample_t *)((char *)e->d_out + off), nullptr, nb,
+                       mute ? e->d_mute + b0 : nullptr, (long long)nblocks * BLK, nblocks, e->stream);
+        if (rc != UHSDR_OK) return rc;
+        CK(e, cudaEventRecord(e->ev_k[si], e->stream));
+        CK(e, cudaStreamWaitEvent(s_out, e->ev_k[si], 0));
+        CK(e, cudaMemcpy2DAsync((char *)audio + off, row, (char *)e->d_out + off, row, width, (size_t)e->nch, cudaMemcpyDeviceToHost, s_out));
+    }
+    // rejoin: the engine stream is the one callers time and synchronise on
+    CK(e, cudaEventRecord(e->ev_done, s_out));
+    CK(e, cudaStreamWaitEvent(e->stream, e->ev_done, 0));
     CK(e, cudaStreamSynchronize(e->stream));
     return UHSDR_OK;
 }

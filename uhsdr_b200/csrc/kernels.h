@@ -20,6 +20,8 @@ struct RxArgs {
     const int *chan_list;       // optional: channels handled by this launch (nullptr = 0..num_items-1)
     int num_items;
     int nblocks;
+    long long chan_stride;      // samples between consecutive channels in iq / audio / audio_f (>= nblocks*32)
+    long long mute_stride;      // bytes between consecutive channels in mute (>= nblocks)
 };
 
 cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);

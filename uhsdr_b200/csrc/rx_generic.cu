@@ -91,11 +91,11 @@ rx_generic_kernel(RxArgs a)
     NrState *nr = (p.nr_enable && a.nr) ? (a.nr + ch) : nullptr;
     float *spec_ring = (p.spectrum_enable && a.spec_ring) ? (a.spec_ring + (size_t)ch * 1024) : nullptr;
 
-    const size_t chan_base = (size_t)ch * (size_t)a.nblocks * BLK;
+    const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
     const int2 *__restrict__ iq = reinterpret_cast<const int2 *>(a.iq) + chan_base;
     int2 *__restrict__ audio = reinterpret_cast<int2 *>(a.audio) + chan_base;
     float *__restrict__ audio_f = a.audio_f ? a.audio_f + chan_base : nullptr;
-    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
     int clip_q = 0, clip_h = 0, clip_f = 0;
     if (lane == 0 && p.shift_kind != 0 && st.conversion_freq != p.shift_freq) {

@@ -206,11 +206,11 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
         }
         const int iq_auto = p.iq_auto, shift_kind = p.shift_kind, shift_down = p.shift_down, lsb = p.lsb;
         const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
-        const size_t chan_base = (size_t)ch * (size_t)a.nblocks * BLK;
+        const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
         const int2 *__restrict__ src = reinterpret_cast<const int2 *>(a.iq) + chan_base;
         int4 *__restrict__ dst = reinterpret_cast<int4 *>(reinterpret_cast<int2 *>(a.audio) + chan_base);
         float2 *__restrict__ dst_f = a.audio_f ? reinterpret_cast<float2 *>(a.audio_f + chan_base) : nullptr;
-        const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+        const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
         // ---- stage chunk 0: one bulk asynchronous copy of 1 KB per channel, tracked by the warp's mbarrier ----
         if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
