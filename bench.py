@@ -228,8 +228,9 @@ def gpu_arm(args):
     # even/odd channels alternate USB path 35 / LSB path 38
     cfg_usb, cfg_lsb = default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
     if nch >= 2 and not args.uniform:
-        for c in range(nch):
-            eng.configure(cfg_usb if (ch0 + c) % 2 == 0 else cfg_lsb, first=c, count=1)
+        first_usb = 0 if ch0 % 2 == 0 else 1
+        eng.configure(cfg_usb, first=first_usb, stride=2)
+        eng.configure(cfg_lsb, first=1 - first_usb, stride=2)
     else:
         eng.configure(cfg_usb)
     iq = gen_iq_device(torch, nch, ns, dev, ch0=ch0)

@@ -182,6 +182,10 @@ int uhsdr_engine_num_channels(const uhsdr_engine_t *e);
 int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count,
                              const uhsdr_chan_cfg_t *cfg, int reset);
 int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg_t *cfg, int reset);
+/* Same for channels first, first+stride, first+2*stride, ... (count of them): one call configures
+ * e.g. every even channel of an interleaved USB / LSB plan. */
+int uhsdr_configure_channels_strided(uhsdr_engine_t *e, int first, int count, int stride,
+                                     const uhsdr_chan_cfg_t *cfg, int reset);
 
 /* AudioDriver_RxProcessor for every channel and nblocks consecutive blocks.
  * iq / audio: channel-major, [num_channels][nblocks*32] elements, HOST memory (pinned or pageable).

@@ -31,11 +31,11 @@ __global__ void tx_boot_kernel(TxState *tx, int n)
 
 __global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
                                  TxParams *txparams, const __grid_constant__ ChanParams newp,
-                                 const __grid_constant__ TxParams newtx, int first, int count, int reset)
+                                 const __grid_constant__ TxParams newtx, int first, int count, int stride, int reset)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    const int ch = first + i;
+    const int ch = first + i * stride;
     params[ch] = newp;
     if (txparams) txparams[ch] = newtx;
     ChanState &s = state[ch];
@@ -82,11 +82,11 @@ __global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *
 
 cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
                              TxParams *txparams, const ChanParams &newp, const TxParams &newtx, int first, int count,
-                             int reset, cudaStream_t stream)
+                             int stride, int reset, cudaStream_t stream)
 {
     const int threads = 64;
     configure_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(params, state, nr, spec_ring, tx, txparams,
-                                                                               newp, newtx, first, count, reset);
+                                                                               newp, newtx, first, count, stride, reset);
     return cudaGetLastError();
 }
 

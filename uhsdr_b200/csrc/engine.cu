@@ -179,7 +179,15 @@ int uhsdr_engine_sync(uhsdr_engine_t *e)
 
 int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count, const uhsdr_chan_cfg_t *cfg, int reset)
 {
-    if (!e || !cfg || first < 0 || count <= 0 || first + count > e->nch) { if (e) e->last_error = "configure: bad channel range or NULL cfg"; return UHSDR_ERR_ARG; }
+    return uhsdr_configure_channels_strided(e, first, count, 1, cfg, reset);
+}
+
+int uhsdr_configure_channels_strided(uhsdr_engine_t *e, int first, int count, int stride, const uhsdr_chan_cfg_t *cfg, int reset)
+{
+    if (!e || !cfg || first < 0 || count <= 0 || stride < 1 || (long long)first + (long long)(count - 1) * stride >= e->nch) {
+        if (e) e->last_error = "configure: bad channel range or NULL cfg";
+        return UHSDR_ERR_ARG;
+    }
     ChanParams p;
     std::string err;
     int rc = build_chan_params(e->tables, *cfg, &p, &err);
@@ -207,9 +215,9 @@ int uhsdr_configure_channels(uhsdr_engine_t *e, int first, int count, const uhsd
         CK(e, cudaMalloc(&e->d_txp, n * sizeof(TxParams)));
         CK(e, cudaMemsetAsync(e->d_txp, 0, n * sizeof(TxParams), e->stream));
     }
-    CK(e, launch_configure(e->d_params, e->d_state, e->d_nr, e->d_spec, e->d_tx, e->d_txp, p, tp, first, count, reset, e->stream));
+    CK(e, launch_configure(e->d_params, e->d_state, e->d_nr, e->d_spec, e->d_tx, e->d_txp, p, tp, first, count, stride, reset, e->stream));
     e->launches++;
-    for (int c = first; c < first + count; c++) { e->h_params[c] = p; e->h_tx_enabled[c] = tp.enabled; }
+    for (int i = 0; i < count; i++) { const int c = first + i * stride; e->h_params[c] = p; e->h_tx_enabled[c] = tp.enabled; }
     e->lists_dirty = true;
     return UHSDR_OK;
 }

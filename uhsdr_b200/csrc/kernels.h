@@ -56,6 +56,6 @@ cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, co
 // reset rules (reset != 0: boot state; 0: AudioDriver_SetProcessingChain semantics)
 cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,
                              TxParams *txparams, const ChanParams &newp, const TxParams &newtx, int first, int count,
-                             int reset, cudaStream_t stream);
+                             int stride, int reset, cudaStream_t stream);
 
 }  // namespace uhsdr

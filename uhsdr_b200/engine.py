@@ -28,7 +28,7 @@ ERR_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_TABLES, ERR_UNSUPPORTED, ERR_STATE = -1, -
 EXPORTS = [
     "uhsdr_b200_abi_version", "uhsdr_b200_backend", "uhsdr_strerror", "uhsdr_last_error",
     "uhsdr_default_chan_cfg", "uhsdr_engine_create", "uhsdr_engine_destroy", "uhsdr_engine_num_channels",
-    "uhsdr_configure_channels", "uhsdr_configure_channel", "uhsdr_rx_process", "uhsdr_rx_process_device",
+    "uhsdr_configure_channels", "uhsdr_configure_channel", "uhsdr_configure_channels_strided", "uhsdr_rx_process", "uhsdr_rx_process_device",
     "uhsdr_tx_process", "uhsdr_tx_process_device", "uhsdr_engine_sync", "uhsdr_engine_stream",
     "uhsdr_get_spectrum", "uhsdr_get_spectrum_device", "uhsdr_get_status", "uhsdr_engine_launch_count",
 ]
@@ -63,6 +63,7 @@ def load_library(exact: bool = False) -> ctypes.CDLL:
     L.uhsdr_engine_num_channels.argtypes = [vp]
     L.uhsdr_configure_channels.argtypes = [vp, ci, ci, ctypes.POINTER(ChanCfg), ci]
     L.uhsdr_configure_channel.argtypes = [vp, ci, ctypes.POINTER(ChanCfg), ci]
+    L.uhsdr_configure_channels_strided.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ChanCfg), ci]
     L.uhsdr_rx_process.argtypes = [vp, vp, vp, ci, vp]
     L.uhsdr_rx_process_device.argtypes = [vp, vp, vp, vp, ci, vp]
     L.uhsdr_tx_process.argtypes = [vp, vp, vp, ci, vp]
@@ -118,9 +119,11 @@ class Engine:
     def backend(self) -> str:
         return self._lib.uhsdr_b200_backend().decode()
 
-    def configure(self, cfg: ChanCfg, first: int = 0, count: int | None = None, reset: bool = True) -> None:
-        count = self.num_channels - first if count is None else count
-        self._check(self._lib.uhsdr_configure_channels(self._h, first, count, ctypes.byref(cfg), 1 if reset else 0))
+    def configure(self, cfg: ChanCfg, first: int = 0, count: int | None = None, reset: bool = True, stride: int = 1) -> None:
+        """AudioDriver_SetProcessingChain for channels first, first+stride, ... (count of them)."""
+        if count is None:
+            count = (self.num_channels - first + stride - 1) // stride
+        self._check(self._lib.uhsdr_configure_channels_strided(self._h, first, count, stride, ctypes.byref(cfg), 1 if reset else 0))
 
     def rx(self, iq: np.ndarray, mute: np.ndarray | None = None) -> np.ndarray:
         """iq: int32 [num_channels, nsamples, 2] host array -> audio int32 of the same shape."""
