@@ -157,8 +157,13 @@ def gen_iq_device(torch, nch, nsamples, device, ch0=0, seed=0x55485344):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms (B200_PROFILING.md recipe).  Started
+    before the warm-up (nvidia-smi needs a few hundred ms to come up); only the samples whose
+    timestamps fall inside [t_begin, t_end] -- the timed region plus, when that is shorter than
+    MIN_LOAD_S, an untimed continuation of the very same launches -- are summarised."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MIN_LOAD_S = 1.5
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
@@ -172,8 +177,10 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin: float, t_end: float):
+        import datetime
         if self.p is not None:
+            time.sleep(0.15)
             self.p.terminate()
             try:
                 self.p.wait(timeout=5)
@@ -181,23 +188,34 @@ class ClockSampler:
                 self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons, total = [], [], [], set(), 0
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1])); smax.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(parts[2]), float(parts[3])
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+            total += 1
+            if ts < t_begin - 0.05 or ts > t_end + 0.05:
+                continue
+            sm.append(clk); smax.append(cmax)
+            try:
+                power.append(float(parts[4]))
+            except ValueError:
+                pass
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[6:10]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         self.f.close()
         os.unlink(self.f.name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_total": total}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None,
+                "window": "timed region + untimed continuation of the same launches (>= %.1f s under load)" % self.MIN_LOAD_S}
 
 
 def gpu_arm(args):
@@ -221,8 +239,10 @@ def gpu_arm(args):
 
     nch, T = args.channels, args.blocks
     ns = T * 32
-    # host-side partitioning: rank r owns global channels [r*nch, (r+1)*nch)
-    ch0 = rank * nch
+    # host-side partitioning: rank r owns a contiguous range of the world*nch global channels
+    from uhsdr_b200.partition import channel_range
+    ch0, ch1 = channel_range(rank, world, world * nch)
+    assert ch1 - ch0 == nch
     eng = Engine(nch, device=local_rank)
     from uhsdr_b200.config import DEMOD_LSB, default_cfg
     # even/odd channels alternate USB path 35 / LSB path 38
@@ -245,21 +265,28 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.cuda.stream(ext):
         for _ in range(args.warmup):
             eng.rx_device(iq, audio, T)
         barrier()
         launches0 = eng.launch_count
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        t_begin = time.time()
         ev0.record(ext)
         for _ in range(args.steps):
             eng.rx_device(iq, audio, T)
         ev1.record(ext)
         barrier()
-        clocks = sampler.stop() if rank == 0 else None
         launches = eng.launch_count - launches0
+        # keep the same load running (untimed) until the clock sampler has seen MIN_LOAD_S of it
+        while rank == 0 and time.time() - t_begin < ClockSampler.MIN_LOAD_S:
+            for _ in range(4):
+                eng.rx_device(iq, audio, T)
+            torch.cuda.synchronize()
+        clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
+        barrier()
     ms = ev0.elapsed_time(ev1)
     if dist is not None:
         tms = torch.tensor([ms], dtype=torch.float64, device=dev)

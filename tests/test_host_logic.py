@@ -58,25 +58,55 @@ def test_synth_is_deterministic_and_sliceable():
     assert not np.array_equal(a, lsb)
 
 
+def test_channel_range_and_kind_partition():
+    from uhsdr_b200.partition import channel_range, partition_by_kind
+    for total, world in ((4096, 1), (65536, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [channel_range(r, world, total) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        channel_range(2, 2, 8)
+    kinds = ["am"] * 5 + ["sam"] * 6 + ["fm"] * 7            # BASELINE configs[2]-style mixed plan
+    owned = partition_by_kind(kinds, 2)
+    assert sorted(owned[0] + owned[1]) == list(range(18))
+    for r in range(2):
+        mix = [kinds[c] for c in owned[r]]
+        assert mix == sorted(mix, key=["am", "sam", "fm"].index)           # grouped by kind
+        assert abs(mix.count("am") - 2.5) <= 0.5 and mix.count("sam") == 3 and abs(mix.count("fm") - 3.5) <= 0.5
+
+
 def test_rank_partition_gloo_world2(tmp_path):
-    """bench.py's sharding rule: rank r owns global channels [r*C, (r+1)*C); ranks agree on the
-    max-over-ranks time through one all_reduce.  Exercised with 2 CPU processes over gloo."""
+    """bench.py's sharding rule (uhsdr_b200.partition): rank r owns a contiguous global channel range,
+    no data-path collective; the ranks only agree on the max-over-ranks time through one all_reduce.
+    Exercised with 2 CPU processes over gloo."""
     script = tmp_path / "w.py"
     script.write_text(
-        "import os, torch, torch.distributed as dist\n"
+        "import os, sys, torch, torch.distributed as dist\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from uhsdr_b200.partition import channel_range, partition_by_kind\n"
         "dist.init_process_group('gloo')\n"
         "r, w = dist.get_rank(), dist.get_world_size()\n"
-        "C = 6\n"
-        "mine = torch.arange(r * C, (r + 1) * C)\n"
+        "total = 13\n"
+        "lo, hi = channel_range(r, w, total)\n"
+        "mine = torch.full((8,), -1, dtype=torch.int64)\n"
+        "mine[: hi - lo] = torch.arange(lo, hi)\n"
         "allc = [torch.empty_like(mine) for _ in range(w)]\n"
         "dist.all_gather(allc, mine)\n"
-        "got = torch.cat(allc)\n"
-        "assert torch.equal(got, torch.arange(w * C)), got\n"
+        "got = torch.cat([a[a >= 0] for a in allc])\n"
+        "assert torch.equal(got, torch.arange(total)), got\n"
+        "kinds = ['usb', 'lsb'] * 5 + ['fm'] * 4\n"
+        "own = partition_by_kind(kinds, w)[r]\n"
+        "cnt = torch.tensor([sum(kinds[c] == k for c in own) for k in ('usb', 'lsb', 'fm')])\n"
+        "tot = cnt.clone(); dist.all_reduce(tot)\n"
+        "assert tot.tolist() == [5, 5, 4], tot\n"
+        "assert all(abs(2 * c - t) <= 1 for c, t in zip(cnt.tolist(), tot.tolist()))\n"
         "t = torch.tensor([10.0 + r], dtype=torch.float64)\n"
         "dist.all_reduce(t, op=dist.ReduceOp.MAX)\n"
         "assert t.item() == 10.0 + w - 1\n"
         "dist.barrier()\n"
-        "print('rank', r, 'ok')\n")
+        "sys.stdout.write(f'rank{r}ok\\n'); sys.stdout.flush()\n")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     import socket
     with socket.socket() as sk:          # a free port: a fixed one collides with concurrent runs
@@ -86,7 +116,7 @@ def test_rank_partition_gloo_world2(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert "rank0ok" in out.stdout and "rank1ok" in out.stdout, out.stdout
 
 
 def test_bench_reference_arm_exits_cleanly_on_nonzero_rank():
