@@ -50,6 +50,7 @@ struct uhsdr_engine {
     int64_t launches = 0;
     int sm_count = 148;
     int use_fused = 1;
+    int use_tc = 1;          // tensor-core Hilbert variant of the fused kernel (shipping build)
 };
 
 static std::string g_create_error;
@@ -138,6 +139,8 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (!e->tables.load(tables, tables_bytes, &err)) { g_create_error = err; delete e; return UHSDR_ERR_TABLES; }
     const char *nf = getenv("UHSDR_B200_NO_FUSED");
     if (nf && nf[0] == '1') e->use_fused = 0;
+    const char *nt = getenv("UHSDR_B200_NO_TC");
+    if ((nt && nt[0] == '1') || !rx_ssb_tc_available()) e->use_tc = 0;
     auto fail = [&](const char *what, cudaError_t er) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(er);
         uhsdr_engine_destroy(e);
@@ -267,7 +270,8 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     if (!e->h_list_fused.empty()) {
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
-        if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
+        if (nblocks % 4 == 0 && e->use_tc) CK(e, launch_rx_ssb_tc(a, e->fused_coefs, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
+        else if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
         else CK(e, launch_rx_generic(a, stream));
         e->launches++;
     }

@@ -561,7 +561,7 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
         // the ring whenever the departing sample was the maximum -- data dependent and divergent).  The
         // same exact maximum comes from the van Herk / Gil-Werman decomposition with blocks = chunks of
         // 32: for the sample at offset o of the current chunk
-        //   ring_max = max( prefix_max(cur)[o],  o <= 16 ? max(M(prev), suffix(prev2)[16 + o]) : suffix(prev)[o - 16] )
+        //   ring_max = max( prefix_max(cur)[o],  o < 16 ? max(M(prev), suffix(prev2)[16 + o]) : suffix(prev)[o - 16] )
         // smax[s1] / smax[s2]: suffix maxima of the previous / second previous chunk.  History x[-48..-1]
         // fills prev completely and prev2 from offset 16 on (the only part ever read).
         int s1 = 0, s2 = 1;
@@ -600,7 +600,7 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
                             const int o = k8 + j;
                             x[j] = in[o * SMS + g];
                             dly[j] = sm.ring[((wp + j - AGC_W) & (RING - 1)) * SMS + g];
-                            cmx[j] = (o <= 16) ? fmaxf(mprev, S2[(16 + o) * SMS + g]) : S1[(o - 16) * SMS + g];
+                            cmx[j] = (o < 16) ? fmaxf(mprev, S2[(16 + o) * SMS + g]) : S1[(o - 16) * SMS + g];
                         }
                         // ---- pass 1 (sample-serial): detector state -> volts ----
 #pragma unroll
