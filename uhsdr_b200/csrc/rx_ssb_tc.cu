@@ -247,6 +247,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             }
         }
         const int iq_auto = p.iq_auto, shift_kind = p.shift_kind, shift_down = p.shift_down;
+        const bool any_auto = __any_sync(0xffffffffu, iq_auto != 0);
+        const bool fast_fe = __all_sync(0xffffffffu, iq_auto != 0 && shift_kind == 1);
         const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
         const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
         const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base);
@@ -310,8 +312,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                     ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
                     const float kS = 0.0000152587890625f;                        // 2^-16
                     float c1b[4], c2b[4];
-                    if (iq_auto) {
-                        // Moseley & Slump block statistics (:2274-2279) for the four blocks
+                    if (any_auto) {
+                        // Moseley & Slump block statistics (:2274-2279) for the four blocks; sign(i) * q as a sign-bit
+                        // transfer (differs from Math_sign_new only for i == 0, where the term is +-q instead of 0)
                         float s1[4], s2[4], s3[4];
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
@@ -319,16 +322,17 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
                                 const float vi = fi[4 * b + k], vq = fq[4 * b + k];
-                                s1[b] += __fmul_rn(sign_new(vi), vq); s2[b] += fabsf(vi); s3[b] += fabsf(vq);
+                                s1[b] += __uint_as_float(__float_as_uint(vq) ^ (__float_as_uint(vi) & 0x80000000u));
+                                s2[b] += fabsf(vi); s3[b] += fabsf(vq);
                             }
                         }
 #pragma unroll
                         for (int dlt = 1; dlt < 8; dlt <<= 1) {
 #pragma unroll
                             for (int b = 0; b < 4; b++) {
-                                s1[b] += __shfl_xor_sync(gmask, s1[b], dlt, 8);
-                                s2[b] += __shfl_xor_sync(gmask, s2[b], dlt, 8);
-                                s3[b] += __shfl_xor_sync(gmask, s3[b], dlt, 8);
+                                s1[b] += __shfl_xor_sync(0xffffffffu, s1[b], dlt, 8);
+                                s2[b] += __shfl_xor_sync(0xffffffffu, s2[b], dlt, 8);
+                                s3[b] += __shfl_xor_sync(0xffffffffu, s3[b], dlt, 8);
                             }
                         }
                         // first-order low-pass over blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295):
@@ -340,41 +344,55 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                             t1 = fmaf(0.997f, t1, -kE * s1[b]); t2 = fmaf(0.997f, t2, kE * s2[b]); t3 = fmaf(0.997f, t3, kE * s3[b]);
                             if ((r & 3) == b) { m1 = t1; m2 = t2; m3 = t3; }
                         }
-                        ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
                         const float den = m2 * m2;
                         const float c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
                         const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
                         const float c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
-                            c1b[b] = __shfl_sync(gmask, c1m, b, 8);
-                            c2b[b] = __shfl_sync(gmask, c2m, b, 8);
+                            c1b[b] = __shfl_sync(0xffffffffu, c1m, b, 8);
+                            c2b[b] = __shfl_sync(0xffffffffu, c2m, b, 8);
                         }
-                        ls.c1 = c1b[3]; ls.c2 = c2b[3];
+                        if (iq_auto) { ls.te1 = t1; ls.te2 = t2; ls.te3 = t3; ls.c1 = c1b[3]; ls.c2 = c2b[3]; }
                     }
                     // per-lane Fs/4 pattern: sample 2p (e = 0) has phase (2r) & 3 in {0, 2}, sample 2p+1 phase +1
                     const float sg0 = (shift_kind == 1 && (r & 1)) ? -1.0f : 1.0f;
                     const float sg1 = (shift_kind == 1) ? (shift_down ? -sg0 : sg0) : 1.0f;
                     float *pi0 = xi + ((2 * r) & 3) * XP + XH + (r >> 1), *pq0 = xq + ((2 * r) & 3) * XP + XH + (r >> 1);
+                    if (fast_fe) {
+                        // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
+                        //   even sample: i' = c2 i, q' = q + c1 i, scaled by k0;  odd sample: (i', q') -> (q', -i') scaled by k1
+                        const float k0 = kS * sg0, k1 = kS * sg1;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int b = i >> 1;
+                        for (int i = 0; i < 8; i++) {
+                            const int b = i >> 1;
+                            const float a0 = c2b[b] * k0, d0 = c1b[b] * k0, a1 = c1b[b] * k1, d1 = -c2b[b] * k1;
+                            pi0[4 * i] = fi[2 * i] * a0;
+                            pq0[4 * i] = fmaf(fi[2 * i], d0, fq[2 * i] * k0);
+                            pi0[XP + 4 * i] = fmaf(fi[2 * i + 1], a1, fq[2 * i + 1] * k1);
+                            pq0[XP + 4 * i] = fi[2 * i + 1] * d1;
+                        }
+                    } else {
 #pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            float vi = fi[2 * i + e], vq = fq[2 * i + e];
-                            if (iq_auto) {
-                                vq = fmaf(c1b[b], vi, vq);            // q += M_c1 * i  (:2308-2311)
-                                vi = vi * c2b[b];                     // i *= M_c2      (:2313)
-                            } else {
-                                vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
-                                if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
-                                else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
+                        for (int i = 0; i < 8; i++) {
+                            const int b = i >> 1;
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                float vi = fi[2 * i + e], vq = fq[2 * i + e];
+                                if (iq_auto) {
+                                    vq = fmaf(c1b[b], vi, vq);            // q += M_c1 * i  (:2308-2311)
+                                    vi = vi * c2b[b];                     // i *= M_c2      (:2313)
+                                } else {
+                                    vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
+                                    if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
+                                    else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
+                                }
+                                float oi, oq;
+                                if (e == 0 || shift_kind != 1) { oi = vi * (kS * sg0); oq = vq * (kS * sg0); }
+                                else { oi = vq * (kS * sg1); oq = vi * (-kS * sg1); }
+                                pi0[e * XP + 4 * i] = oi;
+                                pq0[e * XP + 4 * i] = oq;
                             }
-                            float oi, oq;
-                            if (e == 0 || shift_kind != 1) { oi = vi * (kS * sg0); oq = vq * (kS * sg0); }
-                            else { oi = vq * (kS * sg1); oq = vi * (-kS * sg1); }
-                            pi0[e * XP + 4 * i] = oi;
-                            pq0[e * XP + 4 * i] = oq;
                         }
                     }
                 }
@@ -463,20 +481,24 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned d_tmem = tmem + (unsigned)((chunk & 1) * 32);
                 const int s0 = (64 * chunk) % HT;                   // ring slot of the window start (decimated sample 64c - 208)
+                // k-step kk: A = rows [264 - 16 kk, +64) of the Toeplitz table (start address - 512 B per step),
+                //            B = ring slots [s0 + 16 kk, +16) (start address + 256 B per step, wrapping at HT slots)
 #pragma unroll 1
                 for (int arr = 0; arr < 2; arr++) {
-                    const unsigned ga = smem_u32(sm.g[2 * arr]), gb = smem_u32(sm.g[2 * arr + 1]);
-                    const unsigned xa = smem_u32(sm.ring[2 * arr]), xb = smem_u32(sm.ring[2 * arr + 1]);
-#pragma unroll
+                    unsigned long long a1 = umma_desc(smem_u32(sm.g[2 * arr]) + 264u * 32u, 128, 256);
+                    unsigned long long a2 = umma_desc(smem_u32(sm.g[2 * arr + 1]) + 264u * 32u, 128, 256);
+                    unsigned long long b1 = umma_desc(smem_u32(sm.ring[2 * arr]) + (unsigned)(s0 >> 3) * 128u, 128, sbo_b);
+                    unsigned long long b2 = umma_desc(smem_u32(sm.ring[2 * arr + 1]) + (unsigned)(s0 >> 3) * 128u, 128, sbo_b);
+                    int s = s0;
+#pragma unroll 1
                     for (int kk = 0; kk < KSTEPS; kk++) {
-                        const unsigned arow = (unsigned)(264 - 16 * kk) * 32;
-                        int s = s0 + 16 * kk; if (s >= HT) s -= HT;
-                        const unsigned bt = (unsigned)(s >> 3) * 128;
-                        const unsigned long long a1 = umma_desc(ga + arow, 128, 256), a2 = umma_desc(gb + arow, 128, 256);
-                        const unsigned long long b1 = umma_desc(xa + bt, 128, sbo_b), b2 = umma_desc(xb + bt, 128, sbo_b);
                         umma_bf16(d_tmem, a1, b1, idesc, (arr > 0 || kk > 0) ? 1u : 0u);
                         umma_bf16(d_tmem, a2, b1, idesc, 1u);
                         umma_bf16(d_tmem, a1, b2, idesc, 1u);
+                        a1 -= 512u >> 4; a2 -= 512u >> 4;
+                        s += 16;
+                        if (s >= HT) { s -= HT; b1 -= (unsigned long long)(((HT - 16) / 8) * 128 >> 4); b2 -= (unsigned long long)(((HT - 16) / 8) * 128 >> 4); }
+                        else { b1 += 256u >> 4; b2 += 256u >> 4; }
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.mma_bar[chunk & 1])) : "memory");
@@ -721,26 +743,33 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         }
         const float scale_gain = p.scale_gain;
         float xl1 = 0.0f, xl2 = 0.0f;        // the last two cascade inputs (state of skipped leading stages)
+        // one step of 32 samples with the skipped stages known at compile time
+        auto run_step = [&](auto maskc, const float *in, float *out) {
+            constexpr unsigned MASK = decltype(maskc)::value;
+#pragma unroll 4
+            for (int i = 0; i < ND; i++) {
+                float x = __fmul_rn(in[i * SMS], scale_gain);
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    if (!(MASK & (1u << s))) {
+                        const float w = fmaf(bc[s][2], bs[s].x1, __fmul_rn(bc[s][4], bs[s].y1));     // next sample's x2 / y2 terms
+                        const float y = fmaf(bc[s][0], x, tq[s]);
+                        tq[s] = fmaf(bc[s][3], y, fmaf(bc[s][1], x, w));
+                        bs[s].x2 = bs[s].x1; bs[s].x1 = x; bs[s].y2 = bs[s].y1; bs[s].y1 = y;
+                        x = y;
+                    }
+                }
+                out[i * SMS] = x;
+            }
+        };
+        if (skipmask != 0xbu) skipmask = 0;      // only the default plan (bass shelf alone) has a specialised loop
         for (int t = 0; t < niter; t++) {
             const int c = t - IT_BQ;
             if (c >= 0 && c < nsteps && active) {
                 const float *in = sm.agc[c & 1] + g;
                 float *out = sm.bq[c & 1] + g;
-#pragma unroll 4
-                for (int i = 0; i < ND; i++) {
-                    float x = __fmul_rn(in[i * SMS], scale_gain);
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                        if (!(skipmask & (1u << s))) {
-                            const float w = fmaf(bc[s][2], bs[s].x1, __fmul_rn(bc[s][4], bs[s].y1));     // next sample's x2 / y2 terms
-                            const float y = fmaf(bc[s][0], x, tq[s]);
-                            tq[s] = fmaf(bc[s][3], y, fmaf(bc[s][1], x, w));
-                            bs[s].x2 = bs[s].x1; bs[s].x1 = x; bs[s].y2 = bs[s].y1; bs[s].y1 = y;
-                            x = y;
-                        }
-                    }
-                    out[i * SMS] = x;
-                }
+                if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out);
+                else run_step(std::integral_constant<unsigned, 0u>{}, in, out);
                 xl1 = __fmul_rn(in[(ND - 1) * SMS], scale_gain); xl2 = __fmul_rn(in[(ND - 2) * SMS], scale_gain);
             }
             __syncthreads();
@@ -793,52 +822,66 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         float4 *__restrict__ dst_f = a.audio_f ? reinterpret_cast<float4 *>(a.audio_f + chan_base) : nullptr;
         const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
-        for (int t = 0; t < niter; t++) {
-            const int c = t - IT_POST;
-            if (c >= 0 && c < nsteps && active) {
-                const float *in = sm.bq[c & 1] + g;
-                int4 *d4 = dst + (size_t)c * 64;
+        // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
+        auto run_block = [&](auto aac, const float *in, int4 *d4, float4 *df, bool muted) {
+            constexpr bool AA = decltype(aac)::value;
 #pragma unroll 2
-                for (int i = 0; i < ND; i++) {
-                    const float x = in[i * SMS];
-                    float o[4];
+            for (int i = 0; i < 8; i++) {
+                const float x = in[i * SMS];
+                float o[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const float pre = fmaf(ih[2], ic[j][2], fmaf(ih[1], ic[j][1], __fmul_rn(ih[0], ic[j][0])));
-                        o[j] = fmaf(x, ic[j][3], pre);
-                    }
-                    ih[0] = ih[1]; ih[1] = ih[2]; ih[2] = x;
+                for (int j = 0; j < 4; j++) {
+                    const float pre = fmaf(ih[2], ic[j][2], fmaf(ih[1], ic[j][1], __fmul_rn(ih[0], ic[j][0])));
+                    o[j] = fmaf(x, ic[j][3], pre);
+                }
+                ih[0] = ih[1]; ih[1] = ih[2]; ih[2] = x;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float y = o[j];
-                        if (any_aa) {
-                            float f = y, acc = 0.0f, fn = y;
+                for (int j = 0; j < 4; j++) {
+                    float y = o[j];
+                    if constexpr (AA) {
+                        float f = y, acc = 0.0f, fn = y;
 #pragma unroll
-                            for (int q = 0; q < 6; q++) {
-                                const float gg = as[q];
-                                fn = fmaf(-ak[q], gg, f);
-                                const float gn = fmaf(fn, ak[q], gg);
-                                acc = fmaf(gn, av[q], acc);
-                                if (q > 0) as[q - 1] = gn;
-                                f = fn;
-                            }
-                            acc = fmaf(fn, av[6], acc);
-                            as[5] = fn;
-                            y = (n == 6) ? acc : y;
+                        for (int q = 0; q < 6; q++) {
+                            const float gg = as[q];
+                            fn = fmaf(-ak[q], gg, f);
+                            const float gn = fmaf(fn, ak[q], gg);
+                            acc = fmaf(gn, av[q], acc);
+                            if (q > 0) as[q - 1] = gn;
+                            f = fn;
                         }
-                        const float w = fmaf(tc[2], ts.x1, __fmul_rn(tc[4], ts.y1));
-                        const float z = fmaf(tc[0], y, tt);
-                        tt = fmaf(tc[3], z, fmaf(tc[1], y, w));
-                        ts.x2 = ts.x1; ts.x1 = y; ts.y2 = ts.y1; ts.y1 = z;
-                        o[j] = __fmul_rn(z, 10.0f);              // LINE_OUT_SCALING_FACTOR (:2860)
+                        acc = fmaf(fn, av[6], acc);
+                        as[5] = fn;
+                        y = (n == 6) ? acc : y;
                     }
-                    const bool muted = mute && mute[c * 4 + (i >> 3)];
-                    if (muted) { o[0] = 0.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }
+                    const float w = fmaf(tc[2], ts.x1, __fmul_rn(tc[4], ts.y1));
+                    const float z = fmaf(tc[0], y, tt);
+                    tt = fmaf(tc[3], z, fmaf(tc[1], y, w));
+                    ts.x2 = ts.x1; ts.x1 = y; ts.y2 = ts.y1; ts.y1 = z;
+                    o[j] = __fmul_rn(z, 10.0f);              // LINE_OUT_SCALING_FACTOR (:2860)
+                }
+                if (muted) {                                  // external_mute: zeros out, all state advanced (:2845-2853)
+                    d4[2 * i] = make_int4(0, 0, 0, 0); d4[2 * i + 1] = make_int4(0, 0, 0, 0);
+                    if (df) df[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                } else {
                     const int w0 = format_audio_word(o[0]), w1 = format_audio_word(o[1]);
                     const int w2 = format_audio_word(o[2]), w3 = format_audio_word(o[3]);
                     d4[2 * i] = make_int4(w0, w0, w1, w1);
                     d4[2 * i + 1] = make_int4(w2, w2, w3, w3);
-                    if (dst_f) dst_f[(size_t)c * 32 + i] = make_float4(o[0], o[1], o[2], o[3]);
+                    if (df) df[i] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        };
+        for (int t = 0; t < niter; t++) {
+            const int c = t - IT_POST;
+            if (c >= 0 && c < nsteps && active) {
+                const float *in = sm.bq[c & 1] + g;
+#pragma unroll 1
+                for (int blk = 0; blk < 4; blk++) {
+                    const bool muted = mute && mute[c * 4 + blk];
+                    int4 *d4 = dst + (size_t)c * 64 + blk * 16;
+                    float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
+                    if (any_aa) run_block(std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    else run_block(std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
                 }
             }
             __syncthreads();
