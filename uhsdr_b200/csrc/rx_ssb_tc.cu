@@ -45,6 +45,7 @@ constexpr int XCH = 2 * 4 * XP + 4;
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int RING = 64;           // AGC delay ring slots
+constexpr int AG = 4;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
 constexpr int NWARP_FIR = FG / 4;
 constexpr int DEC_PAD = 32;        // FusedCoefs::dec carries the 83 taps at [32, 115)
 // tensor-core Hilbert
@@ -57,7 +58,7 @@ constexpr int G_BYTES = GROWS * 32;                // [row/8][k half][row%8][8] 
 constexpr int TMEM_COLS = 64;      // two 64 x 32 fp32 accumulators
 // warp roles
 // (warp id % 4 is the scheduler: the four serial warps and the MMA issuer are spread over all four)
-constexpr int W_POST = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_LAT = NWARP_FIR + 2, W_BQ = NWARP_FIR + 3, W_MMA = NWARP_FIR + 4;
+constexpr int W_POST = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_LAT = NWARP_FIR + 2, W_MMA = NWARP_FIR + 3, W_BQ = NWARP_FIR + 4;
 constexpr int NTHREADS = 32 * (NWARP_FIR + 5);
 // software pipeline, in steps of 128 input samples: step h is decimated at iteration h, its Hilbert
 // outputs leave TMEM at h + 4, lattice h + 5, AGC h + 6, gain + biquad cascade h + 7,
@@ -140,31 +141,28 @@ template <int I, int N, typename F> __device__ __forceinline__ void static_for(F
 
 // Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 96 history slots
 // in front (24 per phase), buffer position b = 4m + k + 14; phase = b & 3, idx = b >> 2.  Each lane
-// makes 4 consecutive outputs m0..m0+3 for I and for Q; element (q, e, ph) of the 7 x 4 float4 loads
+// makes 4 consecutive outputs m0..m0+3 of one signal (the caller loops over I and Q with the same code, which
+// halves the instruction-cache footprint); element (q, e, ph) of the 7 x 4 float4 loads
 // is position 4 (m0 + 4q + e) + ph, i.e. tap K = 16q + 4 (e - j) + ph - 14 of output j.  Fully unrolled:
 // every tap is an immediate constant-bank operand and taps outside [0, 82] generate no instruction.
-__device__ __forceinline__ void decimate4(const float *xpi, const float *xpq, int m0, const FusedCoefs &fc, float ai[4], float aq[4])
+__device__ __forceinline__ void decimate4(const float *xp, int m0, const FusedCoefs &fc, float acc[4])
 {
 #pragma unroll
-    for (int j = 0; j < 4; j++) { ai[j] = 0.0f; aq[j] = 0.0f; }
+    for (int j = 0; j < 4; j++) acc[j] = 0.0f;
     static_for<0, 7>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        float4 vi[4], vq[4];
+        float4 v[4];
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) { vi[ph] = lds128(xpi + ph * XP + m0 + 4 * q); vq[ph] = lds128(xpq + ph * XP + m0 + 4 * q); }
+        for (int ph = 0; ph < 4; ph++) v[ph] = lds128(xp + ph * XP + m0 + 4 * q);
         static_for<0, 4>([&](auto ec) {
             constexpr int e = decltype(ec)::value;
             static_for<0, 4>([&](auto pc) {
                 constexpr int ph = decltype(pc)::value;
-                const float xi = (e == 0) ? vi[ph].x : (e == 1) ? vi[ph].y : (e == 2) ? vi[ph].z : vi[ph].w;
-                const float xq = (e == 0) ? vq[ph].x : (e == 1) ? vq[ph].y : (e == 2) ? vq[ph].z : vq[ph].w;
+                const float x = (e == 0) ? v[ph].x : (e == 1) ? v[ph].y : (e == 2) ? v[ph].z : v[ph].w;
                 static_for<0, 4>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     constexpr int K = 16 * q + 4 * (e - j) + ph - 14;
-                    if constexpr (K >= 0 && K < 83) {
-                        ai[j] = fmaf(fc.dec[DEC_PAD + K], xi, ai[j]);
-                        aq[j] = fmaf(fc.dec[DEC_PAD + K], xq, aq[j]);
-                    }
+                    if constexpr (K >= 0 && K < 83) acc[j] = fmaf(fc.dec[DEC_PAD + K], x, acc[j]);
                 });
             });
         });
@@ -399,20 +397,19 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 __syncwarp();
                 // ---- decimate: outputs 4r .. 4r+3 for I and Q -> 16-bit rounding, bf16 split, Hilbert ring ----
                 {
-                    float ai[4], aq[4];
-                    decimate4(xi, xq, 4 * r, fc, ai, aq);
-                    unsigned i1[4], i2[4], q1[4], q2[4];
+                    const int sl = (208 + ND * t + 4 * r) % HT;          // ring slot of decimated sample 32 t + 4 r
+                    const int off = ring_off(g, sl);
+#pragma unroll 1
+                    for (int c = 0; c < 2; c++) {
+                        float acc[4];
+                        decimate4(c ? xq : xi, 4 * r, fc, acc);
+                        const bool neg = c && lsb;                         // LSB: I - Q, the Q samples are stored negated
+                        unsigned h1[4], h2[4];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        split_bf16(round16(ai[j]), i1[j], i2[j]);
-                        split_bf16(round16(lsb ? -aq[j] : aq[j]), q1[j], q2[j]);
+                        for (int j = 0; j < 4; j++) split_bf16(round16(neg ? -acc[j] : acc[j]), h1[j], h2[j]);
+                        *reinterpret_cast<uint2 *>(sm.ring[2 * c] + off) = make_uint2(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16));
+                        *reinterpret_cast<uint2 *>(sm.ring[2 * c + 1] + off) = make_uint2(h2[0] | (h2[1] << 16), h2[2] | (h2[3] << 16));
                     }
-                    const int s = (208 + ND * t + 4 * r) % HT;          // ring slot of decimated sample 32 t + 4 r
-                    const int off = ring_off(g, s);
-                    *reinterpret_cast<uint2 *>(sm.ring[0] + off) = make_uint2(i1[0] | (i1[1] << 16), i1[2] | (i1[3] << 16));
-                    *reinterpret_cast<uint2 *>(sm.ring[1] + off) = make_uint2(i2[0] | (i2[1] << 16), i2[2] | (i2[3] << 16));
-                    *reinterpret_cast<uint2 *>(sm.ring[2] + off) = make_uint2(q1[0] | (q1[1] << 16), q1[2] | (q1[3] << 16));
-                    *reinterpret_cast<uint2 *>(sm.ring[3] + off) = make_uint2(q2[0] | (q2[1] << 16), q2[2] | (q2[3] << 16));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
                 }
                 __syncwarp();
@@ -535,21 +532,31 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             if (c >= 0 && c < nsteps) {
                 const float *in = sm.aud[c & 1];
                 float *out = sm.lat[c & 1];
-#pragma unroll 4
-                for (int i = 0; i < ND; i++) {
-                    float f = in[i * SMS + gq], acc = 0.0f, fn = f;
+#pragma unroll 1
+                for (int i0 = 0; i0 < ND; i0 += 8) {
+                    // the 8 inputs first: their shared-memory latency is paid once, not once per sample
+                    float xin[8], yo[8];
 #pragma unroll
-                    for (int j = 0; j < 10; j++) {
-                        const float gg = s[j];
-                        fn = fmaf(-k[j], gg, f);
-                        const float gn = fmaf(fn, k[j], gg);
-                        acc = fmaf(gn, v[j], acc);
-                        if (j > 0) s[j - 1] = gn;
-                        f = fn;
+                    for (int i = 0; i < 8; i++) xin[i] = in[(i0 + i) * SMS + gq];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float f = xin[i], acc = 0.0f, fn = f;
+#pragma unroll
+                        for (int j = 0; j < 10; j++) {
+                            const float gg = s[j];
+                            fn = fmaf(-k[j], gg, f);
+                            const float gn = fmaf(fn, k[j], gg);
+                            acc = fmaf(gn, v[j], acc);
+                            if (j > 0) s[j - 1] = gn;
+                            f = fn;
+                        }
+                        yo[i] = fmaf(fn, v[10], acc);
+                        s[9] = fn;
                     }
-                    acc = fmaf(fn, v[10], acc);
-                    s[9] = fn;
-                    if (active) out[i * SMS + g] = acc;
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) out[(i0 + i) * SMS + g] = yo[i];
+                    }
                 }
             }
             __syncthreads();
@@ -591,7 +598,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 sm.smax[s2][o * SMS + g] = m;
             }
         }
-        int wp = 0;          // ring slot of the first sample of the next group of 8 (multiple of 8)
+        int wp = 0;          // ring slot of the first sample of the next group (multiple of AG)
         const bool any_hang = __any_sync(0xffffffffu, active && (ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0));
         for (int t = 0; t < niter; t++) {
             const int c = t - IT_AGC;
@@ -605,25 +612,25 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                     const float mprev = S1[0];
                     float pmax = 0.0f;
 #pragma unroll 1
-                    for (int k8 = 0; k8 < ND; k8 += 8) {
-                        // all operands of 8 samples first.  The delayed sample x[n-49] of group element j sits at ring
-                        // slot wp + j - 49: j = 0 -> (wp - 56) + 7, j >= 1 -> (wp - 48) + (j - 1); no wrap inside a group.
-                        const float *dA = ringp + ((wp - 56) & (RING - 1)) * SMS + g;
+                    for (int k8 = 0; k8 < ND; k8 += AG) {
+                        // all operands of the AG samples first.  The delayed sample x[n-49] of group element j sits at ring
+                        // slot wp + j - 49: j = 0 -> (wp - 48 - AG) + (AG - 1), j >= 1 -> (wp - 48) + (j - 1); no wrap inside a group.
+                        const float *dA = ringp + ((wp - 48 - AG) & (RING - 1)) * SMS + g;
                         const float *dB = ringp + ((wp - 48) & (RING - 1)) * SMS + g;
                         float *wr = ringp + wp * SMS + g;
                         const bool two = k8 < 16;                   // window still reaches into the chunk before the previous one
                         const float *pc = two ? S2 + (16 + k8) * SMS : S1 + (k8 - 16) * SMS;
                         const float *pin = in + k8 * SMS;
-                        float x[8], dly[8], cmx[8], vv[8];
+                        float x[AG], dly[AG], cmx[AG], vv[AG];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < AG; j++) {
                             x[j] = pin[j * SMS];
-                            dly[j] = (j == 0) ? dA[7 * SMS] : dB[(j - 1) * SMS];
+                            dly[j] = (j == 0) ? dA[(AG - 1) * SMS] : dB[(j - 1) * SMS];
                             const float sfx = pc[j * SMS];
                             cmx[j] = two ? fmaxf(mprev, sfx) : sfx;
                         }
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < AG; j++) {
                             const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
                             pmax = fmaxf(pmax, abs_in);
                             ar.fast_backaverage = fmaf(ap.fast_backmult, abs_out, __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
@@ -673,7 +680,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                             vv[j] = ar.volts;
                         }
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
+                        for (int j = 0; j < AG; j++) {
                             // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
                             // operations, the cubic in Horner form
                             const unsigned ub = __float_as_uint(__fmul_rn(ap.inv_max_input, vv[j]));
@@ -688,7 +695,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                             out[(k8 + j) * SMS] = __fmul_rn(dly[j], mult);
                             wr[j * SMS] = x[j];
                         }
-                        wp = (wp + 8) & (RING - 1);
+                        wp = (wp + AG) & (RING - 1);
                     }
                     ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
                     {
@@ -696,10 +703,13 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                         float *Sn = sm.smax[s2] + g;
                         const float *rb = ringp + ((wp - ND) & (RING - 1)) * SMS + g;       // the 32 newest samples: no wrap (wp is a multiple of 32 here)
                         float m = 0.0f;
-#pragma unroll 8
-                        for (int o = ND - 1; o >= 0; o--) {
-                            m = fmaxf(m, fabsf(rb[o * SMS]));
-                            Sn[o * SMS] = m;
+#pragma unroll 1
+                        for (int o8 = ND - 8; o8 >= 0; o8 -= 8) {
+                            float rv[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) rv[j] = rb[(o8 + j) * SMS];
+#pragma unroll
+                            for (int j = 7; j >= 0; j--) { m = fmaxf(m, fabsf(rv[j])); Sn[(o8 + j) * SMS] = m; }
                         }
                         const int tmp = s1; s1 = s2; s2 = tmp;
                     }
@@ -746,20 +756,28 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         // one step of 32 samples with the skipped stages known at compile time
         auto run_step = [&](auto maskc, const float *in, float *out) {
             constexpr unsigned MASK = decltype(maskc)::value;
-#pragma unroll 4
-            for (int i = 0; i < ND; i++) {
-                float x = __fmul_rn(in[i * SMS], scale_gain);
+#pragma unroll 1
+            for (int i0 = 0; i0 < ND; i0 += 8) {
+                float xv[8];
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    if (!(MASK & (1u << s))) {
-                        const float w = fmaf(bc[s][2], bs[s].x1, __fmul_rn(bc[s][4], bs[s].y1));     // next sample's x2 / y2 terms
-                        const float y = fmaf(bc[s][0], x, tq[s]);
-                        tq[s] = fmaf(bc[s][3], y, fmaf(bc[s][1], x, w));
-                        bs[s].x2 = bs[s].x1; bs[s].x1 = x; bs[s].y2 = bs[s].y1; bs[s].y1 = y;
-                        x = y;
+                for (int i = 0; i < 8; i++) xv[i] = in[(i0 + i) * SMS];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    float x = __fmul_rn(xv[i], scale_gain);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        if (!(MASK & (1u << s))) {
+                            const float w = fmaf(bc[s][2], bs[s].x1, __fmul_rn(bc[s][4], bs[s].y1));     // next sample's x2 / y2 terms
+                            const float y = fmaf(bc[s][0], x, tq[s]);
+                            tq[s] = fmaf(bc[s][3], y, fmaf(bc[s][1], x, w));
+                            bs[s].x2 = bs[s].x1; bs[s].x1 = x; bs[s].y2 = bs[s].y1; bs[s].y1 = y;
+                            x = y;
+                        }
                     }
+                    xv[i] = x;
                 }
-                out[i * SMS] = x;
+#pragma unroll
+                for (int i = 0; i < 8; i++) out[(i0 + i) * SMS] = xv[i];
             }
         };
         if (skipmask != 0xbu) skipmask = 0;      // only the default plan (bass shelf alone) has a specialised loop
@@ -822,52 +840,65 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         float4 *__restrict__ dst_f = a.audio_f ? reinterpret_cast<float4 *>(a.audio_f + chan_base) : nullptr;
         const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
+        // A 0 dB shelf has b0 = 1, b1 = -a1, b2 = -a2 (audio_driver.c:906-964 with A = 1): with consistent state
+        // (y1 = x1, y2 = x2) the stage is the identity.  Then it is not computed (the reference's own result differs
+        // from its input by float rounding only); the state follows the signal so that later launches agree.
+        const bool tr_unity = __all_sync(0xffffffffu, !active || (tc[0] == 1.0f && tc[1] == -tc[3] && tc[2] == -tc[4] &&
+                                                                  ts.x1 == ts.y1 && ts.x2 == ts.y2));
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
-        auto run_block = [&](auto aac, const float *in, int4 *d4, float4 *df, bool muted) {
-            constexpr bool AA = decltype(aac)::value;
-#pragma unroll 2
-            for (int i = 0; i < 8; i++) {
-                const float x = in[i * SMS];
-                float o[4];
+        auto run_block = [&](auto aac, auto trc, const float *in, int4 *d4, float4 *df, bool muted) {
+            constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value;
+            const int mm = muted ? 0 : -1;                // external_mute: zeros out, all state advanced (:2845-2853)
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                float xv[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float pre = fmaf(ih[2], ic[j][2], fmaf(ih[1], ic[j][1], __fmul_rn(ih[0], ic[j][0])));
-                    o[j] = fmaf(x, ic[j][3], pre);
-                }
-                ih[0] = ih[1]; ih[1] = ih[2]; ih[2] = x;
+                for (int i = 0; i < 4; i++) xv[i] = in[(4 * h + i) * SMS];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float y = o[j];
-                    if constexpr (AA) {
-                        float f = y, acc = 0.0f, fn = y;
+                for (int i = 0; i < 4; i++) {
+                    const float x = xv[i];
+                    float o[4];
 #pragma unroll
-                        for (int q = 0; q < 6; q++) {
-                            const float gg = as[q];
-                            fn = fmaf(-ak[q], gg, f);
-                            const float gn = fmaf(fn, ak[q], gg);
-                            acc = fmaf(gn, av[q], acc);
-                            if (q > 0) as[q - 1] = gn;
-                            f = fn;
-                        }
-                        acc = fmaf(fn, av[6], acc);
-                        as[5] = fn;
-                        y = (n == 6) ? acc : y;
+                    for (int j = 0; j < 4; j++) {
+                        const float pre = fmaf(ih[2], ic[j][2], fmaf(ih[1], ic[j][1], __fmul_rn(ih[0], ic[j][0])));
+                        o[j] = fmaf(x, ic[j][3], pre);
                     }
-                    const float w = fmaf(tc[2], ts.x1, __fmul_rn(tc[4], ts.y1));
-                    const float z = fmaf(tc[0], y, tt);
-                    tt = fmaf(tc[3], z, fmaf(tc[1], y, w));
-                    ts.x2 = ts.x1; ts.x1 = y; ts.y2 = ts.y1; ts.y1 = z;
-                    o[j] = __fmul_rn(z, 10.0f);              // LINE_OUT_SCALING_FACTOR (:2860)
-                }
-                if (muted) {                                  // external_mute: zeros out, all state advanced (:2845-2853)
-                    d4[2 * i] = make_int4(0, 0, 0, 0); d4[2 * i + 1] = make_int4(0, 0, 0, 0);
-                    if (df) df[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                } else {
-                    const int w0 = format_audio_word(o[0]), w1 = format_audio_word(o[1]);
-                    const int w2 = format_audio_word(o[2]), w3 = format_audio_word(o[3]);
-                    d4[2 * i] = make_int4(w0, w0, w1, w1);
-                    d4[2 * i + 1] = make_int4(w2, w2, w3, w3);
-                    if (df) df[i] = make_float4(o[0], o[1], o[2], o[3]);
+                    ih[0] = ih[1]; ih[1] = ih[2]; ih[2] = x;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float y = o[j];
+                        if constexpr (AA) {
+                            float f = y, acc = 0.0f, fn = y;
+#pragma unroll
+                            for (int q = 0; q < 6; q++) {
+                                const float gg = as[q];
+                                fn = fmaf(-ak[q], gg, f);
+                                const float gn = fmaf(fn, ak[q], gg);
+                                acc = fmaf(gn, av[q], acc);
+                                if (q > 0) as[q - 1] = gn;
+                                f = fn;
+                            }
+                            acc = fmaf(fn, av[6], acc);
+                            as[5] = fn;
+                            y = (n == 6) ? acc : y;
+                        }
+                        float z = y;
+                        if constexpr (TR) {
+                            const float w = fmaf(tc[2], ts.x1, __fmul_rn(tc[4], ts.y1));
+                            z = fmaf(tc[0], y, tt);
+                            tt = fmaf(tc[3], z, fmaf(tc[1], y, w));
+                            ts.x2 = ts.x1; ts.x1 = y; ts.y2 = ts.y1; ts.y1 = z;
+                        }
+                        o[j] = z;
+                    }
+                    if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }
+                    const int pos = 4 * h + i;
+                    const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)) & mm, w1 = format_audio_word(__fmul_rn(o[1], 10.0f)) & mm;   // LINE_OUT_SCALING_FACTOR (:2860)
+                    const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
+                    d4[2 * pos] = make_int4(w0, w0, w1, w1);
+                    d4[2 * pos + 1] = make_int4(w2, w2, w3, w3);
+                    if (df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
+                                            : make_float4(__fmul_rn(o[0], 10.0f), __fmul_rn(o[1], 10.0f), __fmul_rn(o[2], 10.0f), __fmul_rn(o[3], 10.0f));
                 }
             }
         };
@@ -880,8 +911,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                     const bool muted = mute && mute[c * 4 + blk];
                     int4 *d4 = dst + (size_t)c * 64 + blk * 16;
                     float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
-                    if (any_aa) run_block(std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
-                    else run_block(std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    if (any_aa) run_block(std::true_type{}, std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    else run_block(std::false_type{}, std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
                 }
             }
             __syncthreads();
