@@ -58,7 +58,7 @@ constexpr int G_BYTES = GROWS * 32;                // [row/8][k half][row%8][8] 
 constexpr int TMEM_COLS = 64;      // two 64 x 32 fp32 accumulators
 // warp roles
 // (warp id % 4 is the scheduler: the four serial warps and the MMA issuer are spread over all four)
-constexpr int W_POST = NWARP_FIR, W_AGC = NWARP_FIR + 1, W_LAT = NWARP_FIR + 2, W_MMA = NWARP_FIR + 3, W_BQ = NWARP_FIR + 4;
+constexpr int W_AGC = NWARP_FIR, W_POST = NWARP_FIR + 1, W_LAT = NWARP_FIR + 2, W_MMA = NWARP_FIR + 3, W_BQ = NWARP_FIR + 4;
 constexpr int NTHREADS = 32 * (NWARP_FIR + 5);
 // software pipeline, in steps of 128 input samples: step h is decimated at iteration h, its Hilbert
 // outputs leave TMEM at h + 4, lattice h + 5, AGC h + 6, gain + biquad cascade h + 7,
@@ -251,11 +251,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
         const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base);
 
-        // input prefetch: 8 x int4 (pairs r + 8i of the step) one step ahead, straight from global memory
+        // input prefetch: 8 x int4 = the 16 consecutive samples 16r .. 16r+15 of the step, one step ahead, straight from global memory
         int4 pre[8];
         if (nsteps > 0) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) pre[i] = active ? __ldg(src + r + 8 * i) : make_int4(0, 0, 0, 0);
+            for (int i = 0; i < 8; i++) pre[i] = active ? __ldg(src + 8 * r + i) : make_int4(0, 0, 0, 0);
         }
         __syncwarp();
 
@@ -288,10 +288,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 }
             }
             if (t < nsteps) {
-                // ---- front end: the whole 128-sample step at once.  Pairs p = r + 8i (samples 2p, 2p+1), block b = i >> 1.
-                // The 2^-16 input scaling (audio_driver.c:2680-2685) is exact, so it is folded into the correction
-                // factors; the Fs/4 translation (freq_shift.c:219-262) is a per-lane sign/swap pattern folded into
-                // the same factors.
+                // ---- front end: the whole 128-sample step at once.  Lane r owns the 16 consecutive samples 16r .. 16r+15,
+                // i.e. one half of block r >> 1, and stores them as one float4 per decimator phase.  The 2^-16 input
+                // scaling (audio_driver.c:2680-2685) is exact, so it is folded into the correction factors; the Fs/4
+                // translation (freq_shift.c:219-262) is a sign/swap pattern of period 4 folded into the same factors.
                 {
                     float fi[16], fq[16];
                     int lvmax = 0;
@@ -304,94 +304,82 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                     // fetch the next step behind the FIR work
                     if (t + 1 < nsteps && active) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) pre[i] = __ldg(src + (size_t)(t + 1) * 64 + r + 8 * i);
+                        for (int i = 0; i < 8; i++) pre[i] = __ldg(src + (size_t)(t + 1) * 64 + 8 * r + i);
                     }
                     lvmax >>= 16;                                                // audio_driver.c:2662-2675
                     ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
                     const float kS = 0.0000152587890625f;                        // 2^-16
-                    float c1b[4], c2b[4];
+                    float c1m = 0.0f, c2m = 1.0f;                                // M_c1, M_c2 of this lane's block
                     if (any_auto) {
-                        // Moseley & Slump block statistics (:2274-2279) for the four blocks; sign(i) * q as a sign-bit
-                        // transfer (differs from Math_sign_new only for i == 0, where the term is +-q instead of 0)
-                        float s1[4], s2[4], s3[4];
+                        // Moseley & Slump block statistics (:2274-2279); sign(i) * q as a sign-bit transfer (differs from
+                        // Math_sign_new only for i == 0, where the term is +-q instead of 0)
+                        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            s1[b] = 0.0f; s2[b] = 0.0f; s3[b] = 0.0f;
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                const float vi = fi[4 * b + k], vq = fq[4 * b + k];
-                                s1[b] += __uint_as_float(__float_as_uint(vq) ^ (__float_as_uint(vi) & 0x80000000u));
-                                s2[b] += fabsf(vi); s3[b] += fabsf(vq);
-                            }
+                        for (int k = 0; k < 16; k++) {
+                            s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
+                            s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
                         }
-#pragma unroll
-                        for (int dlt = 1; dlt < 8; dlt <<= 1) {
-#pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                s1[b] += __shfl_xor_sync(0xffffffffu, s1[b], dlt, 8);
-                                s2[b] += __shfl_xor_sync(0xffffffffu, s2[b], dlt, 8);
-                                s3[b] += __shfl_xor_sync(0xffffffffu, s3[b], dlt, 8);
-                            }
-                        }
-                        // first-order low-pass over blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295):
-                        // lane r computes the pair of block r & 3, the group shares them by shuffle
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 1, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 1, 8);
+                        // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
                         float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                         const float kE = 0.003f * 0.03125f * kS;
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
-                            t1 = fmaf(0.997f, t1, -kE * s1[b]); t2 = fmaf(0.997f, t2, kE * s2[b]); t3 = fmaf(0.997f, t3, kE * s3[b]);
-                            if ((r & 3) == b) { m1 = t1; m2 = t2; m3 = t3; }
+                            const float b1 = __shfl_sync(0xffffffffu, s1, 2 * b, 8), b2 = __shfl_sync(0xffffffffu, s2, 2 * b, 8), b3 = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
+                            t1 = fmaf(0.997f, t1, -kE * b1); t2 = fmaf(0.997f, t2, kE * b2); t3 = fmaf(0.997f, t3, kE * b3);
+                            if ((r >> 1) == b) { m1 = t1; m2 = t2; m3 = t3; }
                         }
                         const float den = m2 * m2;
-                        const float c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
                         const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
-                        const float c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            c1b[b] = __shfl_sync(0xffffffffu, c1m, b, 8);
-                            c2b[b] = __shfl_sync(0xffffffffu, c2m, b, 8);
+                        if (iq_auto) {
+                            ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
+                            c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
+                            c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
+                            ls.c1 = c1m; ls.c2 = c2m;                            // lanes 6, 7 hold the block-3 values the state keeps
                         }
-                        if (iq_auto) { ls.te1 = t1; ls.te2 = t2; ls.te3 = t3; ls.c1 = c1b[3]; ls.c2 = c2b[3]; }
                     }
-                    // per-lane Fs/4 pattern: sample 2p (e = 0) has phase (2r) & 3 in {0, 2}, sample 2p+1 phase +1
-                    const float sg0 = (shift_kind == 1 && (r & 1)) ? -1.0f : 1.0f;
-                    const float sg1 = (shift_kind == 1) ? (shift_down ? -sg0 : sg0) : 1.0f;
-                    float *pi0 = xi + ((2 * r) & 3) * XP + XH + (r >> 1), *pq0 = xq + ((2 * r) & 3) * XP + XH + (r >> 1);
+                    float oi[16], oq[16];
                     if (fast_fe) {
                         // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
-                        //   even sample: i' = c2 i, q' = q + c1 i, scaled by k0;  odd sample: (i', q') -> (q', -i') scaled by k1
-                        const float k0 = kS * sg0, k1 = kS * sg1;
+                        //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
+                        const float sgd = shift_down ? -1.0f : 1.0f;
+                        const float fa = c2m * kS, fd = c1m * kS, fas = fa * sgd, fds = fd * sgd, ks = kS * sgd;
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int b = i >> 1;
-                            const float a0 = c2b[b] * k0, d0 = c1b[b] * k0, a1 = c1b[b] * k1, d1 = -c2b[b] * k1;
-                            pi0[4 * i] = fi[2 * i] * a0;
-                            pq0[4 * i] = fmaf(fi[2 * i], d0, fq[2 * i] * k0);
-                            pi0[XP + 4 * i] = fmaf(fi[2 * i + 1], a1, fq[2 * i + 1] * k1);
-                            pq0[XP + 4 * i] = fi[2 * i + 1] * d1;
+                        for (int k = 0; k < 16; k += 4) {
+                            oi[k] = fi[k] * fa;                                   oq[k] = fmaf(fi[k], fd, fq[k] * kS);
+                            oi[k + 1] = fmaf(fi[k + 1], fds, fq[k + 1] * ks);     oq[k + 1] = fi[k + 1] * -fas;
+                            oi[k + 2] = fi[k + 2] * -fa;                          oq[k + 2] = fmaf(fi[k + 2], -fd, fq[k + 2] * -kS);
+                            oi[k + 3] = fmaf(fi[k + 3], -fds, fq[k + 3] * -ks);   oq[k + 3] = fi[k + 3] * fas;
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int b = i >> 1;
-#pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                float vi = fi[2 * i + e], vq = fq[2 * i + e];
-                                if (iq_auto) {
-                                    vq = fmaf(c1b[b], vi, vq);            // q += M_c1 * i  (:2308-2311)
-                                    vi = vi * c2b[b];                     // i *= M_c2      (:2313)
-                                } else {
-                                    vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
-                                    if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
-                                    else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
-                                }
-                                float oi, oq;
-                                if (e == 0 || shift_kind != 1) { oi = vi * (kS * sg0); oq = vq * (kS * sg0); }
-                                else { oi = vq * (kS * sg1); oq = vi * (-kS * sg1); }
-                                pi0[e * XP + 4 * i] = oi;
-                                pq0[e * XP + 4 * i] = oq;
+                        for (int k = 0; k < 16; k++) {
+                            float vi = fi[k], vq = fq[k];
+                            if (iq_auto) {
+                                vq = fmaf(c1m, vi, vq);               // q += M_c1 * i  (:2308-2311)
+                                vi = vi * c2m;                        // i *= M_c2      (:2313)
+                            } else {
+                                vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
+                                if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
+                                else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
                             }
+                            vi *= kS; vq *= kS;
+                            if (shift_kind == 1) {
+                                const float sgd = shift_down ? -1.0f : 1.0f;
+                                const int ph = k & 3;
+                                const float ti = vi, tq_ = vq;
+                                if (ph == 1) { vi = tq_ * sgd; vq = -ti * sgd; }
+                                else if (ph == 2) { vi = -ti; vq = -tq_; }
+                                else if (ph == 3) { vi = -tq_ * sgd; vq = ti * sgd; }
+                            }
+                            oi[k] = vi; oq[k] = vq;
                         }
+                    }
+                    // sample 16r + 4k + ph -> phase array ph, slot XH + 4r + k: one float4 per phase
+#pragma unroll
+                    for (int ph = 0; ph < 4; ph++) {
+                        *reinterpret_cast<float4 *>(xi + ph * XP + XH + 4 * r) = make_float4(oi[ph], oi[ph + 4], oi[ph + 8], oi[ph + 12]);
+                        *reinterpret_cast<float4 *>(xq + ph * XP + XH + 4 * r) = make_float4(oq[ph], oq[ph + 4], oq[ph + 8], oq[ph + 12]);
                     }
                 }
                 __syncwarp();
@@ -449,6 +437,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 st->s2_hist_q[i] = lsb ? -vq : vq;
             }
             int clip = ls.clip;
+            ls.c1 = __shfl_sync(gmask, ls.c1, 6, 8); ls.c2 = __shfl_sync(gmask, ls.c2, 6, 8);
             clip |= __shfl_xor_sync(gmask, clip, 1, 8); clip |= __shfl_xor_sync(gmask, clip, 2, 8); clip |= __shfl_xor_sync(gmask, clip, 4, 8);
             if (r == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
