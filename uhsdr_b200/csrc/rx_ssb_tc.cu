@@ -44,7 +44,7 @@ constexpr int XH = 24;
 constexpr int XCH = 2 * 4 * XP + 4;
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
-constexpr int RING = 64;           // AGC delay ring slots
+constexpr int LR = 5 * ND;          // rows of the lattice-output ring (decimated samples)
 constexpr int AG = 4;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
 constexpr int NWARP_FIR = FG / 4;
 constexpr int DEC_PAD = 32;        // FusedCoefs::dec carries the 83 taps at [32, 115)
@@ -71,10 +71,9 @@ struct Smem {
     alignas(128) unsigned char g[4][G_BYTES];         // Toeplitz tables: hil_i c1, c2, hil_q c1, c2
     alignas(16) float x[FG * XCH];                    // decimator staging, polyphase layout
     float aud[2][ND * SMS];
-    float lat[2][ND * SMS];
-    float agc[2][ND * SMS];
+    float lat[LR * SMS];              // lattice output, a ring of 5 steps: AGC detector and gain stage read x[n-49] from it
+    float agc[2][ND * SMS];           // AGC "volts" per sample (detector -> gain stage)
     float bq[2][ND * SMS];
-    float agc_ring[RING * SMS];
     float smax[2][ND * SMS];
     alignas(8) unsigned long long mma_bar[2];
     unsigned tmem_base;
@@ -520,7 +519,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             const int c = t - IT_LAT;
             if (c >= 0 && c < nsteps) {
                 const float *in = sm.aud[c & 1];
-                float *out = sm.lat[c & 1];
+                float *out = sm.lat + (c % 5) * ND * SMS;
 #pragma unroll 1
                 for (int i0 = 0; i0 < ND; i0 += 8) {
                     // the 8 inputs first: their shared-memory latency is paid once, not once per sample
@@ -558,18 +557,21 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
     }
 
     if (warp == W_AGC) {
-        // ---- WDSP AGC (audio_agc.c:349-595), mono, 12 ksps: 49-sample look-ahead ----
+        // ---- WDSP AGC (audio_agc.c:349-595), mono, 12 ksps, 49-sample look-ahead: the detector.  It turns the lattice
+        // output x[n] (and the delayed sample x[n-49] for the back-averages) into the control voltage "volts" per
+        // sample; the gain law and the multiplication of x[n-49] run one pipeline stage later (BQ warp).
         const AgcP ap = p.agc;
         AgcRun ar = { 0, 0, st->agc_ring_max, st->agc_volts, st->agc_save_volts, st->agc_fast_backaverage,
                       st->agc_hang_backaverage, st->agc_hang_counter, st->agc_decay_type, st->agc_state,
                       st->agc_action, st->agc_hang_action };
-        float *ringp = sm.agc_ring;
+        float *latp = sm.lat + g;
+        // history x[-49..-1] from the 192-slot state ring -> rows of steps -1 and -2 of the lattice-output ring
         const int in_index = st->agc_in_index;
         if (active) {
             for (int kk = 1; kk <= AGC_W; kk++) {
                 int idx = in_index - (kk - 1);
                 idx %= AGC_RB; if (idx < 0) idx += AGC_RB;
-                ringp[((RING - kk) & (RING - 1)) * SMS + g] = st->agc_ring[idx];
+                latp[(LR - kk) * SMS] = st->agc_ring[idx];
             }
         }
         // Sliding maximum of |x| over the newest 49 samples (audio_agc.c:409-429 rescans on demand): van Herk /
@@ -578,130 +580,111 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
         if (active) {
             float m = 0.0f;
             for (int o = ND - 1; o >= 0; o--) {
-                m = fmaxf(m, fabsf(ringp[((RING - (ND - o)) & (RING - 1)) * SMS + g]));
+                m = fmaxf(m, fabsf(latp[(LR - ND + o) * SMS]));
                 sm.smax[s1][o * SMS + g] = m;
             }
             m = 0.0f;
             for (int o = ND - 1; o >= 16; o--) {
-                m = fmaxf(m, fabsf(ringp[((RING - (2 * ND - o)) & (RING - 1)) * SMS + g]));
+                m = fmaxf(m, fabsf(latp[(LR - 2 * ND + o) * SMS]));
                 sm.smax[s2][o * SMS + g] = m;
             }
         }
-        int wp = 0;          // ring slot of the first sample of the next group (multiple of AG)
+        __syncwarp();
         const bool any_hang = __any_sync(0xffffffffu, active && (ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0));
         for (int t = 0; t < niter; t++) {
             const int c = t - IT_AGC;
-            if (c >= 0 && c < nsteps && active) {
-                const float *in = sm.lat[c & 1] + g;
+            if (c >= 0 && c < nsteps && active && ap.mode != 5) {
+                const int row0 = (c % 5) * ND;                  // ring row of the first sample of this step
+                const float *in = latp + row0 * SMS;
                 float *out = sm.agc[c & 1] + g;
-                if (ap.mode == 5) {
-                    for (int i = 0; i < ND; i++) out[i * SMS] = __fmul_rn(in[i * SMS], ap.fixed_gain);   // AGC off (audio_agc.c:354-365)
-                } else {
-                    const float *S1 = sm.smax[s1] + g, *S2 = sm.smax[s2] + g;
-                    const float mprev = S1[0];
-                    float pmax = 0.0f;
+                const float *S1 = sm.smax[s1] + g, *S2 = sm.smax[s2] + g;
+                const float mprev = S1[0];
+                float pmax = 0.0f;
 #pragma unroll 1
-                    for (int k8 = 0; k8 < ND; k8 += AG) {
-                        // all operands of the AG samples first.  The delayed sample x[n-49] of group element j sits at ring
-                        // slot wp + j - 49: j = 0 -> (wp - 48 - AG) + (AG - 1), j >= 1 -> (wp - 48) + (j - 1); no wrap inside a group.
-                        const float *dA = ringp + ((wp - 48 - AG) & (RING - 1)) * SMS + g;
-                        const float *dB = ringp + ((wp - 48) & (RING - 1)) * SMS + g;
-                        float *wr = ringp + wp * SMS + g;
-                        const bool two = k8 < 16;                   // window still reaches into the chunk before the previous one
-                        const float *pc = two ? S2 + (16 + k8) * SMS : S1 + (k8 - 16) * SMS;
-                        const float *pin = in + k8 * SMS;
-                        float x[AG], dly[AG], cmx[AG], vv[AG];
+                for (int k8 = 0; k8 < ND; k8 += AG) {
+                    // all operands of the AG samples first.  The delayed sample x[n-49] of group element j sits at ring
+                    // row (row0 + k8 + j - 49) mod LR; a group wraps at most between its first and second element.
+                    int ra = row0 + k8 - AGC_W; if (ra < 0) ra += LR;
+                    int rb = ra + 1; if (rb >= LR) rb -= LR;
+                    const float *dA = latp + ra * SMS, *dB = latp + rb * SMS;
+                    const bool two = k8 < 16;                   // window still reaches into the chunk before the previous one
+                    const float *pc = two ? S2 + (16 + k8) * SMS : S1 + (k8 - 16) * SMS;
+                    const float *pin = in + k8 * SMS;
+                    float x[AG], dly[AG], cmx[AG];
 #pragma unroll
-                        for (int j = 0; j < AG; j++) {
-                            x[j] = pin[j * SMS];
-                            dly[j] = (j == 0) ? dA[(AG - 1) * SMS] : dB[(j - 1) * SMS];
-                            const float sfx = pc[j * SMS];
-                            cmx[j] = two ? fmaxf(mprev, sfx) : sfx;
-                        }
+                    for (int j = 0; j < AG; j++) {
+                        x[j] = pin[j * SMS];
+                        dly[j] = (j == 0) ? dA[0] : dB[(j - 1) * SMS];
+                        const float sfx = pc[j * SMS];
+                        cmx[j] = two ? fmaxf(mprev, sfx) : sfx;
+                    }
 #pragma unroll
-                        for (int j = 0; j < AG; j++) {
-                            const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
-                            pmax = fmaxf(pmax, abs_in);
-                            ar.fast_backaverage = fmaf(ap.fast_backmult, abs_out, __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
-                            ar.hang_backaverage = fmaf(ap.hang_backmult, abs_out, __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
-                            ar.ring_max = fmaxf(pmax, cmx[j]);
-                            const float dv = __fsub_rn(ar.ring_max, ar.volts);
-                            const bool attack = ar.ring_max >= ar.volts;
-                            float mult_sel = ap.attack_mult;
-                            bool upd = true;
-                            int nstate = ar.state;
-                            if (!any_hang) {
-                                const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
-                                                                  : ((ar.state == 1) && (ar.volts > ar.save_volts));
-                                if (attack && ar.state >= 2) ar.save_volts = ar.volts;
-                                mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
-                                nstate = attack ? 0 : (fast ? 1 : 3);
+                    for (int j = 0; j < AG; j++) {
+                        const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
+                        pmax = fmaxf(pmax, abs_in);
+                        ar.fast_backaverage = fmaf(ap.fast_backmult, abs_out, __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
+                        ar.hang_backaverage = fmaf(ap.hang_backmult, abs_out, __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
+                        ar.ring_max = fmaxf(pmax, cmx[j]);
+                        const float dv = __fsub_rn(ar.ring_max, ar.volts);
+                        const bool attack = ar.ring_max >= ar.volts;
+                        float mult_sel = ap.attack_mult;
+                        bool upd = true;
+                        int nstate = ar.state;
+                        if (!any_hang) {
+                            // hang AGC disabled on every channel of this warp (the default, ui_configuration.c:81): only
+                            // states 0 / 1 / 3 occur and the 5-state machine reduces to selects
+                            const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
+                                                              : ((ar.state == 1) && (ar.volts > ar.save_volts));
+                            if (attack && ar.state >= 2) ar.save_volts = ar.volts;
+                            mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
+                            nstate = attack ? 0 : (fast ? 1 : 3);
+                        } else {
+                            if (ar.hang_counter > 0) --ar.hang_counter;
+                            if (attack) {
+                                if (ar.state >= 2) ar.save_volts = ar.volts;
+                                nstate = 0;
                             } else {
-                                if (ar.hang_counter > 0) --ar.hang_counter;
-                                if (attack) {
-                                    if (ar.state >= 2) ar.save_volts = ar.volts;
-                                    nstate = 0;
-                                } else {
-                                    switch (ar.state) {
-                                    case 0:
-                                        if (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage)) { nstate = 1; mult_sel = ap.fast_decay_mult; }
-                                        else if (ap.hang_enable && (ar.hang_backaverage > ap.hang_level)) {
-                                            nstate = 2; ar.hang_counter = (int)__fmul_rn(ap.hangtime, ap.sample_rate); ar.decay_type = 1; upd = false;
-                                        } else { nstate = 3; mult_sel = ap.decay_mult; ar.decay_type = 0; }
-                                        break;
-                                    case 1:
-                                        if (ar.volts > ar.save_volts) mult_sel = ap.fast_decay_mult;
-                                        else if (ar.hang_counter > 0) { nstate = 2; upd = false; }
-                                        else if (ar.decay_type == 0) { nstate = 3; mult_sel = ap.decay_mult; }
-                                        else { nstate = 4; mult_sel = ap.hang_decay_mult; }
-                                        break;
-                                    case 2:
-                                        if (ar.hang_counter == 0) { nstate = 4; mult_sel = ap.hang_decay_mult; } else upd = false;
-                                        break;
-                                    case 3: mult_sel = ap.decay_mult; break;
-                                    default: mult_sel = ap.hang_decay_mult; break;
-                                    }
+                                switch (ar.state) {
+                                case 0:
+                                    if (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage)) { nstate = 1; mult_sel = ap.fast_decay_mult; }
+                                    else if (ap.hang_enable && (ar.hang_backaverage > ap.hang_level)) {
+                                        nstate = 2; ar.hang_counter = (int)__fmul_rn(ap.hangtime, ap.sample_rate); ar.decay_type = 1; upd = false;
+                                    } else { nstate = 3; mult_sel = ap.decay_mult; ar.decay_type = 0; }
+                                    break;
+                                case 1:
+                                    if (ar.volts > ar.save_volts) mult_sel = ap.fast_decay_mult;
+                                    else if (ar.hang_counter > 0) { nstate = 2; upd = false; }
+                                    else if (ar.decay_type == 0) { nstate = 3; mult_sel = ap.decay_mult; }
+                                    else { nstate = 4; mult_sel = ap.hang_decay_mult; }
+                                    break;
+                                case 2:
+                                    if (ar.hang_counter == 0) { nstate = 4; mult_sel = ap.hang_decay_mult; } else upd = false;
+                                    break;
+                                case 3: mult_sel = ap.decay_mult; break;
+                                default: mult_sel = ap.hang_decay_mult; break;
                                 }
                             }
-                            ar.state = nstate;
-                            if (upd) ar.volts = fmaf(dv, mult_sel, ar.volts);
-                            if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
-                            vv[j] = ar.volts;
                         }
-#pragma unroll
-                        for (int j = 0; j < AG; j++) {
-                            // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
-                            // operations, the cubic in Horner form
-                            const unsigned ub = __float_as_uint(__fmul_rn(ap.inv_max_input, vv[j]));
-                            const float F = __uint_as_float((ub & 0x007fffffu) | 0x3f000000u);      // frexpf mantissa in [0.5, 1)
-                            const float E = (float)((int)(ub >> 23) - 126);
-                            float Y = fmaf(1.23149591368684f, F, -4.11852516267426f);
-                            Y = fmaf(Y, F, 6.02197014179219f);
-                            Y = fmaf(Y, F, -3.13396450166353f);
-                            float vo = __fmul_rn(__fadd_rn(Y, E), 0.3010299956639812f);
-                            vo = fminf(vo, 0.0f);
-                            const float mult = __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), vv[j]);
-                            out[(k8 + j) * SMS] = __fmul_rn(dly[j], mult);
-                            wr[j * SMS] = x[j];
-                        }
-                        wp = (wp + AG) & (RING - 1);
+                        ar.state = nstate;
+                        if (upd) ar.volts = fmaf(dv, mult_sel, ar.volts);
+                        if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
+                        out[(k8 + j) * SMS] = ar.volts;
                     }
-                    ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
-                    {
-                        // suffix maxima of this step replace those of the step before the previous one; roles rotate
-                        float *Sn = sm.smax[s2] + g;
-                        const float *rb = ringp + ((wp - ND) & (RING - 1)) * SMS + g;       // the 32 newest samples: no wrap (wp is a multiple of 32 here)
-                        float m = 0.0f;
+                }
+                ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
+                {
+                    // suffix maxima of this step replace those of the step before the previous one; roles rotate
+                    float *Sn = sm.smax[s2] + g;
+                    float m = 0.0f;
 #pragma unroll 1
-                        for (int o8 = ND - 8; o8 >= 0; o8 -= 8) {
-                            float rv[8];
+                    for (int o8 = ND - 8; o8 >= 0; o8 -= 8) {
+                        float rv[8];
 #pragma unroll
-                            for (int j = 0; j < 8; j++) rv[j] = rb[(o8 + j) * SMS];
+                        for (int j = 0; j < 8; j++) rv[j] = in[(o8 + j) * SMS];
 #pragma unroll
-                            for (int j = 7; j >= 0; j--) { m = fmaxf(m, fabsf(rv[j])); Sn[(o8 + j) * SMS] = m; }
-                        }
-                        const int tmp = s1; s1 = s2; s2 = tmp;
+                        for (int j = 7; j >= 0; j--) { m = fmaxf(m, fabsf(rv[j])); Sn[(o8 + j) * SMS] = m; }
                     }
+                    const int tmp = s1; s1 = s2; s2 = tmp;
                 }
             }
             __syncthreads();
@@ -710,10 +693,12 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             const long long T = (long long)nsteps * ND;
             int new_in = (int)(((long long)st->agc_in_index + T) % AGC_RB);
             int new_out = (int)((((long long)st->agc_out_index + T) % AGC_RB + AGC_RB) % AGC_RB);
+            const int rend = (int)(T % LR);                      // ring row one past the newest sample
             for (int kk = 1; kk <= AGC_W; kk++) {
                 int idx = new_in - (kk - 1);
                 idx %= AGC_RB; if (idx < 0) idx += AGC_RB;
-                st->agc_ring[idx] = ringp[((wp - kk) & (RING - 1)) * SMS + g];
+                int rr = rend - kk; if (rr < 0) rr += LR;
+                st->agc_ring[idx] = latp[rr * SMS];
             }
             st->agc_in_index = new_in; st->agc_out_index = new_out;
             st->agc_ring_max = ar.ring_max; st->agc_volts = ar.volts; st->agc_save_volts = ar.save_volts;
@@ -725,7 +710,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
     }
 
     if (warp == W_BQ) {
-        // ---- fixed gain (:2513-2524) and the 4-stage DF1 cascade IIR_biquad_1 (:2527) at 12 ksps.  Per stage the terms
+        // ---- AGC gain law on the delayed sample (audio_agc.c:563-570; mode 5 = fixed gain :354-365), then the
+        // fixed gain (:2513-2524) and the 4-stage DF1 cascade IIR_biquad_1 (:2527) at 12 ksps.  Per stage the terms
         // that do not depend on the newest input are summed ahead of time (t), so the sample-to-sample critical path is
         // one FMA per stage.  Stages whose coefficients are {1,0,0,0,0} on every channel of the CTA (notch / peak off:
         // the default) are skipped; their state is the last two samples that went through.
@@ -741,18 +727,42 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             tq[s] = fmaf(bc[s][3], bs[s].y1, fmaf(bc[s][1], bs[s].x1, fmaf(bc[s][2], bs[s].x2, __fmul_rn(bc[s][4], bs[s].y2))));   // same order as in the loop
         }
         const float scale_gain = p.scale_gain;
+        const AgcP ap = p.agc;
+        const bool agc_off = ap.mode == 5;
+        const float *latp = sm.lat + g;
         float xl1 = 0.0f, xl2 = 0.0f;        // the last two cascade inputs (state of skipped leading stages)
         // one step of 32 samples with the skipped stages known at compile time
-        auto run_step = [&](auto maskc, const float *in, float *out) {
+        auto run_step = [&](auto maskc, const float *in, float *out, int row0) {
             constexpr unsigned MASK = decltype(maskc)::value;
 #pragma unroll 1
             for (int i0 = 0; i0 < ND; i0 += 8) {
-                float xv[8];
+                // volts of the 8 samples and the delayed samples x[n-49] (AGC off: the current samples x[n])
+                int ra = row0 + i0 - (agc_off ? 0 : AGC_W); if (ra < 0) ra += LR;
+                int rb = ra + 1; if (rb >= LR) rb -= LR;
+                const float *dA = latp + ra * SMS, *dB = latp + rb * SMS;
+                float xv[8], vv[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) xv[i] = in[(i0 + i) * SMS];
+                for (int i = 0; i < 8; i++) { vv[i] = in[(i0 + i) * SMS]; xv[i] = (i == 0) ? dA[0] : dB[(i - 1) * SMS]; }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
+                    // operations, the cubic in Horner form
+                    const unsigned ub = __float_as_uint(__fmul_rn(ap.inv_max_input, vv[i]));
+                    const float F = __uint_as_float((ub & 0x007fffffu) | 0x3f000000u);      // frexpf mantissa in [0.5, 1)
+                    const float E = (float)((int)(ub >> 23) - 126);
+                    float Y = fmaf(1.23149591368684f, F, -4.11852516267426f);
+                    Y = fmaf(Y, F, 6.02197014179219f);
+                    Y = fmaf(Y, F, -3.13396450166353f);
+                    float vo = __fmul_rn(__fadd_rn(Y, E), 0.3010299956639812f);
+                    vo = fminf(vo, 0.0f);
+                    const float mult = agc_off ? ap.fixed_gain : __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), vv[i]);
+                    xv[i] = __fmul_rn(xv[i], mult);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     float x = __fmul_rn(xv[i], scale_gain);
+                    if (i == 6) xl2 = x;
+                    if (i == 7) xl1 = x;
 #pragma unroll
                     for (int s = 0; s < 4; s++) {
                         if (!(MASK & (1u << s))) {
@@ -775,9 +785,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
             if (c >= 0 && c < nsteps && active) {
                 const float *in = sm.agc[c & 1] + g;
                 float *out = sm.bq[c & 1] + g;
-                if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out);
-                else run_step(std::integral_constant<unsigned, 0u>{}, in, out);
-                xl1 = __fmul_rn(in[(ND - 1) * SMS], scale_gain); xl2 = __fmul_rn(in[(ND - 2) * SMS], scale_gain);
+                if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out, (c % 5) * ND);
+                else run_step(std::integral_constant<unsigned, 0u>{}, in, out, (c % 5) * ND);
             }
             __syncthreads();
         }
