@@ -270,7 +270,9 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     if (!e->h_list_fused.empty()) {
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
-        if (nblocks % 4 == 0 && e->use_tc) CK(e, launch_rx_ssb_tc(a, e->fused_coefs, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
+        // the tensor-core kernel stores 32-byte vectors; rows are nblocks*256 bytes apart, so only the base matters
+        const bool tc_ok = e->use_tc && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 16 == 0) && (chan_stride % 4 == 0);
+        if (nblocks % 4 == 0 && tc_ok) CK(e, launch_rx_ssb_tc(a, e->fused_coefs, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
         else if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
         else CK(e, launch_rx_generic(a, stream));
         e->launches++;

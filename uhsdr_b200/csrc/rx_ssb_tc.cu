@@ -45,7 +45,7 @@ constexpr int XCH = 2 * 4 * XP + 4;
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int LR = 5 * ND;          // rows of the lattice-output ring (decimated samples)
-constexpr int AG = 4;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
+constexpr int AG = 8;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
 constexpr int NWARP_FIR = FG / 4;
 constexpr int DEC_PAD = 32;        // FusedCoefs::dec carries the 83 taps at [32, 115)
 // tensor-core Hilbert
@@ -148,16 +148,21 @@ __device__ __forceinline__ void decimate4(const float *xp, int m0, const FusedCo
 {
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[j] = 0.0f;
+    float4 v[2][4];                       // the loads of group q + 1 are issued before the FMAs of group q
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) v[0][ph] = lds128(xp + ph * XP + m0);
     static_for<0, 7>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        float4 v[4];
+        if constexpr (q < 6) {
 #pragma unroll
-        for (int ph = 0; ph < 4; ph++) v[ph] = lds128(xp + ph * XP + m0 + 4 * q);
+            for (int ph = 0; ph < 4; ph++) v[(q + 1) & 1][ph] = lds128(xp + ph * XP + m0 + 4 * (q + 1));
+        }
         static_for<0, 4>([&](auto ec) {
             constexpr int e = decltype(ec)::value;
             static_for<0, 4>([&](auto pc) {
                 constexpr int ph = decltype(pc)::value;
-                const float x = (e == 0) ? v[ph].x : (e == 1) ? v[ph].y : (e == 2) ? v[ph].z : v[ph].w;
+                const float4 vv = v[q & 1][ph];
+                const float x = (e == 0) ? vv.x : (e == 1) ? vv.y : (e == 2) ? vv.z : vv.w;
                 static_for<0, 4>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     constexpr int K = 16 * q + 4 * (e - j) + ph - 14;
@@ -322,10 +327,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                         // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
                         float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                         const float kE = 0.003f * 0.03125f * kS;
+                        float bs1[4], bs2[4], bs3[4];           // all twelve broadcasts in flight before the recurrence uses them
 #pragma unroll
                         for (int b = 0; b < 4; b++) {
-                            const float b1 = __shfl_sync(0xffffffffu, s1, 2 * b, 8), b2 = __shfl_sync(0xffffffffu, s2, 2 * b, 8), b3 = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
-                            t1 = fmaf(0.997f, t1, -kE * b1); t2 = fmaf(0.997f, t2, kE * b2); t3 = fmaf(0.997f, t3, kE * b3);
+                            bs1[b] = __shfl_sync(0xffffffffu, s1, 2 * b, 8); bs2[b] = __shfl_sync(0xffffffffu, s2, 2 * b, 8); bs3[b] = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
                             if ((r >> 1) == b) { m1 = t1; m2 = t2; m3 = t3; }
                         }
                         const float den = m2 * m2;
@@ -600,6 +609,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                 const float *S1 = sm.smax[s1] + g, *S2 = sm.smax[s2] + g;
                 const float mprev = S1[0];
                 float pmax = 0.0f;
+                auto detect = [&](auto hangc) {
+                    constexpr bool HANG = decltype(hangc)::value;
 #pragma unroll 1
                 for (int k8 = 0; k8 < ND; k8 += AG) {
                     // all operands of the AG samples first.  The delayed sample x[n-49] of group element j sits at ring
@@ -630,7 +641,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                         float mult_sel = ap.attack_mult;
                         bool upd = true;
                         int nstate = ar.state;
-                        if (!any_hang) {
+                        if constexpr (!HANG) {
                             // hang AGC disabled on every channel of this warp (the default, ui_configuration.c:81): only
                             // states 0 / 1 / 3 occur and the 5-state machine reduces to selects
                             const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
@@ -671,6 +682,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                         out[(k8 + j) * SMS] = ar.volts;
                     }
                 }
+                };
+                if (any_hang) detect(std::true_type{}); else detect(std::false_type{});
                 ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
                 {
                     // suffix maxima of this step replace those of the step before the previous one; roles rotate
@@ -893,8 +906,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
                     const int pos = 4 * h + i;
                     const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)) & mm, w1 = format_audio_word(__fmul_rn(o[1], 10.0f)) & mm;   // LINE_OUT_SCALING_FACTOR (:2860)
                     const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
-                    d4[2 * pos] = make_int4(w0, w0, w1, w1);
-                    d4[2 * pos + 1] = make_int4(w2, w2, w3, w3);
+                    // the four output samples {l, r} x 4 = 32 bytes: one 256-bit store (STG.E.ENL2.256)
+                    asm volatile("st.global.v8.b32 [%0], {%1, %1, %2, %2, %3, %3, %4, %4};" ::"l"(d4 + 2 * pos), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
                     if (df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
                                             : make_float4(__fmul_rn(o[0], 10.0f), __fmul_rn(o[1], 10.0f), __fmul_rn(o[2], 10.0f), __fmul_rn(o[3], 10.0f));
                 }
