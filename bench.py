@@ -47,6 +47,16 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def measured_traffic():
+    """DRAM bytes per channel-sample of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except OSError:
+        return None
+
+
 def channel_cfg(ch: int):
     from uhsdr_b200.config import DEMOD_LSB, DEMOD_USB, default_cfg
     return default_cfg(dmod_mode=DEMOD_USB, filter_path=35) if ch % 2 == 0 else default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
@@ -362,6 +372,9 @@ def gpu_arm(args):
         per_gpu_samples = nch * ns
         achieved_gbs = per_gpu_samples * BYTES_PER_SAMPLE / (ms_per_step * 1e-3) / 1e9
         achieved_tf = per_gpu_samples * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12
+        tr = measured_traffic()
+        launch_samples = per_gpu_samples / max(1, launches / args.steps)
+        traffic = tr["dram_bytes_per_channel_sample"] * launch_samples if tr else None
         line = {
             "metric": "channel-samples/s, full SSB RX chain", "value": value, "unit": "channel-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -371,11 +384,14 @@ def gpu_arm(args):
                        "channels_per_gpu": nch, "blocks_per_step": T, "parallelism": f"channels sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2 ({2 * io_bytes / 2**20:.0f} MiB streamed per step)"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
-                         "kernel_ms_per_launch": launch_ms,
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
+                         "kernel": "rx_ssb_tc_kernel", "kernel_ms_per_launch": launch_ms,
+                         "algorithmic_bytes_per_launch": launch_samples * BYTES_PER_SAMPLE,
+                         "traffic_source": tr["source"] if tr else None,
                          "fp32": {"achieved_tflops": achieved_tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
                                   "frac": achieved_tf / FP32_PEAK_TFLOPS_NOMINAL, "flop_per_channel_sample": FLOP_PER_SAMPLE,
-                                  "note": "FP32 FMA pipe is the binding roof of the fused chain (SURVEY.md 8d); peak = 148 SM x 128 lanes x 2 x 1.965 GHz"}},
+                                  "note": "direct-form FLOP count of the chain (SURVEY.md 8d) against the FP32 FMA pipe, 148 SM x 128 lanes x 2 x 1.965 GHz; "
+                                          "199 of the 346 FLOP (the Hilbert pair) run on the tensor cores as a bf16-split Toeplitz GEMM"}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "channel-samples/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "parity": parity,

@@ -1,0 +1,98 @@
+"""GPU parity tests for the kernel-selection logic of the shipping build: the tensor-core fused kernel
+(rx_ssb_tc.cu, the default for narrow SSB/CW), the CUDA-core fused kernel (rx_ssb_fused.cu, used when
+UHSDR_B200_NO_TC=1 or the output buffer is not 32-byte aligned) and the general kernel (call sizes that
+are not a multiple of 4 blocks).  Every variant must meet north_star's tolerance against the oracle, and
+a channel may move between them from call to call (the state records are shared)."""
+import numpy as np
+import pytest
+
+from cases import RX_CASES
+from conftest import oracle_channel
+from test_rx_parity_gpu import check_tolerance, run_engine_float
+from uhsdr_b200 import synth
+from uhsdr_b200.config import DEMOD_LSB, default_cfg
+from uhsdr_b200.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+FUSED_LABELS = ["usb_p35", "lsb_p38", "usb_p44_antialias", "cw_p8", "usb_agc_fast_hang", "usb_notch_peak_eq", "usb_manual_iq", "usb_agc_off"]
+CASES = [c for c in RX_CASES if c[0] in FUSED_LABELS]
+
+
+@pytest.mark.parametrize("label,kw,nblocks", CASES, ids=[c[0] for c in CASES])
+def test_cuda_core_fused_kernel_within_tolerance(built, monkeypatch, label, kw, nblocks):
+    monkeypatch.setenv("UHSDR_B200_NO_TC", "1")          # read at engine creation
+    cfg = default_cfg(**kw)
+    nb = 4 * nblocks
+    iq = np.stack([synth.rx_iq(cfg, 200 + c, nb * 32, seed=44) for c in range(3)])
+    with Engine(3) as eng:
+        eng.configure(cfg)
+        words, fl = run_engine_float(eng, iq)
+    for c in range(3):
+        with oracle_channel(cfg) as o:
+            want_w, want_f = o.rx(iq[c])
+        check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
+
+
+def test_tensor_core_and_cuda_core_kernels_agree(built, monkeypatch):
+    """Same inputs through both fused kernels: the float audio agrees to ~1e-5 of the peak."""
+    import torch
+    cfg_u, cfg_l = default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
+    nch, nb = 56, 128
+    iq = np.stack([synth.rx_iq(cfg_u if c % 2 == 0 else cfg_l, c, nb * 32, seed=9) for c in range(nch)])
+    outs = []
+    for no_tc in ("0", "1"):
+        monkeypatch.setenv("UHSDR_B200_NO_TC", no_tc)
+        with Engine(nch) as eng:
+            eng.configure(cfg_u, first=0, stride=2)
+            eng.configure(cfg_l, first=1, stride=2)
+            outs.append(run_engine_float(eng, iq)[1].astype(np.float64))
+    err = np.abs(outs[0] - outs[1]).max() / np.abs(outs[1]).max()
+    assert err < 5e-5, err
+    assert np.isfinite(outs[0]).all()
+
+
+def test_state_carries_between_kernels(built):
+    """32 blocks (tensor-core kernel), 5 blocks (general kernel: not a multiple of 4), 27 blocks (general),
+    64 blocks (tensor-core kernel again) on the same channels == one oracle run of 128 blocks."""
+    cfg = default_cfg()
+    nch, nb = 4, 128
+    iq = np.stack([synth.rx_iq(cfg, 300 + c, nb * 32, seed=45) for c in range(nch)])
+    parts_w, parts_f = [], []
+    with Engine(nch) as eng:
+        eng.configure(cfg)
+        b0 = 0
+        for n in (32, 5, 27, 64):
+            w, f = run_engine_float(eng, iq[:, b0 * 32:(b0 + n) * 32])
+            parts_w.append(w); parts_f.append(f)
+            b0 += n
+    words, fl = np.concatenate(parts_w, axis=1), np.concatenate(parts_f, axis=1)
+    for c in range(nch):
+        with oracle_channel(cfg) as o:
+            want_w, want_f = o.rx(iq[c])
+        check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"mixed-kernels/ch{c}")
+
+
+def test_unaligned_output_buffer_takes_the_cuda_core_kernel(built):
+    """The tensor-core kernel stores 32-byte vectors; an output buffer that is only 16-byte aligned must still
+    give correct results (engine falls back to the CUDA-core fused kernel)."""
+    import torch
+    cfg = default_cfg()
+    nch, nb = 2, 64
+    iq = np.stack([synth.rx_iq(cfg, 400 + c, nb * 32, seed=46) for c in range(nch)])
+    dev = torch.device("cuda", 0)
+    d_iq = torch.from_numpy(iq).to(dev)
+    raw = torch.empty(nch * nb * 32 * 2 + 4, dtype=torch.int32, device=dev)
+    d_out = raw[4:].view(nch, nb * 32, 2)                    # base + 16 bytes
+    assert d_out.data_ptr() % 32 == 16
+    with Engine(nch) as eng:
+        eng.configure(cfg)
+        eng.rx_device(d_iq, d_out, nb)
+        eng.sync()
+    got = d_out.cpu().numpy()
+    for c in range(nch):
+        with oracle_channel(cfg) as o:
+            want_w, _ = o.rx(iq[c])
+        diff = (got[c, :, 0].astype(np.int64) >> 16) - (want_w[:, 0].astype(np.int64) >> 16)
+        assert np.max(np.abs(diff)) <= 1
+        assert np.array_equal(got[c, :, 0], got[c, :, 1])
