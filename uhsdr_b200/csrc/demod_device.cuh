@@ -1,4 +1,5 @@
-// demod_device.cuh -- sample-serial demodulators (run by one lane per channel).
+// demod_device.cuh -- sample-serial demodulators (run by one lane per channel).  The state type is a template
+// parameter: ChanState (general kernel, state staged in shared memory) or SerState (rx_serial.cu, per-thread copy).
 #pragma once
 #include "dsp_device.cuh"
 #include "uhsdr_b200.h"
@@ -6,7 +7,8 @@
 namespace uhsdr {
 
 // AudioDriver_FadeLeveler, audio_driver.c:1911-1923
-__device__ __forceinline__ float fade_leveler(const ChanParams &p, ChanState &st, float audio, float corr)
+template <class S>
+__device__ __forceinline__ float fade_leveler(const ChanParams &p, S &st, float audio, float corr)
 {
     st.fade_dc27 = __fadd_rn(__fmul_rn(p.sam_mtauR, st.fade_dc27), __fmul_rn(p.sam_onem_mtauR, audio));
     st.fade_dc_insert = __fadd_rn(__fmul_rn(p.sam_mtauI, st.fade_dc_insert), __fmul_rn(p.sam_onem_mtauI, corr));
@@ -16,7 +18,8 @@ __device__ __forceinline__ float fade_leveler(const ChanParams &p, ChanState &st
 // AudioDriver_DemodSAM, audio_driver.c:1990-2166, for nb blocks of n_per_blk decimated samples.
 // AM: envelope sqrt(i^2+q^2) (+ fade leveler).  SAM: NCO, phase detector, optional sideband
 // selection through two 7-stage all-pass networks, 2nd-order loop filter.
-__device__ inline void demod_am_sam(const ChanParams &p, ChanState &st, const float *__restrict__ pool,
+template <class S>
+__device__ inline void demod_am_sam(const ChanParams &p, S &st, const float *__restrict__ pool,
                                     const float *ib, const float *qb, float *a, int nb, int n_per_blk)
 {
     const float sampleRate = (float)p.decimated_freq;
@@ -89,7 +92,8 @@ __device__ inline void demod_am_sam(const ChanParams &p, ChanState &st, const fl
 
 // AudioDriver_DemodFM, audio_driver.c:1544-1737 (no subaudible-tone detection), nb blocks at
 // 48 ksps.  Returns a bit mask: bit b set = block b un-squelched (signal_active).
-__device__ inline int demod_fm(const ChanParams &p, ChanState &st, const float *__restrict__ pool,
+template <class S>
+__device__ inline int demod_fm(const ChanParams &p, S &st, const float *__restrict__ pool,
                                const float *ib, const float *qb, float *a, int nb)
 {
     int mask = 0;

@@ -37,8 +37,12 @@ struct uhsdr_engine {
     std::vector<int> h_tx_enabled;
     // dispatch lists (rebuilt after configure)
     bool lists_dirty = true;
-    std::vector<int> h_list_fused, h_list_generic;
-    int *d_list_fused = nullptr, *d_list_generic = nullptr;
+    std::vector<int> h_list_fused, h_list_generic, h_list_split;
+    int *d_list_fused = nullptr, *d_list_generic = nullptr, *d_list_split = nullptr;
+    int split_floats_per_block = 0;      // scratch floats per block and channel of the split path
+    float *d_scratch = nullptr;
+    size_t d_scratch_bytes = 0;
+    int use_split = 1;       // general path as front (FIR) kernel + thread-per-channel serial kernel
     FusedCoefs fused_coefs;
     bool fused_coefs_valid = false;
     int fused_s1_ci = -1, fused_s2_ci = -1, fused_s2_cq = -1;
@@ -107,7 +111,7 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec);
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
-    cudaFree(e->d_list_fused); cudaFree(e->d_list_generic);
+    cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_scratch);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
     for (auto &v : e->ev_in) if (v) cudaEventDestroy(v);
     for (auto &v : e->ev_k) if (v) cudaEventDestroy(v);
@@ -139,6 +143,8 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (!e->tables.load(tables, tables_bytes, &err)) { g_create_error = err; delete e; return UHSDR_ERR_TABLES; }
     const char *nf = getenv("UHSDR_B200_NO_FUSED");
     if (nf && nf[0] == '1') e->use_fused = 0;
+    const char *ns = getenv("UHSDR_B200_NO_SPLIT");
+    if (ns && ns[0] == '1') e->use_split = 0;
     const char *nt = getenv("UHSDR_B200_NO_TC");
     if ((nt && nt[0] == '1') || !rx_ssb_tc_available()) e->use_tc = 0;
     auto fail = [&](const char *what, cudaError_t er) {
@@ -162,6 +168,7 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if ((er = cudaMemset(e->d_state, 0, n * sizeof(ChanState))) != cudaSuccess) return fail("cudaMemset state", er);
     if ((er = cudaMalloc(&e->d_list_fused, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_generic, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_list_split, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     e->h_params.assign(n, ChanParams{});
     e->h_tx_enabled.assign(n, 0);
     *out = e;
@@ -234,8 +241,9 @@ int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg
 // fused kernel (rx_ssb_fused.cu); everything else runs on the general kernel.
 static int rebuild_lists(uhsdr_engine *e)
 {
-    e->h_list_fused.clear(); e->h_list_generic.clear();
+    e->h_list_fused.clear(); e->h_list_generic.clear(); e->h_list_split.clear();
     e->fused_s1_ci = -1;
+    e->split_floats_per_block = 0;
     for (int c = 0; c < e->nch; c++) {
         const ChanParams &p = e->h_params[c];
         if (!p.configured) { e->last_error = "rx/tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
@@ -244,8 +252,15 @@ static int rebuild_lists(uhsdr_engine *e)
             if (e->fused_s1_ci < 0) { e->fused_s1_ci = p.s1_ci; e->fused_s2_ci = p.s2_ci; e->fused_s2_cq = p.s2_cq; }
             else if (p.s1_ci != e->fused_s1_ci || p.s2_ci != e->fused_s2_ci || p.s2_cq != e->fused_s2_cq) fused = false;
         }
-        (fused ? e->h_list_fused : e->h_list_generic).push_back(c);
+        if (fused) e->h_list_fused.push_back(c);
+        else if (e->use_split && !p.nr_enable) {
+            // everything but the spectral noise reduction (warp-cooperative FFT frames) runs on the split path
+            e->h_list_split.push_back(c);
+            e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));
+        } else e->h_list_generic.push_back(c);
     }
+    if (!e->h_list_split.empty())
+        CK(e, cudaMemcpyAsync(e->d_list_split, e->h_list_split.data(), e->h_list_split.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     if (!e->h_list_fused.empty()) {
         CK(e, cudaMemcpyAsync(e->d_list_fused, e->h_list_fused.data(), e->h_list_fused.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
         const float *pool = e->tables.pool.data();
@@ -266,7 +281,7 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     RxArgs a;
     a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
     a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
-    a.chan_stride = chan_stride; a.mute_stride = mute_stride;
+    a.chan_stride = chan_stride; a.mute_stride = mute_stride; a.scratch = nullptr; a.scratch_stride = 0;
     if (!e->h_list_fused.empty()) {
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
@@ -281,6 +296,21 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         a.chan_list = e->d_list_generic; a.num_items = (int)e->h_list_generic.size();
         CK(e, launch_rx_generic(a, stream));
         e->launches++;
+    }
+    if (!e->h_list_split.empty()) {
+        a.chan_list = e->d_list_split; a.num_items = (int)e->h_list_split.size();
+        a.scratch_stride = (long long)nblocks * e->split_floats_per_block;
+        const size_t need = (size_t)a.num_items * (size_t)a.scratch_stride * sizeof(float);
+        if (need > e->d_scratch_bytes) {
+            CK(e, cudaStreamSynchronize(stream));
+            cudaFree(e->d_scratch); e->d_scratch = nullptr; e->d_scratch_bytes = 0;
+            CK(e, cudaMalloc(&e->d_scratch, need));
+            e->d_scratch_bytes = need;
+        }
+        a.scratch = e->d_scratch;
+        CK(e, launch_rx_front(a, stream));
+        CK(e, launch_rx_serial(a, stream));
+        e->launches += 2;
     }
     return UHSDR_OK;
 }

@@ -22,9 +22,16 @@ struct RxArgs {
     int nblocks;
     long long chan_stride;      // samples between consecutive channels in iq / audio / audio_f (>= nblocks*32)
     long long mute_stride;      // bytes between consecutive channels in mute (>= nblocks)
+    float *scratch;             // split path: FIR-stage outputs, [num_items][scratch_stride] floats
+    long long scratch_stride;
 };
 
 cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);
+// split general path: time-parallel front end + FIR stages (one warp per channel, rx_generic.cu) into
+// a.scratch, then the sample-serial stages with one channel per thread (rx_serial.cu)
+cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream);
+cudaError_t launch_rx_serial(const RxArgs &a, cudaStream_t stream);
+int rx_split_floats_per_block(const ChanParams &p);     // scratch floats per 32-sample block and channel
 
 // fused narrow-SSB receiver (rx_ssb_fused.cu)
 bool fused_eligible(const ChanParams &p);

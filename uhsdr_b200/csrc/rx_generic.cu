@@ -59,6 +59,12 @@ __device__ __forceinline__ void shift_history(float *buf, int H, int nnew, int l
     __syncwarp();
 }
 
+// FRONT = false: the whole chain.  FRONT = true (split path): front end and FIR stages only; what the
+// sample-serial stages need goes to a.scratch, [slot][scratch_stride] floats per launch:
+//   SSB topologies   demodulated audio at the decimated rate           [nblocks * 32 / M]
+//   AM / SAM         decimated I, then decimated Q                     2 x [nblocks * 32 / M]
+//   FM               low-passed I, then Q at 48 ksps                   2 x [nblocks * 32]
+template <bool FRONT>
 __global__ void __launch_bounds__(32 * G_WARPS)
 rx_generic_kernel(RxArgs a)
 {
@@ -254,13 +260,30 @@ rx_generic_kernel(RxArgs a)
             __syncwarp();
             shift_history(w.bi, H2, ns, lane);
         } else if (p.topo == TOPO_AM_SAM) {
-            if (lane == 0) demod_am_sam(p, st, pool, w.bi + H2, w.bq + H2, w.aud, nb, ndec_blk);
+            if constexpr (!FRONT) { if (lane == 0) demod_am_sam(p, st, pool, w.bi + H2, w.bq + H2, w.aud, nb, ndec_blk); }
             __syncwarp();
         } else {   // TOPO_FM
-            if (lane == 0) signal_active_mask = demod_fm(p, st, pool, w.bi + H2, w.bq + H2, w.aud, nb);
-            signal_active_mask = __shfl_sync(0xffffffffu, signal_active_mask, 0);
+            if constexpr (!FRONT) {
+                if (lane == 0) signal_active_mask = demod_fm(p, st, pool, w.bi + H2, w.bq + H2, w.aud, nb);
+                signal_active_mask = __shfl_sync(0xffffffffu, signal_active_mask, 0);
+            }
         }
         __syncwarp();
+        if constexpr (FRONT) {
+            float *sc = a.scratch + (size_t)slot * (size_t)a.scratch_stride;
+            if (p.topo == TOPO_AM_SAM) {
+                const size_t half = (size_t)a.nblocks * ndec_blk, o = (size_t)blk0 * ndec_blk;
+                for (int m = lane; m < ndec; m += 32) { sc[o + m] = w.bi[H2 + m]; sc[half + o + m] = w.bq[H2 + m]; }
+            } else if (p.topo == TOPO_FM) {
+                const size_t half = (size_t)a.nblocks * BLK, o = (size_t)blk0 * BLK;
+                for (int n = lane; n < ns; n += 32) { sc[o + n] = w.bi[H2 + n]; sc[half + o + n] = w.bq[H2 + n]; }
+            } else {
+                const size_t o = (size_t)blk0 * ndec_blk;
+                for (int m = lane; m < ndec; m += 32) sc[o + m] = w.aud[m];
+            }
+            __syncwarp();
+            continue;
+        }
 
         // ---- audio post-processing, block by block (RxProcessor_DemodAudioPostprocessing) ----
         for (int b = 0; b < nb; b++) {
@@ -364,19 +387,35 @@ rx_generic_kernel(RxArgs a)
     }
 }
 
-cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream)
+template <bool FRONT> static cudaError_t launch_generic(const RxArgs &a, cudaStream_t stream)
 {
     static bool attr_set = false;
     const size_t smem = sizeof(WarpWork) * G_WARPS;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rx_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(rx_generic_kernel<FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int grid = (a.num_items + G_WARPS - 1) / G_WARPS;
     if (grid == 0) return cudaSuccess;
-    rx_generic_kernel<<<grid, 32 * G_WARPS, smem, stream>>>(a);
+    rx_generic_kernel<FRONT><<<grid, 32 * G_WARPS, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream) { return launch_generic<false>(a, stream); }
+
+cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream)
+{
+    if (a.scratch == nullptr || a.chan_list == nullptr) return cudaErrorInvalidValue;
+    return launch_generic<true>(a, stream);
+}
+
+// scratch floats per 32-sample block: see the layout at rx_generic_kernel
+int rx_split_floats_per_block(const ChanParams &p)
+{
+    if (p.topo == TOPO_FM) return 2 * BLK;
+    if (p.topo == TOPO_AM_SAM) return 2 * (BLK / p.M);
+    return BLK / p.M;
 }
 
 }  // namespace uhsdr

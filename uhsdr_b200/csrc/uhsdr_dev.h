@@ -118,6 +118,26 @@ struct ChanState {
     long long blocks;
 };
 
+// The sample-serial part of ChanState (same member names), the per-thread working copy of rx_serial.cu.
+struct SerState {
+    float interp_hist[INTERP_HIST];
+    float pre_s[MAX_LAT], aa_s[MAX_LAT], sql_s[MAX_LAT];
+    BiquadS bq1[4], bq2;
+    float agc_ring[AGC_RB];
+    int agc_out_index, agc_in_index;
+    float agc_ring_max, agc_volts, agc_save_volts, agc_fast_backaverage, agc_hang_backaverage;
+    int agc_hang_counter, agc_decay_type, agc_state;
+    float agc_wold;
+    int agc_action, agc_hang_action;
+    float sam_fil_out, sam_lowpass, sam_omega2, sam_phs, sam_dsI, sam_dsQ;
+    float sam_a[24], sam_b[24], sam_c[24], sam_d[24];
+    int sam_count;
+    float fade_dc27, fade_dc_insert;
+    int carrier_freq_offset;
+    float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
+    int fm_count, fm_squelched;
+};
+
 // Spectral NR state, audio_nr.c (allocated only when a channel enables DSP_NR_ENABLE)
 struct NrState {
     float bufs[4][256];      // mmb.nr_audio_buff[k]: [0..127] packed input, [128..255] processed output
