@@ -253,7 +253,7 @@ static int rebuild_lists(uhsdr_engine *e)
             else if (p.s1_ci != e->fused_s1_ci || p.s2_ci != e->fused_s2_ci || p.s2_cq != e->fused_s2_cq) fused = false;
         }
         if (fused) e->h_list_fused.push_back(c);
-        else if (e->use_split && !p.nr_enable) {
+        else if (e->use_split && rx_split_floats_per_block(p) > 0) {
             // everything but the spectral noise reduction (warp-cooperative FFT frames) runs on the split path
             e->h_list_split.push_back(c);
             e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));

@@ -410,9 +410,11 @@ cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream)
     return launch_generic<true>(a, stream);
 }
 
-// scratch floats per 32-sample block: see the layout at rx_generic_kernel
+// scratch floats per 32-sample block: see the layout at rx_generic_kernel; 0 = the chain has a shape the serial
+// kernel keeps no registers for (it stays on the general kernel)
 int rx_split_floats_per_block(const ChanParams &p)
 {
+    if (p.nr_enable || p.pre.n > 10 || (p.aa.n != 0 && p.aa.n != 6) || p.interp_plen > INTERP_HIST + 1) return 0;
     if (p.topo == TOPO_FM) return 2 * BLK;
     if (p.topo == TOPO_AM_SAM) return 2 * (BLK / p.M);
     return BLK / p.M;

@@ -54,6 +54,54 @@ __device__ __forceinline__ void store_ser(ChanState &g, const SerState &s)
 
 }  // namespace
 
+// arm_fir_interpolate_f32 (:2560-2577) for one block with the interpolation factor and the polyphase length known
+// at compile time: output n = i*L + j uses taps c[(L-1-j) + k*L] on ip[INTERP_HIST - (P-1) + i + k], k ascending.
+template <int L, int P>
+__device__ __forceinline__ void interp_block(const float *ip, const float *__restrict__ ic, float *o48)
+{
+    float c[L][P];
+#pragma unroll
+    for (int j = 0; j < L; j++)
+#pragma unroll
+        for (int k = 0; k < P; k++) c[j][k] = __ldg(ic + (L - 1 - j) + k * L);
+    float x[P];
+#pragma unroll
+    for (int k = 0; k < P - 1; k++) x[k + 1] = ip[INTERP_HIST - (P - 1) + k];
+#pragma unroll 4
+    for (int i = 0; i < BLK / L; i++) {
+#pragma unroll
+        for (int k = 0; k < P - 1; k++) x[k] = x[k + 1];
+        x[P - 1] = ip[INTERP_HIST + i];
+#pragma unroll
+        for (int j = 0; j < L; j++) {
+            float sum = 0.0f;
+#pragma unroll
+            for (int k = 0; k < P; k++) sum = mad(x[k], c[j][k], sum);
+            o48[i * L + j] = sum;
+        }
+    }
+}
+
+// arm_iir_lattice_f32 (arm_iir_lattice_f32.c:348-440) with coefficients and state in registers, NS stage slots with
+// the filter's n stages at the end: front slots have k = v = 0 and pass the sample through unchanged (bit-exact)
+template <int NS>
+__device__ __forceinline__ float lattice_regs(float x, const float (&k)[NS], const float (&v)[NS + 1], float (&s)[NS])
+{
+    float f = x, acc = 0.0f, fn = x;
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        const float g = s[j];
+        fn = __fsub_rn(f, __fmul_rn(k[j], g));
+        const float gn = __fadd_rn(__fmul_rn(fn, k[j]), g);
+        acc = __fadd_rn(acc, __fmul_rn(gn, v[j]));
+        if (j > 0) s[j - 1] = gn;
+        f = fn;
+    }
+    acc = __fadd_rn(acc, __fmul_rn(fn, v[NS]));
+    s[NS - 1] = fn;
+    return acc;
+}
+
 __global__ void __launch_bounds__(SER_THREADS)
 rx_serial_kernel(RxArgs a)
 {
@@ -75,10 +123,43 @@ rx_serial_kernel(RxArgs a)
     float *__restrict__ audio_f = a.audio_f ? a.audio_f + chan_base : nullptr;
     const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
+    // ---- coefficients and the small recurrences' state in registers ----
+    const AgcP ap = p.agc;
     AgcRun ar = { st.agc_out_index, st.agc_in_index, st.agc_ring_max, st.agc_volts, st.agc_save_volts,
                   st.agc_fast_backaverage, st.agc_hang_backaverage, st.agc_hang_counter, st.agc_decay_type,
                   st.agc_state, st.agc_action, st.agc_hang_action };
-    float ip[INTERP_HIST + BLK];                    // interpolator input: [history | decimated block]
+    float pk[10], pv[11], ps[10];                   // lattice pre-filter, front-padded to 10 stages
+    const int pn = p.pre.n, ppad = 10 - pn;
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        pk[j] = (j >= ppad) ? __ldg(pool + p.pre.k_off + (j - ppad)) : 0.0f;
+        pv[j] = (j >= ppad) ? __ldg(pool + p.pre.v_off + (j - ppad)) : 0.0f;
+        ps[j] = (j >= ppad) ? st.pre_s[j - ppad] : 0.0f;
+    }
+    pv[10] = (pn > 0) ? __ldg(pool + p.pre.v_off + pn) : 1.0f;
+    const bool aa_on = p.aa.n == 6 && !fm;
+    float ak[6], av[7], as_[6];                     // anti-alias lattice (6 stages where present)
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        ak[j] = aa_on ? __ldg(pool + p.aa.k_off + j) : 0.0f;
+        av[j] = aa_on ? __ldg(pool + p.aa.v_off + j) : 0.0f;
+        as_[j] = aa_on ? st.aa_s[j] : 0.0f;
+    }
+    av[6] = aa_on ? __ldg(pool + p.aa.v_off + 6) : 1.0f;
+    float bc[4][5], tc[5];
+    BiquadS bs[4], ts = st.bq2;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) bc[s][q] = p.bq1[s][q];
+        bs[s] = st.bq1[s];
+    }
+#pragma unroll
+    for (int q = 0; q < 5; q++) tc[q] = p.bq2[q];
+    const float scale_gain = p.scale_gain, fm_scaling = p.fm_scaling;
+    const bool remove_dc = ap.remove_dc && ap.mode != 5;
+    float agc_wold = st.agc_wold;
+    float ip[INTERP_HIST + BLK / 2];                // interpolator input: [history | decimated block]
     for (int i = 0; i < INTERP_HIST; i++) ip[i] = st.interp_hist[i];
     const int L = p.interp_L, P = p.interp_plen;
     const float *__restrict__ ic = pool + p.interp_c;
@@ -89,69 +170,93 @@ rx_serial_kernel(RxArgs a)
         // ---- demodulation ----
         if (fm) {
             float bi[BLK], bq[BLK];
-            for (int n = 0; n < BLK; n++) { bi[n] = sc[(size_t)blk * BLK + n]; bq[n] = sc[half + (size_t)blk * BLK + n]; }
+            const float4 *si = reinterpret_cast<const float4 *>(sc + (size_t)blk * BLK), *sq = reinterpret_cast<const float4 *>(sc + half + (size_t)blk * BLK);
+            for (int n = 0; n < BLK / 4; n++) {
+                const float4 vi = si[n], vq = sq[n];
+                bi[4 * n] = vi.x; bi[4 * n + 1] = vi.y; bi[4 * n + 2] = vi.z; bi[4 * n + 3] = vi.w;
+                bq[4 * n] = vq.x; bq[4 * n + 1] = vq.y; bq[4 * n + 2] = vq.z; bq[4 * n + 3] = vq.w;
+            }
             signal_active = demod_fm(p, st, pool, bi, bq, ad, 1) != 0;
         } else if (amsam) {
             float bi[BLK / 2], bq[BLK / 2];
             for (int n = 0; n < nd; n++) { bi[n] = sc[(size_t)blk * nd + n]; bq[n] = sc[half + (size_t)blk * nd + n]; }
             demod_am_sam(p, st, pool, bi, bq, ad, 1, nd);
         } else {
-            for (int n = 0; n < nd; n++) ad[n] = sc[(size_t)blk * nd + n];
+            const float4 *sa = reinterpret_cast<const float4 *>(sc + (size_t)blk * nd);
+            for (int n = 0; n < nd / 4; n++) { const float4 v = sa[n]; ad[4 * n] = v.x; ad[4 * n + 1] = v.y; ad[4 * n + 2] = v.z; ad[4 * n + 3] = v.w; }
         }
         // ---- audio post-processing (RxProcessor_DemodAudioPostprocessing) ----
         if (!fm) {
-            for (int i = 0; i < nd; i++) {
-                float x = ad[i];
-                if (p.pre.n > 0) x = lattice_step(x, st.pre_s, pool + p.pre.k_off, pool + p.pre.v_off, p.pre.n);
-                if (p.agc.mode == 5) x = __fmul_rn(x, p.agc.fixed_gain);
-                else x = agc_step(x, p.agc, ar, st.agc_ring);
-                ad[i] = x;
-            }
-            if (p.agc.remove_dc && p.agc.mode != 5) {
-                // audio_agc.c:577-594: w = x + wold*0.9999 evaluated in double
-                for (int i = 0; i < nd; i++) {
-                    const float wv = (float)((double)ad[i] + (double)st.agc_wold * 0.9999);
-                    ad[i] = __fsub_rn(wv, st.agc_wold);
-                    st.agc_wold = wv;
-                }
-            }
+            // lattice pre-filter :2473-2475, AGC :2485 (+ DC remover audio_agc.c:577-594, double expression),
             // fixed gain :2513-2524, biquad_1 :2527
             for (int i = 0; i < nd; i++) {
-                float x = __fmul_rn(ad[i], p.scale_gain);
-                for (int s = 0; s < 4; s++) x = biquad_step(x, p.bq1[s], st.bq1[s]);
+                float x = ad[i];
+                if (pn > 0) x = lattice_regs<10>(x, pk, pv, ps);
+                if (ap.mode == 5) x = __fmul_rn(x, ap.fixed_gain);
+                else x = agc_step(x, ap, ar, st.agc_ring);
+                ad[i] = x;
+            }
+            if (remove_dc) {
+                for (int i = 0; i < nd; i++) {
+                    const float wv = (float)((double)ad[i] + (double)agc_wold * 0.9999);
+                    ad[i] = __fsub_rn(wv, agc_wold);
+                    agc_wold = wv;
+                }
+            }
+            for (int i = 0; i < nd; i++) {
+                float x = __fmul_rn(ad[i], scale_gain);
+#pragma unroll
+                for (int s = 0; s < 4; s++) x = biquad_step(x, bc[s], bs[s]);
                 ip[INTERP_HIST + i] = x;
             }
-            // arm_fir_interpolate_f32 :2560-2577: output n = i*L + j uses taps c[(L-1-j) + k*L]
-            for (int n = 0; n < BLK; n++) {
-                const int i = n / L, j = n - i * L;
-                const float *x = ip + INTERP_HIST - (P - 1) + i;
-                float sum = 0.0f;
-                for (int k = 0; k < P; k++) sum = mad(x[k], __ldg(ic + (L - 1 - j) + k * L), sum);
-                o48[n] = sum;
+            if (L == 4 && P == 4) interp_block<4, 4>(ip, ic, o48);
+            else if (L == 4 && P == 1) interp_block<4, 1>(ip, ic, o48);
+            else if (L == 2 && P == 8) interp_block<2, 8>(ip, ic, o48);
+            else if (L == 2 && P == 2) interp_block<2, 2>(ip, ic, o48);
+            else {
+                for (int n = 0; n < BLK; n++) {
+                    const int i = n / L, j = n - i * L;
+                    const float *x = ip + INTERP_HIST - (P - 1) + i;
+                    float sum = 0.0f;
+                    for (int k = 0; k < P; k++) sum = mad(x[k], __ldg(ic + (L - 1 - j) + k * L), sum);
+                    o48[n] = sum;
+                }
             }
             for (int i = 0; i < INTERP_HIST; i++) ip[i] = ip[nd + i];      // keep the newest INTERP_HIST decimated samples
         } else {
             // FM: rescale only (:2819-2828); the S-meter-only AGC on a_buffer[0] is not run
-            for (int n = 0; n < BLK; n++) o48[n] = __fmul_rn(ad[n], p.fm_scaling);
+            for (int n = 0; n < BLK; n++) o48[n] = __fmul_rn(ad[n], fm_scaling);
         }
-        // anti-alias lattice :2581-2583, treble biquad :2832
-        for (int n = 0; n < BLK; n++) {
-            float x = o48[n];
-            if (p.aa.n > 0 && !fm) x = lattice_step(x, st.aa_s, pool + p.aa.k_off, pool + p.aa.v_off, p.aa.n);
-            o48[n] = biquad_step(x, p.bq2, st.bq2);
-        }
-        // output stage :2845-2941
+        // anti-alias lattice :2581-2583, treble biquad :2832, output stage :2845-2941
         const bool muted = (mute && mute[blk]) || !signal_active;
         int2 *dst = audio + (size_t)blk * BLK;
+#pragma unroll 2
         for (int n = 0; n < BLK; n += 2) {
-            const float v0 = muted ? 0.0f : __fmul_rn(o48[n], 10.0f), v1 = muted ? 0.0f : __fmul_rn(o48[n + 1], 10.0f);
-            const int w0 = muted ? 0 : format_audio_word(v0), w1 = muted ? 0 : format_audio_word(v1);
+            float v[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                float x = o48[n + e];
+                if (aa_on) x = lattice_regs<6>(x, ak, av, as_);
+                x = biquad_step(x, tc, ts);
+                v[e] = muted ? 0.0f : __fmul_rn(x, 10.0f);
+            }
+            const int w0 = muted ? 0 : format_audio_word(v[0]), w1 = muted ? 0 : format_audio_word(v[1]);
             *reinterpret_cast<int4 *>(dst + n) = make_int4(w0, w0, w1, w1);
-            if (audio_f) *reinterpret_cast<float2 *>(audio_f + (size_t)blk * BLK + n) = make_float2(v0, v1);
+            if (audio_f) *reinterpret_cast<float2 *>(audio_f + (size_t)blk * BLK + n) = make_float2(v[0], v[1]);
         }
     }
 
     for (int i = 0; i < INTERP_HIST; i++) st.interp_hist[i] = ip[i];
+#pragma unroll
+    for (int j = 0; j < 10; j++) if (j >= ppad) st.pre_s[j - ppad] = ps[j];
+    if (aa_on) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) st.aa_s[j] = as_[j];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) st.bq1[s] = bs[s];
+    st.bq2 = ts;
+    st.agc_wold = agc_wold;
     st.agc_out_index = ar.out_index; st.agc_in_index = ar.in_index; st.agc_ring_max = ar.ring_max;
     st.agc_volts = ar.volts; st.agc_save_volts = ar.save_volts; st.agc_fast_backaverage = ar.fast_backaverage;
     st.agc_hang_backaverage = ar.hang_backaverage; st.agc_hang_counter = ar.hang_counter;
