@@ -395,8 +395,19 @@ int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio
     TxArgs a;
     a.params = e->d_params; a.state = e->d_state; a.tx = e->d_tx; a.txp = e->d_txp; a.pool = e->d_pool;
     a.audio = audio_dev; a.iq = iq_dev; a.iq_f = iq_f_dev; a.mute = mute_dev; a.nblocks = nblocks; a.num_items = e->nch;
+    a.scratch = nullptr;
+    if (e->use_split && (uintptr_t)audio_dev % 16 == 0) {
+        const size_t need = (size_t)e->nch * (size_t)nblocks * BLK * sizeof(float);
+        if (need > e->d_scratch_bytes) {
+            CK(e, cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_scratch); e->d_scratch = nullptr; e->d_scratch_bytes = 0;
+            CK(e, cudaMalloc(&e->d_scratch, need));
+            e->d_scratch_bytes = need;
+        }
+        a.scratch = e->d_scratch;
+    }
     CK(e, launch_tx_ssb(a, e->stream));
-    e->launches++;
+    e->launches += a.scratch ? 2 : 1;
     return UHSDR_OK;
 }
 

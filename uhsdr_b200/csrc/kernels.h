@@ -54,6 +54,7 @@ struct TxArgs {
     const uint8_t *mute;
     int num_items;
     int nblocks;
+    float *scratch;             // split path: output of the serial stages, [num_channels][nblocks*32] floats (nullptr = single kernel)
 };
 cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream);
 cudaError_t launch_tx_boot(TxState *tx, int n, cudaStream_t stream);

@@ -111,6 +111,11 @@ struct TxWork {
     TxState st;
 };
 
+// SPLIT = false: the whole chain in one kernel (serial stages on lane 0).  SPLIT = true: the sample-serial stages
+// (AudioBufferFill, lattice, biquads, compressor) have been run by tx_serial_kernel, one channel per thread, and
+// their output sits in a.scratch [channel][nblocks*32]; this kernel does the 201-tap Hilbert pair, the frequency
+// translation and the output formatting.
+template <bool SPLIT>
 __global__ void __launch_bounds__(32 * TX_WARPS)
 tx_ssb_kernel(TxArgs a)
 {
@@ -146,6 +151,10 @@ tx_ssb_kernel(TxArgs a)
         const bool muted = mute && mute[blk];
         float vi = 0.0f, vq = 0.0f;
         if (!muted && tp.enabled) {
+            float v;
+            if constexpr (SPLIT) {
+                v = a.scratch[((size_t)ch * a.nblocks + blk) * BLK + lane];
+            } else {
             // AudioBufferFill
             const int2 s = mic[(size_t)blk * BLK + lane];
             float x = (float)s.x;
@@ -186,7 +195,7 @@ tx_ssb_kernel(TxArgs a)
                 }
             }
             __syncwarp();
-            float v = w.scr[lane];
+            v = w.scr[lane];
             if (tp.comp_enabled) {
                 // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
                 const uint32_t inb = st.alc_delay_inbuf % 320u, outb = (st.alc_delay_inbuf + BLK) % 320u;
@@ -195,6 +204,7 @@ tx_ssb_kernel(TxArgs a)
                 __syncwarp();
                 v = __fmul_rn(st.delay[outb + lane], w.scr[BLK + lane]);
                 if (lane == 0) st.alc_delay_inbuf = inb;
+            }
             }
             w.a[H2 + lane] = v;
             __syncwarp();
@@ -252,21 +262,112 @@ tx_ssb_kernel(TxArgs a)
     for (int i = lane; i < H2; i += 32) w.st.hist[i] = w.a[i];
     if (lane == 0) { st.blocks += a.nblocks; rst->osc_vect_q = osc_q; rst->osc_vect_i = osc_i; rst->conversion_freq = conv; }
     __syncwarp();
-    {
+    if constexpr (SPLIT) {
+        for (int i = lane; i < H2; i += 32) a.tx[ch].hist[i] = w.st.hist[i];
+        if (lane == 0) a.tx[ch].blocks = st.blocks;
+    } else {
         uint32_t *dst = reinterpret_cast<uint32_t *>(a.tx + ch);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&w.st);
         for (int i = lane; i < (int)(sizeof(TxState) / 4); i += 32) dst[i] = src[i];
     }
 }
 
+// The sample-serial stages of the SSB modulator, one channel per thread (see rx_serial.cu for the idea):
+// AudioBufferFill (tx_processor.c:339-405), IIR_TXFilter lattice + IIR_TX_biquad (:416-429), VoiceCompressor
+// with its 320-sample look-ahead delay (:173-242).  Muted blocks advance nothing, as in TxProcessor_Run.
+static constexpr int TXS_THREADS = 32;
+
+__global__ void __launch_bounds__(TXS_THREADS)
+tx_serial_kernel(TxArgs a)
+{
+    const int ch = blockIdx.x * TXS_THREADS + threadIdx.x;
+    if (ch >= a.num_items) return;
+    const TxParams &tp = a.txp[ch];
+    if (!tp.enabled) return;
+    const float *__restrict__ pool = a.pool;
+    TxState &g = a.tx[ch];
+    float lat_s[MAX_LAT];
+    for (int i = 0; i < MAX_LAT; i++) lat_s[i] = g.lat_s[i];
+    BiquadS bq[3];
+    float bc[3][5];
+    for (int s = 0; s < 3; s++) { bq[s] = g.bq[s]; for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
+    float alc_val = g.alc_val, peak_audio = g.peak_audio;
+    uint32_t inbuf = g.alc_delay_inbuf;
+    float delay[320];
+    for (int i = 0; i < 320; i++) delay[i] = g.delay[i];
+    const float gain_calc = tp.gain_calc, postfilt_gain = tp.postfilt_gain, alc_decay = tp.alc_decay;
+    const bool gain_on = (double)gain_calc != 1.0, comp = tp.comp_enabled != 0;
+    const float *lk = pool + tp.lat.k_off, *lv = pool + tp.lat.v_off;
+    const int ln = tp.lat.n;
+    const size_t base = (size_t)ch * (size_t)a.nblocks * BLK;
+    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + base;
+    float *__restrict__ out = a.scratch + base;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+
+    for (int blk = 0; blk < a.nblocks; blk++) {
+        if (mute && mute[blk]) continue;
+        float v[BLK], alc[BLK];
+        float mx = 0.0f, mn = 0.0f;
+        for (int i = 0; i < BLK; i += 2) {
+            const int4 s = *reinterpret_cast<const int4 *>(mic + (size_t)blk * BLK + i);
+            float x0 = (float)s.x, x1 = (float)s.z;
+            if (gain_on) { x0 = __fmul_rn(x0, gain_calc); x1 = __fmul_rn(x1, gain_calc); }
+            if (i == 0) { mx = x0; mn = x0; }
+            mx = fmaxf(mx, fmaxf(x0, x1)); mn = fminf(mn, fminf(x0, x1));
+            v[i] = x0; v[i + 1] = x1;
+        }
+        peak_audio = (-mn > mx) ? -mn : mx;
+        for (int i = 0; i < BLK; i++) {
+            float x = lattice_step(v[i], lat_s, lk, lv, ln);
+            for (int s = 0; s < 3; s++) x = biquad_step(x, bc[s], bq[s]);
+            v[i] = x;
+        }
+        if (comp) {
+            for (int i = 0; i < BLK; i++) {
+                const float x = __fmul_rn(v[i], postfilt_gain);
+                v[i] = x;
+                // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
+                const float alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(x, alc_val)), 30000.0f) - 1.0);
+                if (alc_var < 0.0f) {
+                    alc_val = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
+                } else {
+                    alc_val = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
+                    if ((double)alc_val < 0.001) alc_val = (float)0.001;
+                }
+                if (alc_val > 1.0f) alc_val = 1.0f;
+                alc[i] = __fmul_rn(alc_val, 1.00f);
+            }
+            inbuf += BLK;
+            // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
+            const uint32_t inb = inbuf % 320u, outb = (inbuf + BLK) % 320u;
+            for (int i = 0; i < BLK; i++) delay[inb + i] = v[i];
+            for (int i = 0; i < BLK; i++) v[i] = __fmul_rn(delay[outb + i], alc[i]);
+            inbuf = inb;
+        }
+        for (int i = 0; i < BLK; i += 4) *reinterpret_cast<float4 *>(out + (size_t)blk * BLK + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    for (int i = 0; i < MAX_LAT; i++) g.lat_s[i] = lat_s[i];
+    for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
+    g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;
+    for (int i = 0; i < 320; i++) g.delay[i] = delay[i];
+}
+
 cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
 {
     const size_t smem = sizeof(TxWork) * TX_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const int grid = (a.num_items + TX_WARPS - 1) / TX_WARPS;
     if (grid == 0) return cudaSuccess;
-    tx_ssb_kernel<<<grid, 32 * TX_WARPS, smem, stream>>>(a);
+    if (a.scratch) {
+        // split path: serial stages with one channel per thread, then the FIR pair with one warp per channel
+        cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tx_serial_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, 0, stream>>>(a);
+        tx_ssb_kernel<true><<<grid, 32 * TX_WARPS, smem, stream>>>(a);
+        return cudaGetLastError();
+    }
+    cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tx_ssb_kernel<false><<<grid, 32 * TX_WARPS, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
