@@ -37,8 +37,8 @@ struct uhsdr_engine {
     std::vector<int> h_tx_enabled;
     // dispatch lists (rebuilt after configure)
     bool lists_dirty = true;
-    std::vector<int> h_list_fused, h_list_generic, h_list_split;
-    int *d_list_fused = nullptr, *d_list_generic = nullptr, *d_list_split = nullptr;
+    std::vector<int> h_list_fused, h_list_generic, h_list_split, h_list_split_nr;
+    int *d_list_fused = nullptr, *d_list_generic = nullptr, *d_list_split = nullptr, *d_list_split_nr = nullptr;
     int split_floats_per_block = 0;      // scratch floats per block and channel of the split path
     float *d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
@@ -111,7 +111,7 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec);
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
-    cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_scratch);
+    cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_list_split_nr); cudaFree(e->d_scratch);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
     for (auto &v : e->ev_in) if (v) cudaEventDestroy(v);
     for (auto &v : e->ev_k) if (v) cudaEventDestroy(v);
@@ -169,6 +169,7 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if ((er = cudaMalloc(&e->d_list_fused, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_generic, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_split, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_list_split_nr, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     e->h_params.assign(n, ChanParams{});
     e->h_tx_enabled.assign(n, 0);
     *out = e;
@@ -241,7 +242,7 @@ int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg
 // fused kernel (rx_ssb_fused.cu); everything else runs on the general kernel.
 static int rebuild_lists(uhsdr_engine *e)
 {
-    e->h_list_fused.clear(); e->h_list_generic.clear(); e->h_list_split.clear();
+    e->h_list_fused.clear(); e->h_list_generic.clear(); e->h_list_split.clear(); e->h_list_split_nr.clear();
     e->fused_s1_ci = -1;
     e->split_floats_per_block = 0;
     for (int c = 0; c < e->nch; c++) {
@@ -254,13 +255,15 @@ static int rebuild_lists(uhsdr_engine *e)
         }
         if (fused) e->h_list_fused.push_back(c);
         else if (e->use_split && rx_split_floats_per_block(p) > 0) {
-            // everything but the spectral noise reduction (warp-cooperative FFT frames) runs on the split path
-            e->h_list_split.push_back(c);
+            // channels with the spectral noise reduction take two serial phases around the warp-cooperative NR kernel
+            (p.nr_enable ? e->h_list_split_nr : e->h_list_split).push_back(c);
             e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));
         } else e->h_list_generic.push_back(c);
     }
     if (!e->h_list_split.empty())
         CK(e, cudaMemcpyAsync(e->d_list_split, e->h_list_split.data(), e->h_list_split.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if (!e->h_list_split_nr.empty())
+        CK(e, cudaMemcpyAsync(e->d_list_split_nr, e->h_list_split_nr.data(), e->h_list_split_nr.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     if (!e->h_list_fused.empty()) {
         CK(e, cudaMemcpyAsync(e->d_list_fused, e->h_list_fused.data(), e->h_list_fused.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
         const float *pool = e->tables.pool.data();
@@ -297,8 +300,10 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         CK(e, launch_rx_generic(a, stream));
         e->launches++;
     }
-    if (!e->h_list_split.empty()) {
-        a.chan_list = e->d_list_split; a.num_items = (int)e->h_list_split.size();
+    for (int with_nr = 0; with_nr < 2; with_nr++) {
+        const std::vector<int> &lst = with_nr ? e->h_list_split_nr : e->h_list_split;
+        if (lst.empty()) continue;
+        a.chan_list = with_nr ? e->d_list_split_nr : e->d_list_split; a.num_items = (int)lst.size();
         a.scratch_stride = (long long)nblocks * e->split_floats_per_block;
         const size_t need = (size_t)a.num_items * (size_t)a.scratch_stride * sizeof(float);
         if (need > e->d_scratch_bytes) {
@@ -309,8 +314,15 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         }
         a.scratch = e->d_scratch;
         CK(e, launch_rx_front(a, stream));
-        CK(e, launch_rx_serial(a, stream));
-        e->launches += 2;
+        if (!with_nr) {
+            CK(e, launch_rx_serial(a, 0, stream));
+            e->launches += 2;
+        } else {
+            CK(e, launch_rx_serial(a, 1, stream));
+            CK(e, launch_rx_nr(a, stream));
+            CK(e, launch_rx_serial(a, 2, stream));
+            e->launches += 4;
+        }
     }
     return UHSDR_OK;
 }

@@ -30,7 +30,8 @@ cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);
 // split general path: time-parallel front end + FIR stages (one warp per channel, rx_generic.cu) into
 // a.scratch, then the sample-serial stages with one channel per thread (rx_serial.cu)
 cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream);
-cudaError_t launch_rx_serial(const RxArgs &a, cudaStream_t stream);
+cudaError_t launch_rx_serial(const RxArgs &a, int phase, cudaStream_t stream);   // phase: see rx_serial.cu
+cudaError_t launch_rx_nr(const RxArgs &a, cudaStream_t stream);                   // spectral NR on a.scratch, in place
 int rx_split_floats_per_block(const ChanParams &p);     // scratch floats per 32-sample block and channel
 
 // fused narrow-SSB receiver (rx_ssb_fused.cu)

@@ -410,11 +410,38 @@ cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream)
     return launch_generic<true>(a, stream);
 }
 
+// Spectral noise reduction of the split path (AudioDriver_RxProcessorNoiseReduction, audio_driver.c:2328-2434, with
+// the deferred task of audio_nr.c run after every block): one warp per channel walks through the AGC output in
+// a.scratch block by block, in place.
+__global__ void __launch_bounds__(32 * G_WARPS)
+rx_nr_kernel(RxArgs a)
+{
+    __shared__ __align__(16) float fft[G_WARPS][512];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * G_WARPS + warp;
+    if (slot >= a.num_items) return;
+    const int ch = a.chan_list[slot];
+    const ChanParams &p = a.params[ch];
+    if (!p.nr_enable || !a.nr) return;
+    const int nd = BLK / p.M;
+    float *sc = a.scratch + (size_t)slot * (size_t)a.scratch_stride;
+    for (int blk = 0; blk < a.nblocks; blk++) nr_block(p, a.nr[ch], a.pool, sc + (size_t)blk * nd, nd, fft[warp], lane);
+}
+
+cudaError_t launch_rx_nr(const RxArgs &a, cudaStream_t stream)
+{
+    const int grid = (a.num_items + G_WARPS - 1) / G_WARPS;
+    if (grid == 0) return cudaSuccess;
+    if (a.scratch == nullptr || a.chan_list == nullptr) return cudaErrorInvalidValue;
+    rx_nr_kernel<<<grid, 32 * G_WARPS, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 // scratch floats per 32-sample block: see the layout at rx_generic_kernel; 0 = the chain has a shape the serial
 // kernel keeps no registers for (it stays on the general kernel)
 int rx_split_floats_per_block(const ChanParams &p)
 {
-    if (p.nr_enable || p.pre.n > 10 || (p.aa.n != 0 && p.aa.n != 6) || p.interp_plen > INTERP_HIST + 1) return 0;
+    if (p.pre.n > 10 || (p.aa.n != 0 && p.aa.n != 6) || p.interp_plen > INTERP_HIST + 1) return 0;
     if (p.topo == TOPO_FM) return 2 * BLK;
     if (p.topo == TOPO_AM_SAM) return 2 * (BLK / p.M);
     return BLK / p.M;

@@ -102,8 +102,11 @@ __device__ __forceinline__ float lattice_regs(float x, const float (&k)[NS], con
     return acc;
 }
 
+// phase 0: the whole serial chain.  Channels with the spectral noise reduction, which sits between the AGC and the
+// biquad cascade (audio_driver.c:2501-2509) and works on warp-cooperative FFT frames (rx_nr_kernel), run it in two
+// launches: phase 1 = demodulation, lattice, AGC, result back into a.scratch; phase 2 = everything after the NR.
 __global__ void __launch_bounds__(SER_THREADS)
-rx_serial_kernel(RxArgs a)
+rx_serial_kernel(RxArgs a, int phase)
 {
     const int slot = blockIdx.x * SER_THREADS + threadIdx.x;
     if (slot >= a.num_items) return;
@@ -116,7 +119,7 @@ rx_serial_kernel(RxArgs a)
     const int M = p.M;
     const int nd = BLK / M;                         // decimated samples per block (FM: M = 1, unused)
     const bool fm = p.topo == TOPO_FM, amsam = p.topo == TOPO_AM_SAM;
-    const float *__restrict__ sc = a.scratch + (size_t)slot * (size_t)a.scratch_stride;
+    float *sc = a.scratch + (size_t)slot * (size_t)a.scratch_stride;
     const size_t half = fm ? (size_t)a.nblocks * BLK : (size_t)a.nblocks * nd;
     const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
     int2 *__restrict__ audio = reinterpret_cast<int2 *>(a.audio) + chan_base;
@@ -168,7 +171,9 @@ rx_serial_kernel(RxArgs a)
         float ad[BLK], o48[BLK];
         bool signal_active = true;
         // ---- demodulation ----
-        if (fm) {
+        if (phase == 2) {
+            for (int n = 0; n < nd; n++) ad[n] = sc[(size_t)blk * nd + n];
+        } else if (fm) {
             float bi[BLK], bq[BLK];
             const float4 *si = reinterpret_cast<const float4 *>(sc + (size_t)blk * BLK), *sq = reinterpret_cast<const float4 *>(sc + half + (size_t)blk * BLK);
             for (int n = 0; n < BLK / 4; n++) {
@@ -189,18 +194,24 @@ rx_serial_kernel(RxArgs a)
         if (!fm) {
             // lattice pre-filter :2473-2475, AGC :2485 (+ DC remover audio_agc.c:577-594, double expression),
             // fixed gain :2513-2524, biquad_1 :2527
-            for (int i = 0; i < nd; i++) {
-                float x = ad[i];
-                if (pn > 0) x = lattice_regs<10>(x, pk, pv, ps);
-                if (ap.mode == 5) x = __fmul_rn(x, ap.fixed_gain);
-                else x = agc_step(x, ap, ar, st.agc_ring);
-                ad[i] = x;
-            }
-            if (remove_dc) {
+            if (phase != 2) {
                 for (int i = 0; i < nd; i++) {
-                    const float wv = (float)((double)ad[i] + (double)agc_wold * 0.9999);
-                    ad[i] = __fsub_rn(wv, agc_wold);
-                    agc_wold = wv;
+                    float x = ad[i];
+                    if (pn > 0) x = lattice_regs<10>(x, pk, pv, ps);
+                    if (ap.mode == 5) x = __fmul_rn(x, ap.fixed_gain);
+                    else x = agc_step(x, ap, ar, st.agc_ring);
+                    ad[i] = x;
+                }
+                if (remove_dc) {
+                    for (int i = 0; i < nd; i++) {
+                        const float wv = (float)((double)ad[i] + (double)agc_wold * 0.9999);
+                        ad[i] = __fsub_rn(wv, agc_wold);
+                        agc_wold = wv;
+                    }
+                }
+                if (phase == 1) {
+                    for (int n = 0; n < nd; n++) sc[(size_t)blk * nd + n] = ad[n];
+                    continue;
                 }
             }
             for (int i = 0; i < nd; i++) {
@@ -264,12 +275,12 @@ rx_serial_kernel(RxArgs a)
     store_ser(a.state[ch], st);
 }
 
-cudaError_t launch_rx_serial(const RxArgs &a, cudaStream_t stream)
+cudaError_t launch_rx_serial(const RxArgs &a, int phase, cudaStream_t stream)
 {
     if (a.num_items <= 0) return cudaSuccess;
     if (a.scratch == nullptr || a.chan_list == nullptr) return cudaErrorInvalidValue;
     const int grid = (a.num_items + SER_THREADS - 1) / SER_THREADS;
-    rx_serial_kernel<<<grid, SER_THREADS, 0, stream>>>(a);
+    rx_serial_kernel<<<grid, SER_THREADS, 0, stream>>>(a, phase);
     return cudaGetLastError();
 }
 
