@@ -22,6 +22,9 @@ struct uhsdr_engine {
     int nch = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
+    cudaStream_t aux_stream = nullptr;          // split paths: serial kernels of slice s run beside the FIR kernel of slice s+1
+    static constexpr int kSplitSlices = 4;
+    cudaEvent_t ev_split[2 * kSplitSlices] = {}, ev_fork = nullptr, ev_join = nullptr;
     static constexpr int kMaxSlices = 16;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     cudaEvent_t ev_done = nullptr;
@@ -113,6 +116,10 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
     cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_list_split_nr); cudaFree(e->d_scratch);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    for (auto &v : e->ev_split) if (v) cudaEventDestroy(v);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (auto &v : e->ev_in) if (v) cudaEventDestroy(v);
     for (auto &v : e->ev_k) if (v) cudaEventDestroy(v);
     if (e->ev_done) cudaEventDestroy(e->ev_done);
@@ -159,6 +166,16 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     for (auto &v : e->ev_in) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     for (auto &v : e->ev_k) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     if ((er = cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    {
+        // the serial kernels are small and latency-bound: highest priority, so that their few CTAs are placed as soon
+        // as the FIR kernel of the next slice frees a slot
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if ((er = cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", er);
+    }
+    for (auto &v : e->ev_split) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    if ((er = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    if ((er = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     const size_t n = (size_t)num_channels;
     if ((er = cudaMalloc(&e->d_pool, e->tables.pool.size() * sizeof(float))) != cudaSuccess) return fail("cudaMalloc pool", er);
     if ((er = cudaMemcpy(e->d_pool, e->tables.pool.data(), e->tables.pool.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy pool", er);
@@ -300,29 +317,56 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         CK(e, launch_rx_generic(a, stream));
         e->launches++;
     }
-    for (int with_nr = 0; with_nr < 2; with_nr++) {
-        const std::vector<int> &lst = with_nr ? e->h_list_split_nr : e->h_list_split;
-        if (lst.empty()) continue;
-        a.chan_list = with_nr ? e->d_list_split_nr : e->d_list_split; a.num_items = (int)lst.size();
-        a.scratch_stride = (long long)nblocks * e->split_floats_per_block;
-        const size_t need = (size_t)a.num_items * (size_t)a.scratch_stride * sizeof(float);
+    // Split general path.  The call is cut into time slices: the FIR front kernel of slice s+1 (this stream) runs
+    // beside the sample-serial kernels of slice s (aux stream); neither fills the GPU on its own.
+    if (!e->h_list_split.empty() || !e->h_list_split_nr.empty()) {
+        const int nsl = (nblocks >= 64) ? uhsdr_engine::kSplitSlices : 1;
+        const int per = ((nblocks + nsl - 1) / nsl + 3) / 4 * 4;
+        const size_t n_all = e->h_list_split.size() + e->h_list_split_nr.size();
+        const size_t need = n_all * (size_t)nblocks * (size_t)e->split_floats_per_block * sizeof(float) + 64 * n_all * nsl;
         if (need > e->d_scratch_bytes) {
             CK(e, cudaStreamSynchronize(stream));
+            CK(e, cudaStreamSynchronize(e->aux_stream));
             cudaFree(e->d_scratch); e->d_scratch = nullptr; e->d_scratch_bytes = 0;
             CK(e, cudaMalloc(&e->d_scratch, need));
             e->d_scratch_bytes = need;
         }
-        a.scratch = e->d_scratch;
-        CK(e, launch_rx_front(a, stream));
-        if (!with_nr) {
-            CK(e, launch_rx_serial(a, 0, stream));
-            e->launches += 2;
-        } else {
-            CK(e, launch_rx_serial(a, 1, stream));
-            CK(e, launch_rx_nr(a, stream));
-            CK(e, launch_rx_serial(a, 2, stream));
-            e->launches += 4;
+        CK(e, cudaEventRecord(e->ev_fork, stream));
+        CK(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        float *sc = e->d_scratch;
+        int si = 0;
+        for (int b0 = 0; b0 < nblocks; b0 += per, si++) {
+            const int nb = std::min(per, nblocks - b0);
+            RxArgs s = a;
+            s.nblocks = nb;
+            s.iq = (const char *)iq_dev + (size_t)b0 * BLK * sizeof(uhsdr_iq_sample_t);
+            s.audio = (char *)audio_dev + (size_t)b0 * BLK * sizeof(uhsdr_audio_sample_t);
+            s.audio_f = audio_f_dev ? audio_f_dev + (size_t)b0 * BLK : nullptr;
+            s.mute = mute_dev ? mute_dev + b0 : nullptr;
+            s.scratch_stride = (long long)nb * e->split_floats_per_block;
+            for (int with_nr = 0; with_nr < 2; with_nr++) {
+                const std::vector<int> &lst = with_nr ? e->h_list_split_nr : e->h_list_split;
+                if (lst.empty()) continue;
+                s.chan_list = with_nr ? e->d_list_split_nr : e->d_list_split; s.num_items = (int)lst.size();
+                s.scratch = sc;
+                sc += (size_t)s.num_items * (size_t)s.scratch_stride;
+                CK(e, launch_rx_front(s, stream));
+                cudaEvent_t ev = e->ev_split[2 * si + with_nr];
+                CK(e, cudaEventRecord(ev, stream));
+                CK(e, cudaStreamWaitEvent(e->aux_stream, ev, 0));
+                if (!with_nr) {
+                    CK(e, launch_rx_serial(s, 0, e->aux_stream));
+                    e->launches += 2;
+                } else {
+                    CK(e, launch_rx_serial(s, 1, e->aux_stream));
+                    CK(e, launch_rx_nr(s, e->aux_stream));
+                    CK(e, launch_rx_serial(s, 2, e->aux_stream));
+                    e->launches += 4;
+                }
+            }
         }
+        CK(e, cudaEventRecord(e->ev_join, e->aux_stream));
+        CK(e, cudaStreamWaitEvent(stream, e->ev_join, 0));
     }
     return UHSDR_OK;
 }
@@ -407,19 +451,42 @@ int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio
     TxArgs a;
     a.params = e->d_params; a.state = e->d_state; a.tx = e->d_tx; a.txp = e->d_txp; a.pool = e->d_pool;
     a.audio = audio_dev; a.iq = iq_dev; a.iq_f = iq_f_dev; a.mute = mute_dev; a.nblocks = nblocks; a.num_items = e->nch;
-    a.scratch = nullptr;
+    a.scratch = nullptr; a.chan_stride = (long long)nblocks * BLK; a.mute_stride = nblocks;
     if (e->use_split && (uintptr_t)audio_dev % 16 == 0) {
+        // split modulator, time-sliced: serial kernel of slice s+1 (aux stream) beside the FIR kernel of slice s
         const size_t need = (size_t)e->nch * (size_t)nblocks * BLK * sizeof(float);
         if (need > e->d_scratch_bytes) {
             CK(e, cudaStreamSynchronize(e->stream));
+            CK(e, cudaStreamSynchronize(e->aux_stream));
             cudaFree(e->d_scratch); e->d_scratch = nullptr; e->d_scratch_bytes = 0;
             CK(e, cudaMalloc(&e->d_scratch, need));
             e->d_scratch_bytes = need;
         }
-        a.scratch = e->d_scratch;
+        const int nsl = (nblocks >= 64) ? uhsdr_engine::kSplitSlices : 1;
+        const int per = ((nblocks + nsl - 1) / nsl + 3) / 4 * 4;
+        CK(e, cudaEventRecord(e->ev_fork, e->stream));
+        CK(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        float *sc = e->d_scratch;
+        int si = 0;
+        for (int b0 = 0; b0 < nblocks; b0 += per, si++) {
+            TxArgs s = a;
+            s.nblocks = std::min(per, nblocks - b0);
+            s.audio = (const char *)audio_dev + (size_t)b0 * BLK * sizeof(uhsdr_audio_sample_t);
+            s.iq = (char *)iq_dev + (size_t)b0 * BLK * sizeof(uhsdr_iq_sample_t);
+            s.iq_f = iq_f_dev ? iq_f_dev + (size_t)b0 * BLK * 2 : nullptr;
+            s.mute = mute_dev ? mute_dev + b0 : nullptr;
+            s.scratch = sc;
+            sc += (size_t)e->nch * (size_t)s.nblocks * BLK;
+            CK(e, launch_tx_serial(s, e->aux_stream));
+            CK(e, cudaEventRecord(e->ev_split[si], e->aux_stream));
+            CK(e, cudaStreamWaitEvent(e->stream, e->ev_split[si], 0));
+            CK(e, launch_tx_ssb(s, e->stream));
+            e->launches += 2;
+        }
+        return UHSDR_OK;
     }
     CK(e, launch_tx_ssb(a, e->stream));
-    e->launches += a.scratch ? 2 : 1;
+    e->launches++;
     return UHSDR_OK;
 }
 

@@ -56,8 +56,13 @@ struct TxArgs {
     int num_items;
     int nblocks;
     float *scratch;             // split path: output of the serial stages, [num_channels][nblocks*32] floats (nullptr = single kernel)
+    long long chan_stride;      // samples between consecutive channels in audio / iq / iq_f (>= nblocks*32)
+    long long mute_stride;      // bytes between consecutive channels in mute
 };
+// scratch == nullptr: the whole modulator in one kernel.  Otherwise launch_tx_serial (one channel per thread:
+// AudioBufferFill, lattice, biquads, compressor -> scratch) first, then launch_tx_ssb (Hilbert pair, translation, output).
 cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream);
+cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream);
 cudaError_t launch_tx_boot(TxState *tx, int n, cudaStream_t stream);
 cudaError_t launch_nr_boot(NrState *nr, int n, cudaStream_t stream);
 

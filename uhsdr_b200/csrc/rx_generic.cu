@@ -380,7 +380,20 @@ rx_generic_kernel(RxArgs a)
         st.blocks += a.nblocks;
     }
     __syncwarp();
-    {
+    if constexpr (FRONT) {
+        // only the fields this kernel owns: the serial kernels of the previous time slice may be updating the rest
+        // of the record at this very moment (engine.cu runs them on a second stream)
+        for (int i = lane; i < H1; i += 32) { gst->s1_hist_i[i] = w.st.s1_hist_i[i]; gst->s1_hist_q[i] = w.st.s1_hist_q[i]; }
+        for (int i = lane; i < H2; i += 32) { gst->s2_hist_i[i] = w.st.s2_hist_i[i]; gst->s2_hist_q[i] = w.st.s2_hist_q[i]; }
+        if (lane == 0) {
+            gst->teta1_old = st.teta1_old; gst->teta2_old = st.teta2_old; gst->teta3_old = st.teta3_old;
+            gst->M_c1 = st.M_c1; gst->M_c2 = st.M_c2;
+            gst->osc_vect_q = st.osc_vect_q; gst->osc_vect_i = st.osc_vect_i; gst->conversion_freq = st.conversion_freq;
+            gst->samp_ptr = st.samp_ptr;
+            gst->adc_clip = st.adc_clip; gst->adc_half_clip = st.adc_half_clip; gst->adc_quarter_clip = st.adc_quarter_clip;
+            gst->blocks = st.blocks;
+        }
+    } else {
         uint32_t *dst = reinterpret_cast<uint32_t *>(gst);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&w.st);
         for (int i = lane; i < (int)(sizeof(ChanState) / 4); i += 32) dst[i] = src[i];

@@ -139,11 +139,11 @@ tx_ssb_kernel(TxArgs a)
     if (tp.shift_kind != 0 && conv != tp.shift_freq) { conv = tp.shift_freq; osc_i = 0.0f; osc_q = 1.0f; }   // freq_shift.c:289-305
     __syncwarp();
     TxState &st = w.st;
-    const size_t base = (size_t)ch * (size_t)a.nblocks * BLK;
+    const size_t base = (size_t)ch * (size_t)a.chan_stride;
     const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + base;
     int2 *__restrict__ iq = reinterpret_cast<int2 *>(a.iq) + base;
     float2 *__restrict__ iq_f = a.iq_f ? reinterpret_cast<float2 *>(a.iq_f) + base : nullptr;
-    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
     const int N = tp.hil_ntaps;
     const float *ci = pool + (tp.lsb ? tp.hil_cq : tp.hil_ci), *cq = pool + (tp.lsb ? tp.hil_ci : tp.hil_cq);
 
@@ -299,10 +299,9 @@ tx_serial_kernel(TxArgs a)
     const bool gain_on = (double)gain_calc != 1.0, comp = tp.comp_enabled != 0;
     const float *lk = pool + tp.lat.k_off, *lv = pool + tp.lat.v_off;
     const int ln = tp.lat.n;
-    const size_t base = (size_t)ch * (size_t)a.nblocks * BLK;
-    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + base;
-    float *__restrict__ out = a.scratch + base;
-    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * a.nblocks : nullptr;
+    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + (size_t)ch * (size_t)a.chan_stride;
+    float *__restrict__ out = a.scratch + (size_t)ch * (size_t)a.nblocks * BLK;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
     for (int blk = 0; blk < a.nblocks; blk++) {
         if (mute && mute[blk]) continue;
@@ -358,16 +357,22 @@ cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
     const int grid = (a.num_items + TX_WARPS - 1) / TX_WARPS;
     if (grid == 0) return cudaSuccess;
     if (a.scratch) {
-        // split path: serial stages with one channel per thread, then the FIR pair with one warp per channel
         cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tx_serial_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, 0, stream>>>(a);
         tx_ssb_kernel<true><<<grid, 32 * TX_WARPS, smem, stream>>>(a);
         return cudaGetLastError();
     }
     cudaError_t e = cudaFuncSetAttribute(tx_ssb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     tx_ssb_kernel<false><<<grid, 32 * TX_WARPS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream)
+{
+    if (a.num_items <= 0) return cudaSuccess;
+    if (a.scratch == nullptr) return cudaErrorInvalidValue;
+    tx_serial_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
