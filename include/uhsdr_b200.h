@@ -136,6 +136,10 @@ typedef struct {
     float   tx_adj_gain_i;       /* ts.tx_adj_gain_var[trans_idx].i                                 */
     float   tx_adj_gain_q;       /* ts.tx_adj_gain_var[trans_idx].q                                 */
     float   iq_phase_balance_tx; /* ads.iq_phase_balance_tx[trans_idx]                              */
+    /* LMS automatic notch (DSP_NOTCH_ENABLE), audio_driver.c:1165-1187, :1746-1763.  The tap count and the
+     * decorrelation delay are fixed by the firmware (DSP_NOTCH_NUMTAPS_MIN == MAX == 64,
+     * DSP_NOTCH_BUFLEN_MIN == MAX == 128, audio_driver.h:486-492); only the convergence rate is a setting. */
+    int32_t notch_mu;            /* ts.dsp.notch_mu, 0..40, default 10 (DSP_NOTCH_MU_DEFAULT)       */
 } uhsdr_chan_cfg_t;
 
 /* Per-channel side outputs (SURVEY.md section 5 "metrics"); none is on the parity-critical path. */

@@ -38,7 +38,7 @@ static void ref_apply_cfg(const uhsdr_chan_cfg_t *c)
     ts.dsp.nr_strength = (uint8_t)c->nr_strength;
     ts.dsp.nb_setting = (uint8_t)c->nb_setting;
     ts.dsp.notch_numtaps = DSP_NOTCH_NUMTAPS_DEFAULT;
-    ts.dsp.notch_mu = DSP_NOTCH_MU_DEFAULT;
+    ts.dsp.notch_mu = (uint8_t)c->notch_mu;
     ts.dsp.notch_delaybuf_len = DSP_NOTCH_DELAYBUF_DEFAULT;
 
     agc_wdsp_conf.mode = (uint8_t)c->agc_mode;

@@ -489,6 +489,49 @@ typedef struct {
 } nr_t;
 
 /* adb.a_buffer[0..1], audio_driver.h:147-157: persists across blocks */
+/* LMS automatic notch: AudioDriver_NotchFilter (audio_driver.c:1746-1763) around arm_lms_norm_f32
+ * (CMSIS FilteringFunctions/arm_lms_norm_f32.c:372-443, the portable loop); setup audio_driver.c:1165-1187
+ * with arm_lms_norm_init_f32.  64 taps, 128-sample decorrelation delay (audio_driver.h:486-492). */
+#define NOTCH_TAPS 64
+#define NOTCH_DELAY 128
+typedef struct {
+    float mu, energy, x0;
+    float coef[NOTCH_TAPS];
+    float state[NOTCH_TAPS + BLK];
+    float delay[NOTCH_DELAY];
+    unsigned long inbuf, outbuf;              /* function statics lms2_inbuf / lms2_outbuf, never reset */
+} notch_t;
+
+static void notch_run(notch_t *n, float *buf, int bs)
+{
+    memcpy(&n->delay[n->inbuf], buf, (size_t)bs * sizeof(float));
+    const float *ref = &n->delay[n->outbuf];
+    /* arm_lms_norm_f32(S, pSrc = buf, pRef = ref, pOut = discarded, pErr = buf): the notched audio is the error */
+    float *pState = n->state, *cur = &n->state[NOTCH_TAPS - 1];
+    float energy = n->energy, x0 = n->x0;
+    for (int i = 0; i < bs; i++) {
+        *cur++ = buf[i];
+        const float in = buf[i];
+        energy -= x0 * x0;
+        energy += in * in;
+        float sum = 0.0f;
+        for (int k = 0; k < NOTCH_TAPS; k++) sum += pState[k] * n->coef[k];
+        const float d = ref[i];
+        const float e = d - sum;
+        buf[i] = e;
+        const float w = (e * n->mu) / (energy + 0.000000119209289f);
+        for (int k = 0; k < NOTCH_TAPS; k++) n->coef[k] += w * pState[k];
+        x0 = *pState;
+        pState++;
+    }
+    n->energy = energy; n->x0 = x0;
+    memmove(n->state, pState, (NOTCH_TAPS - 1) * sizeof(float));
+    n->inbuf += bs;
+    n->outbuf = n->inbuf + bs;
+    n->inbuf %= NOTCH_DELAY;
+    n->outbuf %= NOTCH_DELAY;
+}
+
 typedef struct { float a0[BLK], a1[BLK]; } rx_scratch_t;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -531,6 +574,7 @@ struct port_chan {
     uint32_t samp_ptr;
     /* NR */
     nr_t nr;
+    notch_t notch;
     /* status */
     int adc_clip, adc_half_clip, adc_quarter_clip;
     int64_t blocks;
@@ -564,7 +608,7 @@ static int chan_set_chain(port_chan_t *c, const uhsdr_chan_cfg_t *cfg)
     const port_tables_t *t = c->t;
     if (cfg->struct_size != sizeof(uhsdr_chan_cfg_t)) return UHSDR_ERR_ARG;
     if (cfg->filter_path < 1 || cfg->filter_path >= (int)t->h->num_paths) return UHSDR_ERR_ARG;
-    if (cfg->dsp_active & (UHSDR_DSP_NOTCH_ENABLE | UHSDR_DSP_NB_ENABLE)) return UHSDR_ERR_UNSUPPORTED;
+    if (cfg->dsp_active & UHSDR_DSP_NB_ENABLE) return UHSDR_ERR_UNSUPPORTED;
     if (cfg->spectrum_magnify != 0) return UHSDR_ERR_UNSUPPORTED;
     c->cfg = *cfg;
     const uhsdr_tbl_path_t *p = c->path = &t->path[cfg->filter_path];
@@ -649,6 +693,12 @@ static int chan_set_chain(port_chan_t *c, const uhsdr_chan_cfg_t *cfg)
 
     /* AudioDriver_AgcWdsp_Set, audio_driver.c:628-631 */
     agc_setup(&c->agc, cfg, (float)c->decimated_freq, is_am);
+    /* auto-notch init, audio_driver.c:1165-1187: state, energy and the delay buffer are cleared, the coefficients
+     * only with reset_dsp_nr (a fresh channel starts from zeros anyway) */
+    c->notch.mu = log10f(((cfg->notch_mu + 1.0) / 1500.0) + 1.0);
+    memset(c->notch.state, 0, sizeof(c->notch.state));
+    memset(c->notch.delay, 0, sizeof(c->notch.delay));
+    c->notch.energy = 0.0f; c->notch.x0 = 0.0f;
     return UHSDR_OK;
 }
 
@@ -872,6 +922,9 @@ static int demod_fm(port_chan_t *c, const float *ib, const float *qb, float *a)
 static void rx_postprocess(port_chan_t *c, float *a0, float *a1, int ndec)
 {
     const int mode = c->cfg.dmod_mode;
+    /* audio_driver.c:2443-2456 */
+    if ((c->cfg.dsp_active & UHSDR_DSP_NOTCH_ENABLE) && mode != UHSDR_DEMOD_CW && !(mode == UHSDR_DEMOD_SAM && c->decimated_freq == 24000))
+        notch_run(&c->notch, a0, ndec);
     if (c->pre.n > 0) lattice_run(&c->pre, a0, ndec);
     agc_run(&c->agc, a0, ndec);
     if (c->decimated_freq == 12000 && (c->cfg.dsp_active & UHSDR_DSP_NR_ENABLE)) nr_isr(c, ndec, a0);

@@ -1,7 +1,7 @@
 """Shared parity cases: (label, cfg kwargs, nblocks).  Every distinct signal-flow topology, every
 demodulator and the configuration switches the reference reads on the block path."""
 from uhsdr_b200.config import (DEMOD_AM, DEMOD_CW, DEMOD_DIGI, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, DSP_MNOTCH_ENABLE,
-                               DSP_MPEAK_ENABLE, DSP_NR_ENABLE, FREQ_IQ_CONV_M6KHZ, FREQ_IQ_CONV_OFF, FREQ_IQ_CONV_P12KHZ,
+                               DSP_MPEAK_ENABLE, DSP_NOTCH_ENABLE, DSP_NR_ENABLE, FREQ_IQ_CONV_M6KHZ, FREQ_IQ_CONV_OFF, FREQ_IQ_CONV_P12KHZ,
                                FREQ_IQ_CONV_P6KHZ, SAM_SIDEBAND_LSB, SAM_SIDEBAND_USB)
 
 RX_CASES = [
@@ -31,6 +31,10 @@ RX_CASES = [
     ("usb_agc_fast_hang", dict(agc_mode=4, agc_hang_enable=1), 192),
     ("usb_agc_long_hang", dict(agc_mode=0, agc_hang_enable=1, agc_thresh=40, agc_slope=40), 192),
     ("usb_notch_peak_eq", dict(dsp_active=DSP_MNOTCH_ENABLE | DSP_MPEAK_ENABLE, treble_gain=3, bass_gain=-4), 96),
+    # LMS automatic notch (DSP_NOTCH_ENABLE, audio_driver.c:1746-1763): narrow SSB, wide SSB with a fast rate, AM with the slowest
+    ("usb_p35_autonotch", dict(dsp_active=DSP_NOTCH_ENABLE), 192),
+    ("lsb_p48_autonotch_mu35", dict(dmod_mode=DEMOD_LSB, filter_path=48, dsp_active=DSP_NOTCH_ENABLE, notch_mu=35), 192),
+    ("am_p70_autonotch_mu0", dict(dmod_mode=DEMOD_AM, filter_path=70, dsp_active=DSP_NOTCH_ENABLE, notch_mu=0), 192),
 ]
 
 NR_CASES = [

@@ -78,9 +78,9 @@ def test_port_full_scale_input_sets_clip_flags():
 
 
 def test_port_rejects_unsupported():
-    from uhsdr_b200.config import DSP_NOTCH_ENABLE
+    from uhsdr_b200.config import DSP_NB_ENABLE
     with pytest.raises(ValueError):
-        PortChannel(default_cfg(dsp_active=DSP_NOTCH_ENABLE))
+        PortChannel(default_cfg(dsp_active=DSP_NB_ENABLE, nb_setting=10))
     with pytest.raises(ValueError):
         PortChannel(default_cfg(filter_path=0))
 

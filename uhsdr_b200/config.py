@@ -43,6 +43,7 @@ class ChanCfg(ctypes.Structure):
         ("tx_comp_level", _i32), ("tx_alc_decay", _i32), ("tx_alc_postfilt_gain", _i32),
         ("tx_power_factor", _f32), ("tx_adj_gain_i", _f32), ("tx_adj_gain_q", _f32),
         ("iq_phase_balance_tx", _f32),
+        ("notch_mu", _i32),
     ]
 
     def copy(self) -> "ChanCfg":
@@ -118,4 +119,5 @@ def default_cfg(**kw) -> ChanCfg:
     c.tx_power_factor = 0.5
     c.tx_adj_gain_i = 1.0
     c.tx_adj_gain_q = 1.0
+    c.notch_mu = 10
     return c.replace(**kw) if kw else c

@@ -81,6 +81,7 @@ void default_chan_cfg(uhsdr_chan_cfg_t *c)
     c->tx_filter = UHSDR_TX_FILTER_SOPRANO; c->tx_bass_gain = 4; c->tx_treble_gain = 4; c->tx_mic_gain = 15;
     c->tx_comp_level = 2; c->tx_alc_decay = 10; c->tx_alc_postfilt_gain = 1;
     c->tx_power_factor = 0.5f; c->tx_adj_gain_i = 1.0f; c->tx_adj_gain_q = 1.0f;
+    c->notch_mu = 10;
 }
 
 // ---- biquad designers, audio_driver.c:818-964 (a1/a2 stored already negated) ----------------
@@ -226,7 +227,6 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     if (cfg.struct_size != sizeof(uhsdr_chan_cfg_t)) return fail(UHSDR_ERR_ARG, "uhsdr_chan_cfg_t.struct_size mismatch");
     if (cfg.filter_path < 1 || cfg.filter_path >= (int)t.h->num_paths) return fail(UHSDR_ERR_ARG, "filter_path out of range");
     if (cfg.dmod_mode < UHSDR_DEMOD_USB || cfg.dmod_mode > UHSDR_DEMOD_DIGI) return fail(UHSDR_ERR_UNSUPPORTED, "dmod_mode not implemented (SSBSTEREO/IQ are stereo-only modes)");
-    if (cfg.dsp_active & UHSDR_DSP_NOTCH_ENABLE) return fail(UHSDR_ERR_UNSUPPORTED, "LMS auto-notch (DSP_NOTCH_ENABLE) is not implemented");
     if ((cfg.dsp_active & UHSDR_DSP_NB_ENABLE) && cfg.nb_setting > 0) return fail(UHSDR_ERR_UNSUPPORTED, "LPC noise blanker (DSP_NB_ENABLE) is not implemented");
     if (cfg.spectrum_magnify != 0) return fail(UHSDR_ERR_UNSUPPORTED, "zoom FFT (sd.magnify != 0) is not implemented");
     if (cfg.fm_subaudible_tone_det_freq != 0.0f) return fail(UHSDR_ERR_UNSUPPORTED, "FM subaudible tone detection is not implemented");
@@ -354,6 +354,10 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     p->fm_translate_on = cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF;
 
     // spectral NR, audio_driver.c:1195, :2355, :2501; audio_nr.c:1857-1867, :2034-2059
+    // audio_driver.c:2443-2456 (FM never reaches RxProcessor_DemodAudioPostprocessing's notch: 48 ksps, no decimation)
+    p->notch_enable = ((cfg.dsp_active & UHSDR_DSP_NOTCH_ENABLE) && mode != UHSDR_DEMOD_CW && mode != UHSDR_DEMOD_FM &&
+                       !(mode == UHSDR_DEMOD_SAM && p->decimated_freq == 24000)) ? 1 : 0;
+    p->notch_mu = log10f(((cfg.notch_mu + 1.0) / 1500.0) + 1.0);        // :1170
     p->nr_enable = (p->decimated_freq == 12000 && (cfg.dsp_active & UHSDR_DSP_NR_ENABLE) && mode != UHSDR_DEMOD_FM) ? 1 : 0;
     {
         const int width_i = t.filt[fp.id].width;

@@ -275,7 +275,10 @@ static int rebuild_lists(uhsdr_engine *e)
             // channels with the spectral noise reduction take two serial phases around the warp-cooperative NR kernel
             (p.nr_enable ? e->h_list_split_nr : e->h_list_split).push_back(c);
             e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));
-        } else e->h_list_generic.push_back(c);
+        } else {
+            if (p.notch_enable) { e->last_error = "rx: the LMS auto-notch runs on the split path only (UHSDR_B200_NO_SPLIT is set, or the chain is not split-eligible)"; return UHSDR_ERR_UNSUPPORTED; }
+            e->h_list_generic.push_back(c);
+        }
     }
     if (!e->h_list_split.empty())
         CK(e, cudaMemcpyAsync(e->d_list_split, e->h_list_split.data(), e->h_list_split.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));

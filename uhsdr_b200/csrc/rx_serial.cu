@@ -22,7 +22,7 @@ namespace {
 
 constexpr int SER_THREADS = 32;
 
-__device__ __forceinline__ void load_ser(SerState &s, const ChanState &g)
+__device__ __forceinline__ void load_ser(SerState &s, const ChanState &g, bool notch)
 {
 #define CP1(f) s.f = g.f;
 #define CPA(f, n) for (int i_ = 0; i_ < (n); i_++) s.f[i_] = g.f[i_];
@@ -33,11 +33,15 @@ __device__ __forceinline__ void load_ser(SerState &s, const ChanState &g)
     CP1(sam_fil_out) CP1(sam_lowpass) CP1(sam_omega2) CP1(sam_phs) CP1(sam_dsI) CP1(sam_dsQ)
     CPA(sam_a, 24) CPA(sam_b, 24) CPA(sam_c, 24) CPA(sam_d, 24) CP1(sam_count) CP1(fade_dc27) CP1(fade_dc_insert) CP1(carrier_freq_offset)
     CP1(fm_i_prev) CP1(fm_q_prev) CP1(fm_lpf_prev) CP1(fm_hpf_prev_a) CP1(fm_hpf_prev_b) CP1(fm_sql_avg) CP1(fm_count) CP1(fm_squelched)
+    if (notch) {
+        CPA(notch_coef, NOTCH_TAPS) CPA(notch_x, NOTCH_TAPS) CPA(notch_delay, NOTCH_DELAY)
+        CP1(notch_energy) CP1(notch_x0) CP1(notch_head) CP1(notch_inbuf) CP1(notch_outbuf)
+    }
 #undef CP1
 #undef CPA
 }
 
-__device__ __forceinline__ void store_ser(ChanState &g, const SerState &s)
+__device__ __forceinline__ void store_ser(ChanState &g, const SerState &s, bool notch)
 {
 #define CP1(f) g.f = s.f;
 #define CPA(f, n) for (int i_ = 0; i_ < (n); i_++) g.f[i_] = s.f[i_];
@@ -48,6 +52,10 @@ __device__ __forceinline__ void store_ser(ChanState &g, const SerState &s)
     CP1(sam_fil_out) CP1(sam_lowpass) CP1(sam_omega2) CP1(sam_phs) CP1(sam_dsI) CP1(sam_dsQ)
     CPA(sam_a, 24) CPA(sam_b, 24) CPA(sam_c, 24) CPA(sam_d, 24) CP1(sam_count) CP1(fade_dc27) CP1(fade_dc_insert) CP1(carrier_freq_offset)
     CP1(fm_i_prev) CP1(fm_q_prev) CP1(fm_lpf_prev) CP1(fm_hpf_prev_a) CP1(fm_hpf_prev_b) CP1(fm_sql_avg) CP1(fm_count) CP1(fm_squelched)
+    if (notch) {
+        CPA(notch_coef, NOTCH_TAPS) CPA(notch_x, NOTCH_TAPS) CPA(notch_delay, NOTCH_DELAY)
+        CP1(notch_energy) CP1(notch_x0) CP1(notch_head) CP1(notch_inbuf) CP1(notch_outbuf)
+    }
 #undef CP1
 #undef CPA
 }
@@ -102,6 +110,37 @@ __device__ __forceinline__ float lattice_regs(float x, const float (&k)[NS], con
     return acc;
 }
 
+// LMS automatic notch on one decimated block, in place: AudioDriver_NotchFilter (audio_driver.c:1746-1763) around
+// arm_lms_norm_f32 (CMSIS arm_lms_norm_f32.c:372-443, the portable loop).  The adaptive FIR runs on the current
+// audio, the reference input is the audio delayed through the 128-sample line, and the notched audio is the error.
+__device__ __forceinline__ void notch_block(SerState &st, float *buf, int bs, float mu)
+{
+    for (int i = 0; i < bs; i++) st.notch_delay[st.notch_inbuf + i] = buf[i];
+    float energy = st.notch_energy, x0 = st.notch_x0;
+    int head = st.notch_head;
+    for (int i = 0; i < bs; i++) {
+        const float in = buf[i];
+        st.notch_x[(head + NOTCH_TAPS - 1) & (NOTCH_TAPS - 1)] = in;        // window = the newest 64 inputs, oldest at head
+        energy = __fsub_rn(energy, __fmul_rn(x0, x0));
+        energy = __fadd_rn(energy, __fmul_rn(in, in));
+        float sum = 0.0f;
+        for (int k = 0; k < NOTCH_TAPS; k++) sum = __fadd_rn(sum, __fmul_rn(st.notch_x[(head + k) & (NOTCH_TAPS - 1)], st.notch_coef[k]));
+        const float d = st.notch_delay[st.notch_outbuf + i];
+        const float e = __fsub_rn(d, sum);
+        buf[i] = e;
+        const float w = __fdiv_rn(__fmul_rn(e, mu), __fadd_rn(energy, 0.000000119209289f));
+        for (int k = 0; k < NOTCH_TAPS; k++)
+            st.notch_coef[k] = __fadd_rn(st.notch_coef[k], __fmul_rn(w, st.notch_x[(head + k) & (NOTCH_TAPS - 1)]));
+        x0 = st.notch_x[head];
+        head = (head + 1) & (NOTCH_TAPS - 1);
+    }
+    st.notch_energy = energy; st.notch_x0 = x0; st.notch_head = head;
+    st.notch_inbuf += bs;
+    st.notch_outbuf = st.notch_inbuf + bs;
+    st.notch_inbuf %= NOTCH_DELAY;
+    st.notch_outbuf %= NOTCH_DELAY;
+}
+
 // phase 0: the whole serial chain.  Channels with the spectral noise reduction, which sits between the AGC and the
 // biquad cascade (audio_driver.c:2501-2509) and works on warp-cooperative FFT frames (rx_nr_kernel), run it in two
 // launches: phase 1 = demodulation, lattice, AGC, result back into a.scratch; phase 2 = everything after the NR.
@@ -114,7 +153,8 @@ rx_serial_kernel(RxArgs a, int phase)
     const ChanParams &p = a.params[ch];
     const float *__restrict__ pool = a.pool;
     SerState st;
-    load_ser(st, a.state[ch]);
+    const bool notch = p.notch_enable != 0;
+    load_ser(st, a.state[ch], notch);
 
     const int M = p.M;
     const int nd = BLK / M;                         // decimated samples per block (FM: M = 1, unused)
@@ -159,7 +199,7 @@ rx_serial_kernel(RxArgs a, int phase)
     }
 #pragma unroll
     for (int q = 0; q < 5; q++) tc[q] = p.bq2[q];
-    const float scale_gain = p.scale_gain, fm_scaling = p.fm_scaling;
+    const float scale_gain = p.scale_gain, fm_scaling = p.fm_scaling, notch_mu = p.notch_mu;
     const bool remove_dc = ap.remove_dc && ap.mode != 5;
     float agc_wold = st.agc_wold;
     float ip[INTERP_HIST + BLK / 2];                // interpolator input: [history | decimated block]
@@ -195,6 +235,7 @@ rx_serial_kernel(RxArgs a, int phase)
             // lattice pre-filter :2473-2475, AGC :2485 (+ DC remover audio_agc.c:577-594, double expression),
             // fixed gain :2513-2524, biquad_1 :2527
             if (phase != 2) {
+                if (notch) notch_block(st, ad, nd, notch_mu);
                 for (int i = 0; i < nd; i++) {
                     float x = ad[i];
                     if (pn > 0) x = lattice_regs<10>(x, pk, pv, ps);
@@ -272,7 +313,7 @@ rx_serial_kernel(RxArgs a, int phase)
     st.agc_volts = ar.volts; st.agc_save_volts = ar.save_volts; st.agc_fast_backaverage = ar.fast_backaverage;
     st.agc_hang_backaverage = ar.hang_backaverage; st.agc_hang_counter = ar.hang_counter;
     st.agc_decay_type = ar.decay_type; st.agc_state = ar.state; st.agc_action = ar.action; st.agc_hang_action = ar.hang_action;
-    store_ser(a.state[ch], st);
+    store_ser(a.state[ch], st, notch);
 }
 
 cudaError_t launch_rx_serial(const RxArgs &a, int phase, cudaStream_t stream)

@@ -820,7 +820,7 @@ rx_ssb_fused_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fu
 bool fused_eligible(const ChanParams &p)
 {
     return p.configured && p.topo == TOPO_SSB_DEC_FIRST && p.M == 4 && p.s1_ntaps == 83 && p.s2_ntaps == 199 &&
-           p.shift_kind != 2 && !p.nr_enable && !p.spectrum_enable && p.pre.n <= 10 && (p.aa.n == 0 || p.aa.n == 6) &&
+           p.shift_kind != 2 && !p.nr_enable && !p.notch_enable && !p.spectrum_enable && p.pre.n <= 10 && (p.aa.n == 0 || p.aa.n == 6) &&
            p.interp_L == 4 && p.interp_plen >= 1 && p.interp_plen <= 4 && p.agc.attack_buffsize == AGC_W;
 }
 

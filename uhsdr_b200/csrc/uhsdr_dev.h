@@ -79,7 +79,13 @@ struct ChanParams {
     // spectrum
     int spectrum_enable;
     float codec_gain_calc;
+    // LMS automatic notch (audio_driver.c:1165-1187, :2443-2456)
+    int notch_enable;
+    float notch_mu;        // log10f((ts.dsp.notch_mu + 1.0) / 1500.0 + 1.0)
 };
+
+constexpr int NOTCH_TAPS = 64;     // DSP_NOTCH_NUMTAPS_MIN == MAX, audio_driver.h:486-488
+constexpr int NOTCH_DELAY = 128;   // DSP_NOTCH_BUFLEN_MIN == MAX, audio_driver.h:490-492
 
 struct BiquadS { float x1, x2, y1, y2; };
 
@@ -112,6 +118,11 @@ struct ChanState {
     // FM, audio_driver.c:1516-1531
     float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
     int fm_count, fm_squelched;
+    // LMS automatic notch: arm_lms_norm_f32 instance (coefficients, the newest 64 inputs as a circular window with
+    // notch_head = slot of the oldest, energy, x0) and the decorrelation delay line of AudioDriver_NotchFilter
+    float notch_coef[NOTCH_TAPS], notch_x[NOTCH_TAPS], notch_delay[NOTCH_DELAY];
+    float notch_energy, notch_x0;
+    int notch_head, notch_inbuf, notch_outbuf;
     // a_buffer[1] persistence is not needed: every non-FM path has an interpolator
     uint32_t samp_ptr;       // spectrum ring write pointer, audio_driver.c:1816-1824
     int adc_clip, adc_half_clip, adc_quarter_clip;
@@ -136,6 +147,11 @@ struct SerState {
     int carrier_freq_offset;
     float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
     int fm_count, fm_squelched;
+    // LMS automatic notch: arm_lms_norm_f32 instance (coefficients, the newest 64 inputs as a circular window with
+    // notch_head = slot of the oldest, energy, x0) and the decorrelation delay line of AudioDriver_NotchFilter
+    float notch_coef[NOTCH_TAPS], notch_x[NOTCH_TAPS], notch_delay[NOTCH_DELAY];
+    float notch_energy, notch_x0;
+    int notch_head, notch_inbuf, notch_outbuf;
 };
 
 // Spectral NR state, audio_nr.c (allocated only when a channel enables DSP_NR_ENABLE)
