@@ -38,10 +38,10 @@ int rx_split_floats_per_block(const ChanParams &p);     // scratch floats per 32
 bool fused_eligible(const ChanParams &p);
 void fill_fused_coefs(FusedCoefs *fc, const float *dec83, const float *hil_i199, const float *hil_q199);
 cudaError_t launch_rx_ssb_fused(const RxArgs &a, const FusedCoefs &fc, int sm_count, cudaStream_t stream);
-// same chain with the 199-tap Hilbert pair on the tensor cores (rx_ssb_tc.cu; shipping build only).
-// hil_ci / hil_cq: pool offsets of the two Hilbert tap sets.
+// same chain with the 83-tap decimator and the 199-tap Hilbert pair on the tensor cores (rx_ssb_tc.cu; shipping build
+// only).  dec_c / hil_ci / hil_cq: pool offsets of the decimator taps and of the two Hilbert tap sets.
 bool rx_ssb_tc_available();
-cudaError_t launch_rx_ssb_tc(const RxArgs &a, const FusedCoefs &fc, int hil_ci, int hil_cq, int sm_count, cudaStream_t stream);
+cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq, int sm_count, cudaStream_t stream);
 
 struct TxArgs {
     const ChanParams *params;

@@ -1,27 +1,37 @@
-// rx_ssb_tc.cu -- fused narrow-SSB/CW receiver kernel with the 199-tap Hilbert pair on the
-// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).  Shipping build only; the exact
-// build keeps the CUDA-core kernel of rx_ssb_fused.cu.
+// rx_ssb_tc.cu -- fused narrow-SSB/CW receiver kernel with BOTH FIR stages on the 5th-generation tensor
+// cores (tcgen05.mma, accumulators in TMEM).  Shipping build only; the exact build keeps the CUDA-core
+// kernel of rx_ssb_fused.cu.
 //
 // Chain (FilterPathInfo[4..47], mchf-eclipse/drivers/audio/audio_filter.c:147-922; flow in
 // audio_driver.c:2603-2942):
-//   format + IQ correction + Fs/4 translate -> 83-tap /4 decimator on I and Q      (FIR warps, FP32 pipe)
-//   -> 199-tap Hilbert pair @12 ksps -> I +/- Q                                    (tensor cores)
+//   format + IQ correction + Fs/4 translate                                         (front-end warps, FP32 pipe)
+//   -> 83-tap /4 decimator on I and Q                                               (tensor cores)
+//   -> 199-tap Hilbert pair @12 ksps -> I +/- Q                                     (tensor cores)
 //   -> 10-stage lattice IIR | WDSP AGC | gain, 4-stage biquad | x4 interpolator, (anti-alias lattice),
-//      treble biquad, x10, int32 << 16                                             (four serial warps)
+//      treble biquad, x10, int32 << 16                                              (four serial warps)
 //
 // One persistent CTA owns up to 28 channels for the whole launch; every sample crosses HBM once.
 //
-// Hilbert pair as a Toeplitz GEMM (north_star form (1)).  arm_fir_f32 (arm_fir_f32.c:522-529) computes
-// y[n] = sum_k c[k] d[n - 198 + k].  For a chunk of 64 outputs and all channels of the CTA
-//   D[m][ch] = sum_p T[m][p] X[p][ch],   T[m][p] = c[p - m - 10],   p = 0..271 (window of 272 inputs)
-// is a 64 x 32 x 272 GEMM whose A operand is the same for every chunk and channel.  Because T is
-// Toeplitz, the 64 x 16 slab of k-step kk is rows [264 - 16 kk, +64) of ONE table
-// G[r][q] = c[q - r + 254] (328 rows x 16), so the A descriptor just slides through a 10.5 KB table.
-// The B operand is the decimator output itself: a channel-major ring in shared memory in the
-// canonical K-major (no-swizzle) layout, where advancing in time is again an address offset.
-// I and Q accumulate into the same D (USB: I + Q; LSB: the Q samples are stored negated).
-// Arithmetic: BF16 operands, FP32 accumulation, split x = x1 + x2 (16 significant bits), c = c1 + c2,
-// D = c1 x1 + c2 x1 + c1 x2  -- relative error ~4e-6 (106 dB), measured in scripts/micro/umma_toeplitz.cu.
+// Both FIRs are Toeplitz GEMMs (north_star form (1)) with the taps as the A operand and the samples of all
+// channels of the CTA as the B operand, accumulated INCREMENTALLY: every 128-sample step brings one slab of
+// new samples into a small shared-memory ring, and that slab is multiplied into every output chunk it
+// contributes to (the TMEM accumulators of the chunks stay live across steps), so shared memory holds two
+// steps of samples instead of a whole filter window.
+//   decimator (arm_fir_decimate_f32.c:455-486): y[m] = sum_k c[k] x[4m - 82 + k].  Output chunk = 128 outputs
+//     = 512 inputs; with window slot p = input index - (512 chunk - 96):  D[m][col] = sum_p T[m][p] X[p][col],
+//     T[m][p] = c[p - 4m - 14], 38 k-steps of 16.  The 128 x 16 slab of k-step kk is rows [148 - 4kk, +128) of
+//     ONE table G[r][q] = c[q - 4r + 578] stored with linear rows, so the A descriptor slides 64 B per k-step.
+//     I and Q share the taps: columns = 32 I channels | 32 Q channels (N = 64).
+//   Hilbert pair (arm_fir_f32.c:522-529): y[n] = sum_k c[k] d[n - 198 + k].  Output chunk = 128 outputs, window
+//     slot p = index - (128 chunk - 208), T[m][p] = c[p - m - 10], 21 k-steps; slab kk = rows [320 - 16kk, +128)
+//     of G[r][q] = c[q - r + 310].  I and Q accumulate into the same D (USB: I + Q; LSB: Q stored negated).
+// Arithmetic: BF16 operands, FP32 accumulation, samples rounded to 16 significant bits and split exactly
+// x = x1 + x2, taps c = c1 + c2, D = c1 x1 + c2 x1 + c1 x2 -- relative error ~5e-6 per stage (106 dB), measured
+// in scripts/micro/umma_toeplitz.cu and umma_dec_toeplitz.cu.  The rounded values are also what the channel
+// state keeps, so splitting a call in two reproduces the one-call result bit for bit.
+// tcgen05.mma time here is set by operand fetch from shared memory (~128 B/clk: 48 cycles for the 128x64x16
+// decimator MMA, 40 for the 128x32x16 Hilbert MMA); the MMAs are issued under elect.sync so that ptxas emits
+// them back to back (issued from an `if (lane == 0)` region each one costs 56 cycles of a serialisation loop).
 #include <cuda_bf16.h>
 
 #include <type_traits>
@@ -36,51 +46,51 @@ namespace uhsdr {
 
 namespace {
 
-constexpr int FG = 28;             // channel slots per CTA (7 FIR warps x 4 channels)
+constexpr int FG = 28;             // channel slots per CTA (7 front-end warps x 4 channels)
 constexpr int CH4 = 128;           // input samples per step (4 blocks)
 constexpr int ND = 32;             // decimated samples per step
-constexpr int XP = 56;             // per-phase slots of the decimator staging: 24 history (21 used) + 32 new
-constexpr int XH = 24;
-constexpr int XCH = 2 * 4 * XP + 4;
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int LR = 5 * ND;          // rows of the lattice-output ring (decimated samples)
 constexpr int AG = 8;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
-constexpr int NWARP_FIR = FG / 4;
-constexpr int DEC_PAD = 32;        // FusedCoefs::dec carries the 83 taps at [32, 115)
-// tensor-core Hilbert
-constexpr int HT = 336;            // ring time slots per channel (272-slot window + 64 being produced)
-constexpr int HWIN = 272;          // window of one 64-output chunk (17 k-steps of 16)
-constexpr int KSTEPS = HWIN / 16;
-constexpr int GROWS = 328;         // Toeplitz table rows
-constexpr int RING_BYTES = 4 * (HT / 8) * 128;     // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
-constexpr int G_BYTES = GROWS * 32;                // [row/8][k half][row%8][8] bf16
-constexpr int TMEM_COLS = 64;      // two 64 x 32 fp32 accumulators
-// warp roles
-// (warp id % 4 is the scheduler: the four serial warps and the MMA issuer are spread over all four)
-constexpr int W_AGC = NWARP_FIR, W_POST = NWARP_FIR + 1, W_LAT = NWARP_FIR + 2, W_MMA = NWARP_FIR + 3, W_BQ = NWARP_FIR + 4;
-constexpr int NTHREADS = 32 * (NWARP_FIR + 5);
-// software pipeline, in steps of 128 input samples: step h is decimated at iteration h, its Hilbert
-// outputs leave TMEM at h + 4, lattice h + 5, AGC h + 6, gain + biquad cascade h + 7,
-// interpolator / treble / output formatting h + 8
-constexpr int IT_EPI = 4, IT_LAT = 5, IT_AGC = 6, IT_BQ = 7, IT_POST = 8;
+constexpr int NWARP_FE = FG / 4;
+// tensor-core FIRs
+constexpr int V = 8;               // virtual steps in front of the first real one: they carry the filter histories in
+constexpr int XSLOTS = 2 * CH4;    // decimator input ring: two steps
+constexpr int XR_BYTES = 8 * (XSLOTS / 8) * 128;   // one array: [I groups 0..3 | Q groups 0..3][time/8][channel%8][time%8] bf16
+constexpr int XSBO = (XSLOTS / 8) * 128;
+constexpr int HSLOTS = 2 * ND;     // Hilbert input ring: two steps
+constexpr int HR_BYTES = 4 * (HSLOTS / 8) * 128;   // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
+constexpr int HSBO = (HSLOTS / 8) * 128;
+constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
+constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
+constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
+// warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
+constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POST = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;
+constexpr int NTHREADS = 32 * (NWARP_FE + 9);
+// software pipeline, in steps of 128 input samples.  Step s (virtual steps included) is written into the decimator
+// ring at iteration s, its decimator MMAs are issued at s + 1, the decimator outputs leave TMEM for the Hilbert ring
+// at s + 2, the Hilbert MMAs are issued at s + 3, the Hilbert outputs leave TMEM at s + 4, then lattice s + 5,
+// AGC s + 6, gain + biquad cascade s + 7, interpolator / treble / output formatting s + 8.
+constexpr int IT_LAT = V + 5, IT_AGC = V + 6, IT_BQ = V + 7, IT_POST = V + 8;
 constexpr int PIPE_DEPTH = IT_POST;
 
 struct Smem {
-    alignas(128) unsigned char ring[4][RING_BYTES];   // I1, I2, Q1, Q2: bf16 split of the decimator outputs
-    alignas(128) unsigned char g[4][G_BYTES];         // Toeplitz tables: hil_i c1, c2, hil_q c1, c2
-    alignas(16) float x[FG * XCH];                    // decimator staging, polyphase layout
+    alignas(128) unsigned char xring[2][XR_BYTES];    // [I1 | Q1], [I2 | Q2]: bf16 split of the front-end outputs
+    alignas(128) unsigned char hring[4][HR_BYTES];    // I1, I2, Q1, Q2: bf16 split of the decimator outputs
+    alignas(128) unsigned char gh[4][2 * HPLANE];     // Hilbert Toeplitz tables: hil_i c1, c2, hil_q c1, c2
+    alignas(128) unsigned char gd[2][2 * DPLANE];     // decimator Toeplitz tables: c1, c2
     float aud[2][ND * SMS];
     float lat[LR * SMS];              // lattice output, a ring of 5 steps: AGC detector and gain stage read x[n-49] from it
     float agc[2][ND * SMS];           // AGC "volts" per sample (detector -> gain stage)
     float bq[2][ND * SMS];
     float smax[2][ND * SMS];
-    alignas(8) unsigned long long mma_bar[2];
+    int chan[32];                     // channel index of every slot (epilogue warps: state save / restore)
+    alignas(8) unsigned long long bar_dec[2], bar_hil[2];
     unsigned tmem_base;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
@@ -93,19 +103,36 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B; lbo = byte distance
-// between the two 16-byte K halves of a k-step, sbo = byte distance between 8-row groups
+// between the two 16-byte K halves of a k-step, sbo = byte distance between 8-row groups.  The start address
+// sits in the low 14 bits (units of 16 B), so moving an operand is an addition to the descriptor.
 __device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned lbo, unsigned sbo)
 {
     return (unsigned long long)((addr >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) |
            ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-__device__ __forceinline__ void umma_bf16(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate)
+// the three products of one k-step: D (+)= A1 B1; D += A2 B1; D += A1 B2
+__device__ __forceinline__ void umma3_bf16(unsigned tmem_d, unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                                           unsigned long long b2, unsigned idesc, unsigned accumulate)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 q, 0, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t}"
+                 ::"r"(tmem_d), "l"(a1), "l"(a2), "l"(b1), "l"(b2), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(unsigned long long *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // x rounded to 16 significant bits (round to nearest even) and split into two bf16 values whose sum
@@ -123,9 +150,18 @@ __device__ __forceinline__ void split_bf16(float h, unsigned &hi, unsigned &lo)
     hi = u >> 16;
     lo = __float_as_uint(h - __uint_as_float(u & 0xffff0000u)) >> 16;
 }
+// two samples -> one word of the hi array and one of the lo array (element 0 in the low half)
+__device__ __forceinline__ void split_pack2(float x0, float x1, unsigned &whi, unsigned &wlo)
+{
+    const float h0 = round16(x0), h1 = round16(x1);
+    const unsigned u0 = __float_as_uint(h0), u1 = __float_as_uint(h1);
+    whi = __byte_perm(u0, u1, 0x7632);
+    const unsigned l0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)), l1 = __float_as_uint(h1 - __uint_as_float(u1 & 0xffff0000u));
+    wlo = __byte_perm(l0, l1, 0x7632);
+}
 
-// byte offset of (channel slot g, time slot s) inside one ring array
-__device__ __forceinline__ int ring_off(int g, int s) { return (g >> 3) * ((HT / 8) * 128) + (s >> 3) * 128 + (g & 7) * 16 + (s & 7) * 2; }
+// byte offset of (column group gr, channel-in-group c8, time slot s) inside one ring array with `tgs` time groups
+__device__ __forceinline__ int ring_off(int gr, int c8, int s, int tgs) { return gr * (tgs * 128) + (s >> 3) * 128 + c8 * 16 + (s & 7) * 2; }
 
 struct FirLaneState {
     float te1, te2, te3;     // teta*_old
@@ -133,50 +169,20 @@ struct FirLaneState {
     int clip;                // bit0 quarter, bit1 half, bit2 full
 };
 
-template <int I, int N, typename F> __device__ __forceinline__ void static_for(F &&f)
-{
-    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
-}
-
-// Decimator: y[m] = sum_k c[k] x[4m - 82 + k] (arm_fir_decimate_f32.c:455-486).  With 96 history slots
-// in front (24 per phase), buffer position b = 4m + k + 14; phase = b & 3, idx = b >> 2.  Each lane
-// makes 4 consecutive outputs m0..m0+3 of one signal (the caller loops over I and Q with the same code, which
-// halves the instruction-cache footprint); element (q, e, ph) of the 7 x 4 float4 loads
-// is position 4 (m0 + 4q + e) + ph, i.e. tap K = 16q + 4 (e - j) + ph - 14 of output j.  Fully unrolled:
-// every tap is an immediate constant-bank operand and taps outside [0, 82] generate no instruction.
-__device__ __forceinline__ void decimate4(const float *xp, int m0, const FusedCoefs &fc, float acc[4])
-{
-#pragma unroll
-    for (int j = 0; j < 4; j++) acc[j] = 0.0f;
-    float4 v[2][4];                       // the loads of group q + 1 are issued before the FMAs of group q
-#pragma unroll
-    for (int ph = 0; ph < 4; ph++) v[0][ph] = lds128(xp + ph * XP + m0);
-    static_for<0, 7>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        if constexpr (q < 6) {
-#pragma unroll
-            for (int ph = 0; ph < 4; ph++) v[(q + 1) & 1][ph] = lds128(xp + ph * XP + m0 + 4 * (q + 1));
-        }
-        static_for<0, 4>([&](auto ec) {
-            constexpr int e = decltype(ec)::value;
-            static_for<0, 4>([&](auto pc) {
-                constexpr int ph = decltype(pc)::value;
-                const float4 vv = v[q & 1][ph];
-                const float x = (e == 0) ? vv.x : (e == 1) ? vv.y : (e == 2) ? vv.z : vv.w;
-                static_for<0, 4>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int K = 16 * q + 4 * (e - j) + ph - 14;
-                    if constexpr (K >= 0 && K < 83) acc[j] = fmaf(fc.dec[DEC_PAD + K], x, acc[j]);
-                });
-            });
-        });
-    });
-}
+#define TMEM_LD_X32(v, taddr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27," \
+                 "%28,%29,%30,%31}, [%32];"                                                                                \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),   \
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
+                 : "r"(taddr))
 
 }  // namespace
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ FusedCoefs fc, int chans_per_cta, int hil_ci, int hil_cq)
+rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -185,69 +191,68 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
     const int cta_first = blockIdx.x * chans_per_cta;
     const int n_here = min(chans_per_cta, a.num_items - cta_first);
     const int nsteps = a.nblocks / 4;
+    if (nsteps <= 0) return;
     const int niter = nsteps + PIPE_DEPTH;
+    const int s_end = V + nsteps;                      // one past the last real step
     const float *__restrict__ pool = a.pool;
 
-    // ---- one-time setup by all threads: Toeplitz tables, zeroed ring, barriers, TMEM ----
-    for (int i = threadIdx.x; i < 2 * GROWS * 16; i += NTHREADS) {
-        const int which = i / (GROWS * 16), e = i % (GROWS * 16);
+    // ---- one-time setup by all threads: Toeplitz tables, zeroed rings, barriers, TMEM ----
+    for (int i = threadIdx.x; i < 2 * HROWS * 16; i += NTHREADS) {
+        const int which = i / (HROWS * 16), e = i % (HROWS * 16);
         const int r = e >> 4, q = e & 15;
-        const int kidx = q - r + 254;
+        const int kidx = q - r + HC0;
         const float cv = (kidx >= 0 && kidx < 199) ? __ldg(pool + (which ? hil_cq : hil_ci) + kidx) : 0.0f;
         const __nv_bfloat16 c1 = __float2bfloat16_rn(cv);
         const __nv_bfloat16 c2 = __float2bfloat16_rn(cv - __bfloat162float(c1));
-        const int off = (r >> 3) * 256 + (q >> 3) * 128 + (r & 7) * 16 + (q & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16 *>(sm.g[2 * which] + off) = c1;
-        *reinterpret_cast<__nv_bfloat16 *>(sm.g[2 * which + 1] + off) = c2;
+        const int off = (q >> 3) * HPLANE + r * 16 + (q & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(sm.gh[2 * which] + off) = c1;
+        *reinterpret_cast<__nv_bfloat16 *>(sm.gh[2 * which + 1] + off) = c2;
     }
-    for (int i = threadIdx.x; i < 4 * RING_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm.ring)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < DROWS * 16; i += NTHREADS) {
+        const int r = i >> 4, q = i & 15;
+        const int kidx = q - 4 * r + DC0;
+        const float cv = (kidx >= 0 && kidx < 83) ? __ldg(pool + dec_c + kidx) : 0.0f;
+        const __nv_bfloat16 c1 = __float2bfloat16_rn(cv);
+        const __nv_bfloat16 c2 = __float2bfloat16_rn(cv - __bfloat162float(c1));
+        const int off = (q >> 3) * DPLANE + r * 16 + (q & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(sm.gd[0] + off) = c1;
+        *reinterpret_cast<__nv_bfloat16 *>(sm.gd[1] + off) = c2;
+    }
+    for (int i = threadIdx.x; i < 2 * XR_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm.xring)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 4 * HR_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4 *>(sm.hring)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < 32) sm.chan[threadIdx.x] = a.chan_list[cta_first + (threadIdx.x < n_here ? threadIdx.x : 0)];
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mma_bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.mma_bar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_dec[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_dec[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_hil[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sm.bar_hil[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // tables and zeroed ring -> visible to the tensor core
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // tables and zeroed rings -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = sm.tmem_base;
 
-    if (warp < NWARP_FIR) {
-        // ======================= FIR warp: 4 channels x 8 lanes ==================================
+    if (warp < NWARP_FE) {
+        // ======================= front-end warp: 4 channels x 8 lanes ============================
         const int cl = lane >> 3, r = lane & 7;
         const int g = warp * 4 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
         const ChanParams &p = a.params[ch];
         ChanState *st = a.state + ch;
-        float *xi = sm.x + g * XCH, *xq = xi + 4 * XP;
         const unsigned gmask = 0xffu << (8 * cl);
-        const int lsb = p.lsb;
+        // ring rows of this channel: I in column group g / 8, Q in column group 4 + g / 8
+        unsigned char *xi1 = sm.xring[0] + (g >> 3) * XSBO + (g & 7) * 16, *xq1 = xi1 + 4 * XSBO;
+        unsigned char *xi2 = sm.xring[1] + (g >> 3) * XSBO + (g & 7) * 16, *xq2 = xi2 + 4 * XSBO;
 
         FirLaneState ls;
         ls.te1 = st->teta1_old; ls.te2 = st->teta2_old; ls.te3 = st->teta3_old; ls.c1 = st->M_c1; ls.c2 = st->M_c2; ls.clip = 0;
-        for (int b = r; b < 4 * XH; b += 8) {
-            xi[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_i[b] : 0.0f;
-            xq[(b & 3) * XP + (b >> 2)] = active ? st->s1_hist_q[b] : 0.0f;
-        }
-        // Hilbert history d[-198..-1] (state slots 2..199) -> ring slots 10..207
-        if (active) {
-            for (int i = 2 + r; i < 200; i += 8) {
-                const float hi_ = round16(st->s2_hist_i[i]);
-                const float hq_ = round16(lsb ? -st->s2_hist_q[i] : st->s2_hist_q[i]);
-                unsigned i1, i2, q1, q2;
-                split_bf16(hi_, i1, i2); split_bf16(hq_, q1, q2);
-                const int off = ring_off(g, i + 8);
-                *reinterpret_cast<unsigned short *>(sm.ring[0] + off) = (unsigned short)i1;
-                *reinterpret_cast<unsigned short *>(sm.ring[1] + off) = (unsigned short)i2;
-                *reinterpret_cast<unsigned short *>(sm.ring[2] + off) = (unsigned short)q1;
-                *reinterpret_cast<unsigned short *>(sm.ring[3] + off) = (unsigned short)q2;
-            }
-        }
         const int iq_auto = p.iq_auto, shift_kind = p.shift_kind, shift_down = p.shift_down;
         const bool any_auto = __any_sync(0xffffffffu, iq_auto != 0);
         const bool fast_fe = __all_sync(0xffffffffu, iq_auto != 0 && shift_kind == 1);
@@ -257,192 +262,144 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
 
         // input prefetch: 8 x int4 = the 16 consecutive samples 16r .. 16r+15 of the step, one step ahead, straight from global memory
         int4 pre[8];
-        if (nsteps > 0) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) pre[i] = active ? __ldg(src + 8 * r + i) : make_int4(0, 0, 0, 0);
-        }
-        __syncwarp();
+        for (int i = 0; i < 8; i++) pre[i] = active ? __ldg(src + 8 * r + i) : make_int4(0, 0, 0, 0);
 
-        for (int t = 0; t < niter; t++) {
-            // the ring slots written in this step were last read by the MMAs of chunk t/2 - 2
-            if (t < nsteps && (t & 1) == 0 && t >= 4) mbar_wait(&sm.mma_bar[((t >> 1) - 2) & 1], (unsigned)((((t >> 1) - 2) >> 1) & 1));
-            // ---- Hilbert outputs of step t - 4 leave TMEM: rows 0..31 via quadrants 0,1 (warps 0,1), rows 32..63 via 2,3 ----
-            {
-                const int h = t - IT_EPI;
-                if (warp < 4 && h >= 0 && h < nsteps && (warp >> 1) == (h & 1)) {
-                    const int chunk = h >> 1;
-                    mbar_wait(&sm.mma_bar[chunk & 1], (unsigned)((chunk >> 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    unsigned v[32];
-                    const unsigned taddr = tmem + (unsigned)((chunk & 1) * 32) + ((unsigned)(warp * 32) << 16);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                 : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (lane < 16) {
-                        float *aud = sm.aud[h & 1] + ((warp & 1) * 16 + lane) * SMS;
-#pragma unroll
-                        for (int c = 0; c < FG; c++) aud[c] = __uint_as_float(v[c]);
-                    }
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        for (int it = 0; it < niter; it++) {
+            if (it == V - 1 && active) {
+                // decimator history x[-96..-1] (82 used) -> the last 96 slots of virtual step V - 1
+                for (int b = r; b < 96; b += 8) {
+                    unsigned i1, i2, q1, q2;
+                    split_bf16(round16(st->s1_hist_i[b]), i1, i2); split_bf16(round16(st->s1_hist_q[b]), q1, q2);
+                    const int off = (((V - 1) & 1) * CH4 + 32 + b);
+                    const int bo = (off >> 3) * 128 + (off & 7) * 2;
+                    *reinterpret_cast<unsigned short *>(xi1 + bo) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(xi2 + bo) = (unsigned short)i2;
+                    *reinterpret_cast<unsigned short *>(xq1 + bo) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(xq2 + bo) = (unsigned short)q2;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (t < nsteps) {
+            if (it >= V && it < s_end) {
+                const int t = it - V;
                 // ---- front end: the whole 128-sample step at once.  Lane r owns the 16 consecutive samples 16r .. 16r+15,
-                // i.e. one half of block r >> 1, and stores them as one float4 per decimator phase.  The 2^-16 input
-                // scaling (audio_driver.c:2680-2685) is exact, so it is folded into the correction factors; the Fs/4
-                // translation (freq_shift.c:219-262) is a sign/swap pattern of period 4 folded into the same factors.
-                {
-                    float fi[16], fq[16];
-                    int lvmax = 0;
+                // i.e. one half of block r >> 1.  The 2^-16 input scaling (audio_driver.c:2680-2685) is exact, so it is folded
+                // into the correction factors; the Fs/4 translation (freq_shift.c:219-262) is a sign/swap pattern of period 4
+                // folded into the same factors.
+                float fi[16], fq[16];
+                int lvmax = 0;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int4 v = pre[i];
-                        lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
-                        fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
+                for (int i = 0; i < 8; i++) {
+                    const int4 v = pre[i];
+                    lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
+                    fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
+                }
+                // fetch the next step behind the arithmetic
+                if (t + 1 < nsteps && active) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) pre[i] = __ldg(src + (size_t)(t + 1) * 64 + 8 * r + i);
+                }
+                lvmax >>= 16;                                                // audio_driver.c:2662-2675
+                ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
+                const float kS = 0.0000152587890625f;                        // 2^-16
+                float c1m = 0.0f, c2m = 1.0f;                                // M_c1, M_c2 of this lane's block
+                if (any_auto) {
+                    // Moseley & Slump block statistics (:2274-2279); sign(i) * q as a sign-bit transfer (differs from
+                    // Math_sign_new only for i == 0, where the term is +-q instead of 0)
+                    float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
+                        s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
                     }
-                    // fetch the next step behind the FIR work
-                    if (t + 1 < nsteps && active) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 1, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 1, 8);
+                    // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
+                    float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                    const float kE = 0.003f * 0.03125f * kS;
+                    float bs1[4], bs2[4], bs3[4];           // all twelve broadcasts in flight before the recurrence uses them
 #pragma unroll
-                        for (int i = 0; i < 8; i++) pre[i] = __ldg(src + (size_t)(t + 1) * 64 + 8 * r + i);
+                    for (int b = 0; b < 4; b++) {
+                        bs1[b] = __shfl_sync(0xffffffffu, s1, 2 * b, 8); bs2[b] = __shfl_sync(0xffffffffu, s2, 2 * b, 8); bs3[b] = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
                     }
-                    lvmax >>= 16;                                                // audio_driver.c:2662-2675
-                    ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
-                    const float kS = 0.0000152587890625f;                        // 2^-16
-                    float c1m = 0.0f, c2m = 1.0f;                                // M_c1, M_c2 of this lane's block
-                    if (any_auto) {
-                        // Moseley & Slump block statistics (:2274-2279); sign(i) * q as a sign-bit transfer (differs from
-                        // Math_sign_new only for i == 0, where the term is +-q instead of 0)
-                        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
 #pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
-                            s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
-                        }
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 1, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 1, 8);
-                        // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
-                        float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-                        const float kE = 0.003f * 0.03125f * kS;
-                        float bs1[4], bs2[4], bs3[4];           // all twelve broadcasts in flight before the recurrence uses them
+                    for (int b = 0; b < 4; b++) {
+                        t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
+                        if ((r >> 1) == b) { m1 = t1; m2 = t2; m3 = t3; }
+                    }
+                    const float den = m2 * m2;
+                    const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
+                    if (iq_auto) {
+                        ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
+                        c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
+                        c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
+                        ls.c1 = c1m; ls.c2 = c2m;                            // lanes 6, 7 hold the block-3 values the state keeps
+                    }
+                }
+                if (fast_fe) {
+                    // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
+                    //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
+                    const float sgd = shift_down ? -1.0f : 1.0f;
+                    const float fa = c2m * kS, fd = c1m * kS, fas = fa * sgd, fds = fd * sgd, ks = kS * sgd;
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            bs1[b] = __shfl_sync(0xffffffffu, s1, 2 * b, 8); bs2[b] = __shfl_sync(0xffffffffu, s2, 2 * b, 8); bs3[b] = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
-                        }
+                    for (int k = 0; k < 16; k += 4) {
+                        const float i0 = fi[k], i1 = fi[k + 1], i2 = fi[k + 2], i3 = fi[k + 3];
+                        fi[k] = i0 * fa;                                  fq[k] = fmaf(i0, fd, fq[k] * kS);
+                        fi[k + 1] = fmaf(i1, fds, fq[k + 1] * ks);        fq[k + 1] = i1 * -fas;
+                        fi[k + 2] = i2 * -fa;                             fq[k + 2] = fmaf(i2, -fd, fq[k + 2] * -kS);
+                        fi[k + 3] = fmaf(i3, -fds, fq[k + 3] * -ks);      fq[k + 3] = i3 * fas;
+                    }
+                } else {
 #pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
-                            if ((r >> 1) == b) { m1 = t1; m2 = t2; m3 = t3; }
-                        }
-                        const float den = m2 * m2;
-                        const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
+                    for (int k = 0; k < 16; k++) {
+                        float vi = fi[k], vq = fq[k];
                         if (iq_auto) {
-                            ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
-                            c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
-                            c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
-                            ls.c1 = c1m; ls.c2 = c2m;                            // lanes 6, 7 hold the block-3 values the state keeps
+                            vq = fmaf(c1m, vi, vq);               // q += M_c1 * i  (:2308-2311)
+                            vi = vi * c2m;                        // i *= M_c2      (:2313)
+                        } else {
+                            vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
+                            if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
+                            else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
                         }
-                    }
-                    float oi[16], oq[16];
-                    if (fast_fe) {
-                        // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
-                        //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
-                        const float sgd = shift_down ? -1.0f : 1.0f;
-                        const float fa = c2m * kS, fd = c1m * kS, fas = fa * sgd, fds = fd * sgd, ks = kS * sgd;
-#pragma unroll
-                        for (int k = 0; k < 16; k += 4) {
-                            oi[k] = fi[k] * fa;                                   oq[k] = fmaf(fi[k], fd, fq[k] * kS);
-                            oi[k + 1] = fmaf(fi[k + 1], fds, fq[k + 1] * ks);     oq[k + 1] = fi[k + 1] * -fas;
-                            oi[k + 2] = fi[k + 2] * -fa;                          oq[k + 2] = fmaf(fi[k + 2], -fd, fq[k + 2] * -kS);
-                            oi[k + 3] = fmaf(fi[k + 3], -fds, fq[k + 3] * -ks);   oq[k + 3] = fi[k + 3] * fas;
+                        vi *= kS; vq *= kS;
+                        if (shift_kind == 1) {
+                            const float sgd = shift_down ? -1.0f : 1.0f;
+                            const int ph = k & 3;
+                            const float ti = vi, tq_ = vq;
+                            if (ph == 1) { vi = tq_ * sgd; vq = -ti * sgd; }
+                            else if (ph == 2) { vi = -ti; vq = -tq_; }
+                            else if (ph == 3) { vi = -tq_ * sgd; vq = ti * sgd; }
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++) {
-                            float vi = fi[k], vq = fq[k];
-                            if (iq_auto) {
-                                vq = fmaf(c1m, vi, vq);               // q += M_c1 * i  (:2308-2311)
-                                vi = vi * c2m;                        // i *= M_c2      (:2313)
-                            } else {
-                                vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
-                                if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
-                                else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
-                            }
-                            vi *= kS; vq *= kS;
-                            if (shift_kind == 1) {
-                                const float sgd = shift_down ? -1.0f : 1.0f;
-                                const int ph = k & 3;
-                                const float ti = vi, tq_ = vq;
-                                if (ph == 1) { vi = tq_ * sgd; vq = -ti * sgd; }
-                                else if (ph == 2) { vi = -ti; vq = -tq_; }
-                                else if (ph == 3) { vi = -tq_ * sgd; vq = ti * sgd; }
-                            }
-                            oi[k] = vi; oq[k] = vq;
-                        }
-                    }
-                    // sample 16r + 4k + ph -> phase array ph, slot XH + 4r + k: one float4 per phase
-#pragma unroll
-                    for (int ph = 0; ph < 4; ph++) {
-                        *reinterpret_cast<float4 *>(xi + ph * XP + XH + 4 * r) = make_float4(oi[ph], oi[ph + 4], oi[ph + 8], oi[ph + 12]);
-                        *reinterpret_cast<float4 *>(xq + ph * XP + XH + 4 * r) = make_float4(oq[ph], oq[ph + 4], oq[ph + 8], oq[ph + 12]);
+                        fi[k] = vi; fq[k] = vq;
                     }
                 }
-                __syncwarp();
-                // ---- decimate: outputs 4r .. 4r+3 for I and Q -> 16-bit rounding, bf16 split, Hilbert ring ----
+                // ---- 16-bit rounding, bf16 split, decimator ring: slots 16r .. 16r+15 of buffer it & 1 = two 16-byte rows per array.
+                // The MMAs of step it - 2 read this buffer; they were committed one iteration ago.
+                mbar_wait(&sm.bar_dec[it & 1], (unsigned)(((it - 2) >> 1) & 1));
                 {
-                    const int sl = (208 + ND * t + 4 * r) % HT;          // ring slot of decimated sample 32 t + 4 r
-                    const int off = ring_off(g, sl);
-#pragma unroll 1
-                    for (int c = 0; c < 2; c++) {
-                        float acc[4];
-                        decimate4(c ? xq : xi, 4 * r, fc, acc);
-                        const bool neg = c && lsb;                         // LSB: I - Q, the Q samples are stored negated
-                        unsigned h1[4], h2[4];
+                    unsigned wi1[8], wi2[8], wq1[8], wq2[8];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) split_bf16(round16(neg ? -acc[j] : acc[j]), h1[j], h2[j]);
-                        *reinterpret_cast<uint2 *>(sm.ring[2 * c] + off) = make_uint2(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16));
-                        *reinterpret_cast<uint2 *>(sm.ring[2 * c + 1] + off) = make_uint2(h2[0] | (h2[1] << 16), h2[2] | (h2[3] << 16));
+                    for (int k = 0; k < 8; k++) {
+                        split_pack2(fi[2 * k], fi[2 * k + 1], wi1[k], wi2[k]);
+                        split_pack2(fq[2 * k], fq[2 * k + 1], wq1[k], wq2[k]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
+                    const int bo = ((it & 1) * (CH4 / 8) + 2 * r) * 128;
+                    *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]); *reinterpret_cast<uint4 *>(xi1 + bo + 128) = make_uint4(wi1[4], wi1[5], wi1[6], wi1[7]);
+                    *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]); *reinterpret_cast<uint4 *>(xi2 + bo + 128) = make_uint4(wi2[4], wi2[5], wi2[6], wi2[7]);
+                    *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]); *reinterpret_cast<uint4 *>(xq1 + bo + 128) = make_uint4(wq1[4], wq1[5], wq1[6], wq1[7]);
+                    *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]); *reinterpret_cast<uint4 *>(xq2 + bo + 128) = make_uint4(wq2[4], wq2[5], wq2[6], wq2[7]);
                 }
-                __syncwarp();
-                // keep the newest 24 entries of every phase: idx 32..55 -> 0..23 (6 float4 per phase)
-                {
-                    float4 ki[3], kq[3];
-#pragma unroll
-                    for (int u = 0; u < 3; u++) {
-                        const int e = r + 8 * u;             // 0..23 -> (phase, float4)
-                        ki[u] = lds128(xi + (e / 6) * XP + 32 + 4 * (e % 6)); kq[u] = lds128(xq + (e / 6) * XP + 32 + 4 * (e % 6));
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 3; u++) {
-                        const int e = r + 8 * u;
-                        *reinterpret_cast<float4 *>(xi + (e / 6) * XP + 4 * (e % 6)) = ki[u];
-                        *reinterpret_cast<float4 *>(xq + (e / 6) * XP + 4 * (e % 6)) = kq[u];
-                    }
-                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
             }
             __syncthreads();
         }
-        // ---- store state: decimator history, the newest 198 Hilbert inputs, IQ-correction state ----
+        // ---- store state: decimator history = the last 96 samples of the last step, IQ-correction state ----
         if (active) {
-            for (int b = r; b < 4 * XH; b += 8) {
-                st->s1_hist_i[b] = xi[(b & 3) * XP + (b >> 2)];
-                st->s1_hist_q[b] = xq[(b & 3) * XP + (b >> 2)];
-            }
-            // state slot i (2..199) = decimated sample 32 nsteps - 200 + i = ring slot (208 + 32 nsteps - 200 + i) % HT
-            for (int i = 2 + r; i < 200; i += 8) {
-                const int off = ring_off(g, (8 + ND * nsteps + i) % HT);
-                const unsigned i1 = *reinterpret_cast<const unsigned short *>(sm.ring[0] + off), i2 = *reinterpret_cast<const unsigned short *>(sm.ring[1] + off);
-                const unsigned q1 = *reinterpret_cast<const unsigned short *>(sm.ring[2] + off), q2 = *reinterpret_cast<const unsigned short *>(sm.ring[3] + off);
-                const float vi = __uint_as_float(i1 << 16) + __uint_as_float(i2 << 16);
-                const float vq = __uint_as_float(q1 << 16) + __uint_as_float(q2 << 16);
-                st->s2_hist_i[i] = vi;
-                st->s2_hist_q[i] = lsb ? -vq : vq;
+            const int sl = (s_end - 1) & 1;
+            for (int b = r; b < 96; b += 8) {
+                const int off = sl * CH4 + 32 + b;
+                const int bo = (off >> 3) * 128 + (off & 7) * 2;
+                const unsigned i1 = *reinterpret_cast<const unsigned short *>(xi1 + bo), i2 = *reinterpret_cast<const unsigned short *>(xi2 + bo);
+                const unsigned q1 = *reinterpret_cast<const unsigned short *>(xq1 + bo), q2 = *reinterpret_cast<const unsigned short *>(xq2 + bo);
+                st->s1_hist_i[b] = __uint_as_float(i1 << 16) + __uint_as_float(i2 << 16);
+                st->s1_hist_q[b] = __uint_as_float(q1 << 16) + __uint_as_float(q2 << 16);
             }
             int clip = ls.clip;
             ls.c1 = __shfl_sync(gmask, ls.c1, 6, 8); ls.c2 = __shfl_sync(gmask, ls.c2, 6, 8);
@@ -461,47 +418,150 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
 
     if (warp == W_MMA) {
         // ======================= MMA issue: one elected lane ====================================
-        // Chunk c (steps 2c, 2c+1) is complete after iteration min(2c+1, nsteps-1); its 102 MMAs are issued at
-        // the start of the next iteration into accumulator c & 1 and committed to mma_bar[c & 1].
-        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(32 >> 3) << 17) | ((unsigned)(64 >> 4) << 24);
-        const unsigned sbo_b = (HT / 8) * 128;
-        for (int t = 0; t < niter; t++) {
-            int chunk = -1;
-            if (t >= 1 && t <= nsteps) {
-                if ((t & 1) == 0) chunk = (t >> 1) - 1;
-                else if (t == nsteps) chunk = (t - 1) >> 1;
-            }
-            if (chunk >= 0 && lane == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned d_tmem = tmem + (unsigned)((chunk & 1) * 32);
-                const int s0 = (64 * chunk) % HT;                   // ring slot of the window start (decimated sample 64c - 208)
-                // k-step kk: A = rows [264 - 16 kk, +64) of the Toeplitz table (start address - 512 B per step),
-                //            B = ring slots [s0 + 16 kk, +16) (start address + 256 B per step, wrapping at HT slots)
-#pragma unroll 1
-                for (int arr = 0; arr < 2; arr++) {
-                    unsigned long long a1 = umma_desc(smem_u32(sm.g[2 * arr]) + 264u * 32u, 128, 256);
-                    unsigned long long a2 = umma_desc(smem_u32(sm.g[2 * arr + 1]) + 264u * 32u, 128, 256);
-                    unsigned long long b1 = umma_desc(smem_u32(sm.ring[2 * arr]) + (unsigned)(s0 >> 3) * 128u, 128, sbo_b);
-                    unsigned long long b2 = umma_desc(smem_u32(sm.ring[2 * arr + 1]) + (unsigned)(s0 >> 3) * 128u, 128, sbo_b);
-                    int s = s0;
-#pragma unroll 1
-                    for (int kk = 0; kk < KSTEPS; kk++) {
-                        umma_bf16(d_tmem, a1, b1, idesc, (arr > 0 || kk > 0) ? 1u : 0u);
-                        umma_bf16(d_tmem, a2, b1, idesc, 1u);
-                        umma_bf16(d_tmem, a1, b2, idesc, 1u);
-                        a1 -= 512u >> 4; a2 -= 512u >> 4;
-                        s += 16;
-                        if (s >= HT) { s -= HT; b1 -= (unsigned long long)(((HT - 16) / 8) * 128 >> 4); b2 -= (unsigned long long)(((HT - 16) / 8) * 128 >> 4); }
-                        else { b1 += 256u >> 4; b2 += 256u >> 4; }
+        const unsigned idesc_d = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(64 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        const unsigned idesc_h = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(32 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        const unsigned long long ad1 = umma_desc(smem_u32(sm.gd[0]) + DR0 * 16, DPLANE, 128), ad2 = umma_desc(smem_u32(sm.gd[1]) + DR0 * 16, DPLANE, 128);
+        const unsigned long long bx1 = umma_desc(smem_u32(sm.xring[0]), 128, XSBO), bx2 = umma_desc(smem_u32(sm.xring[1]), 128, XSBO);
+        unsigned long long ah[4], bh[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ah[i] = umma_desc(smem_u32(sm.gh[i]) + HR0 * 16, HPLANE, 128); bh[i] = umma_desc(smem_u32(sm.hring[i]), 128, HSBO); }
+        const int oc_last = (s_end - 1) >> 2;
+        for (int it = 0; it < niter; it++) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const int sd = it - 1;               // step whose samples were written into the decimator ring in the previous iteration
+                if (sd >= 0) {
+                    const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * 8), b2 = bx2 + (unsigned)((sd & 1) * (CH4 / 8) * 8);
+                    if (sd >= V && sd < s_end) {
+                        // the 8 k-steps of this step into its own chunk: kk = 6 + 8 (sd & 3) + j
+                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64);
+                        const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + 16 * j, b2 + 16 * j, idesc_d, 1u);
                     }
+                    if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end) {
+                        // the last 96 samples of the step are the history of the next chunk: kk = 0 .. 5, first write of its accumulator
+                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
+#pragma unroll
+                        for (int j = 2; j < 8; j++)
+                            umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + 16 * j, b2 + 16 * j, idesc_d, j > 2 ? 1u : 0u);
+                    }
+                    umma_commit(&sm.bar_dec[sd & 1]);
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sm.mma_bar[chunk & 1])) : "memory");
+                const int sh = it - 3;               // step whose decimator outputs were written into the Hilbert ring in the previous iteration
+                if (sh >= 0) {
+                    if (sh >= 1 && sh < s_end) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int u = 2 * sh + e;                        // global k-step (16 decimated samples)
+                            const int oa = u >> 3, ob = u & 7;
+                            const unsigned boff = (unsigned)((sh & 1) * (ND / 8) * 8 + e * 16);
+#pragma unroll
+                            for (int dd = 0; dd < 3; dd++) {
+                                const int oc = oa + dd;                      // output chunk this slab contributes to
+                                if ((dd < 2 || ob >= 3) && oc >= V / 4 && oc <= oc_last) {
+                                    const int kk = u - 8 * oc + 13;
+                                    const unsigned d_tmem = tmem + HIL_COL0 + (unsigned)((oc & 3) * 32);
+                                    umma3_bf16(d_tmem, ah[0] - 16 * kk, ah[1] - 16 * kk, bh[0] + boff, bh[1] + boff, idesc_h, kk > 0 ? 1u : 0u);
+                                    umma3_bf16(d_tmem, ah[2] - 16 * kk, ah[3] - 16 * kk, bh[2] + boff, bh[3] + boff, idesc_h, 1u);
+                                }
+                            }
+                        }
+                    }
+                    umma_commit(&sm.bar_hil[sh & 1]);
+                }
             }
             __syncwarp();
             __syncthreads();
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+        return;
+    }
+
+    if (warp >= W_EPI && warp < W_EPI + 4) {
+        // ======================= epilogue warps: TMEM lane quadrant warp % 4 =====================
+        // Step s occupies rows 32 (s & 3) .. +31 of its chunk accumulator = the lanes of quadrant s & 3; lane = decimated sample.
+        const int qd = warp & 3;
+        const unsigned lane_base = (unsigned)(qd * 32) << 16;
+        unsigned lsbmask;
+        {
+            const int chn = sm.chan[lane];
+            lsbmask = __ballot_sync(0xffffffffu, lane < n_here && a.params[chn].lsb != 0);
+        }
+        for (int it = 0; it < niter; it++) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int sd = it - 2;
+            if (sd >= 1 && sd < s_end && (sd & 3) == qd) {
+                const int slot = (sd & 1) * ND + lane;
+                const int bo = (slot >> 3) * 128 + (slot & 7) * 2;
+                unsigned char *h0 = sm.hring[0] + bo, *h1 = sm.hring[1] + bo, *h2 = sm.hring[2] + bo, *h3 = sm.hring[3] + bo;
+                // state slot of this lane's sample once the launch is over (s2_hist[2..199] = the newest 198 decimator outputs)
+                const int i_new = ND * (sd - V) + lane - ND * nsteps + 200;
+                if (sd < V) {
+                    // virtual step: Hilbert history d[-198..-1] = state slots 2..199 (already rounded if this kernel wrote them)
+                    const int i_old = ND * (sd - V) + lane + 200;
+                    if (sd >= 2) mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
+#pragma unroll 4
+                    for (int n = 0; n < FG; n++) {
+                        float vi = 0.0f, vq = 0.0f;
+                        if (n < n_here && i_old >= 2) {
+                            ChanState *stn = a.state + sm.chan[n];
+                            vi = round16(stn->s2_hist_i[i_old]); vq = round16(stn->s2_hist_q[i_old]);
+                            if (i_new >= 2) { stn->s2_hist_i[i_new] = vi; stn->s2_hist_q[i_new] = vq; }
+                        }
+                        if ((lsbmask >> n) & 1u) vq = -vq;
+                        unsigned i1, i2, q1, q2;
+                        split_bf16(vi, i1, i2); split_bf16(vq, q1, q2);
+                        const int co = (n >> 3) * HSBO + (n & 7) * 16;
+                        *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
+                        *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
+                    }
+                } else {
+                    mbar_wait(&sm.bar_dec[sd & 1], (unsigned)((sd >> 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned taddr = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64) + lane_base;
+                    unsigned vi[32], vq[32];
+                    TMEM_LD_X32(vi, taddr);
+                    TMEM_LD_X32(vq, taddr + 32u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // the Hilbert MMAs of step sd - 2 read this ring buffer; they were committed one iteration ago
+                    mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
+                    const bool save = i_new >= 2;
+#pragma unroll
+                    for (int n = 0; n < FG; n++) {
+                        const float hi_ = round16(__uint_as_float(vi[n]));
+                        const float hq_ = round16(__uint_as_float(vq[n]));
+                        unsigned i1, i2, q1, q2;
+                        split_bf16(hi_, i1, i2); split_bf16(((lsbmask >> n) & 1u) ? -hq_ : hq_, q1, q2);
+                        const int co = (n >> 3) * HSBO + (n & 7) * 16;
+                        *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
+                        *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
+                        if (save && n < n_here) {
+                            ChanState *stn = a.state + sm.chan[n];
+                            stn->s2_hist_i[i_new] = hi_; stn->s2_hist_q[i_new] = hq_;
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
+            }
+            const int sh = it - 4;
+            if (sh >= V && sh < s_end && (sh & 3) == qd) {
+                // ---- Hilbert outputs of step sh leave TMEM: lane = decimated sample, column = channel ----
+                mbar_wait(&sm.bar_hil[sh & 1], (unsigned)((sh >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                unsigned v[32];
+                const unsigned taddr = tmem + HIL_COL0 + (unsigned)(((sh >> 2) & 3) * 32) + lane_base;
+                TMEM_LD_X32(v, taddr);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float *aud = sm.aud[sh & 1] + lane * SMS;
+#pragma unroll
+                for (int c = 0; c < FG; c++) aud[c] = __uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+        }
         return;
     }
 
@@ -942,9 +1002,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, const __grid_constant__ Fused
     }
 }
 
-cudaError_t launch_rx_ssb_tc(const RxArgs &a, const FusedCoefs &fc, int hil_ci, int hil_cq, int sm_count, cudaStream_t stream)
+cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq, int sm_count, cudaStream_t stream)
 {
-    if (a.num_items <= 0) return cudaSuccess;
+    if (a.num_items <= 0 || a.nblocks <= 0) return cudaSuccess;
     if (a.nblocks % 4 != 0 || a.chan_list == nullptr) return cudaErrorInvalidValue;
     int per = (a.num_items + sm_count - 1) / sm_count;
     per = ((per + 3) / 4) * 4;
@@ -953,7 +1013,7 @@ cudaError_t launch_rx_ssb_tc(const RxArgs &a, const FusedCoefs &fc, int hil_ci, 
     const int grid = (a.num_items + per - 1) / per;
     cudaError_t e = cudaFuncSetAttribute(rx_ssb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
-    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, fc, per, hil_ci, hil_cq);
+    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq);
     return cudaGetLastError();
 }
 
@@ -964,7 +1024,7 @@ bool rx_ssb_tc_available() { return true; }
 #else   // UHSDR_EXACT: reference-order arithmetic has no tensor-core form
 
 namespace uhsdr {
-cudaError_t launch_rx_ssb_tc(const RxArgs &, const FusedCoefs &, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_rx_ssb_tc(const RxArgs &, int, int, int, int, cudaStream_t) { return cudaErrorNotSupported; }
 bool rx_ssb_tc_available() { return false; }
 }  // namespace uhsdr
 
