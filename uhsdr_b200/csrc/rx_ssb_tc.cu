@@ -34,6 +34,7 @@
 // them back to back (issued from an `if (lane == 0)` region each one costs 56 cycles of a serialisation loop).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "dsp_device.cuh"
@@ -57,11 +58,14 @@ constexpr int NWARP_FE = FG / 4;
 // tensor-core FIRs
 constexpr int V = 8;               // virtual steps in front of the first real one: they carry the filter histories in
 constexpr int XSLOTS = 2 * CH4;    // decimator input ring: two steps
-constexpr int XR_BYTES = 8 * (XSLOTS / 8) * 128;   // one array: [I groups 0..3 | Q groups 0..3][time/8][channel%8][time%8] bf16
-constexpr int XSBO = (XSLOTS / 8) * 128;
+constexpr int XLBO = 160;          // byte stride between time groups: 128-byte core matrix + 32 bytes, so that the front-end stores (2 time
+                                   // groups apart between neighbouring lane groups) and the 4 channels of a warp tile one 128-byte bank row
+constexpr int XSBO = (XSLOTS / 8) * XLBO;
+constexpr int XR_BYTES = 8 * XSBO;                 // one array: [I groups 0..3 | Q groups 0..3][time/8][channel%8][time%8] bf16
 constexpr int HSLOTS = 2 * ND;     // Hilbert input ring: two steps
-constexpr int HR_BYTES = 4 * (HSLOTS / 8) * 128;   // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
-constexpr int HSBO = (HSLOTS / 8) * 128;
+constexpr int HLBO = 144;          // time-group stride: core matrix + 16 bytes (the epilogue stores of 32 consecutive slots hit 4 distinct bank groups)
+constexpr int HSBO = (HSLOTS / 8) * HLBO;
+constexpr int HR_BYTES = 4 * HSBO;                 // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
 constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
 constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
@@ -135,30 +139,24 @@ __device__ __forceinline__ void umma_commit(unsigned long long *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// x rounded to 16 significant bits (round to nearest even) and split into two bf16 values whose sum
-// is that rounded value exactly: hi = upper 16 bits (truncation), lo = remainder (<= 8 significant bits).
-// The rounded value is what the channel state keeps, so the split is reproducible across calls.
-__device__ __forceinline__ float round16(float x)
+// x -> two bf16 values: hi = round-to-nearest bf16 of x, lo = the exact remainder x - hi truncated to bf16 (8 more
+// significant bits, so hi + lo carries 16-17 bits of x).  The split is idempotent: splitting h = hi + lo again gives
+// (hi, lo), and h is what the channel state keeps, so cutting a call in two reproduces the one-call result bit for bit.
+__device__ __forceinline__ void split_bf16(float x, unsigned &hi, unsigned &lo)
 {
-    unsigned u = __float_as_uint(x);
-    u += 0x7fu + ((u >> 8) & 1u);
-    return __uint_as_float(u & 0xffffff00u);
+    unsigned short hb;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(hb) : "f"(x));
+    hi = hb;
+    lo = __float_as_uint(x - __uint_as_float(hi << 16)) >> 16;
 }
-__device__ __forceinline__ void split_bf16(float h, unsigned &hi, unsigned &lo)
-{
-    const unsigned u = __float_as_uint(h);
-    hi = u >> 16;
-    lo = __float_as_uint(h - __uint_as_float(u & 0xffff0000u)) >> 16;
-}
-// two samples -> one word of the hi array and one of the lo array (element 0 in the low half)
+// two samples -> one word of the hi array and one of the lo array (element 0 in the low half): one F2FP for both hi
 __device__ __forceinline__ void split_pack2(float x0, float x1, unsigned &whi, unsigned &wlo)
 {
-    const float h0 = round16(x0), h1 = round16(x1);
-    const unsigned u0 = __float_as_uint(h0), u1 = __float_as_uint(h1);
-    whi = __byte_perm(u0, u1, 0x7632);
-    const unsigned l0 = __float_as_uint(h0 - __uint_as_float(u0 & 0xffff0000u)), l1 = __float_as_uint(h1 - __uint_as_float(u1 & 0xffff0000u));
-    wlo = __byte_perm(l0, l1, 0x7632);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(whi) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(whi << 16), r1 = x1 - __uint_as_float(whi & 0xffff0000u);
+    wlo = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
 }
+__device__ __forceinline__ float join_bf16(unsigned hi, unsigned lo) { return __uint_as_float(hi << 16) + __uint_as_float(lo << 16); }
 
 // byte offset of (column group gr, channel-in-group c8, time slot s) inside one ring array with `tgs` time groups
 __device__ __forceinline__ int ring_off(int gr, int c8, int s, int tgs) { return gr * (tgs * 128) + (s >> 3) * 128 + c8 * 16 + (s & 7) * 2; }
@@ -179,10 +177,15 @@ struct FirLaneState {
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
                  : "r"(taddr))
 
+#define TMEM_LD_X8(v, taddr)                                                                       \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"           \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+                 : "r"(taddr))
+
 }  // namespace
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq)
+rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq, int dbg)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -240,13 +243,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 
     if (warp < NWARP_FE) {
         // ======================= front-end warp: 4 channels x 8 lanes ============================
-        const int cl = lane >> 3, r = lane & 7;
+        // lane = 4 r + cl: a quarter-warp of the 16-byte ring stores covers 4 channels x 2 adjacent lane groups = one conflict-free 128-byte row
+        const int cl = lane & 3, r = lane >> 2;
         const int g = warp * 4 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
         const ChanParams &p = a.params[ch];
         ChanState *st = a.state + ch;
-        const unsigned gmask = 0xffu << (8 * cl);
+        const unsigned gmask = 0x11111111u << cl;
         // ring rows of this channel: I in column group g / 8, Q in column group 4 + g / 8
         unsigned char *xi1 = sm.xring[0] + (g >> 3) * XSBO + (g & 7) * 16, *xq1 = xi1 + 4 * XSBO;
         unsigned char *xi2 = sm.xring[1] + (g >> 3) * XSBO + (g & 7) * 16, *xq2 = xi2 + 4 * XSBO;
@@ -270,15 +274,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 // decimator history x[-96..-1] (82 used) -> the last 96 slots of virtual step V - 1
                 for (int b = r; b < 96; b += 8) {
                     unsigned i1, i2, q1, q2;
-                    split_bf16(round16(st->s1_hist_i[b]), i1, i2); split_bf16(round16(st->s1_hist_q[b]), q1, q2);
+                    split_bf16(st->s1_hist_i[b], i1, i2); split_bf16(st->s1_hist_q[b], q1, q2);
                     const int off = (((V - 1) & 1) * CH4 + 32 + b);
-                    const int bo = (off >> 3) * 128 + (off & 7) * 2;
+                    const int bo = (off >> 3) * XLBO + (off & 7) * 2;
                     *reinterpret_cast<unsigned short *>(xi1 + bo) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(xi2 + bo) = (unsigned short)i2;
                     *reinterpret_cast<unsigned short *>(xq1 + bo) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(xq2 + bo) = (unsigned short)q2;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (it >= V && it < s_end) {
+            if (it >= V && it < s_end && !(dbg & 4)) {
                 const int t = it - V;
                 // ---- front end: the whole 128-sample step at once.  Lane r owns the 16 consecutive samples 16r .. 16r+15,
                 // i.e. one half of block r >> 1.  The 2^-16 input scaling (audio_driver.c:2680-2685) is exact, so it is folded
@@ -291,11 +295,6 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     const int4 v = pre[i];
                     lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
                     fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
-                }
-                // fetch the next step behind the arithmetic
-                if (t + 1 < nsteps && active) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) pre[i] = __ldg(src + (size_t)(t + 1) * 64 + 8 * r + i);
                 }
                 lvmax >>= 16;                                                // audio_driver.c:2662-2675
                 ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
@@ -310,14 +309,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
                         s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
                     }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 1, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 1, 8);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 4); s2 += __shfl_xor_sync(0xffffffffu, s2, 4); s3 += __shfl_xor_sync(0xffffffffu, s3, 4);
                     // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
                     float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                     const float kE = 0.003f * 0.03125f * kS;
                     float bs1[4], bs2[4], bs3[4];           // all twelve broadcasts in flight before the recurrence uses them
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        bs1[b] = __shfl_sync(0xffffffffu, s1, 2 * b, 8); bs2[b] = __shfl_sync(0xffffffffu, s2, 2 * b, 8); bs3[b] = __shfl_sync(0xffffffffu, s3, 2 * b, 8);
+                        bs1[b] = __shfl_sync(0xffffffffu, s1, 8 * b + cl); bs2[b] = __shfl_sync(0xffffffffu, s2, 8 * b + cl); bs3[b] = __shfl_sync(0xffffffffu, s3, 8 * b + cl);
                     }
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
@@ -380,13 +379,21 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         split_pack2(fi[2 * k], fi[2 * k + 1], wi1[k], wi2[k]);
                         split_pack2(fq[2 * k], fq[2 * k + 1], wq1[k], wq2[k]);
                     }
-                    const int bo = ((it & 1) * (CH4 / 8) + 2 * r) * 128;
-                    *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]); *reinterpret_cast<uint4 *>(xi1 + bo + 128) = make_uint4(wi1[4], wi1[5], wi1[6], wi1[7]);
-                    *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]); *reinterpret_cast<uint4 *>(xi2 + bo + 128) = make_uint4(wi2[4], wi2[5], wi2[6], wi2[7]);
-                    *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]); *reinterpret_cast<uint4 *>(xq1 + bo + 128) = make_uint4(wq1[4], wq1[5], wq1[6], wq1[7]);
-                    *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]); *reinterpret_cast<uint4 *>(xq2 + bo + 128) = make_uint4(wq2[4], wq2[5], wq2[6], wq2[7]);
+                    const int bo = ((it & 1) * (CH4 / 8) + 2 * r) * XLBO;
+                    *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]); *reinterpret_cast<uint4 *>(xi1 + bo + XLBO) = make_uint4(wi1[4], wi1[5], wi1[6], wi1[7]);
+                    *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]); *reinterpret_cast<uint4 *>(xi2 + bo + XLBO) = make_uint4(wi2[4], wi2[5], wi2[6], wi2[7]);
+                    *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]); *reinterpret_cast<uint4 *>(xq1 + bo + XLBO) = make_uint4(wq1[4], wq1[5], wq1[6], wq1[7]);
+                    *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]); *reinterpret_cast<uint4 *>(xq2 + bo + XLBO) = make_uint4(wq2[4], wq2[5], wq2[6], wq2[7]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
+                // fetch the next step; issued after the fence (a membar that would wait for these loads) and consumed after the
+                // step barrier, where this warp waits for the slower roles anyway
+                if (t + 1 < nsteps && active) {
+                    const int4 *nx = src + (size_t)(t + 1) * 64 + 8 * r;
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
+                }
             }
             __syncthreads();
         }
@@ -395,15 +402,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             const int sl = (s_end - 1) & 1;
             for (int b = r; b < 96; b += 8) {
                 const int off = sl * CH4 + 32 + b;
-                const int bo = (off >> 3) * 128 + (off & 7) * 2;
+                const int bo = (off >> 3) * XLBO + (off & 7) * 2;
                 const unsigned i1 = *reinterpret_cast<const unsigned short *>(xi1 + bo), i2 = *reinterpret_cast<const unsigned short *>(xi2 + bo);
                 const unsigned q1 = *reinterpret_cast<const unsigned short *>(xq1 + bo), q2 = *reinterpret_cast<const unsigned short *>(xq2 + bo);
-                st->s1_hist_i[b] = __uint_as_float(i1 << 16) + __uint_as_float(i2 << 16);
-                st->s1_hist_q[b] = __uint_as_float(q1 << 16) + __uint_as_float(q2 << 16);
+                st->s1_hist_i[b] = join_bf16(i1, i2);
+                st->s1_hist_q[b] = join_bf16(q1, q2);
             }
             int clip = ls.clip;
-            ls.c1 = __shfl_sync(gmask, ls.c1, 6, 8); ls.c2 = __shfl_sync(gmask, ls.c2, 6, 8);
-            clip |= __shfl_xor_sync(gmask, clip, 1, 8); clip |= __shfl_xor_sync(gmask, clip, 2, 8); clip |= __shfl_xor_sync(gmask, clip, 4, 8);
+            ls.c1 = __shfl_sync(gmask, ls.c1, 24 + cl); ls.c2 = __shfl_sync(gmask, ls.c2, 24 + cl);
+            clip |= __shfl_xor_sync(gmask, clip, 4); clip |= __shfl_xor_sync(gmask, clip, 8); clip |= __shfl_xor_sync(gmask, clip, 16);
             if (r == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
                 if (clip & 1) st->adc_quarter_clip = 1;
@@ -421,43 +428,43 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const unsigned idesc_d = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(64 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
         const unsigned idesc_h = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(32 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
         const unsigned long long ad1 = umma_desc(smem_u32(sm.gd[0]) + DR0 * 16, DPLANE, 128), ad2 = umma_desc(smem_u32(sm.gd[1]) + DR0 * 16, DPLANE, 128);
-        const unsigned long long bx1 = umma_desc(smem_u32(sm.xring[0]), 128, XSBO), bx2 = umma_desc(smem_u32(sm.xring[1]), 128, XSBO);
+        const unsigned long long bx1 = umma_desc(smem_u32(sm.xring[0]), XLBO, XSBO), bx2 = umma_desc(smem_u32(sm.xring[1]), XLBO, XSBO);
         unsigned long long ah[4], bh[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { ah[i] = umma_desc(smem_u32(sm.gh[i]) + HR0 * 16, HPLANE, 128); bh[i] = umma_desc(smem_u32(sm.hring[i]), 128, HSBO); }
+        for (int i = 0; i < 4; i++) { ah[i] = umma_desc(smem_u32(sm.gh[i]) + HR0 * 16, HPLANE, 128); bh[i] = umma_desc(smem_u32(sm.hring[i]), HLBO, HSBO); }
         const int oc_last = (s_end - 1) >> 2;
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const int sd = it - 1;               // step whose samples were written into the decimator ring in the previous iteration
                 if (sd >= 0) {
-                    const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * 8), b2 = bx2 + (unsigned)((sd & 1) * (CH4 / 8) * 8);
-                    if (sd >= V && sd < s_end) {
+                    const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16)), b2 = bx2 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16));
+                    if (sd >= V && sd < s_end && !(dbg & 1)) {
                         // the 8 k-steps of this step into its own chunk: kk = 6 + 8 (sd & 3) + j
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64);
                         const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
-#pragma unroll
+#pragma unroll 1
                         for (int j = 0; j < 8; j++)
-                            umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + 16 * j, b2 + 16 * j, idesc_d, 1u);
+                            umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, 1u);
                     }
-                    if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end) {
+                    if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end && !(dbg & 1)) {
                         // the last 96 samples of the step are the history of the next chunk: kk = 0 .. 5, first write of its accumulator
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
-#pragma unroll
+#pragma unroll 1
                         for (int j = 2; j < 8; j++)
-                            umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + 16 * j, b2 + 16 * j, idesc_d, j > 2 ? 1u : 0u);
+                            umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, j > 2 ? 1u : 0u);
                     }
                     umma_commit(&sm.bar_dec[sd & 1]);
                 }
                 const int sh = it - 3;               // step whose decimator outputs were written into the Hilbert ring in the previous iteration
                 if (sh >= 0) {
-                    if (sh >= 1 && sh < s_end) {
-#pragma unroll
+                    if (sh >= 1 && sh < s_end && !(dbg & 2)) {
+#pragma unroll 1
                         for (int e = 0; e < 2; e++) {
                             const int u = 2 * sh + e;                        // global k-step (16 decimated samples)
                             const int oa = u >> 3, ob = u & 7;
-                            const unsigned boff = (unsigned)((sh & 1) * (ND / 8) * 8 + e * 16);
-#pragma unroll
+                            const unsigned boff = (unsigned)(((sh & 1) * (ND / 8) + 2 * e) * (HLBO / 16));
+#pragma unroll 1
                             for (int dd = 0; dd < 3; dd++) {
                                 const int oc = oa + dd;                      // output chunk this slab contributes to
                                 if ((dd < 2 || ob >= 3) && oc >= V / 4 && oc <= oc_last) {
@@ -493,9 +500,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int sd = it - 2;
-            if (sd >= 1 && sd < s_end && (sd & 3) == qd) {
+            if (sd >= 1 && sd < s_end && (sd & 3) == qd && !(dbg & 8)) {
                 const int slot = (sd & 1) * ND + lane;
-                const int bo = (slot >> 3) * 128 + (slot & 7) * 2;
+                const int bo = (slot >> 3) * HLBO + (slot & 7) * 2;
                 unsigned char *h0 = sm.hring[0] + bo, *h1 = sm.hring[1] + bo, *h2 = sm.hring[2] + bo, *h3 = sm.hring[3] + bo;
                 // state slot of this lane's sample once the launch is over (s2_hist[2..199] = the newest 198 decimator outputs)
                 const int i_new = ND * (sd - V) + lane - ND * nsteps + 200;
@@ -503,17 +510,17 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     // virtual step: Hilbert history d[-198..-1] = state slots 2..199 (already rounded if this kernel wrote them)
                     const int i_old = ND * (sd - V) + lane + 200;
                     if (sd >= 2) mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
-#pragma unroll 4
+#pragma unroll 1
                     for (int n = 0; n < FG; n++) {
                         float vi = 0.0f, vq = 0.0f;
                         if (n < n_here && i_old >= 2) {
                             ChanState *stn = a.state + sm.chan[n];
-                            vi = round16(stn->s2_hist_i[i_old]); vq = round16(stn->s2_hist_q[i_old]);
-                            if (i_new >= 2) { stn->s2_hist_i[i_new] = vi; stn->s2_hist_q[i_new] = vq; }
+                            vi = stn->s2_hist_i[i_old]; vq = stn->s2_hist_q[i_old];
                         }
-                        if ((lsbmask >> n) & 1u) vq = -vq;
                         unsigned i1, i2, q1, q2;
                         split_bf16(vi, i1, i2); split_bf16(vq, q1, q2);
+                        if (n < n_here && i_old >= 2 && i_new >= 2) { a.state[sm.chan[n]].s2_hist_i[i_new] = join_bf16(i1, i2); a.state[sm.chan[n]].s2_hist_q[i_new] = join_bf16(q1, q2); }
+                        if ((lsbmask >> n) & 1u) { q1 ^= 0x8000u; q2 ^= 0x8000u; }
                         const int co = (n >> 3) * HSBO + (n & 7) * 16;
                         *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
                         *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
@@ -522,25 +529,28 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     mbar_wait(&sm.bar_dec[sd & 1], (unsigned)((sd >> 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const unsigned taddr = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64) + lane_base;
-                    unsigned vi[32], vq[32];
-                    TMEM_LD_X32(vi, taddr);
-                    TMEM_LD_X32(vq, taddr + 32u);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     // the Hilbert MMAs of step sd - 2 read this ring buffer; they were committed one iteration ago
                     mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
                     const bool save = i_new >= 2;
+#pragma unroll 1
+                    for (int gq = 0; gq < 4; gq++) {              // 8 channels per pass (rolled: the instruction cache is the scarce resource)
+                        unsigned vi[8], vq[8];
+                        TMEM_LD_X8(vi, taddr + (unsigned)(8 * gq));
+                        TMEM_LD_X8(vq, taddr + (unsigned)(32 + 8 * gq));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        const unsigned lm = lsbmask >> (8 * gq);
 #pragma unroll
-                    for (int n = 0; n < FG; n++) {
-                        const float hi_ = round16(__uint_as_float(vi[n]));
-                        const float hq_ = round16(__uint_as_float(vq[n]));
-                        unsigned i1, i2, q1, q2;
-                        split_bf16(hi_, i1, i2); split_bf16(((lsbmask >> n) & 1u) ? -hq_ : hq_, q1, q2);
-                        const int co = (n >> 3) * HSBO + (n & 7) * 16;
-                        *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
-                        *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
-                        if (save && n < n_here) {
-                            ChanState *stn = a.state + sm.chan[n];
-                            stn->s2_hist_i[i_new] = hi_; stn->s2_hist_q[i_new] = hq_;
+                        for (int n8 = 0; n8 < 8; n8++) {
+                            unsigned i1, i2, q1, q2;
+                            split_bf16(__uint_as_float(vi[n8]), i1, i2); split_bf16(__uint_as_float(vq[n8]), q1, q2);
+                            if (save && 8 * gq + n8 < n_here) {
+                                ChanState *stn = a.state + sm.chan[8 * gq + n8];
+                                stn->s2_hist_i[i_new] = join_bf16(i1, i2); stn->s2_hist_q[i_new] = join_bf16(q1, q2);
+                            }
+                            if ((lm >> n8) & 1u) { q1 ^= 0x8000u; q2 ^= 0x8000u; }       // LSB: I - Q
+                            const int co = gq * HSBO + n8 * 16;
+                            *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
+                            *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
                         }
                     }
                 }
@@ -704,9 +714,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         if constexpr (!HANG) {
                             // hang AGC disabled on every channel of this warp (the default, ui_configuration.c:81): only
                             // states 0 / 1 / 3 occur and the 5-state machine reduces to selects
-                            const bool fast = (ar.state == 0) ? (ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage))
-                                                              : ((ar.state == 1) && (ar.volts > ar.save_volts));
-                            if (attack && ar.state >= 2) ar.save_volts = ar.volts;
+                            // (bitwise on purpose: short-circuit evaluation turns into divergent branches in this serial loop)
+                            const int c0 = ar.volts > __fmul_rn(ap.pop_ratio, ar.fast_backaverage), c1 = ar.volts > ar.save_volts;
+                            const bool fast = (((ar.state == 0) & c0) | ((ar.state == 1) & c1)) != 0;
+                            ar.save_volts = (attack & (ar.state >= 2)) ? ar.volts : ar.save_volts;
                             mult_sel = attack ? ap.attack_mult : (fast ? ap.fast_decay_mult : ap.decay_mult);
                             nstate = attack ? 0 : (fast ? 1 : 3);
                         } else {
@@ -1013,7 +1024,8 @@ cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq,
     const int grid = (a.num_items + per - 1) / per;
     cudaError_t e = cudaFuncSetAttribute(rx_ssb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
-    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq);
+    const char *dbg = getenv("UHSDR_B200_TC_DEBUG");      // timing experiments only (results are wrong when set)
+    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq, dbg ? atoi(dbg) : 0);
     return cudaGetLastError();
 }
 
