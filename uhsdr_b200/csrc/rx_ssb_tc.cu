@@ -75,8 +75,9 @@ constexpr int NTHREADS = 32 * (NWARP_FE + 9);
 // software pipeline, in steps of 128 input samples.  Step s (virtual steps included) is written into the decimator
 // ring at iteration s, its decimator MMAs are issued at s + 1, the decimator outputs leave TMEM for the Hilbert ring
 // at s + 2, the Hilbert MMAs are issued at s + 3, the Hilbert outputs leave TMEM at s + 4, then lattice s + 5,
-// AGC s + 6, gain + biquad cascade s + 7, interpolator / treble / output formatting s + 8.
-constexpr int IT_LAT = V + 5, IT_AGC = V + 6, IT_BQ = V + 7, IT_POST = V + 8;
+// AGC detector s + 6, AGC gain law s + 7 (on the two epilogue warps that are idle in that iteration), biquad cascade s + 8,
+// interpolator / treble / output formatting s + 9.
+constexpr int IT_LAT = V + 5, IT_AGC = V + 6, IT_GAIN = V + 7, IT_BQ = V + 8, IT_POST = V + 9;
 constexpr int PIPE_DEPTH = IT_POST;
 
 struct Smem {
@@ -87,6 +88,7 @@ struct Smem {
     float aud[2][ND * SMS];
     float lat[LR * SMS];              // lattice output, a ring of 5 steps: AGC detector and gain stage read x[n-49] from it
     float agc[2][ND * SMS];           // AGC "volts" per sample (detector -> gain stage)
+    float gq[2][ND * SMS];            // delayed sample x gain (gain stage -> biquad cascade)
     float bq[2][ND * SMS];
     float smax[2][ND * SMS];
     int chan[32];                     // channel index of every slot (epilogue warps: state save / restore)
@@ -177,10 +179,8 @@ struct FirLaneState {
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
                  : "r"(taddr))
 
-#define TMEM_LD_X8(v, taddr)                                                                       \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"           \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
-                 : "r"(taddr))
+#define TMEM_LD_X4(v, taddr) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr))
 
 }  // namespace
 
@@ -243,8 +243,13 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 
     if (warp < NWARP_FE) {
         // ======================= front-end warp: 4 channels x 8 lanes ============================
-        // lane = 4 r + cl: a quarter-warp of the 16-byte ring stores covers 4 channels x 2 adjacent lane groups = one conflict-free 128-byte row
-        const int cl = lane & 3, r = lane >> 2;
+        // A 128-sample step is done in two passes of 64 samples (two 32-sample blocks); in a pass lane slot r owns the 8
+        // consecutive samples 8r .. 8r+7, i.e. a quarter of block r >> 2.  (Two short passes instead of one long one: half the
+        // instructions in the loop body -- the instruction cache is the scarce resource of this kernel.)
+        // lane = 4 r' + cl with r = r' with its two low bits swapped: the lanes of a quarter-warp then hold 4 channels x two
+        // time groups 2 apart, which tile one conflict-free 128-byte bank row of the ring (time-group stride 160 B).
+        const int cl = lane & 3, rp = lane >> 2;
+        const int r = (rp & 4) | ((rp & 1) << 1) | ((rp >> 1) & 1);
         const int g = warp * 4 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
@@ -262,17 +267,17 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const bool fast_fe = __all_sync(0xffffffffu, iq_auto != 0 && shift_kind == 1);
         const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
         const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
-        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base);
+        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base) + 4 * r;
 
-        // input prefetch: 8 x int4 = the 16 consecutive samples 16r .. 16r+15 of the step, one step ahead, straight from global memory
-        int4 pre[8];
+        // input prefetch: 4 x int4 = the 8 samples of the next pass, straight from global memory into registers
+        int4 pre[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) pre[i] = active ? __ldg(src + 8 * r + i) : make_int4(0, 0, 0, 0);
+        for (int i = 0; i < 4; i++) pre[i] = active ? __ldg(src + i) : make_int4(0, 0, 0, 0);
 
         for (int it = 0; it < niter; it++) {
             if (it == V - 1 && active) {
                 // decimator history x[-96..-1] (82 used) -> the last 96 slots of virtual step V - 1
-                for (int b = r; b < 96; b += 8) {
+                for (int b = rp; b < 96; b += 8) {
                     unsigned i1, i2, q1, q2;
                     split_bf16(st->s1_hist_i[b], i1, i2); split_bf16(st->s1_hist_q[b], q1, q2);
                     const int off = (((V - 1) & 1) * CH4 + 32 + b);
@@ -284,114 +289,125 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             }
             if (it >= V && it < s_end && !(dbg & 4)) {
                 const int t = it - V;
-                // ---- front end: the whole 128-sample step at once.  Lane r owns the 16 consecutive samples 16r .. 16r+15,
-                // i.e. one half of block r >> 1.  The 2^-16 input scaling (audio_driver.c:2680-2685) is exact, so it is folded
-                // into the correction factors; the Fs/4 translation (freq_shift.c:219-262) is a sign/swap pattern of period 4
-                // folded into the same factors.
-                float fi[16], fq[16];
-                int lvmax = 0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int4 v = pre[i];
-                    lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
-                    fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
-                }
-                lvmax >>= 16;                                                // audio_driver.c:2662-2675
-                ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
-                const float kS = 0.0000152587890625f;                        // 2^-16
-                float c1m = 0.0f, c2m = 1.0f;                                // M_c1, M_c2 of this lane's block
-                if (any_auto) {
-                    // Moseley & Slump block statistics (:2274-2279); sign(i) * q as a sign-bit transfer (differs from
-                    // Math_sign_new only for i == 0, where the term is +-q instead of 0)
-                    float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
-                        s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
-                    }
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 4); s2 += __shfl_xor_sync(0xffffffffu, s2, 4); s3 += __shfl_xor_sync(0xffffffffu, s3, 4);
-                    // first-order low-pass over the four blocks (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
-                    float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
-                    const float kE = 0.003f * 0.03125f * kS;
-                    float bs1[4], bs2[4], bs3[4];           // all twelve broadcasts in flight before the recurrence uses them
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        bs1[b] = __shfl_sync(0xffffffffu, s1, 8 * b + cl); bs2[b] = __shfl_sync(0xffffffffu, s2, 8 * b + cl); bs3[b] = __shfl_sync(0xffffffffu, s3, 8 * b + cl);
-                    }
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
-                        if ((r >> 1) == b) { m1 = t1; m2 = t2; m3 = t3; }
-                    }
-                    const float den = m2 * m2;
-                    const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
-                    if (iq_auto) {
-                        ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
-                        c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
-                        c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
-                        ls.c1 = c1m; ls.c2 = c2m;                            // lanes 6, 7 hold the block-3 values the state keeps
-                    }
-                }
-                if (fast_fe) {
-                    // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
-                    //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
-                    const float sgd = shift_down ? -1.0f : 1.0f;
-                    const float fa = c2m * kS, fd = c1m * kS, fas = fa * sgd, fds = fd * sgd, ks = kS * sgd;
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4) {
-                        const float i0 = fi[k], i1 = fi[k + 1], i2 = fi[k + 2], i3 = fi[k + 3];
-                        fi[k] = i0 * fa;                                  fq[k] = fmaf(i0, fd, fq[k] * kS);
-                        fi[k + 1] = fmaf(i1, fds, fq[k + 1] * ks);        fq[k + 1] = i1 * -fas;
-                        fi[k + 2] = i2 * -fa;                             fq[k + 2] = fmaf(i2, -fd, fq[k + 2] * -kS);
-                        fi[k + 3] = fmaf(i3, -fds, fq[k + 3] * -ks);      fq[k + 3] = i3 * fas;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) {
-                        float vi = fi[k], vq = fq[k];
-                        if (iq_auto) {
-                            vq = fmaf(c1m, vi, vq);               // q += M_c1 * i  (:2308-2311)
-                            vi = vi * c2m;                        // i *= M_c2      (:2313)
-                        } else {
-                            vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
-                            if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
-                            else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
-                        }
-                        vi *= kS; vq *= kS;
-                        if (shift_kind == 1) {
-                            const float sgd = shift_down ? -1.0f : 1.0f;
-                            const int ph = k & 3;
-                            const float ti = vi, tq_ = vq;
-                            if (ph == 1) { vi = tq_ * sgd; vq = -ti * sgd; }
-                            else if (ph == 2) { vi = -ti; vq = -tq_; }
-                            else if (ph == 3) { vi = -tq_ * sgd; vq = ti * sgd; }
-                        }
-                        fi[k] = vi; fq[k] = vq;
-                    }
-                }
-                // ---- 16-bit rounding, bf16 split, decimator ring: slots 16r .. 16r+15 of buffer it & 1 = two 16-byte rows per array.
-                // The MMAs of step it - 2 read this buffer; they were committed one iteration ago.
+                // The MMAs of step it - 2 read the ring buffer written now; they were committed one iteration ago.
                 mbar_wait(&sm.bar_dec[it & 1], (unsigned)(((it - 2) >> 1) & 1));
-                {
-                    unsigned wi1[8], wi2[8], wq1[8], wq2[8];
+#pragma unroll 1
+                for (int h = 0; h < 2; h++) {
+                    // ---- front end of one pass.  The 2^-16 input scaling (audio_driver.c:2680-2685) is exact, so it is folded
+                    // into the correction factors; the Fs/4 translation (freq_shift.c:219-262) is a sign/swap pattern of
+                    // period 4 folded into the same factors.
+                    float fi[8], fq[8];
+                    int lvmax = 0;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        split_pack2(fi[2 * k], fi[2 * k + 1], wi1[k], wi2[k]);
-                        split_pack2(fq[2 * k], fq[2 * k + 1], wq1[k], wq2[k]);
+                    for (int i = 0; i < 4; i++) {
+                        const int4 v = pre[i];
+                        lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
+                        fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
                     }
-                    const int bo = ((it & 1) * (CH4 / 8) + 2 * r) * XLBO;
-                    *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]); *reinterpret_cast<uint4 *>(xi1 + bo + XLBO) = make_uint4(wi1[4], wi1[5], wi1[6], wi1[7]);
-                    *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]); *reinterpret_cast<uint4 *>(xi2 + bo + XLBO) = make_uint4(wi2[4], wi2[5], wi2[6], wi2[7]);
-                    *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]); *reinterpret_cast<uint4 *>(xq1 + bo + XLBO) = make_uint4(wq1[4], wq1[5], wq1[6], wq1[7]);
-                    *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]); *reinterpret_cast<uint4 *>(xq2 + bo + XLBO) = make_uint4(wq2[4], wq2[5], wq2[6], wq2[7]);
+                    // the second pass of this step is fetched behind the arithmetic of the first
+                    if (h == 0 && active) {
+                        const int4 *nx = src + (size_t)t * 64 + 32;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
+                    }
+                    lvmax >>= 16;                                                // audio_driver.c:2662-2675
+                    ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
+                    const float kS = 0.0000152587890625f;                        // 2^-16
+                    float c1m = 0.0f, c2m = 1.0f;                                // M_c1, M_c2 of this lane's block
+                    if (any_auto) {
+                        // Moseley & Slump block statistics (:2274-2279); sign(i) * q as a sign-bit transfer (differs from
+                        // Math_sign_new only for i == 0, where the term is +-q instead of 0)
+                        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
+                            s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
+                        }
+                        // the four lanes of a block: slots r & 3 = lane bits 2, 3
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 4); s2 += __shfl_xor_sync(0xffffffffu, s2, 4); s3 += __shfl_xor_sync(0xffffffffu, s3, 4);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 8);
+                        // first-order low-pass over the two blocks of the pass (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
+                        float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+                        const float kE = 0.003f * 0.03125f * kS;
+                        float bs1[2], bs2[2], bs3[2];
+#pragma unroll
+                        for (int b = 0; b < 2; b++) {
+                            bs1[b] = __shfl_sync(0xffffffffu, s1, 16 * b + cl); bs2[b] = __shfl_sync(0xffffffffu, s2, 16 * b + cl); bs3[b] = __shfl_sync(0xffffffffu, s3, 16 * b + cl);
+                        }
+#pragma unroll
+                        for (int b = 0; b < 2; b++) {
+                            t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
+                            if ((r >> 2) == b) { m1 = t1; m2 = t2; m3 = t3; }
+                        }
+                        const float den = m2 * m2;
+                        const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
+                        if (iq_auto) {
+                            ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
+                            c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
+                            c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
+                            ls.c1 = c1m; ls.c2 = c2m;                            // after the second pass, slots 4..7 hold the block-3 values the state keeps
+                        }
+                    }
+                    if (fast_fe) {
+                        // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
+                        //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
+                        const float sgd = shift_down ? -1.0f : 1.0f;
+                        const float fa = c2m * kS, fd = c1m * kS, fas = fa * sgd, fds = fd * sgd, ks = kS * sgd;
+#pragma unroll
+                        for (int k = 0; k < 8; k += 4) {
+                            const float i0 = fi[k], i1 = fi[k + 1], i2 = fi[k + 2], i3 = fi[k + 3];
+                            fi[k] = i0 * fa;                                  fq[k] = fmaf(i0, fd, fq[k] * kS);
+                            fi[k + 1] = fmaf(i1, fds, fq[k + 1] * ks);        fq[k + 1] = i1 * -fas;
+                            fi[k + 2] = i2 * -fa;                             fq[k + 2] = fmaf(i2, -fd, fq[k + 2] * -kS);
+                            fi[k + 3] = fmaf(i3, -fds, fq[k + 3] * -ks);      fq[k + 3] = i3 * fas;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            float vi = fi[k], vq = fq[k];
+                            if (iq_auto) {
+                                vq = fmaf(c1m, vi, vq);               // q += M_c1 * i  (:2308-2311)
+                                vi = vi * c2m;                        // i *= M_c2      (:2313)
+                            } else {
+                                vi = vi * adj_i; vq = vq * adj_q;     // manual gain / phase (:2259-2267)
+                                if (phase_bal < 0.0f) vq = fmaf(vi, phase_bal, vq);
+                                else if (phase_bal > 0.0f) vi = fmaf(vq, phase_bal, vi);
+                            }
+                            vi *= kS; vq *= kS;
+                            if (shift_kind == 1) {
+                                const float sgd = shift_down ? -1.0f : 1.0f;
+                                const int ph = k & 3;
+                                const float ti = vi, tq_ = vq;
+                                if (ph == 1) { vi = tq_ * sgd; vq = -ti * sgd; }
+                                else if (ph == 2) { vi = -ti; vq = -tq_; }
+                                else if (ph == 3) { vi = -tq_ * sgd; vq = ti * sgd; }
+                            }
+                            fi[k] = vi; fq[k] = vq;
+                        }
+                    }
+                    // ---- bf16 split, decimator ring: slots 64 h + 8 r .. +7 of buffer it & 1 = one 16-byte row per array
+                    {
+                        unsigned wi1[4], wi2[4], wq1[4], wq2[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            split_pack2(fi[2 * k], fi[2 * k + 1], wi1[k], wi2[k]);
+                            split_pack2(fq[2 * k], fq[2 * k + 1], wq1[k], wq2[k]);
+                        }
+                        const int bo = ((it & 1) * (CH4 / 8) + 8 * h + r) * XLBO;
+                        *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]);
+                        *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]);
+                        *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]);
+                        *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
-                // fetch the next step; issued after the fence (a membar that would wait for these loads) and consumed after the
-                // step barrier, where this warp waits for the slower roles anyway
+                // fetch the first pass of the next step; issued after the fence (a membar that would wait for these loads) and
+                // consumed after the step barrier, where this warp waits for the slower roles anyway
                 if (t + 1 < nsteps && active) {
-                    const int4 *nx = src + (size_t)(t + 1) * 64 + 8 * r;
+                    const int4 *nx = src + (size_t)(t + 1) * 64;
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
+                    for (int i = 0; i < 4; i++)
                         asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
                 }
             }
@@ -409,9 +425,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 st->s1_hist_q[b] = join_bf16(q1, q2);
             }
             int clip = ls.clip;
-            ls.c1 = __shfl_sync(gmask, ls.c1, 24 + cl); ls.c2 = __shfl_sync(gmask, ls.c2, 24 + cl);
+            ls.c1 = __shfl_sync(gmask, ls.c1, 16 + cl); ls.c2 = __shfl_sync(gmask, ls.c2, 16 + cl);
             clip |= __shfl_xor_sync(gmask, clip, 4); clip |= __shfl_xor_sync(gmask, clip, 8); clip |= __shfl_xor_sync(gmask, clip, 16);
-            if (r == 0) {
+            if (rp == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
                 if (clip & 1) st->adc_quarter_clip = 1;
                 if (clip & 2) st->adc_half_clip = 1;
@@ -493,10 +509,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const int qd = warp & 3;
         const unsigned lane_base = (unsigned)(qd * 32) << 16;
         unsigned lsbmask;
+        float g_inv_max, g_slope, g_target, g_fixed;
+        bool g_off;
         {
             const int chn = sm.chan[lane];
             lsbmask = __ballot_sync(0xffffffffu, lane < n_here && a.params[chn].lsb != 0);
+            const AgcP &ap = a.params[chn].agc;
+            g_inv_max = ap.inv_max_input; g_slope = ap.slope_constant; g_target = ap.out_target; g_fixed = ap.fixed_gain; g_off = ap.mode == 5;
         }
+        const int gcol = lane < n_here ? lane : 0;
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int sd = it - 2;
@@ -533,22 +554,23 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
                     const bool save = i_new >= 2;
 #pragma unroll 1
-                    for (int gq = 0; gq < 4; gq++) {              // 8 channels per pass (rolled: the instruction cache is the scarce resource)
-                        unsigned vi[8], vq[8];
-                        TMEM_LD_X8(vi, taddr + (unsigned)(8 * gq));
-                        TMEM_LD_X8(vq, taddr + (unsigned)(32 + 8 * gq));
+                    for (int gq = 0; gq < FG / 4; gq++) {         // 4 channels per pass (rolled: the instruction cache is the scarce resource)
+                        unsigned vi[4], vq[4];
+                        TMEM_LD_X4(vi, taddr + (unsigned)(4 * gq));
+                        TMEM_LD_X4(vq, taddr + (unsigned)(32 + 4 * gq));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        const unsigned lm = lsbmask >> (8 * gq);
+                        const unsigned lm = lsbmask >> (4 * gq);
+                        const int cbase = (gq >> 1) * HSBO + (gq & 1) * 64;
 #pragma unroll
-                        for (int n8 = 0; n8 < 8; n8++) {
+                        for (int n8 = 0; n8 < 4; n8++) {
                             unsigned i1, i2, q1, q2;
                             split_bf16(__uint_as_float(vi[n8]), i1, i2); split_bf16(__uint_as_float(vq[n8]), q1, q2);
-                            if (save && 8 * gq + n8 < n_here) {
-                                ChanState *stn = a.state + sm.chan[8 * gq + n8];
+                            if (save && 4 * gq + n8 < n_here) {
+                                ChanState *stn = a.state + sm.chan[4 * gq + n8];
                                 stn->s2_hist_i[i_new] = join_bf16(i1, i2); stn->s2_hist_q[i_new] = join_bf16(q1, q2);
                             }
                             if ((lm >> n8) & 1u) { q1 ^= 0x8000u; q2 ^= 0x8000u; }       // LSB: I - Q
-                            const int co = gq * HSBO + n8 * 16;
+                            const int co = cbase + n8 * 16;
                             *reinterpret_cast<unsigned short *>(h0 + co) = (unsigned short)i1; *reinterpret_cast<unsigned short *>(h1 + co) = (unsigned short)i2;
                             *reinterpret_cast<unsigned short *>(h2 + co) = (unsigned short)q1; *reinterpret_cast<unsigned short *>(h3 + co) = (unsigned short)q2;
                         }
@@ -568,6 +590,48 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 float *aud = sm.aud[sh & 1] + lane * SMS;
 #pragma unroll
                 for (int c = 0; c < FG; c++) aud[c] = __uint_as_float(v[c]);
+            }
+            // ---- AGC gain law (audio_agc.c:563-570; mode 5 = fixed gain :354-365) for the step the detector finished in the previous
+            // iteration: elementwise, lane = channel, on the two warps that have no epilogue in this iteration (16 samples each).
+            // out = x[n - 49] * (out_target - slope_constant * min(0, log10f_fast(volts / max_input))) / volts
+            {
+                const int c = it - IT_GAIN;
+                const int k1 = (qd - it - 1) & 3;                       // 0: first half, 2: second half, 1 / 3: busy with an epilogue
+                if (c >= 0 && c < nsteps && !(k1 & 1)) {
+                    const int i0 = k1 * 8;
+                    const float *vin = sm.agc[c & 1] + gcol;
+                    float *out = sm.gq[c & 1] + gcol;
+                    const float *latp = sm.lat + gcol;
+                    int ra = (c % 5) * ND + i0 - (g_off ? 0 : AGC_W); if (ra < 0) ra += LR;
+#pragma unroll 1
+                    for (int i8 = 0; i8 < 16; i8 += 8) {
+                        float xv[8], vv[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            int rr = ra + i8 + i; if (rr >= LR) rr -= LR;
+                            vv[i] = vin[(i0 + i8 + i) * SMS]; xv[i] = latp[rr * SMS];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
+                            // operations, the cubic in Horner form
+                            const unsigned ub = __float_as_uint(__fmul_rn(g_inv_max, vv[i]));
+                            const float F = __uint_as_float((ub & 0x007fffffu) | 0x3f000000u);      // frexpf mantissa in [0.5, 1)
+                            const float E = (float)((int)(ub >> 23) - 126);
+                            float Y = fmaf(1.23149591368684f, F, -4.11852516267426f);
+                            Y = fmaf(Y, F, 6.02197014179219f);
+                            Y = fmaf(Y, F, -3.13396450166353f);
+                            float vo = __fmul_rn(__fadd_rn(Y, E), 0.3010299956639812f);
+                            vo = fminf(vo, 0.0f);
+                            const float mult = g_off ? g_fixed : __fdividef(fmaf(-g_slope, vo, g_target), vv[i]);
+                            xv[i] = __fmul_rn(xv[i], mult);
+                        }
+                        if (lane < n_here) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) out[(i0 + i8 + i) * SMS] = xv[i];
+                        }
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
@@ -794,8 +858,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
     }
 
     if (warp == W_BQ) {
-        // ---- AGC gain law on the delayed sample (audio_agc.c:563-570; mode 5 = fixed gain :354-365), then the
-        // fixed gain (:2513-2524) and the 4-stage DF1 cascade IIR_biquad_1 (:2527) at 12 ksps.  Per stage the terms
+        // ---- the fixed gain (:2513-2524) and the 4-stage DF1 cascade IIR_biquad_1 (:2527) at 12 ksps.  Per stage the terms
         // that do not depend on the newest input are summed ahead of time (t), so the sample-to-sample critical path is
         // one FMA per stage.  Stages whose coefficients are {1,0,0,0,0} on every channel of the CTA (notch / peak off:
         // the default) are skipped; their state is the last two samples that went through.
@@ -811,37 +874,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             tq[s] = fmaf(bc[s][3], bs[s].y1, fmaf(bc[s][1], bs[s].x1, fmaf(bc[s][2], bs[s].x2, __fmul_rn(bc[s][4], bs[s].y2))));   // same order as in the loop
         }
         const float scale_gain = p.scale_gain;
-        const AgcP ap = p.agc;
-        const bool agc_off = ap.mode == 5;
-        const float *latp = sm.lat + g;
         float xl1 = 0.0f, xl2 = 0.0f;        // the last two cascade inputs (state of skipped leading stages)
         // one step of 32 samples with the skipped stages known at compile time
-        auto run_step = [&](auto maskc, const float *in, float *out, int row0) {
+        auto run_step = [&](auto maskc, const float *in, float *out) {
             constexpr unsigned MASK = decltype(maskc)::value;
 #pragma unroll 1
             for (int i0 = 0; i0 < ND; i0 += 8) {
-                // volts of the 8 samples and the delayed samples x[n-49] (AGC off: the current samples x[n])
-                int ra = row0 + i0 - (agc_off ? 0 : AGC_W); if (ra < 0) ra += LR;
-                int rb = ra + 1; if (rb >= LR) rb -= LR;
-                const float *dA = latp + ra * SMS, *dB = latp + rb * SMS;
-                float xv[8], vv[8];
+                float xv[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) { vv[i] = in[(i0 + i) * SMS]; xv[i] = (i == 0) ? dA[0] : dB[(i - 1) * SMS]; }
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
-                    // operations, the cubic in Horner form
-                    const unsigned ub = __float_as_uint(__fmul_rn(ap.inv_max_input, vv[i]));
-                    const float F = __uint_as_float((ub & 0x007fffffu) | 0x3f000000u);      // frexpf mantissa in [0.5, 1)
-                    const float E = (float)((int)(ub >> 23) - 126);
-                    float Y = fmaf(1.23149591368684f, F, -4.11852516267426f);
-                    Y = fmaf(Y, F, 6.02197014179219f);
-                    Y = fmaf(Y, F, -3.13396450166353f);
-                    float vo = __fmul_rn(__fadd_rn(Y, E), 0.3010299956639812f);
-                    vo = fminf(vo, 0.0f);
-                    const float mult = agc_off ? ap.fixed_gain : __fdividef(fmaf(-ap.slope_constant, vo, ap.out_target), vv[i]);
-                    xv[i] = __fmul_rn(xv[i], mult);
-                }
+                for (int i = 0; i < 8; i++) xv[i] = in[(i0 + i) * SMS];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     float x = __fmul_rn(xv[i], scale_gain);
@@ -867,10 +908,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         for (int t = 0; t < niter; t++) {
             const int c = t - IT_BQ;
             if (c >= 0 && c < nsteps && active) {
-                const float *in = sm.agc[c & 1] + g;
+                const float *in = sm.gq[c & 1] + g;
                 float *out = sm.bq[c & 1] + g;
-                if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out, (c % 5) * ND);
-                else run_step(std::integral_constant<unsigned, 0u>{}, in, out, (c % 5) * ND);
+                if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out);
+                else run_step(std::integral_constant<unsigned, 0u>{}, in, out);
             }
             __syncthreads();
         }
@@ -925,12 +966,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // A 0 dB shelf has b0 = 1, b1 = -a1, b2 = -a2 (audio_driver.c:906-964 with A = 1): with consistent state
         // (y1 = x1, y2 = x2) the stage is the identity.  Then it is not computed (the reference's own result differs
         // from its input by float rounding only); the state follows the signal so that later launches agree.
+        const bool plain = (mute == nullptr) && (dst_f == nullptr);
         const bool tr_unity = __all_sync(0xffffffffu, !active || (tc[0] == 1.0f && tc[1] == -tc[3] && tc[2] == -tc[4] &&
                                                                   ts.x1 == ts.y1 && ts.x2 == ts.y2));
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
-        auto run_block = [&](auto aac, auto trc, const float *in, int4 *d4, float4 *df, bool muted) {
-            constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value;
-            const int mm = muted ? 0 : -1;                // external_mute: zeros out, all state advanced (:2845-2853)
+        // PLAIN: no mute array and no float copy of the audio asked for (the throughput case): no masking, no second store
+        auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int4 *d4, float4 *df, bool muted) {
+            constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
+            const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 float xv[4];
@@ -979,7 +1022,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
                     // the four output samples {l, r} x 4 = 32 bytes: one 256-bit store (STG.E.ENL2.256)
                     asm volatile("st.global.v8.b32 [%0], {%1, %1, %2, %2, %3, %3, %4, %4};" ::"l"(d4 + 2 * pos), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-                    if (df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
+                    if (!PLAIN && df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
                                             : make_float4(__fmul_rn(o[0], 10.0f), __fmul_rn(o[1], 10.0f), __fmul_rn(o[2], 10.0f), __fmul_rn(o[3], 10.0f));
                 }
             }
@@ -990,12 +1033,13 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 const float *in = sm.bq[c & 1] + g;
 #pragma unroll 1
                 for (int blk = 0; blk < 4; blk++) {
-                    const bool muted = mute && mute[c * 4 + blk];
                     int4 *d4 = dst + (size_t)c * 64 + blk * 16;
+                    if (plain && !any_aa && tr_unity) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in + blk * 8 * SMS, d4, nullptr, false); continue; }
+                    const bool muted = mute && mute[c * 4 + blk];
                     float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
-                    if (any_aa) run_block(std::true_type{}, std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
-                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
-                    else run_block(std::false_type{}, std::true_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
                 }
             }
             __syncthreads();
