@@ -663,12 +663,17 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             if (c >= 0 && c < nsteps) {
                 const float *in = sm.aud[c & 1];
                 float *out = sm.lat + (c % 5) * ND * SMS;
+                // the inputs of the next group of 8 are fetched before the current group is computed: their shared-memory
+                // latency (long under the tensor core's operand traffic) stays off the recurrence
+                float nxt[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) nxt[i] = in[i * SMS + gq];
 #pragma unroll 1
                 for (int i0 = 0; i0 < ND; i0 += 8) {
-                    // the 8 inputs first: their shared-memory latency is paid once, not once per sample
                     float xin[8], yo[8];
+                    const int inx = min(i0 + 8, ND - 8);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) xin[i] = in[(i0 + i) * SMS + gq];
+                    for (int i = 0; i < 8; i++) { xin[i] = nxt[i]; nxt[i] = in[(inx + i) * SMS + gq]; }
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         float f = xin[i], acc = 0.0f, fn = f;
@@ -745,17 +750,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 float pmax = 0.0f;
                 auto detect = [&](auto hangc) {
                     constexpr bool HANG = decltype(hangc)::value;
-#pragma unroll 1
-                for (int k8 = 0; k8 < ND; k8 += AG) {
-                    // all operands of the AG samples first.  The delayed sample x[n-49] of group element j sits at ring
-                    // row (row0 + k8 + j - 49) mod LR; a group wraps at most between its first and second element.
+                // operands of one group of AG samples.  The delayed sample x[n-49] of group element j sits at ring row
+                // (row0 + k8 + j - 49) mod LR; a group wraps at most between its first and second element.
+                auto load_group = [&](int k8, float (&x)[AG], float (&dly)[AG], float (&cmx)[AG]) {
                     int ra = row0 + k8 - AGC_W; if (ra < 0) ra += LR;
                     int rb = ra + 1; if (rb >= LR) rb -= LR;
                     const float *dA = latp + ra * SMS, *dB = latp + rb * SMS;
                     const bool two = k8 < 16;                   // window still reaches into the chunk before the previous one
                     const float *pc = two ? S2 + (16 + k8) * SMS : S1 + (k8 - 16) * SMS;
                     const float *pin = in + k8 * SMS;
-                    float x[AG], dly[AG], cmx[AG];
 #pragma unroll
                     for (int j = 0; j < AG; j++) {
                         x[j] = pin[j * SMS];
@@ -763,6 +766,16 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         const float sfx = pc[j * SMS];
                         cmx[j] = two ? fmaxf(mprev, sfx) : sfx;
                     }
+                };
+                // the operands of the next group are fetched before the current group is computed (shared-memory latency off the recurrence)
+                float xn[AG], dn[AG], cn[AG];
+                load_group(0, xn, dn, cn);
+#pragma unroll 1
+                for (int k8 = 0; k8 < ND; k8 += AG) {
+                    float x[AG], dly[AG], cmx[AG];
+#pragma unroll
+                    for (int j = 0; j < AG; j++) { x[j] = xn[j]; dly[j] = dn[j]; cmx[j] = cn[j]; }
+                    load_group(min(k8 + AG, ND - AG), xn, dn, cn);
 #pragma unroll
                     for (int j = 0; j < AG; j++) {
                         const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
@@ -971,14 +984,16 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                                                                   ts.x1 == ts.y1 && ts.x2 == ts.y2));
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
         // PLAIN: no mute array and no float copy of the audio asked for (the throughput case): no masking, no second store
-        auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int4 *d4, float4 *df, bool muted) {
+        float nx[4];                          // the next 4 inputs, fetched from the queue one half block ahead of their use
+        auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int blk, int4 *d4, float4 *df, bool muted) {
             constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
             const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 float xv[4];
+                const int nrow = min(8 * blk + 4 * h + 4, ND - 4);
 #pragma unroll
-                for (int i = 0; i < 4; i++) xv[i] = in[(4 * h + i) * SMS];
+                for (int i = 0; i < 4; i++) { xv[i] = nx[i]; nx[i] = in[(nrow + i) * SMS]; }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float x = xv[i];
@@ -1031,15 +1046,17 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             const int c = t - IT_POST;
             if (c >= 0 && c < nsteps && active) {
                 const float *in = sm.bq[c & 1] + g;
+#pragma unroll
+                for (int i = 0; i < 4; i++) nx[i] = in[i * SMS];
 #pragma unroll 1
                 for (int blk = 0; blk < 4; blk++) {
                     int4 *d4 = dst + (size_t)c * 64 + blk * 16;
-                    if (plain && !any_aa && tr_unity) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in + blk * 8 * SMS, d4, nullptr, false); continue; }
+                    if (plain && !any_aa && tr_unity) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in, blk, d4, nullptr, false); continue; }
                     const bool muted = mute && mute[c * 4 + blk];
                     float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
-                    if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
-                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
-                    else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in + blk * 8 * SMS, d4, df, muted);
+                    if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
+                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, std::false_type{}, in, blk, d4, df, muted);
+                    else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
                 }
             }
             __syncthreads();
