@@ -53,7 +53,7 @@ constexpr int ND = 32;             // decimated samples per step
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int LR = 5 * ND;          // rows of the lattice-output ring (decimated samples)
-constexpr int AG = 8;              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
+constexpr int AG = 2;              // AGC samples per loop iteration (short body: level-0 instruction cache)              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
 constexpr int NWARP_FE = FG / 4;
 // tensor-core FIRs
 constexpr int V = 8;               // virtual steps in front of the first real one: they carry the filter histories in
@@ -604,15 +604,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     const float *latp = sm.lat + gcol;
                     int ra = (c % 5) * ND + i0 - (g_off ? 0 : AGC_W); if (ra < 0) ra += LR;
 #pragma unroll 1
-                    for (int i8 = 0; i8 < 16; i8 += 8) {
-                        float xv[8], vv[8];
+                    for (int i8 = 0; i8 < 16; i8 += 4) {
+                        float xv[4], vv[4];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
+                        for (int i = 0; i < 4; i++) {
                             int rr = ra + i8 + i; if (rr >= LR) rr -= LR;
                             vv[i] = vin[(i0 + i8 + i) * SMS]; xv[i] = latp[rr * SMS];
                         }
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
+                        for (int i = 0; i < 4; i++) {
                             // Math_log10f_fast (uhsdr_math.c:27-41) of inv_max_input * volts (> 0): exponent / mantissa by bit
                             // operations, the cubic in Horner form
                             const unsigned ub = __float_as_uint(__fmul_rn(g_inv_max, vv[i]));
@@ -628,7 +628,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         }
                         if (lane < n_here) {
 #pragma unroll
-                            for (int i = 0; i < 8; i++) out[(i0 + i8 + i) * SMS] = xv[i];
+                            for (int i = 0; i < 4; i++) out[(i0 + i8 + i) * SMS] = xv[i];
                         }
                     }
                 }
@@ -663,19 +663,24 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             if (c >= 0 && c < nsteps) {
                 const float *in = sm.aud[c & 1];
                 float *out = sm.lat + (c % 5) * ND * SMS;
-                // the inputs of the next group of 8 are fetched before the current group is computed: their shared-memory
-                // latency (long under the tensor core's operand traffic) stays off the recurrence
-                float nxt[8];
+                // Two samples per loop iteration: the loop body (~80 instructions) then stays resident in the 6 KB level-0
+                // instruction cache this warp shares with three warps that run other code; longer bodies are refetched line
+                // by line from the next cache level at ~50 cycles per 8 instructions.  The inputs of the next iteration are
+                // fetched before the current one is computed, so their shared-memory latency stays off the recurrence.
+                constexpr int LG = 2;
+                float nxt[2][LG];                        // two iterations ahead
+                const float *pin = in + gq;
+                float *pout = out + gq;
 #pragma unroll
-                for (int i = 0; i < 8; i++) nxt[i] = in[i * SMS + gq];
+                for (int i = 0; i < LG; i++) { nxt[0][i] = pin[i * SMS]; nxt[1][i] = pin[(LG + i) * SMS]; }
 #pragma unroll 1
-                for (int i0 = 0; i0 < ND; i0 += 8) {
-                    float xin[8], yo[8];
-                    const int inx = min(i0 + 8, ND - 8);
+                for (int i0 = 0; i0 < ND; i0 += LG) {
+                    float xin[LG], yo[LG];
+                    const int inx = min(i0 + 2 * LG, ND - LG);
 #pragma unroll
-                    for (int i = 0; i < 8; i++) { xin[i] = nxt[i]; nxt[i] = in[(inx + i) * SMS + gq]; }
+                    for (int i = 0; i < LG; i++) { xin[i] = nxt[0][i]; nxt[0][i] = nxt[1][i]; nxt[1][i] = pin[(inx + i) * SMS]; }
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < LG; i++) {
                         float f = xin[i], acc = 0.0f, fn = f;
 #pragma unroll
                         for (int j = 0; j < 10; j++) {
@@ -691,7 +696,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     }
                     if (active) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) out[(i0 + i) * SMS + g] = yo[i];
+                        for (int i = 0; i < LG; i++) pout[(i0 + i) * SMS] = yo[i];
                     }
                 }
             }
@@ -768,14 +773,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     }
                 };
                 // the operands of the next group are fetched before the current group is computed (shared-memory latency off the recurrence)
-                float xn[AG], dn[AG], cn[AG];
+                float xn[AG], dn[AG], cn[AG], xm[AG], dm[AG], cm[AG];
                 load_group(0, xn, dn, cn);
+                load_group(AG, xm, dm, cm);
 #pragma unroll 1
                 for (int k8 = 0; k8 < ND; k8 += AG) {
                     float x[AG], dly[AG], cmx[AG];
 #pragma unroll
-                    for (int j = 0; j < AG; j++) { x[j] = xn[j]; dly[j] = dn[j]; cmx[j] = cn[j]; }
-                    load_group(min(k8 + AG, ND - AG), xn, dn, cn);
+                    for (int j = 0; j < AG; j++) { x[j] = xn[j]; dly[j] = dn[j]; cmx[j] = cn[j]; xn[j] = xm[j]; dn[j] = dm[j]; cn[j] = cm[j]; }
+                    load_group(min(k8 + 2 * AG, ND - AG), xm, dm, cm);
 #pragma unroll
                     for (int j = 0; j < AG; j++) {
                         const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
@@ -984,18 +990,18 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                                                                   ts.x1 == ts.y1 && ts.x2 == ts.y2));
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
         // PLAIN: no mute array and no float copy of the audio asked for (the throughput case): no masking, no second store
-        float nx[4];                          // the next 4 inputs, fetched from the queue one half block ahead of their use
+        float nx[2][2];                       // the inputs of the next two loop iterations, fetched from the queue ahead of their use
         auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int blk, int4 *d4, float4 *df, bool muted) {
             constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
             const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
 #pragma unroll 1
-            for (int h = 0; h < 2; h++) {
-                float xv[4];
-                const int nrow = min(8 * blk + 4 * h + 4, ND - 4);
+            for (int h = 0; h < 4; h++) {               // two decimated samples per iteration (short body: level-0 instruction cache)
+                float xv[2];
+                const int nrow = min(8 * blk + 2 * h + 4, ND - 2);
 #pragma unroll
-                for (int i = 0; i < 4; i++) { xv[i] = nx[i]; nx[i] = in[(nrow + i) * SMS]; }
+                for (int i = 0; i < 2; i++) { xv[i] = nx[0][i]; nx[0][i] = nx[1][i]; nx[1][i] = in[(nrow + i) * SMS]; }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < 2; i++) {
                     const float x = xv[i];
                     float o[4];
 #pragma unroll
@@ -1032,7 +1038,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         o[j] = z;
                     }
                     if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }
-                    const int pos = 4 * h + i;
+                    const int pos = 2 * h + i;
                     const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)) & mm, w1 = format_audio_word(__fmul_rn(o[1], 10.0f)) & mm;   // LINE_OUT_SCALING_FACTOR (:2860)
                     const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
                     // the four output samples {l, r} x 4 = 32 bytes: one 256-bit store (STG.E.ENL2.256)
@@ -1047,7 +1053,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             if (c >= 0 && c < nsteps && active) {
                 const float *in = sm.bq[c & 1] + g;
 #pragma unroll
-                for (int i = 0; i < 4; i++) nx[i] = in[i * SMS];
+                for (int i = 0; i < 2; i++) { nx[0][i] = in[i * SMS]; nx[1][i] = in[(2 + i) * SMS]; }
 #pragma unroll 1
                 for (int blk = 0; blk < 4; blk++) {
                     int4 *d4 = dst + (size_t)c * 64 + blk * 16;
