@@ -185,7 +185,7 @@ struct FirLaneState {
 }  // namespace
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq, int dbg)
+rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq, int dbg, int pace)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -449,6 +449,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll
         for (int i = 0; i < 4; i++) { ah[i] = umma_desc(smem_u32(sm.gh[i]) + HR0 * 16, HPLANE, 128); bh[i] = umma_desc(smem_u32(sm.hring[i]), HLBO, HSBO); }
         const int oc_last = (s_end - 1) >> 2;
+        // The operand fetch of the MMAs saturates shared memory; issued back to back they starve the LDS of the serial warps for
+        // the length of the burst.  A short pause after every k-step leaves gaps for them (the MMAs have the whole iteration).
+        auto pause = [&]() { if (pace > 0) { const long long t0 = clock64(); while (clock64() - t0 < pace) { } } };
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
@@ -460,15 +463,19 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64);
                         const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
 #pragma unroll 1
-                        for (int j = 0; j < 8; j++)
+                        for (int j = 0; j < 8; j++) {
                             umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, 1u);
+                            pause();
+                        }
                     }
                     if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end && !(dbg & 1)) {
                         // the last 96 samples of the step are the history of the next chunk: kk = 0 .. 5, first write of its accumulator
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
 #pragma unroll 1
-                        for (int j = 2; j < 8; j++)
+                        for (int j = 2; j < 8; j++) {
                             umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, j > 2 ? 1u : 0u);
+                            pause();
+                        }
                     }
                     umma_commit(&sm.bar_dec[sd & 1]);
                 }
@@ -488,6 +495,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                                     const unsigned d_tmem = tmem + HIL_COL0 + (unsigned)((oc & 3) * 32);
                                     umma3_bf16(d_tmem, ah[0] - 16 * kk, ah[1] - 16 * kk, bh[0] + boff, bh[1] + boff, idesc_h, kk > 0 ? 1u : 0u);
                                     umma3_bf16(d_tmem, ah[2] - 16 * kk, ah[3] - 16 * kk, bh[2] + boff, bh[3] + boff, idesc_h, 1u);
+                                    pause();
                                 }
                             }
                         }
@@ -1092,7 +1100,8 @@ cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq,
     cudaError_t e = cudaFuncSetAttribute(rx_ssb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     const char *dbg = getenv("UHSDR_B200_TC_DEBUG");      // timing experiments only (results are wrong when set)
-    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq, dbg ? atoi(dbg) : 0);
+    const char *pace = getenv("UHSDR_B200_TC_PACE");
+    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq, dbg ? atoi(dbg) : 0, pace ? atoi(pace) : 120);
     return cudaGetLastError();
 }
 
