@@ -391,7 +391,7 @@ def gpu_arm(args):
                          "fp32": {"achieved_tflops": achieved_tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
                                   "frac": achieved_tf / FP32_PEAK_TFLOPS_NOMINAL, "flop_per_channel_sample": FLOP_PER_SAMPLE,
                                   "note": "direct-form FLOP count of the chain (SURVEY.md 8d) against the FP32 FMA pipe, 148 SM x 128 lanes x 2 x 1.965 GHz; "
-                                          "199 of the 346 FLOP (the Hilbert pair) run on the tensor cores as a bf16-split Toeplitz GEMM"}},
+                                          "282 of the 346 FLOP (the 83-tap decimator and the 199-tap Hilbert pair) run on the tensor cores as bf16-split Toeplitz GEMMs"}},
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "channel-samples/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "parity": parity,
