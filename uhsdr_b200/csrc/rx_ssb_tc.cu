@@ -269,10 +269,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
         const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base) + 4 * r;
 
-        // input prefetch: 4 x int4 = the 8 samples of the next pass, straight from global memory into registers
-        int4 pre[4];
+        // input prefetch: 2 x 4 x int4 = the 8 samples of either pass of the next step, straight from global memory into registers
+        int4 pre[4], pre1[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) pre[i] = active ? __ldg(src + i) : make_int4(0, 0, 0, 0);
+        for (int i = 0; i < 4; i++) { pre[i] = active ? __ldg(src + i) : make_int4(0, 0, 0, 0); pre1[i] = active ? __ldg(src + 32 + i) : make_int4(0, 0, 0, 0); }
 
         for (int it = 0; it < niter; it++) {
             if (it == V - 1 && active) {
@@ -304,12 +304,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         lvmax = max(lvmax, max(abs(v.x), abs(v.z)));
                         fi[2 * i] = (float)v.x; fq[2 * i] = (float)v.y; fi[2 * i + 1] = (float)v.z; fq[2 * i + 1] = (float)v.w;
                     }
-                    // the second pass of this step is fetched behind the arithmetic of the first
-                    if (h == 0 && active) {
-                        const int4 *nx = src + (size_t)t * 64 + 32;
+                    if (h == 0) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
+                        for (int i = 0; i < 4; i++) pre[i] = pre1[i];      // the second pass runs on the other half of the prefetch
                     }
                     lvmax >>= 16;                                                // audio_driver.c:2662-2675
                     ls.clip |= (lvmax > 1024 ? 1 : 0) | (lvmax > 2048 ? 2 : 0) | (lvmax > 4096 ? 4 : 0);
@@ -402,13 +399,16 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
-                // fetch the first pass of the next step; issued after the fence (a membar that would wait for these loads) and
-                // consumed after the step barrier, where this warp waits for the slower roles anyway
+                // fetch the next step; issued after the fence (a membar that would wait for these loads) and
+                // consumed after the step barrier, where this warp waits for the slower roles anyway (both passes: a load issued
+                // inside the step does not arrive in time for its second pass)
                 if (t + 1 < nsteps && active) {
                     const int4 *nx = src + (size_t)(t + 1) * 64;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                    for (int i = 0; i < 4; i++) {
                         asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
+                        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre1[i].x), "=r"(pre1[i].y), "=r"(pre1[i].z), "=r"(pre1[i].w) : "l"(nx + 32 + i));
+                    }
                 }
             }
             __syncthreads();
@@ -765,31 +765,38 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     constexpr bool HANG = decltype(hangc)::value;
                 // operands of one group of AG samples.  The delayed sample x[n-49] of group element j sits at ring row
                 // (row0 + k8 + j - 49) mod LR; a group wraps at most between its first and second element.
-                auto load_group = [&](int k8, float (&x)[AG], float (&dly)[AG], float (&cmx)[AG]) {
-                    int ra = row0 + k8 - AGC_W; if (ra < 0) ra += LR;
-                    int rb = ra + 1; if (rb >= LR) rb -= LR;
-                    const float *dA = latp + ra * SMS, *dB = latp + rb * SMS;
-                    const bool two = k8 < 16;                   // window still reaches into the chunk before the previous one
-                    const float *pc = two ? S2 + (16 + k8) * SMS : S1 + (k8 - 16) * SMS;
-                    const float *pin = in + k8 * SMS;
-#pragma unroll
-                    for (int j = 0; j < AG; j++) {
-                        x[j] = pin[j * SMS];
-                        dly[j] = (j == 0) ? dA[0] : dB[(j - 1) * SMS];
-                        const float sfx = pc[j * SMS];
-                        cmx[j] = two ? fmaxf(mprev, sfx) : sfx;
-                    }
+                // Operands of the next group of AG = 2 samples, fetched with running pointers (no per-group index arithmetic).
+                // The delayed sample x[n-49] of element j sits at ring row (row0 + k8 + j - 49) mod LR; the sliding-maximum
+                // operand comes from the suffix maxima of the step before the previous one while k8 < 16 (combined with the
+                // whole previous step, mprev), afterwards from those of the previous step (mp = 0: all values are >= 0).
+                // The last two calls run past the step; what they fetch is valid shared memory and never used.
+                int ra0 = row0 - AGC_W; if (ra0 < 0) ra0 += LR;
+                const float *const lat_end = latp + LR * SMS;
+                const float *px = in, *pa = latp + ra0 * SMS, *pb = pa + SMS, *pc = S2 + 16 * SMS;
+                if (pb >= lat_end) pb -= LR * SMS;
+                float mp = mprev;
+                int kl = 0;
+                float *po = out;
+                auto load_next = [&](float (&x)[AG], float (&dly)[AG], float (&cmx)[AG]) {
+                    static_assert(AG == 2, "two samples per group");
+                    x[0] = px[0]; x[1] = px[SMS];
+                    dly[0] = pa[0]; dly[1] = pb[0];
+                    cmx[0] = fmaxf(mp, pc[0]); cmx[1] = fmaxf(mp, pc[SMS]);
+                    px += AG * SMS; pc += AG * SMS; kl += AG;
+                    pa += AG * SMS; if (pa >= lat_end) pa -= LR * SMS;
+                    pb += AG * SMS; if (pb >= lat_end) pb -= LR * SMS;
+                    if (kl == 16) { pc = S1; mp = 0.0f; }
                 };
-                // the operands of the next group are fetched before the current group is computed (shared-memory latency off the recurrence)
+                // the operands of the next two iterations are fetched ahead of the current one (shared-memory latency off the recurrence)
                 float xn[AG], dn[AG], cn[AG], xm[AG], dm[AG], cm[AG];
-                load_group(0, xn, dn, cn);
-                load_group(AG, xm, dm, cm);
+                load_next(xn, dn, cn);
+                load_next(xm, dm, cm);
 #pragma unroll 1
                 for (int k8 = 0; k8 < ND; k8 += AG) {
                     float x[AG], dly[AG], cmx[AG];
 #pragma unroll
                     for (int j = 0; j < AG; j++) { x[j] = xn[j]; dly[j] = dn[j]; cmx[j] = cn[j]; xn[j] = xm[j]; dn[j] = dm[j]; cn[j] = cm[j]; }
-                    load_group(min(k8 + 2 * AG, ND - AG), xm, dm, cm);
+                    load_next(xm, dm, cm);
 #pragma unroll
                     for (int j = 0; j < AG; j++) {
                         const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
@@ -841,8 +848,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         ar.state = nstate;
                         if (upd) ar.volts = fmaf(dv, mult_sel, ar.volts);
                         if (ar.volts < ap.min_volts) { ar.volts = ap.min_volts; ar.action = 0; } else { ar.action = 1; }
-                        out[(k8 + j) * SMS] = ar.volts;
+                        po[j * SMS] = ar.volts;
                     }
+                    po += AG * SMS;
                 }
                 };
                 if (any_hang) detect(std::true_type{}); else detect(std::false_type{});
@@ -999,6 +1007,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
         // PLAIN: no mute array and no float copy of the audio asked for (the throughput case): no masking, no second store
         float nx[2][2];                       // the inputs of the next two loop iterations, fetched from the queue ahead of their use
+        // The lean variant (no anti-alias lattice, unity treble, no mute array, no float copy) folds LINE_OUT_SCALING_FACTOR into the
+        // interpolator taps: one multiplication less per output sample (the product differs from the reference's by final rounding).
+        const bool lean = plain && !any_aa && tr_unity;
+        if (lean) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+#pragma unroll
+                for (int kq = 0; kq < 4; kq++) ic[j][kq] *= 10.0f;
+        }
         auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int blk, int4 *d4, float4 *df, bool muted) {
             constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
             const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
@@ -1045,10 +1062,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         }
                         o[j] = z;
                     }
-                    if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }
+                    if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }     // (lean: scaled by 10, undone at the end)
                     const int pos = 2 * h + i;
-                    const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)) & mm, w1 = format_audio_word(__fmul_rn(o[1], 10.0f)) & mm;   // LINE_OUT_SCALING_FACTOR (:2860)
-                    const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
+                    const float sc = PLAIN ? 1.0f : 10.0f;       // LINE_OUT_SCALING_FACTOR (:2860); PLAIN runs only as the lean variant
+                    const int w0 = format_audio_word(PLAIN ? o[0] : __fmul_rn(o[0], sc)) & mm, w1 = format_audio_word(PLAIN ? o[1] : __fmul_rn(o[1], sc)) & mm;
+                    const int w2 = format_audio_word(PLAIN ? o[2] : __fmul_rn(o[2], sc)) & mm, w3 = format_audio_word(PLAIN ? o[3] : __fmul_rn(o[3], sc)) & mm;
                     // the four output samples {l, r} x 4 = 32 bytes: one 256-bit store (STG.E.ENL2.256)
                     asm volatile("st.global.v8.b32 [%0], {%1, %1, %2, %2, %3, %3, %4, %4};" ::"l"(d4 + 2 * pos), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
                     if (!PLAIN && df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
@@ -1065,7 +1083,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll 1
                 for (int blk = 0; blk < 4; blk++) {
                     int4 *d4 = dst + (size_t)c * 64 + blk * 16;
-                    if (plain && !any_aa && tr_unity) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in, blk, d4, nullptr, false); continue; }
+                    if (lean) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in, blk, d4, nullptr, false); continue; }
                     const bool muted = mute && mute[c * 4 + blk];
                     float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
                     if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
@@ -1083,6 +1101,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll
                 for (int j = 0; j < 6; j++) st->aa_s[j] = as[j];
             }
+            if (lean) { ts.x1 *= 0.1f; ts.y1 = ts.x1; ts.x2 *= 0.1f; ts.y2 = ts.x2; }
             st->bq2 = ts;
         }
     }
