@@ -96,3 +96,54 @@ def test_unaligned_output_buffer_takes_the_cuda_core_kernel(built):
         diff = (got[c, :, 0].astype(np.int64) >> 16) - (want_w[:, 0].astype(np.int64) >> 16)
         assert np.max(np.abs(diff)) <= 1
         assert np.array_equal(got[c, :, 0], got[c, :, 1])
+
+
+def test_tensor_core_kernel_short_calls_carry_both_filter_histories(built):
+    """The tensor-core kernel feeds the decimator / Hilbert histories through virtual steps and, for calls shorter than
+    the 198-sample Hilbert history (fewer than 7 steps of 4 blocks), moves the part of the old history that survives.
+    A run cut into calls of 1..6 steps must equal the one-call run bit for bit, and both must match the oracle."""
+    cfg_u, cfg_l = default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
+    sizes = [4, 8, 4, 12, 16, 20, 24, 4, 28, 8]            # blocks per call (all multiples of 4: tensor-core kernel)
+    nb, nch = sum(sizes), 30                                 # 30 channels: two CTAs, the second one ragged
+    cfgs = [cfg_u if c % 3 else cfg_l for c in range(nch)]
+    iq = np.stack([synth.rx_iq(cfgs[c], 500 + c, nb * 32, seed=46) for c in range(nch)])
+    outs = []
+    for cut in (False, True):
+        with Engine(nch) as eng:
+            for c in range(nch):
+                eng.configure(cfgs[c], first=c, count=1)
+            if not cut:
+                outs.append(run_engine_float(eng, iq))
+            else:
+                ws, fs, pos = [], [], 0
+                for n in sizes:
+                    w, f = run_engine_float(eng, iq[:, pos * 32:(pos + n) * 32])
+                    ws.append(w); fs.append(f); pos += n
+                outs.append((np.concatenate(ws, axis=1), np.concatenate(fs, axis=1)))
+    (w1, f1), (w2, f2) = outs
+    assert np.array_equal(w1, w2)
+    assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32))
+    for c in (0, 1, 27, 28, 29):
+        with oracle_channel(cfgs[c]) as o:
+            want_w, want_f = o.rx(iq[c])
+        check_tolerance(f1[c], want_f, w1[c, :, 0], want_w[:, 0], f"short_calls/ch{c}")
+
+
+def test_tensor_core_kernel_mute_and_float_copy(built):
+    """external_mute through the tensor-core kernel: muted blocks are zeros, every filter state still advances
+    (audio_driver.c:2845-2853), and the run without a mute array / float copy (the lean output path) gives the same words."""
+    cfg = default_cfg()
+    nch, nb = 5, 64
+    iq = np.stack([synth.rx_iq(cfg, 600 + c, nb * 32, seed=47) for c in range(nch)])
+    mute = np.zeros((nch, nb), dtype=np.uint8)
+    mute[:, 8:13] = 1
+    mute[2, 40:] = 1
+    with Engine(nch) as eng:
+        eng.configure(cfg)
+        w_m, f_m = run_engine_float(eng, iq, mute)
+    with Engine(nch) as eng:
+        eng.configure(cfg)
+        w_plain = eng.rx(iq)                                 # host-buffer entry point: no mute, no float copy
+    mask = np.repeat(mute.astype(bool), 32, axis=1)
+    assert np.all(w_m[mask] == 0) and np.all(f_m[mask] == 0.0)
+    assert np.array_equal(w_m[~mask], w_plain[~mask])

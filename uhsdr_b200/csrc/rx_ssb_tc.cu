@@ -1007,15 +1007,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // one 32-sample block (8 decimated samples -> 32 outputs = 256 bytes of the channel's row)
         // PLAIN: no mute array and no float copy of the audio asked for (the throughput case): no masking, no second store
         float nx[2][2];                       // the inputs of the next two loop iterations, fetched from the queue ahead of their use
-        // The lean variant (no anti-alias lattice, unity treble, no mute array, no float copy) folds LINE_OUT_SCALING_FACTOR into the
-        // interpolator taps: one multiplication less per output sample (the product differs from the reference's by final rounding).
+        // the lean variant: no anti-alias lattice, unity treble, no mute array, no float copy (same arithmetic, fewer instructions)
         const bool lean = plain && !any_aa && tr_unity;
-        if (lean) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-#pragma unroll
-                for (int kq = 0; kq < 4; kq++) ic[j][kq] *= 10.0f;
-        }
         auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int blk, int4 *d4, float4 *df, bool muted) {
             constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
             const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
@@ -1062,11 +1055,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         }
                         o[j] = z;
                     }
-                    if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }     // (lean: scaled by 10, undone at the end)
+                    if constexpr (!TR) { ts.x1 = o[3]; ts.y1 = o[3]; ts.x2 = o[2]; ts.y2 = o[2]; }
                     const int pos = 2 * h + i;
-                    const float sc = PLAIN ? 1.0f : 10.0f;       // LINE_OUT_SCALING_FACTOR (:2860); PLAIN runs only as the lean variant
-                    const int w0 = format_audio_word(PLAIN ? o[0] : __fmul_rn(o[0], sc)) & mm, w1 = format_audio_word(PLAIN ? o[1] : __fmul_rn(o[1], sc)) & mm;
-                    const int w2 = format_audio_word(PLAIN ? o[2] : __fmul_rn(o[2], sc)) & mm, w3 = format_audio_word(PLAIN ? o[3] : __fmul_rn(o[3], sc)) & mm;
+                    const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)) & mm, w1 = format_audio_word(__fmul_rn(o[1], 10.0f)) & mm;   // LINE_OUT_SCALING_FACTOR (:2860)
+                    const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)) & mm, w3 = format_audio_word(__fmul_rn(o[3], 10.0f)) & mm;
                     // the four output samples {l, r} x 4 = 32 bytes: one 256-bit store (STG.E.ENL2.256)
                     asm volatile("st.global.v8.b32 [%0], {%1, %1, %2, %2, %3, %3, %4, %4};" ::"l"(d4 + 2 * pos), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
                     if (!PLAIN && df) df[pos] = muted ? make_float4(0.0f, 0.0f, 0.0f, 0.0f)
@@ -1101,7 +1093,6 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll
                 for (int j = 0; j < 6; j++) st->aa_s[j] = as[j];
             }
-            if (lean) { ts.x1 *= 0.1f; ts.y1 = ts.x1; ts.x2 *= 0.1f; ts.y2 = ts.x2; }
             st->bq2 = ts;
         }
     }
