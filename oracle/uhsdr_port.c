@@ -486,6 +486,7 @@ typedef struct {
     int first_time, nr_first_time_count;
     float alpha;
     int decimation_active;
+    float nb_work[128 + 26];                  /* alt_noise_blanking's static working_buffer, audio_nr.c:2282 */
 } nr_t;
 
 /* adb.a_buffer[0..1], audio_driver.h:147-157: persists across blocks */
@@ -598,6 +599,7 @@ static int lattice_from_table(const port_tables_t *t, int idx, lattice_t *l)
 }
 
 static void nr_init(port_chan_t *c);
+static int nb_active(const uhsdr_chan_cfg_t *cfg) { return (cfg->dsp_active & UHSDR_DSP_NB_ENABLE) && cfg->nb_setting > 0; }   /* ui_driver.c:405-408 */
 static void nr_isr(port_chan_t *c, int n, float *buf);
 static void nr_task(port_chan_t *c);
 static void tx_setup(port_chan_t *c);
@@ -608,7 +610,6 @@ static int chan_set_chain(port_chan_t *c, const uhsdr_chan_cfg_t *cfg)
     const port_tables_t *t = c->t;
     if (cfg->struct_size != sizeof(uhsdr_chan_cfg_t)) return UHSDR_ERR_ARG;
     if (cfg->filter_path < 1 || cfg->filter_path >= (int)t->h->num_paths) return UHSDR_ERR_ARG;
-    if (cfg->dsp_active & UHSDR_DSP_NB_ENABLE) return UHSDR_ERR_UNSUPPORTED;
     if (cfg->spectrum_magnify != 0) return UHSDR_ERR_UNSUPPORTED;
     c->cfg = *cfg;
     const uhsdr_tbl_path_t *p = c->path = &t->path[cfg->filter_path];
@@ -927,7 +928,8 @@ static void rx_postprocess(port_chan_t *c, float *a0, float *a1, int ndec)
         notch_run(&c->notch, a0, ndec);
     if (c->pre.n > 0) lattice_run(&c->pre, a0, ndec);
     agc_run(&c->agc, a0, ndec);
-    if (c->decimated_freq == 12000 && (c->cfg.dsp_active & UHSDR_DSP_NR_ENABLE)) nr_isr(c, ndec, a0);
+    /* audio_driver.c:2501: is_dsp_nb_active() || is_dsp_nr() */
+    if (c->decimated_freq == 12000 && ((c->cfg.dsp_active & UHSDR_DSP_NR_ENABLE) || nb_active(&c->cfg))) nr_isr(c, ndec, a0);
 
     const float post_agc_gain_scaling = (c->path->sample_rate_dec == 4) ? 3.46 : (3.46 * 0.6);
     const float scale_gain = post_agc_gain_scaling * ((mode == UHSDR_DEMOD_AM || mode == UHSDR_DEMOD_SAM) ? 0.5 : 0.333);

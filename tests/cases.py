@@ -1,7 +1,7 @@
 """Shared parity cases: (label, cfg kwargs, nblocks).  Every distinct signal-flow topology, every
 demodulator and the configuration switches the reference reads on the block path."""
 from uhsdr_b200.config import (DEMOD_AM, DEMOD_CW, DEMOD_DIGI, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, DSP_MNOTCH_ENABLE,
-                               DSP_MPEAK_ENABLE, DSP_NOTCH_ENABLE, DSP_NR_ENABLE, FREQ_IQ_CONV_M6KHZ, FREQ_IQ_CONV_OFF, FREQ_IQ_CONV_P12KHZ,
+                               DSP_MPEAK_ENABLE, DSP_NB_ENABLE, DSP_NOTCH_ENABLE, DSP_NR_ENABLE, FREQ_IQ_CONV_M6KHZ, FREQ_IQ_CONV_OFF, FREQ_IQ_CONV_P12KHZ,
                                FREQ_IQ_CONV_P6KHZ, SAM_SIDEBAND_LSB, SAM_SIDEBAND_USB)
 
 RX_CASES = [
@@ -41,6 +41,17 @@ NR_CASES = [
     ("usb_p35_nr_dec", dict(dsp_active=DSP_NR_ENABLE), 320),
     ("usb_p44_nr_nodec", dict(filter_path=44, dsp_active=DSP_NR_ENABLE), 224),
     ("usb_p35_nr_decoff", dict(dsp_active=DSP_NR_ENABLE, nr_decimation_enable=0, nr_strength=100), 224),
+]
+
+# LPC impulse noise blanker (DSP_NB_ENABLE, alt_noise_blanking audio_nr.c:2210-2539); inputs carry seeded impulses
+# (synth.add_impulses, NB_IMPULSES of them).  Alone it is integer/float-exact (no FFT); with the spectral NR behind it
+# the FFT rounding applies.  The thresholds (16 - nb_setting)/2 sigma x sqrt(LPC power) are low enough that the repair path
+# runs many times in every case (the tonal test signal makes the LPC power, hence the threshold, large).
+NB_IMPULSES = 24
+NB_CASES = [
+    ("usb_p35_nb12", dict(dsp_active=DSP_NB_ENABLE, nb_setting=12), 320),
+    ("usb_p44_nb14_nodec", dict(filter_path=44, dsp_active=DSP_NB_ENABLE, nb_setting=14), 224),
+    ("usb_p35_nb15_nr", dict(dsp_active=DSP_NB_ENABLE | DSP_NR_ENABLE, nb_setting=15), 320),
 ]
 
 SPECTRUM_CASES = [

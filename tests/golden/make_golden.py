@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from cases import NR_CASES, RX_CASES, SPECTRUM_CASES, TX_CASES  # noqa: E402
+from cases import NB_CASES, NB_IMPULSES, NR_CASES, RX_CASES, SPECTRUM_CASES, TX_CASES  # noqa: E402
 from oracle.refchain import RefChannel  # noqa: E402
 from uhsdr_b200 import synth  # noqa: E402
 from uhsdr_b200.config import default_cfg  # noqa: E402
@@ -21,9 +21,11 @@ from uhsdr_b200.config import default_cfg  # noqa: E402
 
 def main():
     out = {}
-    for label, kw, nblocks in RX_CASES + NR_CASES:
+    for label, kw, nblocks in RX_CASES + NR_CASES + NB_CASES:
         cfg = default_cfg(**kw)
         iq = synth.rx_iq(cfg, 5, nblocks * 32, seed=1234)
+        if (label, kw, nblocks) in NB_CASES:
+            iq = synth.add_impulses(iq, 1234, NB_IMPULSES)
         with RefChannel(cfg) as r:
             audio, audio_f = r.rx(iq)
             st = r.status()

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import NR_CASES, RX_CASES
+from cases import NB_CASES, NR_CASES, RX_CASES
 from oracle import refchain
 from oracle.port import PortChannel
 from uhsdr_b200 import synth
@@ -78,9 +78,8 @@ def test_port_full_scale_input_sets_clip_flags():
 
 
 def test_port_rejects_unsupported():
-    from uhsdr_b200.config import DSP_NB_ENABLE
     with pytest.raises(ValueError):
-        PortChannel(default_cfg(dsp_active=DSP_NB_ENABLE, nb_setting=10))
+        PortChannel(default_cfg(spectrum_magnify=2))
     with pytest.raises(ValueError):
         PortChannel(default_cfg(filter_path=0))
 
@@ -115,6 +114,27 @@ def test_port_nr_matches_golden_within_fft_rounding(golden, label, kw, nblocks):
     err = audio_f.astype(np.float64) - want
     assert np.max(np.abs(err)) <= 1e-5 * np.max(np.abs(want))
     assert 10 * np.log10(np.mean(want ** 2) / np.mean(err ** 2)) > 100.0
+
+
+@pytest.mark.parametrize("label,kw,nblocks", NB_CASES, ids=[c[0] for c in NB_CASES])
+def test_port_noise_blanker_matches_golden(golden, label, kw, nblocks):
+    """LPC impulse blanker: alone it has no FFT on its path -> bit-exact; with the spectral NR behind it, FFT rounding.
+    The golden inputs carry impulses, and the blanker must have repaired them (its output differs from the run without it)."""
+    from uhsdr_b200.config import DSP_NB_ENABLE, DSP_NR_ENABLE
+    cfg = default_cfg(**kw)
+    iq = golden[f"{label}/iq"]
+    with PortChannel(cfg) as p:
+        audio, audio_f = p.rx(iq)
+    want = golden[f"{label}/audio_f"]
+    if cfg.dsp_active & DSP_NR_ENABLE:
+        err = audio_f.astype(np.float64) - want.astype(np.float64)
+        assert np.max(np.abs(err)) <= 1e-5 * np.max(np.abs(want))
+    else:
+        assert np.array_equal(audio[:, 0], golden[f"{label}/audio_l"])
+        assert np.array_equal(audio_f.view(np.uint32), want.view(np.uint32))
+    with PortChannel(default_cfg(**dict(kw, nb_setting=1))) as p:      # threshold 7.5 sigma x sqrt(LPC power): never fires, same latency
+        _, delayed_f = p.rx(iq)
+    assert np.count_nonzero(delayed_f != audio_f) > 500
 
 
 @pytest.mark.parametrize("label,kw", SPECTRUM_CASES, ids=[c[0] for c in SPECTRUM_CASES])

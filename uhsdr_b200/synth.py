@@ -53,6 +53,18 @@ def rx_iq(cfg: ChanCfg, channel: int, nsamples: int, seed: int = 0x55485344, sta
     return out
 
 
+def add_impulses(iq: np.ndarray, seed: int, count: int, amplitude: float = 25000.0) -> np.ndarray:
+    """Copy of `iq` with `count` one-sample impulses (ignition-noise like) on I and Q at seeded random positions --
+    the input the LPC noise blanker (alt_noise_blanking, audio_nr.c:2210) is there for."""
+    out = iq.astype(np.int64)
+    rng = np.random.default_rng([seed, 0x4e42])
+    pos = rng.choice(np.arange(64, len(iq) - 64), size=count, replace=False)
+    sg = rng.choice([-1.0, 1.0], size=(count, 2))
+    out[pos, 0] += np.round(sg[:, 0] * amplitude * 65536.0).astype(np.int64)
+    out[pos, 1] += np.round(sg[:, 1] * 0.7 * amplitude * 65536.0).astype(np.int64)
+    return out.clip(-2**31, 2**31 - 1).astype(np.int32)
+
+
 def tx_mic(channel: int, nsamples: int, seed: int = 0x55485344, start: int = 0) -> np.ndarray:
     """int32 [nsamples, 2] microphone block stream: two-tone 700 + 1900 Hz, amplitude 8000 each, in `l`."""
     n = np.arange(start, start + nsamples, dtype=np.float64)
