@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import NR_CASES, SPECTRUM_CASES, TX_CASES
+from cases import NB_CASES, NB_IMPULSES, NR_CASES, SPECTRUM_CASES, TX_CASES
 from conftest import oracle_channel
 from test_rx_parity_gpu import check_tolerance, run_engine_float
 from uhsdr_b200 import synth
@@ -37,6 +37,34 @@ def test_spectral_nr_within_tolerance(built, label, kw, nblocks, exact):
         assert np.flatnonzero(np.abs(fl[c]) > thr)[0] == np.flatnonzero(np.abs(want_f) > thr)[0], label
         assert np.all(fl[c][: 32 * 32] == 0) and np.all(want_f[: 32 * 32] == 0)
         check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,nblocks", NB_CASES, ids=[c[0] for c in NB_CASES])
+def test_lpc_noise_blanker(built, label, kw, nblocks, exact):
+    """alt_noise_blanking (audio_nr.c:2210-2539) on inputs with impulses, settings at which the repair path fires on most
+    frames.  The blanker is a threshold decision followed by a replacement, so it keeps the reference's operation order in
+    both builds: alone (no FFT on the path) the exact build must be bit-exact, and the fast build / the case with the
+    spectral NR behind it must stay within the float tolerance -- one different decision would break it by far."""
+    from uhsdr_b200.config import DSP_NR_ENABLE
+    cfg = default_cfg(**kw)
+    nb = 3 * nblocks
+    nch = 3
+    iq = np.stack([synth.add_impulses(synth.rx_iq(cfg, 40 + c, nb * 32, seed=19), 19 + c, 3 * NB_IMPULSES) for c in range(nch)])
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        h = (nb // 3) * 32
+        w1, f1 = run_engine_float(eng, iq[:, :h])
+        w2, f2 = run_engine_float(eng, iq[:, h:])
+    words, fl = np.concatenate([w1, w2], axis=1), np.concatenate([f1, f2], axis=1)
+    for c in range(nch):
+        with oracle_channel(cfg) as o:
+            want_w, want_f = o.rx(iq[c])
+        if exact and not (cfg.dsp_active & DSP_NR_ENABLE):
+            assert np.array_equal(words[c], want_w), (label, c)
+            assert np.array_equal(fl[c].view(np.uint32), want_f.view(np.uint32)), (label, c)
+        else:
+            check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
 
 
 @pytest.mark.parametrize("label,kw", SPECTRUM_CASES, ids=[c[0] for c in SPECTRUM_CASES])

@@ -185,9 +185,8 @@ def test_errors_are_loud(built):
         with pytest.raises(UhsdrError) as ei:
             eng.rx(np.zeros((2, 64, 2), dtype=np.int32))          # not configured
         assert ei.value.code == -6
-        from uhsdr_b200.config import DSP_NB_ENABLE
         with pytest.raises(UhsdrError) as ei:
-            eng.configure(default_cfg(dsp_active=DSP_NB_ENABLE, nb_setting=10))
+            eng.configure(default_cfg(spectrum_magnify=2))          # zoom FFT: not implemented
         assert ei.value.code == -5
         with pytest.raises(UhsdrError):
             eng.configure(default_cfg(filter_path=70))              # AM path with an SSB mode

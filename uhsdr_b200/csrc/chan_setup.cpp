@@ -227,7 +227,6 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     if (cfg.struct_size != sizeof(uhsdr_chan_cfg_t)) return fail(UHSDR_ERR_ARG, "uhsdr_chan_cfg_t.struct_size mismatch");
     if (cfg.filter_path < 1 || cfg.filter_path >= (int)t.h->num_paths) return fail(UHSDR_ERR_ARG, "filter_path out of range");
     if (cfg.dmod_mode < UHSDR_DEMOD_USB || cfg.dmod_mode > UHSDR_DEMOD_DIGI) return fail(UHSDR_ERR_UNSUPPORTED, "dmod_mode not implemented (SSBSTEREO/IQ are stereo-only modes)");
-    if ((cfg.dsp_active & UHSDR_DSP_NB_ENABLE) && cfg.nb_setting > 0) return fail(UHSDR_ERR_UNSUPPORTED, "LPC noise blanker (DSP_NB_ENABLE) is not implemented");
     if (cfg.spectrum_magnify != 0) return fail(UHSDR_ERR_UNSUPPORTED, "zoom FFT (sd.magnify != 0) is not implemented");
     if (cfg.fm_subaudible_tone_det_freq != 0.0f) return fail(UHSDR_ERR_UNSUPPORTED, "FM subaudible tone detection is not implemented");
     if (cfg.iq_freq_mode < 0 || cfg.iq_freq_mode > 4) return fail(UHSDR_ERR_ARG, "iq_freq_mode out of range");
@@ -358,7 +357,12 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     p->notch_enable = ((cfg.dsp_active & UHSDR_DSP_NOTCH_ENABLE) && mode != UHSDR_DEMOD_CW && mode != UHSDR_DEMOD_FM &&
                        !(mode == UHSDR_DEMOD_SAM && p->decimated_freq == 24000)) ? 1 : 0;
     p->notch_mu = log10f(((cfg.notch_mu + 1.0) / 1500.0) + 1.0);        // :1170
-    p->nr_enable = (p->decimated_freq == 12000 && (cfg.dsp_active & UHSDR_DSP_NR_ENABLE) && mode != UHSDR_DEMOD_FM) ? 1 : 0;
+    const bool nb_active = (cfg.dsp_active & UHSDR_DSP_NB_ENABLE) && cfg.nb_setting > 0;          // is_dsp_nb_active, ui_driver.c:405-408
+    const bool nr_active = (cfg.dsp_active & UHSDR_DSP_NR_ENABLE) != 0;
+    p->nr_enable = (p->decimated_freq == 12000 && (nr_active || nb_active) && mode != UHSDR_DEMOD_FM) ? 1 : 0;
+    p->nr_spectral = p->nr_enable && nr_active;
+    p->nb_enable = p->nr_enable && nb_active;
+    p->nb_level = 16 - (int)(uint8_t)cfg.nb_setting;
     {
         const int width_i = t.filt[fp.id].width;
         p->nr_decim = (cfg.nr_decimation_enable && width_i < 2701) ? 1 : 0;

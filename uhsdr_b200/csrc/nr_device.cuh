@@ -14,6 +14,97 @@ constexpr int NR_FIFO = 5;     // NR_BUFFER_FIFO_SIZE = NR_BUFFER_NUM + 1 (freed
 
 __device__ __forceinline__ int nr_fifo_count(int head, int tail) { int len = head - tail; return len < 0 ? len + NR_FIFO : len; }
 
+// LPC impulse noise blanker, alt_noise_blanking (audio_nr.c:2210-2539): one 128-sample frame in place in `frame`
+// (global memory), `w` = 512 floats of shared memory.  Order-10 LPC of the frame (autocorrelation + Levinson-Durbin),
+// inverse filter + matched filter, threshold at nb_level/2 standard deviations x sqrt(LPC power), up to 5 impulses of
+// 7 samples replaced by the windowed sum of a forward and a backward prediction; 26 samples stay in the working
+// buffer between frames (output = input delayed by 13).  Every sum keeps the order of the CMSIS portable kernels
+// (arm_dot_prod_f32, arm_fir_f32 with freshly zeroed state, arm_var_f32, arm_power_f32), with separate multiply and
+// add in both builds: the detection is a threshold decision, so the blanker is bit-exact or it is wrong.
+// Lanes: autocorrelation lag i on lane i, the two FIRs over samples, the short serial parts on lane 0.
+__device__ inline void nb_frame(const ChanParams &p, NrState &nr, float *frame, float *w, int lane)
+{
+    constexpr int ORD = 10, PL = 3, IMP = 7;
+    float *wb = w, *temp = w + 160, *temp2 = w + 288, *R = w + 416, *lpcs = w + 432, *rev = w + 448;
+    int *ipos = reinterpret_cast<int *>(w + 464);              // [0] count, [1..5] positions
+    for (int i = lane; i < 2 * PL + 2 * ORD; i += 32) wb[i] = nr.nb_work[i];
+    for (int i = lane; i < 128; i += 32) wb[2 * PL + 2 * ORD + i] = frame[i];                 // :2344
+    __syncwarp();
+    const float *x = wb + ORD + PL;
+    if (lane <= ORD) {                                                                        // :2356-2360
+        float sum = 0.0f;
+        for (int n = 0; n < 128 - lane; n++) sum = __fadd_rn(sum, __fmul_rn(x[n], x[n + lane]));
+        R[lane] = sum;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float l[ORD + 1], any[ORD + 1];
+        const float r0 = (float)((double)R[0] * (1.0 + 1.0e-9));                              // :2367
+        l[0] = 1.0f;
+        for (int i = 1; i <= ORD; i++) l[i] = 0.0f;
+        float alfa = r0;
+        for (int m = 1; m <= ORD; m++) {                                                      // Levinson-Durbin, :2376-2392
+            float s = 0.0f;
+            for (int u = 1; u < m; u++) s = __fadd_rn(s, __fmul_rn(l[u], R[m - u]));
+            const float k = __fdiv_rn(-__fadd_rn(R[m], s), alfa);
+            for (int v = 1; v < m; v++) any[v] = __fadd_rn(l[v], __fmul_rn(k, l[m - v]));
+            for (int v = 1; v < m; v++) l[v] = any[v];
+            l[m] = k;
+            alfa = __fmul_rn(alfa, __fsub_rn(1.0f, __fmul_rn(k, k)));
+        }
+        for (int o = 0; o <= ORD; o++) { lpcs[o] = l[o]; rev[ORD - o] = l[o]; }
+    }
+    __syncwarp();
+    for (int n = lane; n < 128; n += 32) {                                                    // inverse filter, :2402
+        float acc = 0.0f;
+        for (int k = 0; k <= ORD; k++) { const int j = n - ORD + k; acc = __fadd_rn(acc, __fmul_rn(j >= 0 ? x[j] : 0.0f, rev[k])); }
+        temp[n] = acc;
+    }
+    __syncwarp();
+    for (int n = lane; n < 128; n += 32) {                                                    // matched filter, :2406
+        float acc = 0.0f;
+        for (int k = 0; k <= ORD; k++) { const int j = n - ORD + k; acc = __fadd_rn(acc, __fmul_rn(j >= 0 ? temp[j] : 0.0f, lpcs[k])); }
+        temp2[n] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float sum = 0.0f, sumsq = 0.0f;                                                       // arm_var_f32, :2409
+        for (int n = 0; n < 128; n++) { const float in = temp2[n]; sumsq = __fadd_rn(sumsq, __fmul_rn(in, in)); sum = __fadd_rn(sum, in); }
+        const float sigma2 = __fdiv_rn(__fsub_rn(sumsq, __fdiv_rn(__fmul_rn(sum, sum), 128.0f)), 127.0f);
+        float lpc_power = 0.0f;                                                               // arm_power_f32 over `order` values, :2411
+        for (int i = 0; i < ORD; i++) lpc_power = __fadd_rn(lpc_power, __fmul_rn(lpcs[i], lpcs[i]));
+        const float thr = (float)((double)(float)p.nb_level * 0.5 * (double)sqrtf(__fmul_rn(sigma2, lpc_power)));   // :2414
+        int sp = ORD + PL, count = 0;
+        do {                                                                                  // :2423-2437
+            if ((temp2[sp] > thr) || (temp2[sp] < (-thr))) { ipos[1 + count] = sp - ORD; count++; sp += PL; }
+            sp++;
+        } while ((sp < 128) && (count < 5));
+        ipos[0] = count;
+        float nl[ORD], nrv[ORD];                                                              // negated predictors, :2446-2447
+        for (int i = 0; i < ORD; i++) { nl[i] = -lpcs[1 + i]; nrv[i] = -rev[i]; }
+        for (int j = 0; j < count; j++) {                                                     // :2450-2510
+            const int pj = ipos[1 + j];
+            float Rfw[IMP + ORD], Rbw[IMP + ORD];
+            for (int k = 0; k < ORD; k++) { Rfw[k] = wb[pj + k]; Rbw[IMP + k] = wb[ORD + PL + pj + PL + k + 1]; }
+            for (int i = 0; i < IMP; i++) {
+                float a = 0.0f, b = 0.0f;
+                for (int k = 0; k < ORD; k++) a = __fadd_rn(a, __fmul_rn(nrv[k], Rfw[i + k]));
+                Rfw[i + ORD] = a;
+                for (int k = 0; k < ORD; k++) b = __fadd_rn(b, __fmul_rn(nl[k], Rbw[IMP - i + k]));
+                Rbw[IMP - i - 1] = b;
+            }
+            for (int i = 0; i < IMP; i++) {
+                const float wbw = (float)(1.0 * i / (IMP - 1)), wfw = (float)(1.0 * (IMP - 1 - i) / (IMP - 1));   // :2349-2353
+                wb[ORD + pj + i] = __fadd_rn(__fmul_rn(wfw, Rfw[ORD + i]), __fmul_rn(wbw, Rbw[i]));
+            }
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < 128; i += 32) frame[i] = wb[ORD + PL + i];                         // :2520-2521
+    for (int i = lane; i < 2 * PL + 2 * ORD; i += 32) nr.nb_work[i] = wb[128 + i];
+    __syncwarp();
+}
+
 // One 128-sample frame in place in `frame` (global memory), using `fft` (512 floats of shared memory).
 __device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float *__restrict__ pool, float *frame, float *fft, int lane)
 {
@@ -184,7 +275,8 @@ __device__ inline void nr_block(const ChanParams &p, NrState &nr, const float *_
         const int cur = nr.current_buffer_idx % 4;
         const int k = nr.in_fifo[nr.in_tail];
         __syncwarp();
-        nr_spectral(p, nr, pool, nr.bufs[k], fft, lane);
+        if (p.nb_enable) { nb_frame(p, nr, nr.bufs[k], fft, lane); __threadfence_block(); __syncwarp(); }   // AudioNr_RunNoiseReduction, audio_nr.c:362-365
+        if (p.nr_spectral) nr_spectral(p, nr, pool, nr.bufs[k], fft, lane);
         __threadfence_block();
         __syncwarp();
         for (int i = lane; i < 128; i += 32) nr.bufs[cur][128 + i] = nr.bufs[k][i];

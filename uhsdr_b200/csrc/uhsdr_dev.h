@@ -69,7 +69,10 @@ struct ChanParams {
     float fm_scaling;
     int fm_translate_on;
     // spectral NR
-    int nr_enable;         // sampleRateDecim == 12000 && DSP_NR_ENABLE
+    int nr_enable;         // the NR frame interface runs: sampleRateDecim == 12000 && (is_dsp_nr() || is_dsp_nb_active()), audio_driver.c:2501
+    int nr_spectral;       // is_dsp_nr(): spectral_noise_reduction_3 on every frame
+    int nb_enable;         // is_dsp_nb_active(): alt_noise_blanking on every frame (before the spectral NR), audio_nr.c:362-365
+    int nb_level;          // 16 - ts.dsp.nb_setting (threshold in half standard deviations, audio_nr.c:2414)
     int nr_decim;          // nr_params.NR_decimation_active
     float nr_alpha;
     int nr_vad_low, nr_vad_high;
@@ -163,6 +166,7 @@ struct NrState {
     float dec_hist[4], int_hist[20];    // DECIMATE_NR (3 used) / INTERPOLATE_NR (19 used) histories
     float last_sample[128], last_ifft[128], Hk[128], Hk_old[128], Nest0[128], xt[128], pslp[128];
     int first_time, init_counter;
+    float nb_work[128 + 26];  // alt_noise_blanking's static working_buffer (audio_nr.c:2282): 26 samples carried between frames
 };
 
 // TxProcessor_Run, SSB voice branch (tx_processor.c:891-1078): parameters and state
