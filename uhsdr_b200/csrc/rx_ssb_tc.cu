@@ -34,7 +34,6 @@
 // them back to back (issued from an `if (lane == 0)` region each one costs 56 cycles of a serialisation loop).
 #include <cuda_bf16.h>
 
-#include <cstdlib>
 #include <type_traits>
 
 #include "dsp_device.cuh"
@@ -68,6 +67,7 @@ constexpr int HSBO = (HSLOTS / 8) * HLBO;
 constexpr int HR_BYTES = 4 * HSBO;                 // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
 constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
 constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
+constexpr int MMA_PAUSE = 120;        // cycles between k-steps of the MMA issue (sweep in profiles/r01_tc2_experiments.txt)
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
 constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POST = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;
@@ -185,7 +185,7 @@ struct FirLaneState {
 }  // namespace
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq, int dbg, int pace)
+rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c, int hil_ci, int hil_cq)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -287,7 +287,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (it >= V && it < s_end && !(dbg & 4)) {
+            if (it >= V && it < s_end) {
                 const int t = it - V;
                 // The MMAs of step it - 2 read the ring buffer written now; they were committed one iteration ago.
                 mbar_wait(&sm.bar_dec[it & 1], (unsigned)(((it - 2) >> 1) & 1));
@@ -451,14 +451,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const int oc_last = (s_end - 1) >> 2;
         // The operand fetch of the MMAs saturates shared memory; issued back to back they starve the LDS of the serial warps for
         // the length of the burst.  A short pause after every k-step leaves gaps for them (the MMAs have the whole iteration).
-        auto pause = [&]() { if (pace > 0) { const long long t0 = clock64(); while (clock64() - t0 < pace) { } } };
+        auto pause = [&]() { const long long t0 = clock64(); while (clock64() - t0 < MMA_PAUSE) { } };
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const int sd = it - 1;               // step whose samples were written into the decimator ring in the previous iteration
                 if (sd >= 0) {
                     const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16)), b2 = bx2 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16));
-                    if (sd >= V && sd < s_end && !(dbg & 1)) {
+                    if (sd >= V && sd < s_end) {
                         // the 8 k-steps of this step into its own chunk: kk = 6 + 8 (sd & 3) + j
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64);
                         const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
@@ -468,7 +468,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             pause();
                         }
                     }
-                    if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end && !(dbg & 1)) {
+                    if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end) {
                         // the last 96 samples of the step are the history of the next chunk: kk = 0 .. 5, first write of its accumulator
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
 #pragma unroll 1
@@ -481,7 +481,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
                 const int sh = it - 3;               // step whose decimator outputs were written into the Hilbert ring in the previous iteration
                 if (sh >= 0) {
-                    if (sh >= 1 && sh < s_end && !(dbg & 2)) {
+                    if (sh >= 1 && sh < s_end) {
 #pragma unroll 1
                         for (int e = 0; e < 2; e++) {
                             const int u = 2 * sh + e;                        // global k-step (16 decimated samples)
@@ -529,7 +529,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         for (int it = 0; it < niter; it++) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int sd = it - 2;
-            if (sd >= 1 && sd < s_end && (sd & 3) == qd && !(dbg & 8)) {
+            if (sd >= 1 && sd < s_end && (sd & 3) == qd) {
                 const int slot = (sd & 1) * ND + lane;
                 const int bo = (slot >> 3) * HLBO + (slot & 7) * 2;
                 unsigned char *h0 = sm.hring[0] + bo, *h1 = sm.hring[1] + bo, *h2 = sm.hring[2] + bo, *h3 = sm.hring[3] + bo;
@@ -1109,9 +1109,7 @@ cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq,
     const int grid = (a.num_items + per - 1) / per;
     cudaError_t e = cudaFuncSetAttribute(rx_ssb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
-    const char *dbg = getenv("UHSDR_B200_TC_DEBUG");      // timing experiments only (results are wrong when set)
-    const char *pace = getenv("UHSDR_B200_TC_PACE");
-    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq, dbg ? atoi(dbg) : 0, pace ? atoi(pace) : 120);
+    rx_ssb_tc_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(a, per, dec_c, hil_ci, hil_cq);
     return cudaGetLastError();
 }
 
