@@ -67,7 +67,7 @@ constexpr int HSBO = (HSLOTS / 8) * HLBO;
 constexpr int HR_BYTES = 4 * HSBO;                 // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
 constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
 constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
-constexpr int MMA_PAUSE = 120;        // cycles between k-steps of the MMA issue (sweep in profiles/r01_tc2_experiments.txt)
+constexpr int MMA_PAUSE = 120;        // cycles between k-steps of the MMA issue (sweep: profiles/r01_tc2_experiments.txt)
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
 constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POST = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;
