@@ -25,7 +25,7 @@ struct uhsdr_engine {
     cudaStream_t aux_stream = nullptr;          // split paths: serial kernels of slice s run beside the FIR kernel of slice s+1
     static constexpr int kSplitSlices = 4;
     cudaEvent_t ev_split[2 * kSplitSlices] = {}, ev_fork = nullptr, ev_join = nullptr;
-    static constexpr int kMaxSlices = 16;
+    static constexpr int kMaxSlices = 40;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     cudaEvent_t ev_done = nullptr;
     HostTables tables;
@@ -408,7 +408,13 @@ int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio
     if (mute) CK(e, cudaMemcpyAsync(e->d_mute, mute, mbytes, cudaMemcpyHostToDevice, e->stream));
     // slices: multiples of 4 blocks (the fused kernel's chunk) unless the call is small
     int nsl = 1;
-    if (bytes >= ((size_t)32 << 20) && nblocks >= 64) nsl = std::min<int>(uhsdr_engine::kMaxSlices, 8);
+    if (bytes >= ((size_t)32 << 20) && nblocks >= 64) {
+        // the first H2D and the last D2H are not overlapped: more slices = less of that, until a slice is too short to fill the link
+        // (measured at 4096 channels x 1500 blocks, 1.57 GB each way: 8 slices 5.25e9, 12: 5.4e9, 20: 5.8e9, 24: 5.8e9 channel-samples/s)
+        const char *ov = getenv("UHSDR_B200_SLICES");
+        nsl = ov ? atoi(ov) : (int)std::min<size_t>(24, bytes / ((size_t)48 << 20));
+        nsl = std::max(1, std::min<int>(uhsdr_engine::kMaxSlices - 1, std::min(nsl, nblocks / 16)));
+    }
     int per = ((nblocks + nsl - 1) / nsl + 3) / 4 * 4;
     if (per <= 0) per = nblocks;
     // everything queued earlier on the compute stream (configure kernels, a previous device-side
