@@ -65,6 +65,9 @@ TX_CASES = [
     ("tx_usb_p6k_bass_comp8", dict(iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_filter=3, tx_comp_level=8, iq_phase_balance_tx=0.01, tx_adj_gain_i=0.97), 160),
     ("tx_lsb_notrans_tenor_nocomp", dict(dmod_mode=DEMOD_LSB, iq_freq_mode=FREQ_IQ_CONV_OFF, tx_filter=2, tx_comp_level=-1, iq_phase_balance_tx=-0.02, tx_power_factor=0.05), 160),
     ("tx_usb_custom_comp", dict(tx_comp_level=13, tx_alc_decay=3, tx_alc_postfilt_gain=9, tx_mic_gain=40, iq_freq_mode=FREQ_IQ_CONV_P12KHZ), 160),
+    # AM modulator (TxProcessor_AM, tx_processor.c:736-800): both sidebands + carrier, default -12 kHz translation and +6 kHz NCO
+    ("tx_am", dict(dmod_mode=DEMOD_AM, filter_path=70), 160),
+    ("tx_am_p6k_comp10", dict(dmod_mode=DEMOD_AM, filter_path=70, iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_comp_level=10, tx_mic_gain=30), 160),
 ]
 
 # float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these

@@ -139,9 +139,10 @@ def test_tx_ssb(built, label, kw, nblocks, exact):
     assert np.array_equal(got[0], want)
 
 
-def test_tx_non_ssb_is_rejected(built):
+def test_tx_modes_without_a_modulator_are_rejected(built):
+    from uhsdr_b200.config import DEMOD_FM
     with Engine(1) as eng:
-        eng.configure(default_cfg(dmod_mode=DEMOD_AM, filter_path=70))
+        eng.configure(default_cfg(dmod_mode=DEMOD_FM, filter_path=2))
         with pytest.raises(UhsdrError) as ei:
             eng.tx(np.zeros((1, 64, 2), dtype=np.int32))
         assert ei.value.code == -5

@@ -167,8 +167,8 @@ def test_port_tx_matches_golden_bit_exact(golden, label, kw, nblocks):
     assert np.any(iq != 0)
 
 
-def test_port_tx_rejects_non_ssb():
-    from uhsdr_b200.config import DEMOD_AM
-    with PortChannel(default_cfg(dmod_mode=DEMOD_AM, filter_path=70)) as p:
+def test_port_tx_rejects_modes_without_a_modulator():
+    from uhsdr_b200.config import DEMOD_FM
+    with PortChannel(default_cfg(dmod_mode=DEMOD_FM, filter_path=2)) as p:
         with pytest.raises(RuntimeError):
             p.tx(np.zeros((64, 2), dtype=np.int32))

@@ -47,7 +47,9 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
 {
     memset(tp, 0, sizeof(*tp));
     const int mode = cfg.dmod_mode;
-    tp->enabled = (mode == UHSDR_DEMOD_USB || mode == UHSDR_DEMOD_LSB) ? 1 : 0;    // is_ssb(), uhsdr_board.h:809
+    tp->am = (mode == UHSDR_DEMOD_AM && cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF) ? 1 : 0;      // no AM unless in a translate mode, tx_processor.c:999
+    tp->enabled = (mode == UHSDR_DEMOD_USB || mode == UHSDR_DEMOD_LSB || tp->am) ? 1 : 0;    // is_ssb(), uhsdr_board.h:809
+    tp->alc_gain_scaling = tp->am ? 0.23 : 1.00;
     tp->lsb = mode == UHSDR_DEMOD_LSB;
     {
         float gain_calc = (uint8_t)cfg.tx_mic_gain;      // ts.tx_mic_gain_mult (codec.c:321)
@@ -189,7 +191,7 @@ tx_ssb_kernel(TxArgs a)
                             if ((double)st.alc_val < 0.001) st.alc_val = (float)0.001;
                         }
                         if (st.alc_val > 1.0f) st.alc_val = 1.0f;
-                        w.scr[BLK + i] = __fmul_rn(st.alc_val, 1.00f);
+                        w.scr[BLK + i] = __fmul_rn(st.alc_val, tp.alc_gain_scaling);
                     }
                     st.alc_delay_inbuf += BLK;
                 }
@@ -222,6 +224,10 @@ tx_ssb_kernel(TxArgs a)
             for (int i = lane; i < H2; i += 32) w.a[i] = keep[cnt++];
             __syncwarp();
             vi = yi; vq = yq;
+            if (tp.am) {                     // both AM sidebands and the carrier (2 x AM_CARRIER_LEVEL = 10200), tx_processor.c:783-790
+                vi = __fadd_rn(__fsub_rn(yi, yq), 10200.0f);
+                vq = __fsub_rn(__fsub_rn(yq, yi), 10200.0f);
+            }
             // FreqShift (:483-486)
             if (tp.shift_kind == 1) {
                 float ib = tp.shift_down ? vq : vi, qb = tp.shift_down ? vi : vq;
@@ -334,7 +340,7 @@ tx_serial_kernel(TxArgs a)
                     if ((double)alc_val < 0.001) alc_val = (float)0.001;
                 }
                 if (alc_val > 1.0f) alc_val = 1.0f;
-                alc[i] = __fmul_rn(alc_val, 1.00f);
+                alc[i] = __fmul_rn(alc_val, tp.alc_gain_scaling);
             }
             inbuf += BLK;
             // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)

@@ -171,7 +171,9 @@ struct NrState {
 
 // TxProcessor_Run, SSB voice branch (tx_processor.c:891-1078): parameters and state
 struct TxParams {
-    int enabled;             // is_ssb(dmod_mode)
+    int enabled;             // is_ssb(dmod_mode), or AM with a frequency-translate mode (tx_processor.c:996-1006)
+    int am;                  // TxProcessor_AM: both sidebands + carrier after the Hilbert pair (:783-790)
+    float alc_gain_scaling;  // SSB_ALC_GAIN_CORRECTION 1.00 / AM_ALC_GAIN_CORRECTION 0.23 (audio_driver.h:417, :428)
     int lsb;                 // dmod_mode == DEMOD_LSB: I/Q filters swapped (tx_processor.c:477-478)
     float gain_calc;         // mic gain / MIC_GAIN_RESCALE * 2^-16 (tx_processor.c:360-381)
     LatticeP lat;            // IIR_TXFilter
