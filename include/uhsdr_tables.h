@@ -86,7 +86,9 @@ typedef struct {
     int32_t tx_lattice_soprano;    /* IIR_TX_SOPRANO,     tx_processor.c:92-102                  */
     int32_t tx_lattice_tenor;      /* IIR_TX_WIDE_TREBLE                                         */
     int32_t tx_lattice_bass;       /* IIR_TX_WIDE_BASS                                           */
-    int32_t reserved[8];
+    int32_t tx_lattice_fm;         /* IIR_TX_2k7_FM, tx_processor.c:104-107 (-1 in blobs older than this field) */
+    int32_t dds_table_array;       /* DDS_TABLE (1024 x int16 as floats), softdds/dds_table.c:19 */
+    int32_t reserved[6];
 } uhsdr_tbl_extras_t;
 
 #ifdef __cplusplus

@@ -11,6 +11,7 @@
  */
 #include "audio_driver.c"
 #include "iq_tx_filter.h"
+#include "softdds/dds_table.h"
 #include "uhsdr_tables.h"
 extern const float32_t SQRT_von_Hann_256[256];   /* audio_nr.c:76 */
 #include <stdio.h>
@@ -104,6 +105,12 @@ int main(int argc, char **argv)
     ex.tx_lattice_soprano = add_lattice(&IIR_TX_SOPRANO);
     ex.tx_lattice_tenor = add_lattice(&IIR_TX_WIDE_TREBLE);
     ex.tx_lattice_bass = add_lattice(&IIR_TX_WIDE_BASS);
+    ex.tx_lattice_fm = add_lattice(&IIR_TX_2k7_FM);
+    {
+        static float dds[DDS_TBL_SIZE];
+        for (int i = 0; i < DDS_TBL_SIZE; i++) dds[i] = (float)DDS_TABLE[i];
+        ex.dds_table_array = add_array(dds, DDS_TBL_SIZE);
+    }
 
     /* von_Hann_1024 is a function-local constant of ui_spectrum.c (ui_spectrum.c:362); the
      * Makefile extracts it into a raw float file that is appended here. */

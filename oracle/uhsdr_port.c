@@ -586,6 +586,7 @@ struct port_chan {
     float alc_val, alc_decay, peak_audio;
     float tx_delay[320];
     uint32_t alc_delay_inbuf;
+    float tx_fm_hpf_a, tx_fm_hpf_b; uint32_t tx_fm_accum;   /* TxProcessor_FM statics, tx_processor.c:537-538 */
     float tx_postfilt_gain_var;
 };
 

@@ -68,6 +68,10 @@ TX_CASES = [
     # AM modulator (TxProcessor_AM, tx_processor.c:736-800): both sidebands + carrier, default -12 kHz translation and +6 kHz NCO
     ("tx_am", dict(dmod_mode=DEMOD_AM, filter_path=70), 160),
     ("tx_am_p6k_comp10", dict(dmod_mode=DEMOD_AM, filter_path=70, iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_comp_level=10, tx_mic_gain=30), 160),
+    # FM modulator (TxProcessor_FM, tx_processor.c:534-589): pre-emphasis + NCO on the sine table, 2.5 and 5 kHz deviation
+    ("tx_fm", dict(dmod_mode=DEMOD_FM, filter_path=2), 160),
+    ("tx_fm_5k_p6k", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_dev_5khz=1, iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_mic_gain=60), 160),
+    ("tx_fm_m6k", dict(dmod_mode=DEMOD_FM, filter_path=2, iq_freq_mode=FREQ_IQ_CONV_M6KHZ), 160),
 ]
 
 # float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these

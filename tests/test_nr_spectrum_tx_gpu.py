@@ -140,9 +140,9 @@ def test_tx_ssb(built, label, kw, nblocks, exact):
 
 
 def test_tx_modes_without_a_modulator_are_rejected(built):
-    from uhsdr_b200.config import DEMOD_FM
+    from uhsdr_b200.config import DEMOD_CW
     with Engine(1) as eng:
-        eng.configure(default_cfg(dmod_mode=DEMOD_FM, filter_path=2))
+        eng.configure(default_cfg(dmod_mode=DEMOD_CW, filter_path=8))
         with pytest.raises(UhsdrError) as ei:
             eng.tx(np.zeros((1, 64, 2), dtype=np.int32))
         assert ei.value.code == -5

@@ -168,7 +168,7 @@ def test_port_tx_matches_golden_bit_exact(golden, label, kw, nblocks):
 
 
 def test_port_tx_rejects_modes_without_a_modulator():
-    from uhsdr_b200.config import DEMOD_FM
-    with PortChannel(default_cfg(dmod_mode=DEMOD_FM, filter_path=2)) as p:
+    from uhsdr_b200.config import DEMOD_CW
+    with PortChannel(default_cfg(dmod_mode=DEMOD_CW, filter_path=8)) as p:
         with pytest.raises(RuntimeError):
             p.tx(np.zeros((64, 2), dtype=np.int32))
