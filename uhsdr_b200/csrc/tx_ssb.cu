@@ -48,8 +48,9 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
     memset(tp, 0, sizeof(*tp));
     const int mode = cfg.dmod_mode;
     tp->am = (mode == UHSDR_DEMOD_AM && cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF) ? 1 : 0;      // no AM unless in a translate mode, tx_processor.c:999
-    tp->enabled = (mode == UHSDR_DEMOD_USB || mode == UHSDR_DEMOD_LSB || tp->am) ? 1 : 0;    // is_ssb(), uhsdr_board.h:809
-    tp->alc_gain_scaling = tp->am ? 0.23 : 1.00;
+    tp->fm = (mode == UHSDR_DEMOD_FM && cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF) ? 1 : 0;      // same rule for FM, :1010
+    tp->enabled = (mode == UHSDR_DEMOD_USB || mode == UHSDR_DEMOD_LSB || tp->am || tp->fm) ? 1 : 0;    // is_ssb(), uhsdr_board.h:809
+    tp->alc_gain_scaling = tp->am ? 0.23 : (tp->fm ? 0.95 : 1.00);
     tp->lsb = mode == UHSDR_DEMOD_LSB;
     {
         float gain_calc = (uint8_t)cfg.tx_mic_gain;      // ts.tx_mic_gain_mult (codec.c:321)
@@ -60,6 +61,7 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
     int li = t.ex->tx_lattice_soprano;
     if (cfg.tx_filter == UHSDR_TX_FILTER_BASS) li = t.ex->tx_lattice_bass;
     else if (cfg.tx_filter == UHSDR_TX_FILTER_TENOR) li = t.ex->tx_lattice_tenor;
+    if (mode == UHSDR_DEMOD_FM) li = t.ex->tx_lattice_fm;             // IIR_TX_2k7_FM, tx_processor.c:104-107
     if (li < 0 || li >= (int)t.h->num_lattices || t.lat[li].num_stages > MAX_LAT) { if (err) *err = "TX lattice missing from the table blob"; return UHSDR_ERR_TABLES; }
     tp->lat.n = t.lat[li].num_stages; tp->lat.k_off = t.off(t.lat[li].k_array); tp->lat.v_off = t.off(t.lat[li].v_array);
     shelf(tp->bq[0], true, 1700, 0.9, cfg.tx_treble_gain, 48000);
@@ -95,16 +97,37 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
         tp->osc_cos = cos(rate); tp->osc_sin = sin(rate);
     }
     {
-        float scaling = 1.133;                            // SSB_GAIN_COMP
+        float scaling = tp->fm ? 0.875 : 1.133;           // FM_MOD_AMPLITUDE_SCALING / SSB_GAIN_COMP == AM_GAIN_COMP
         scaling *= (1 << 16);                             // IQ_BIT_SCALE_UP
         tp->final_gain_i = cfg.tx_power_factor * cfg.tx_adj_gain_i * scaling;
         tp->final_gain_q = cfg.tx_power_factor * cfg.tx_adj_gain_q * scaling;
     }
     tp->phase_bal = cfg.iq_phase_balance_tx;
+    if (tp->fm) {
+        tp->fm_word = (65536 * abs(shift)) / 48000;
+        tp->fm_swap = shift < 0;
+        tp->fm_mult = cfg.fm_dev_5khz ? 2 : 1;
+        tp->dds_off = t.off(t.ex->dds_table_array);
+        if (tp->dds_off < 0) { if (err) *err = "DDS sine table missing from the table blob"; return UHSDR_ERR_TABLES; }
+    }
     return UHSDR_OK;
 }
 
 // ---- device ---------------------------------------------------------------------------------
+// One sample of TxProcessor_FM (tx_processor.c:544-585): pre-emphasis differentiator hpf_b = 0.05 (hpf_b + a - hpf_a) (double
+// product), then the 16-bit NCO accumulator `acc += word + a1 * FM_MOD_SCALING * mult; acc %= 65536` -- the += goes through
+// float, and a negative sum wraps the way the x86-64 build of the reference does it (conversion to 64 bits, low word).
+// Returns the index into the 1024-entry sine table.
+__device__ __forceinline__ uint32_t fm_step(float a, float &hpf_a, float &hpf_b, uint32_t &accum, const TxParams &tp)
+{
+    hpf_b = (float)(0.05 * (double)__fsub_rn(__fadd_rn(hpf_b, a), hpf_a));
+    hpf_a = a;
+    const float inc = __fadd_rn((float)(uint32_t)tp.fm_word, __fmul_rn(__fmul_rn(hpf_b, 16.0f), tp.fm_mult));
+    accum = (uint32_t)(long long)__float2ll_rz(__fadd_rn((float)accum, inc));
+    accum %= 65536u;
+    return accum >> 6;
+}
+
 static constexpr int TX_WARPS = 4;
 
 struct TxWork {
@@ -207,7 +230,23 @@ tx_ssb_kernel(TxArgs a)
                 v = __fmul_rn(st.delay[outb + lane], w.scr[BLK + lane]);
                 if (lane == 0) st.alc_delay_inbuf = inb;
             }
+            if (tp.fm) {                     // pre-emphasis + NCO accumulator are sample-serial: lane 0
+                __syncwarp();
+                w.scr[lane] = v;
+                __syncwarp();
+                if (lane == 0) for (int i = 0; i < BLK; i++) w.scr[i] = (float)fm_step(w.scr[i], st.fm_hpf_a, st.fm_hpf_b, st.fm_accum, tp);
+                __syncwarp();
+                v = w.scr[lane];
+                __syncwarp();
             }
+            }
+            if (tp.fm) {
+                // TxProcessor_FM, tx_processor.c:575-585: I = sine table at the accumulator, Q a quarter turn behind
+                // (softdds_phase_shift90), buffers swapped for a negative translate frequency; no Hilbert pair, no FreqShift
+                const uint32_t idx = (uint32_t)v;
+                const float s0 = __ldg(pool + tp.dds_off + idx), s1 = __ldg(pool + tp.dds_off + ((idx + 768u) & 1023u));
+                vi = tp.fm_swap ? s1 : s0; vq = tp.fm_swap ? s0 : s1;
+            } else {
             w.a[H2 + lane] = v;
             __syncwarp();
             // Hilbert pair, y[n] = sum_k c[k] a[n - (N-1) + k]
@@ -254,6 +293,7 @@ tx_ssb_kernel(TxArgs a)
                 if (tp.shift_down) { vq = ni; vi = nq; } else { vi = ni; vq = nq; }
                 __syncwarp();
             }
+            }
         }
         // IqFinalProcessing
         vi = __fmul_rn(vi, tp.final_gain_i);
@@ -298,6 +338,8 @@ tx_serial_kernel(TxArgs a)
     float bc[3][5];
     for (int s = 0; s < 3; s++) { bq[s] = g.bq[s]; for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
     float alc_val = g.alc_val, peak_audio = g.peak_audio;
+    float fm_hpf_a = g.fm_hpf_a, fm_hpf_b = g.fm_hpf_b;
+    uint32_t fm_accum = g.fm_accum;
     uint32_t inbuf = g.alc_delay_inbuf;
     float delay[320];
     for (int i = 0; i < 320; i++) delay[i] = g.delay[i];
@@ -349,8 +391,12 @@ tx_serial_kernel(TxArgs a)
             for (int i = 0; i < BLK; i++) v[i] = __fmul_rn(delay[outb + i], alc[i]);
             inbuf = inb;
         }
+        if (tp.fm) {
+            for (int i = 0; i < BLK; i++) v[i] = (float)fm_step(v[i], fm_hpf_a, fm_hpf_b, fm_accum, tp);      // table index for the FIR-stage kernel
+        }
         for (int i = 0; i < BLK; i += 4) *reinterpret_cast<float4 *>(out + (size_t)blk * BLK + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
+    g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum;
     for (int i = 0; i < MAX_LAT; i++) g.lat_s[i] = lat_s[i];
     for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
     g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;

@@ -173,7 +173,12 @@ struct NrState {
 struct TxParams {
     int enabled;             // is_ssb(dmod_mode), or AM with a frequency-translate mode (tx_processor.c:996-1006)
     int am;                  // TxProcessor_AM: both sidebands + carrier after the Hilbert pair (:783-790)
-    float alc_gain_scaling;  // SSB_ALC_GAIN_CORRECTION 1.00 / AM_ALC_GAIN_CORRECTION 0.23 (audio_driver.h:417, :428)
+    float alc_gain_scaling;  // SSB_ALC_GAIN_CORRECTION 1.00 / AM_ALC_GAIN_CORRECTION 0.23 (audio_driver.h:417, :428) / FM_ALC_GAIN_CORRECTION 0.95
+    int fm;                  // TxProcessor_FM (tx_processor.c:534-589): pre-emphasis + NCO on the sine table instead of the Hilbert pair
+    int fm_word;             // (65536 * |translate_freq|) / 48000, :569
+    int fm_swap;             // translate_freq < 0: I and Q buffers swapped, :572-573
+    float fm_mult;           // 2 for 5 kHz deviation, else 1
+    int dds_off;             // pool offset of DDS_TABLE (1024 entries)
     int lsb;                 // dmod_mode == DEMOD_LSB: I/Q filters swapped (tx_processor.c:477-478)
     float gain_calc;         // mic gain / MIC_GAIN_RESCALE * 2^-16 (tx_processor.c:360-381)
     LatticeP lat;            // IIR_TXFilter
@@ -197,6 +202,8 @@ struct TxState {
     float hist[H2];          // shared input history of the two 201-tap Hilbert filters
     float peak_audio;
     long long blocks;
+    float fm_hpf_a, fm_hpf_b;   // TxProcessor_FM statics hpf_prev_a / hpf_prev_b / fm_mod_accum (tx_processor.c:537-538)
+    uint32_t fm_accum;
 };
 
 // Coefficients of the fused narrow-SSB kernel, passed by value as a kernel parameter so that
