@@ -203,8 +203,8 @@ int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio
 int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev,
                             uhsdr_audio_sample_t *audio_dev, float *audio_f_dev,
                             int nblocks, const uint8_t *mute_dev);
-/* TxProcessor_Run, SSB voice branch (tx_processor.c:891, :989-995) and AM branch (:996-1006, needs a
- * frequency-translate mode): mic audio in, I/Q out.  Other modes: UHSDR_ERR_UNSUPPORTED. */
+/* TxProcessor_Run, SSB voice branch (tx_processor.c:891, :989-995), AM branch (:996-1006) and FM branch (:1007-1016; AM and
+ * FM need a frequency-translate mode): mic audio in, I/Q out.  Other modes (CW, digital): UHSDR_ERR_UNSUPPORTED. */
 int uhsdr_tx_process(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio, uhsdr_iq_sample_t *iq,
                      int nblocks, const uint8_t *mute);
 int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio_dev,

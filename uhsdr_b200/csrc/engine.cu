@@ -453,7 +453,7 @@ int uhsdr_tx_process_device(uhsdr_engine_t *e, const uhsdr_audio_sample_t *audio
     {
         if (!e->h_params[c].configured) { e->last_error = "tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
         if (!e->h_tx_enabled[c]) {
-            e->last_error = "tx: channel " + std::to_string(c) + " has no modulator: the SSB (USB/LSB) and AM (with a frequency-translate mode) voice modulators are implemented";
+            e->last_error = "tx: channel " + std::to_string(c) + " has no modulator: the SSB (USB/LSB) voice modulator and the AM / FM ones (with a frequency-translate mode) are implemented";
             return UHSDR_ERR_UNSUPPORTED;
         }
     }
