@@ -88,7 +88,9 @@ typedef struct {
     int32_t tx_lattice_bass;       /* IIR_TX_WIDE_BASS                                           */
     int32_t tx_lattice_fm;         /* IIR_TX_2k7_FM, tx_processor.c:104-107 (-1 in blobs older than this field) */
     int32_t dds_table_array;       /* DDS_TABLE (1024 x int16 as floats), softdds/dds_table.c:19 */
-    int32_t reserved[6];
+    int32_t zoom_biquad_array;     /* mag_coeffs[1..5], 5 x (4 stages x 5) floats, audio_driver.c:204-363 */
+    int32_t zoom_decim_array;      /* FirZoomFFTDecimate[1..5].pCoeffs, 5 x 4 taps, fir_rx_decimate_4.c:108-181 */
+    int32_t reserved[4];
 } uhsdr_tbl_extras_t;
 
 #ifdef __cplusplus

@@ -107,6 +107,15 @@ int main(int argc, char **argv)
     ex.tx_lattice_bass = add_lattice(&IIR_TX_WIDE_BASS);
     ex.tx_lattice_fm = add_lattice(&IIR_TX_2k7_FM);
     {
+        static float zb[5 * 20], zd[5 * 4];
+        for (int m = 1; m <= 5; m++) {
+            for (int i = 0; i < 20; i++) zb[(m - 1) * 20 + i] = mag_coeffs[m][i];
+            for (int i = 0; i < 4; i++) zd[(m - 1) * 4 + i] = FirZoomFFTDecimate[m].pCoeffs[i];
+        }
+        ex.zoom_biquad_array = add_array(zb, 5 * 20);
+        ex.zoom_decim_array = add_array(zd, 5 * 4);
+    }
+    {
         static float dds[DDS_TBL_SIZE];
         for (int i = 0; i < DDS_TBL_SIZE; i++) dds[i] = (float)DDS_TABLE[i];
         ex.dds_table_array = add_array(dds, DDS_TBL_SIZE);

@@ -572,6 +572,8 @@ struct port_chan {
     int fm_count, fm_squelched;
     /* spectrum ring, audio_driver.c:1811-1826 */
     float fft_ring[1024];
+    biquad_t zoom_bq_i[4], zoom_bq_q[4];      /* IIR_biquad_Zoom_FFT_I/Q, audio_driver.c:165-192 (state survives a reconfiguration) */
+    firdec_t zoom_dec_i, zoom_dec_q;          /* DECIMATE_ZOOM_FFT_I/Q, re-initialised by AudioDriver_Spectrum_Set :1073-1086 */
     uint32_t samp_ptr;
     /* NR */
     nr_t nr;
@@ -611,8 +613,19 @@ static int chan_set_chain(port_chan_t *c, const uhsdr_chan_cfg_t *cfg)
     const port_tables_t *t = c->t;
     if (cfg->struct_size != sizeof(uhsdr_chan_cfg_t)) return UHSDR_ERR_ARG;
     if (cfg->filter_path < 1 || cfg->filter_path >= (int)t->h->num_paths) return UHSDR_ERR_ARG;
-    if (cfg->spectrum_magnify != 0) return UHSDR_ERR_UNSUPPORTED;
+    if (cfg->spectrum_magnify < 0 || cfg->spectrum_magnify > 5) return UHSDR_ERR_ARG;     /* MAGNIFY_MAX */
     c->cfg = *cfg;
+    if (cfg->spectrum_magnify != 0) {                 /* AudioDriver_Spectrum_Set, audio_driver.c:1055-1086 */
+        const float *zb = tbl_array(t, t->ex->zoom_biquad_array, NULL), *zd = tbl_array(t, t->ex->zoom_decim_array, NULL);
+        if (!zb || !zd) return UHSDR_ERR_TABLES;
+        const int m = cfg->spectrum_magnify;
+        for (int s = 0; s < 4; s++) {
+            memcpy(c->zoom_bq_i[s].c, zb + (m - 1) * 20 + 5 * s, 5 * sizeof(float));
+            memcpy(c->zoom_bq_q[s].c, zb + (m - 1) * 20 + 5 * s, 5 * sizeof(float));
+        }
+        firdec_reset(&c->zoom_dec_i, 4, 1 << m, zd + (m - 1) * 4);
+        firdec_reset(&c->zoom_dec_q, 4, 1 << m, zd + (m - 1) * 4);
+    }
     const uhsdr_tbl_path_t *p = c->path = &t->path[cfg->filter_path];
     const int mode = cfg->dmod_mode;
     const int is_am = (mode == UHSDR_DEMOD_AM || mode == UHSDR_DEMOD_SAM);
@@ -967,6 +980,22 @@ static void rx_block(port_chan_t *c, const int32_t *src, int32_t *dst, float *ds
         }
     }
     if (c->cfg.iq_freq_mode) freq_shift(c, ib, qb, translate_freq(c->cfg.iq_freq_mode));
+
+    /* AudioDriver_SpectrumZoomProcessSamples, audio_driver.c:1860-1909: 4-stage biquad low-pass on I and Q (after the
+     * translation), 4-tap FIR decimation by 2^magnify, 32 >> magnify pairs into the ring */
+    if (c->cfg.spectrum_enable && c->cfg.spectrum_magnify != 0) {
+        float zi[BLK], zq[BLK];
+        memcpy(zi, ib, sizeof(zi)); memcpy(zq, qb, sizeof(zq));
+        for (int s = 0; s < 4; s++) biquad_run(&c->zoom_bq_i[s], zi, BLK);
+        for (int s = 0; s < 4; s++) biquad_run(&c->zoom_bq_q[s], zq, BLK);
+        firdec_run(&c->zoom_dec_i, zi, zi, BLK);
+        firdec_run(&c->zoom_dec_q, zq, zq, BLK);
+        for (int i = 0; i < (BLK >> c->cfg.spectrum_magnify); i++) {
+            c->fft_ring[c->samp_ptr++] = zq[i];
+            c->fft_ring[c->samp_ptr++] = zi[i];
+            if (c->samp_ptr >= 1024 - 1) c->samp_ptr = 0;
+        }
+    }
 
     int signal_active = 1;
     const int ndec = BLK / c->decimation_rate;

@@ -57,6 +57,10 @@ NB_CASES = [
 SPECTRUM_CASES = [
     ("spec_usb_p35", dict(spectrum_enable=1)),
     ("spec_fm_gain", dict(spectrum_enable=1, codec_gain_calc=2.5, dmod_mode=DEMOD_FM, filter_path=2)),
+    # zoom FFT (sd.magnify 1..5, AudioDriver_SpectrumZoomProcessSamples audio_driver.c:1860-1909): biquad low-pass + decimation after the translation
+    ("spec_zoom2_usb", dict(spectrum_enable=1, spectrum_magnify=1)),
+    ("spec_zoom8_p6k", dict(spectrum_enable=1, spectrum_magnify=3, iq_freq_mode=FREQ_IQ_CONV_P6KHZ)),
+    ("spec_zoom32_am", dict(spectrum_enable=1, spectrum_magnify=5, dmod_mode=DEMOD_AM, filter_path=70)),
 ]
 
 TX_CASES = [

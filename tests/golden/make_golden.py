@@ -50,11 +50,12 @@ def main():
     # spectrum-display FFT (UiSpectrum_RedrawSpectrum states 0-2) after 37 and after 100 blocks
     for label, kw in SPECTRUM_CASES:
         cfg = default_cfg(**kw)
-        iq = synth.rx_iq(cfg, 4, 100 * 32, seed=55)
+        z = 1 << cfg.spectrum_magnify                # the zoom FFT decimates: as many ring entries as without it
+        iq = synth.rx_iq(cfg, 4, 100 * z * 32, seed=55)
         with RefChannel(cfg) as r:
-            r.rx(iq[: 37 * 32])
+            r.rx(iq[: 37 * z * 32])
             m1 = r.spectrum()
-            r.rx(iq[37 * 32:])
+            r.rx(iq[37 * z * 32:])
             m2 = r.spectrum()
         out[f"{label}/iq"] = iq
         out[f"{label}/mags37"] = m1

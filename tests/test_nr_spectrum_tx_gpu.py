@@ -76,9 +76,10 @@ def test_spectrum_fft(built, label, kw):
     batch = np.stack([iq] * nch)
     with Engine(nch) as eng:
         eng.configure(cfg)
-        eng.rx(batch[:, : 37 * 32])
+        z = 1 << cfg.spectrum_magnify
+        eng.rx(batch[:, : 37 * z * 32])
         m1 = eng.spectrum()
-        eng.rx(batch[:, 37 * 32:])
+        eng.rx(batch[:, 37 * z * 32:])
         m2 = eng.spectrum(first=1, count=2)
     for got, key in ((m1[0], "mags37"), (m1[3], "mags37"), (m2[0], "mags100"), (m2[1], "mags100")):
         want = g[f"{label}/{key}"]

@@ -79,7 +79,7 @@ def test_port_full_scale_input_sets_clip_flags():
 
 def test_port_rejects_unsupported():
     with pytest.raises(ValueError):
-        PortChannel(default_cfg(spectrum_magnify=2))
+        PortChannel(default_cfg(spectrum_magnify=6))            # MAGNIFY_MAX is 5
     with pytest.raises(ValueError):
         PortChannel(default_cfg(filter_path=0))
 
@@ -141,10 +141,11 @@ def test_port_noise_blanker_matches_golden(golden, label, kw, nblocks):
 def test_port_spectrum_matches_golden(golden, label, kw):
     cfg = default_cfg(**kw)
     iq = golden[f"{label}/iq"]
+    z = 1 << cfg.spectrum_magnify
     with PortChannel(cfg) as p:
-        p.rx(iq[: 37 * 32])
+        p.rx(iq[: 37 * z * 32])
         m1 = p.spectrum()
-        p.rx(iq[37 * 32:])
+        p.rx(iq[37 * z * 32:])
         m2 = p.spectrum()
     for got, key in ((m1, "mags37"), (m2, "mags100")):
         want = golden[f"{label}/{key}"]

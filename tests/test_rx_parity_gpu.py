@@ -16,7 +16,7 @@ import pytest
 from cases import LIBM_CASES, RX_CASES
 from conftest import oracle_channel
 from uhsdr_b200 import synth
-from uhsdr_b200.config import DEMOD_LSB, default_cfg
+from uhsdr_b200.config import DEMOD_FM, DEMOD_LSB, default_cfg
 from uhsdr_b200.engine import Engine, UhsdrError
 
 pytestmark = pytest.mark.gpu
@@ -186,7 +186,7 @@ def test_errors_are_loud(built):
             eng.rx(np.zeros((2, 64, 2), dtype=np.int32))          # not configured
         assert ei.value.code == -6
         with pytest.raises(UhsdrError) as ei:
-            eng.configure(default_cfg(spectrum_magnify=2))          # zoom FFT: not implemented
+            eng.configure(default_cfg(fm_subaudible_tone_det_freq=88.5, dmod_mode=DEMOD_FM, filter_path=2))   # FM subtone detection: not implemented
         assert ei.value.code == -5
         with pytest.raises(UhsdrError):
             eng.configure(default_cfg(filter_path=70))              # AM path with an SSB mode

@@ -227,7 +227,7 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     if (cfg.struct_size != sizeof(uhsdr_chan_cfg_t)) return fail(UHSDR_ERR_ARG, "uhsdr_chan_cfg_t.struct_size mismatch");
     if (cfg.filter_path < 1 || cfg.filter_path >= (int)t.h->num_paths) return fail(UHSDR_ERR_ARG, "filter_path out of range");
     if (cfg.dmod_mode < UHSDR_DEMOD_USB || cfg.dmod_mode > UHSDR_DEMOD_DIGI) return fail(UHSDR_ERR_UNSUPPORTED, "dmod_mode not implemented (SSBSTEREO/IQ are stereo-only modes)");
-    if (cfg.spectrum_magnify != 0) return fail(UHSDR_ERR_UNSUPPORTED, "zoom FFT (sd.magnify != 0) is not implemented");
+    if (cfg.spectrum_magnify < 0 || cfg.spectrum_magnify > 5) return fail(UHSDR_ERR_ARG, "spectrum_magnify out of range (0..5, MAGNIFY_MAX)");
     if (cfg.fm_subaudible_tone_det_freq != 0.0f) return fail(UHSDR_ERR_UNSUPPORTED, "FM subaudible tone detection is not implemented");
     if (cfg.iq_freq_mode < 0 || cfg.iq_freq_mode > 4) return fail(UHSDR_ERR_ARG, "iq_freq_mode out of range");
     if (cfg.agc_mode < 0 || cfg.agc_mode > 5) return fail(UHSDR_ERR_ARG, "agc_mode out of range");
@@ -386,6 +386,13 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
         p->nr_xih1 = exp10f((float)30 / 10.0);     // NR2.asnr = 30 (audio_nr.c:95, :1886)
     }
     p->spectrum_enable = cfg.spectrum_enable ? 1 : 0;
+    p->zoom_m = cfg.spectrum_enable ? cfg.spectrum_magnify : 0;
+    if (p->zoom_m) {                                       // AudioDriver_Spectrum_Set, audio_driver.c:1055-1086
+        const int zb = t.off(t.ex->zoom_biquad_array), zd = t.off(t.ex->zoom_decim_array);
+        if (zb < 0 || zd < 0) return fail(UHSDR_ERR_TABLES, "zoom-FFT filters missing from the table blob");
+        p->zoom_bq_off = zb + (p->zoom_m - 1) * 20;
+        p->zoom_dec_off = zd + (p->zoom_m - 1) * 4;
+    }
     p->codec_gain_calc = cfg.codec_gain_calc;
     return UHSDR_OK;
 }

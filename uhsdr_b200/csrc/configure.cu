@@ -64,6 +64,7 @@ __global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *
     for (int k = 0; k < H1; k++) { s.s1_hist_i[k] = 0.0f; s.s1_hist_q[k] = 0.0f; }
     for (int k = 0; k < H2; k++) { s.s2_hist_i[k] = 0.0f; s.s2_hist_q[k] = 0.0f; }
     for (int k = 0; k < INTERP_HIST; k++) s.interp_hist[k] = 0.0f;
+    for (int k = 0; k < 4; k++) { s.zoom_hist_i[k] = 0.0f; s.zoom_hist_q[k] = 0.0f; }     // arm_fir_decimate_init_f32, audio_driver.c:1073-1086
     // auto-notch init (audio_driver.c:1165-1187): LMS state, energy and the delay line are cleared; the coefficients and
     // the delay-line positions (function statics of AudioDriver_NotchFilter) survive a reconfiguration
     for (int k = 0; k < NOTCH_TAPS; k++) s.notch_x[k] = 0.0f;

@@ -162,7 +162,7 @@ rx_generic_kernel(RxArgs a)
                 else if (p.phase_bal > 0.0f) fi = __fadd_rn(fi, __fmul_rn(fq, p.phase_bal));
             }
             // AudioDriver_SpectrumNoZoomProcessSamples, audio_driver.c:1811-1849
-            if (spec_ring) {
+            if (spec_ring && p.zoom_m == 0) {
                 // samp_ptr is always even and < 1022+2: 32 pairs per block, wrap when ptr >= 1023
                 uint32_t ptr = st.samp_ptr + 2u * (uint32_t)lane;
                 if (ptr >= 1024u) ptr -= 1024u;
@@ -200,6 +200,57 @@ rx_generic_kernel(RxArgs a)
                 const float nq = __fsub_rn(__fmul_rn(qb, oq), __fmul_rn(ib, oi));
                 const float ni = __fadd_rn(__fmul_rn(ib, oq), __fmul_rn(qb, oi));
                 if (p.shift_down) { fq = ni; fi = nq; } else { fi = ni; fq = nq; }
+                __syncwarp();
+            }
+            // AudioDriver_SpectrumZoomProcessSamples, audio_driver.c:1860-1909: 4-stage DF1 low-pass on I and on Q (after the
+            // translation), 4-tap FIR decimation by 2^magnify, 32 >> magnify (Q, I) pairs into the ring.  The biquads are
+            // recurrences: lane 0 takes I, lane 1 takes Q; reference operation order (the spectrum is compared to 1e-4).
+            if (spec_ring && p.zoom_m != 0) {
+                __syncwarp();
+                w.scr[lane] = fi; w.scr[BLK + lane] = fq;
+                __syncwarp();
+                const int M = 1 << p.zoom_m, nout = BLK >> p.zoom_m;
+                if (lane < 2) {
+                    float *buf = w.scr + lane * BLK;
+                    BiquadS *bs = lane ? st.zoom_bq_q : st.zoom_bq_i;
+                    const float *zc = pool + p.zoom_bq_off;
+                    for (int sg = 0; sg < 4; sg++) {
+                        const float b0 = __ldg(zc + 5 * sg), b1 = __ldg(zc + 5 * sg + 1), b2 = __ldg(zc + 5 * sg + 2), a1 = __ldg(zc + 5 * sg + 3), a2 = __ldg(zc + 5 * sg + 4);
+                        BiquadS s = bs[sg];
+                        for (int i = 0; i < BLK; i++) {
+                            const float x = buf[i];
+                            const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b0, x), __fmul_rn(b1, s.x1)), __fmul_rn(b2, s.x2)), __fmul_rn(a1, s.y1)), __fmul_rn(a2, s.y2));
+                            s.x2 = s.x1; s.x1 = x; s.y2 = s.y1; s.y1 = acc;
+                            buf[i] = acc;
+                        }
+                        bs[sg] = s;
+                    }
+                    // arm_fir_decimate_f32: output j = sum_k c[k] S[j M + k] over S = 3 old samples ++ the block
+                    float *hist = lane ? st.zoom_hist_q : st.zoom_hist_i;
+                    const float *dc = pool + p.zoom_dec_off;
+                    const float c0 = __ldg(dc), c1 = __ldg(dc + 1), c2 = __ldg(dc + 2), c3 = __ldg(dc + 3);
+                    const float h0 = hist[0], h1 = hist[1], h2 = hist[2];
+                    hist[0] = buf[BLK - 3]; hist[1] = buf[BLK - 2]; hist[2] = buf[BLK - 1];
+                    float outv[BLK / 2];
+                    for (int j = 0; j < nout; j++) {
+                        const int o = j * M;
+                        const float s0 = o >= 3 ? buf[o - 3] : (o == 0 ? h0 : (o == 1 ? h1 : h2));
+                        const float s1 = o >= 2 ? buf[o - 2] : (o == 0 ? h1 : h2);
+                        const float s2 = o >= 1 ? buf[o - 1] : h2;
+                        const float s3 = buf[o];
+                        const float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s0, c0), __fmul_rn(s1, c1)), __fmul_rn(s2, c2)), __fmul_rn(s3, c3));
+                        outv[j] = y;
+                    }
+                    for (int j = 0; j < nout; j++) buf[j] = outv[j];
+                }
+                __syncwarp();
+                if (lane < nout) {
+                    uint32_t ptr = st.samp_ptr + 2u * (uint32_t)lane;
+                    if (ptr >= 1024u) ptr -= 1024u;
+                    spec_ring[ptr] = w.scr[BLK + lane]; spec_ring[ptr + 1] = w.scr[lane];
+                }
+                __syncwarp();
+                if (lane == 0) { uint32_t np = st.samp_ptr + 2u * (uint32_t)nout; if (np >= 1024u) np -= 1024u; st.samp_ptr = np; }
                 __syncwarp();
             }
             w.xi[H1 + b * BLK + lane] = fi;
@@ -390,6 +441,7 @@ rx_generic_kernel(RxArgs a)
             gst->M_c1 = st.M_c1; gst->M_c2 = st.M_c2;
             gst->osc_vect_q = st.osc_vect_q; gst->osc_vect_i = st.osc_vect_i; gst->conversion_freq = st.conversion_freq;
             gst->samp_ptr = st.samp_ptr;
+            for (int k = 0; k < 4; k++) { gst->zoom_bq_i[k] = st.zoom_bq_i[k]; gst->zoom_bq_q[k] = st.zoom_bq_q[k]; gst->zoom_hist_i[k] = st.zoom_hist_i[k]; gst->zoom_hist_q[k] = st.zoom_hist_q[k]; }
             gst->adc_clip = st.adc_clip; gst->adc_half_clip = st.adc_half_clip; gst->adc_quarter_clip = st.adc_quarter_clip;
             gst->blocks = st.blocks;
         }

@@ -81,6 +81,9 @@ struct ChanParams {
     float nr_xih1;                      // pow10f(NR2.asnr / 10), audio_nr.c:1886
     // spectrum
     int spectrum_enable;
+    int zoom_m;            // sd.magnify 1..5 (0 = no zoom): AudioDriver_SpectrumZoomProcessSamples, audio_driver.c:1860-1909
+    int zoom_bq_off;       // pool offset of mag_coeffs[zoom_m] (4 stages x {b0, b1, b2, a1, a2})
+    int zoom_dec_off;      // pool offset of FirZoomFFTDecimate[zoom_m].pCoeffs (4 taps)
     float codec_gain_calc;
     // LMS automatic notch (audio_driver.c:1165-1187, :2443-2456)
     int notch_enable;
@@ -128,6 +131,8 @@ struct ChanState {
     int notch_head, notch_inbuf, notch_outbuf;
     // a_buffer[1] persistence is not needed: every non-FM path has an interpolator
     uint32_t samp_ptr;       // spectrum ring write pointer, audio_driver.c:1816-1824
+    BiquadS zoom_bq_i[4], zoom_bq_q[4];   // IIR_biquad_Zoom_FFT_I/Q state (survives a reconfiguration)
+    float zoom_hist_i[4], zoom_hist_q[4]; // DECIMATE_ZOOM_FFT_I/Q state (3 used; zeroed by AudioDriver_Spectrum_Set)
     int adc_clip, adc_half_clip, adc_quarter_clip;
     long long blocks;
 };

@@ -66,12 +66,12 @@ class Tables:
             self.filters.append((fid, width, name.split(b"\0")[0].decode("latin-1")))
         self.lattices = [struct.unpack_from("<3i", blob, lat_off + 12 * i) for i in range(n_lat)]
         self.interps = [struct.unpack_from("<4i", blob, int_off + 16 * i) for i in range(n_int)]
-        ex = struct.unpack_from("<15i", blob, extras_off)
+        ex = struct.unpack_from("<17i", blob, extras_off)
         self.extras = dict(zip(
             ["nr_decimate_array", "nr_interpolate_array", "sqrt_hann_256_array", "spectrum_window_array",
              "sam_c0_array", "sam_c1_array", "fm_squelch_lattice", "tx_hilbert_i_array", "tx_hilbert_q_array",
              "tx_hilbert_numtaps", "tx_lattice_soprano", "tx_lattice_tenor", "tx_lattice_bass", "tx_lattice_fm",
-             "dds_table_array"], ex))
+             "dds_table_array", "zoom_biquad_array", "zoom_decim_array"], ex))
 
     def width(self, path_index: int) -> int:
         return self.filters[self.paths[path_index].id][1]
