@@ -589,6 +589,8 @@ struct port_chan {
     float tx_delay[320];
     uint32_t alc_delay_inbuf;
     float tx_fm_hpf_a, tx_fm_hpf_b; uint32_t tx_fm_accum;   /* TxProcessor_FM statics, tx_processor.c:537-538 */
+    /* FM subaudible-tone detector, audio_driver.c:1665-1734: Goertzel HIGH / LOW / CTR {r, cos, sin, buf[3]}, smoothed ratio, debounce */
+    float gz_r[3], gz_cos[3], gz_sin[3], gz_buf[3][3], fm_subdet; int fm_tdet, fm_tone_detected; unsigned long fm_gcount;
     float tx_postfilt_gain_var;
 };
 
@@ -708,6 +710,17 @@ static int chan_set_chain(port_chan_t *c, const uhsdr_chan_cfg_t *cfg)
 
     /* AudioDriver_AgcWdsp_Set, audio_driver.c:628-631 */
     agc_setup(&c->agc, cfg, (float)c->decimated_freq, is_am);
+    if (cfg->fm_subaudible_tone_det_freq > 0.0f) {
+        /* AudioManagement_CalcSubaudibleDetFreq, audio_management.c:311-326 + AudioFilter_CalcGoertzel, audio_filter.c:1281-1288 */
+        const float ratio[3] = { 1.04, 0.95, 1.0 };           /* FM_GOERTZEL_HIGH, FM_GOERTZEL_LOW, centre */
+        const uint32_t size = 400 * 32;                         /* FM_SUBAUDIBLE_GOERTZEL_WINDOW * AUDIO_BLOCK_SIZE */
+        const float freq = cfg->fm_subaudible_tone_det_freq, samplerate = 48000;
+        for (int k = 0; k < 3; k++) {
+            float ga = (0.5 + (freq * ratio[k]) * size / samplerate);
+            float gb = (2 * 3.14159265358979f * ga) / size;
+            c->gz_sin[k] = sinf(gb); c->gz_cos[k] = cosf(gb); c->gz_r[k] = 2 * c->gz_cos[k];
+        }
+    }
     /* auto-notch init, audio_driver.c:1165-1187: state, energy and the delay buffer are cleared, the coefficients
      * only with reset_dsp_nr (a fresh channel starts from zeros anyway) */
     c->notch.mu = log10f(((cfg->notch_mu + 1.0) / 1500.0) + 1.0);
@@ -890,11 +903,12 @@ static void demod_am_sam(port_chan_t *c, const float *ib, const float *qb, float
 }
 
 /* AudioDriver_DemodFM, audio_driver.c:1544-1737 (subaudible-tone detection not restated:
- * cfg.fm_subaudible_tone_det_freq must be 0). Returns signal_active. */
+ * with the 3 x Goertzel subaudible-tone detector when cfg.fm_subaudible_tone_det_freq > 0). Returns signal_active. */
 static int demod_fm(port_chan_t *c, const float *ib, const float *qb, float *a)
 {
-    float squelch_buf[BLK];
+    float squelch_buf[BLK], goertzel_buf[BLK];
     if (c->cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF) {
+        const int tone_det_enabled = c->cfg.fm_subaudible_tone_det_freq != 0;
         for (int i = 0; i < BLK; i++) {
             float y = (c->fm_i_prev * qb[i]) - (ib[i] * c->fm_q_prev);
             float x = (c->fm_i_prev * ib[i]) + (qb[i] * c->fm_q_prev);
@@ -902,7 +916,8 @@ static int demod_fm(port_chan_t *c, const float *ib, const float *qb, float *a)
             squelch_buf[i] = angle;
             float av = c->fm_lpf_prev + (0.05 * (angle - c->fm_lpf_prev));
             c->fm_lpf_prev = av;
-            if (!c->fm_squelched || !c->cfg.fm_sql_threshold) {
+            goertzel_buf[i] = av;
+            if (((!c->fm_squelched) && (!tone_det_enabled)) || ((c->fm_tone_detected) && (tone_det_enabled)) || ((!c->cfg.fm_sql_threshold))) {
                 float b = 0.96 * (c->fm_hpf_prev_b + av - c->fm_hpf_prev_a);
                 c->fm_hpf_prev_a = av;
                 c->fm_hpf_prev_b = b;
@@ -927,6 +942,33 @@ static int demod_fm(port_chan_t *c, const float *ib, const float *qb, float *a)
             else if (c->fm_squelched) { if (s >= (float)(thr + 3)) c->fm_squelched = 0; }
             else if (thr > 3) { if (s < (float)(thr - 3)) c->fm_squelched = 1; }
             else { if (s < (float)thr) c->fm_squelched = 1; }
+        }
+        if (tone_det_enabled) {                               /* :1665-1729 */
+            c->fm_gcount++;
+            for (int i = 0; i < BLK; i++)
+                for (int k = 0; k < 3; k++) {                 /* AudioFilter_GoertzelInput, audio_filter.c:1290-1295 (HIGH, LOW, CTR) */
+                    c->gz_buf[k][0] = c->gz_r[k] * c->gz_buf[k][1] - c->gz_buf[k][2] + goertzel_buf[i];
+                    c->gz_buf[k][2] = c->gz_buf[k][1];
+                    c->gz_buf[k][1] = c->gz_buf[k][0];
+                }
+            if (c->fm_gcount >= 400) {                        /* FM_SUBAUDIBLE_GOERTZEL_WINDOW */
+                float en[3];
+                for (int k = 0; k < 3; k++) {                 /* AudioFilter_GoertzelEnergy, :1297-1305 */
+                    float ea = (c->gz_buf[k][1] - (c->gz_buf[k][2] * c->gz_cos[k]));
+                    float eb = (c->gz_buf[k][2] * c->gz_sin[k]);
+                    c->gz_buf[k][0] = 0; c->gz_buf[k][1] = 0; c->gz_buf[k][2] = 0;
+                    en[k] = sqrtf(ea * ea + eb * eb);
+                }
+                float s = en[0] + en[1];
+                float r = en[2];
+                c->fm_subdet = ((1 - 0.9) * c->fm_subdet) + (r / (s / 2) * 0.9);
+                if (c->fm_subdet > 1.75) { c->fm_tdet++; if (c->fm_tdet > 5) c->fm_tdet = 5; }
+                else { if (c->fm_tdet) c->fm_tdet--; }
+                c->fm_tone_detected = c->fm_tdet >= 2;
+                c->fm_gcount = 0;
+            }
+        } else {
+            c->fm_tone_detected = 1;
         }
     }
     return !c->fm_squelched;

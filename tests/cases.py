@@ -54,6 +54,14 @@ NB_CASES = [
     ("usb_p35_nb15_nr", dict(dsp_active=DSP_NB_ENABLE | DSP_NR_ENABLE, nb_setting=15), 320),
 ]
 
+# FM sub-audible tone detection (3 x Goertzel, audio_driver.c:1665-1734): (label, cfg, blocks, tone in the signal / Hz, 0 = none).
+# The audio gate opens at the second evaluation window (block 800) when the tone is there and the detector is tuned to it.
+FM_TONE_CASES = [
+    ("fm_tone100_detected", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_subaudible_tone_det_freq=100.0), 1000, 100.0),
+    ("fm_tone100_detector_at_88", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_subaudible_tone_det_freq=88.5), 1000, 100.0),
+    ("fm_no_tone", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_subaudible_tone_det_freq=100.0), 900, 0.0),
+]
+
 SPECTRUM_CASES = [
     ("spec_usb_p35", dict(spectrum_enable=1)),
     ("spec_fm_gain", dict(spectrum_enable=1, codec_gain_calc=2.5, dmod_mode=DEMOD_FM, filter_path=2)),

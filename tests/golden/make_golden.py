@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from cases import NB_CASES, NB_IMPULSES, NR_CASES, RX_CASES, SPECTRUM_CASES, TX_CASES  # noqa: E402
+from cases import FM_TONE_CASES, NB_CASES, NB_IMPULSES, NR_CASES, RX_CASES, SPECTRUM_CASES, TX_CASES  # noqa: E402
 from oracle.refchain import RefChannel  # noqa: E402
 from uhsdr_b200 import synth  # noqa: E402
 from uhsdr_b200.config import default_cfg  # noqa: E402
@@ -34,6 +34,14 @@ def main():
         out[f"{label}/audio_f"] = audio_f
         out[f"{label}/status"] = np.array([st.adc_clip, st.agc_action, st.fm_squelched, st.sam_carrier_freq_offset], dtype=np.int32)
         assert np.array_equal(audio[:, 0], audio[:, 1])
+    for label, kw, nblocks, tone in FM_TONE_CASES:
+        cfg = default_cfg(**kw)
+        iq = synth.rx_fm_subtone_iq(cfg, 5, nblocks * 32, 100.0, 300.0 if tone else 0.0, seed=1234)
+        with RefChannel(cfg) as r:
+            audio, audio_f = r.rx(iq)
+        out[f"{label}/iq"] = iq
+        out[f"{label}/audio_l"] = audio[:, 0].copy()
+        out[f"{label}/audio_f"] = audio_f
     # mute + reconfigure sequence on one channel
     cfg_a, cfg_b = default_cfg(), default_cfg(filter_path=44, bass_gain=0)
     iq = synth.rx_iq(cfg_a, 9, 160 * 32, seed=77)

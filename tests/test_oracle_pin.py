@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import NB_CASES, NR_CASES, RX_CASES
+from cases import FM_TONE_CASES, NB_CASES, NR_CASES, RX_CASES
 from oracle import refchain
 from oracle.port import PortChannel
 from uhsdr_b200 import synth
@@ -135,6 +135,21 @@ def test_port_noise_blanker_matches_golden(golden, label, kw, nblocks):
     with PortChannel(default_cfg(**dict(kw, nb_setting=1))) as p:      # threshold 7.5 sigma x sqrt(LPC power): never fires, same latency
         _, delayed_f = p.rx(iq)
     assert np.count_nonzero(delayed_f != audio_f) > 500
+
+
+@pytest.mark.parametrize("label,kw,nblocks,tone", FM_TONE_CASES, ids=[c[0] for c in FM_TONE_CASES])
+def test_port_fm_subtone_detector_matches_golden(golden, label, kw, nblocks, tone):
+    """The Goertzel tone detector gates the FM audio: bit-exact against the reference, open from block 800 on only when
+    the tone is in the signal and the detector is tuned to it."""
+    cfg = default_cfg(**kw)
+    with PortChannel(cfg) as p:
+        audio, audio_f = p.rx(golden[f"{label}/iq"])
+    assert np.array_equal(audio[:, 0], golden[f"{label}/audio_l"])
+    nz = np.flatnonzero(audio_f)
+    if label == "fm_tone100_detected":
+        assert nz[0] // 32 == 800
+    else:
+        assert len(nz) == 0
 
 
 @pytest.mark.parametrize("label,kw", SPECTRUM_CASES, ids=[c[0] for c in SPECTRUM_CASES])

@@ -13,10 +13,10 @@ import os
 import numpy as np
 import pytest
 
-from cases import LIBM_CASES, RX_CASES
+from cases import FM_TONE_CASES, LIBM_CASES, RX_CASES
 from conftest import oracle_channel
 from uhsdr_b200 import synth
-from uhsdr_b200.config import DEMOD_FM, DEMOD_LSB, default_cfg
+from uhsdr_b200.config import DEMOD_LSB, default_cfg
 from uhsdr_b200.engine import Engine, UhsdrError
 
 pytestmark = pytest.mark.gpu
@@ -92,6 +92,32 @@ def test_fast_build_within_tolerance(built, label, kw, nblocks):
         with oracle_channel(cfg) as o:
             want_w, want_f = o.rx(iq[c])
         check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,nblocks,tone", FM_TONE_CASES, ids=[c[0] for c in FM_TONE_CASES])
+def test_fm_subaudible_tone_detector(built, label, kw, nblocks, tone, exact):
+    """3 x Goertzel tone detector of the FM demodulator (audio_driver.c:1665-1734): the audio gate must open in the same
+    block as in the oracle (block 800, the second evaluation window) when the tone is present and the detector is tuned
+    to it, and stay shut otherwise; the audio itself within the libm tolerance (atan2f)."""
+    cfg = default_cfg(**kw)
+    nch = 3
+    iq = np.stack([synth.rx_fm_subtone_iq(cfg, 70 + c, nblocks * 32, 100.0, 300.0 if tone else 0.0, seed=21) for c in range(nch)])
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        h = 500 * 32
+        w1, f1 = run_engine_float(eng, iq[:, :h])
+        w2, f2 = run_engine_float(eng, iq[:, h:])
+    words, fl = np.concatenate([w1, w2], axis=1), np.concatenate([f1, f2], axis=1)
+    for c in range(nch):
+        with oracle_channel(cfg) as o:
+            want_w, want_f = o.rx(iq[c])
+        nz_want, nz_got = np.flatnonzero(want_f), np.flatnonzero(fl[c])
+        if label == "fm_tone100_detected":
+            assert nz_want[0] // 32 == 800 and nz_got[0] // 32 == 800, (label, c)
+            check_tolerance(fl[c], want_f, words[c, :, 0], want_w[:, 0], f"{label}/ch{c}")
+        else:
+            assert len(nz_want) == 0 and len(nz_got) == 0, (label, c)
 
 
 def test_golden_vectors_exact_build(built):
@@ -186,7 +212,7 @@ def test_errors_are_loud(built):
             eng.rx(np.zeros((2, 64, 2), dtype=np.int32))          # not configured
         assert ei.value.code == -6
         with pytest.raises(UhsdrError) as ei:
-            eng.configure(default_cfg(fm_subaudible_tone_det_freq=88.5, dmod_mode=DEMOD_FM, filter_path=2))   # FM subtone detection: not implemented
+            eng.configure(default_cfg(dmod_mode=7))               # DEMOD_SSBSTEREO / DEMOD_IQ: stereo-only modes, not implemented
         assert ei.value.code == -5
         with pytest.raises(UhsdrError):
             eng.configure(default_cfg(filter_path=70))              # AM path with an SSB mode

@@ -228,7 +228,6 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
     if (cfg.filter_path < 1 || cfg.filter_path >= (int)t.h->num_paths) return fail(UHSDR_ERR_ARG, "filter_path out of range");
     if (cfg.dmod_mode < UHSDR_DEMOD_USB || cfg.dmod_mode > UHSDR_DEMOD_DIGI) return fail(UHSDR_ERR_UNSUPPORTED, "dmod_mode not implemented (SSBSTEREO/IQ are stereo-only modes)");
     if (cfg.spectrum_magnify < 0 || cfg.spectrum_magnify > 5) return fail(UHSDR_ERR_ARG, "spectrum_magnify out of range (0..5, MAGNIFY_MAX)");
-    if (cfg.fm_subaudible_tone_det_freq != 0.0f) return fail(UHSDR_ERR_UNSUPPORTED, "FM subaudible tone detection is not implemented");
     if (cfg.iq_freq_mode < 0 || cfg.iq_freq_mode > 4) return fail(UHSDR_ERR_ARG, "iq_freq_mode out of range");
     if (cfg.agc_mode < 0 || cfg.agc_mode > 5) return fail(UHSDR_ERR_ARG, "agc_mode out of range");
 
@@ -349,6 +348,18 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
         p->sam_c1 = t.off(t.ex->sam_c1_array);
     }
     p->fm_sql_threshold = (uint8_t)cfg.fm_sql_threshold;
+    p->fm_tone_det = (mode == UHSDR_DEMOD_FM && cfg.fm_subaudible_tone_det_freq > 0.0f) ? 1 : 0;
+    if (p->fm_tone_det) {
+        // AudioManagement_CalcSubaudibleDetFreq + AudioFilter_CalcGoertzel, audio_management.c:311-326, audio_filter.c:1281-1288
+        const float ratio[3] = { 1.04, 0.95, 1.0 };        // FM_HIGH, FM_LOW, FM_CTR
+        const uint32_t size = 400 * 32;                      // FM_SUBAUDIBLE_GOERTZEL_WINDOW * AUDIO_BLOCK_SIZE
+        const float freq = cfg.fm_subaudible_tone_det_freq, samplerate = 48000;
+        for (int k = 0; k < 3; k++) {
+            const float ga = (0.5 + (freq * ratio[k]) * size / samplerate);
+            const float gb = (2 * 3.14159265358979f * ga) / size;
+            p->fm_gz_sin[k] = sinf(gb); p->fm_gz_cos[k] = cosf(gb); p->fm_gz_r[k] = 2 * p->fm_gz_cos[k];
+        }
+    }
     p->fm_scaling = cfg.fm_dev_5khz ? (10000 / 2) : 10000;   // FM_RX_SCALING_5K / _2K5, audio_driver.c:1494-1495
     p->fm_translate_on = cfg.iq_freq_mode != UHSDR_FREQ_IQ_CONV_OFF;
 

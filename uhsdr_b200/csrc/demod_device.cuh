@@ -90,7 +90,7 @@ __device__ inline void demod_am_sam(const ChanParams &p, S &st, const float *__r
     }
 }
 
-// AudioDriver_DemodFM, audio_driver.c:1544-1737 (no subaudible-tone detection), nb blocks at
+// AudioDriver_DemodFM, audio_driver.c:1544-1737 (with the 3 x Goertzel subaudible-tone detector :1665-1734), nb blocks at
 // 48 ksps.  Returns a bit mask: bit b set = block b un-squelched (signal_active).
 template <class S>
 __device__ inline int demod_fm(const ChanParams &p, S &st, const float *__restrict__ pool,
@@ -112,7 +112,15 @@ __device__ inline int demod_fm(const ChanParams &p, S &st, const float *__restri
                 // de-emphasis: a = lpf_prev + 0.05*(angle - lpf_prev), double expression (:1566)
                 const float av = (float)((double)st.fm_lpf_prev + (0.05 * (double)__fsub_rn(angle, st.fm_lpf_prev)));
                 st.fm_lpf_prev = av;
-                if (!st.fm_squelched || !p.fm_sql_threshold) {
+                if (p.fm_tone_det) {                 // AudioFilter_GoertzelInput x 3 on the de-emphasised audio (:1684-1692)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float b0 = __fadd_rn(__fsub_rn(__fmul_rn(p.fm_gz_r[k], st.fm_gz[3 * k + 1]), st.fm_gz[3 * k + 2]), av);
+                        st.fm_gz[3 * k + 2] = st.fm_gz[3 * k + 1]; st.fm_gz[3 * k + 1] = b0; st.fm_gz[3 * k] = b0;
+                    }
+                }
+                // audio gate :1571-1587: open when un-squelched (no tone detection), or when the tone is there, or squelch off
+                if ((!st.fm_squelched && !p.fm_tone_det) || (st.fm_tone_detected && p.fm_tone_det) || !p.fm_sql_threshold) {
                     const float hb = (float)(0.96 * (double)__fsub_rn(__fadd_rn(st.fm_hpf_prev_b, av), st.fm_hpf_prev_a));
                     st.fm_hpf_prev_a = av;
                     st.fm_hpf_prev_b = hb;
@@ -135,6 +143,29 @@ __device__ inline int demod_fm(const ChanParams &p, S &st, const float *__restri
                 else if (st.fm_squelched) { if (s >= (float)(thr + 3)) st.fm_squelched = 0; }
                 else if (thr > 3) { if (s < (float)(thr - 3)) st.fm_squelched = 1; }
                 else { if (s < (float)thr) st.fm_squelched = 1; }
+            }
+            if (p.fm_tone_det) {
+                // every 400 blocks: ratio of the on-frequency energy to the mean of the two off-frequency ones, smoothed,
+                // thresholded at 1.75 and debounced (:1694-1729)
+                st.fm_gcount++;
+                if (st.fm_gcount >= 400) {
+                    float en[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {        // AudioFilter_GoertzelEnergy, audio_filter.c:1297-1305
+                        const float ea = __fsub_rn(st.fm_gz[3 * k + 1], __fmul_rn(st.fm_gz[3 * k + 2], p.fm_gz_cos[k]));
+                        const float eb = __fmul_rn(st.fm_gz[3 * k + 2], p.fm_gz_sin[k]);
+                        st.fm_gz[3 * k] = 0.0f; st.fm_gz[3 * k + 1] = 0.0f; st.fm_gz[3 * k + 2] = 0.0f;
+                        en[k] = __fsqrt_rn(__fadd_rn(__fmul_rn(ea, ea), __fmul_rn(eb, eb)));
+                    }
+                    const float s = __fadd_rn(en[0], en[1]), r = en[2];
+                    st.fm_subdet = (float)(((1 - 0.9) * (double)st.fm_subdet) + ((double)__fdiv_rn(r, __fdiv_rn(s, 2.0f)) * 0.9));
+                    if ((double)st.fm_subdet > 1.75) { st.fm_tdet++; if (st.fm_tdet > 5) st.fm_tdet = 5; }
+                    else if (st.fm_tdet) st.fm_tdet--;
+                    st.fm_tone_detected = st.fm_tdet >= 2 ? 1 : 0;
+                    st.fm_gcount = 0;
+                }
+            } else {
+                st.fm_tone_detected = 1;            // detection disabled: always "detected" (:1731-1734)
             }
         }
         if (!st.fm_squelched) mask |= (1 << b);

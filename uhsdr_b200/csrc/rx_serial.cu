@@ -33,6 +33,7 @@ __device__ __forceinline__ void load_ser(SerState &s, const ChanState &g, bool n
     CP1(sam_fil_out) CP1(sam_lowpass) CP1(sam_omega2) CP1(sam_phs) CP1(sam_dsI) CP1(sam_dsQ)
     CPA(sam_a, 24) CPA(sam_b, 24) CPA(sam_c, 24) CPA(sam_d, 24) CP1(sam_count) CP1(fade_dc27) CP1(fade_dc_insert) CP1(carrier_freq_offset)
     CP1(fm_i_prev) CP1(fm_q_prev) CP1(fm_lpf_prev) CP1(fm_hpf_prev_a) CP1(fm_hpf_prev_b) CP1(fm_sql_avg) CP1(fm_count) CP1(fm_squelched)
+    CPA(fm_gz, 9) CP1(fm_subdet) CP1(fm_gcount) CP1(fm_tdet) CP1(fm_tone_detected)
     if (notch) {
         CPA(notch_coef, NOTCH_TAPS) CPA(notch_x, NOTCH_TAPS) CPA(notch_delay, NOTCH_DELAY)
         CP1(notch_energy) CP1(notch_x0) CP1(notch_head) CP1(notch_inbuf) CP1(notch_outbuf)
@@ -52,6 +53,7 @@ __device__ __forceinline__ void store_ser(ChanState &g, const SerState &s, bool 
     CP1(sam_fil_out) CP1(sam_lowpass) CP1(sam_omega2) CP1(sam_phs) CP1(sam_dsI) CP1(sam_dsQ)
     CPA(sam_a, 24) CPA(sam_b, 24) CPA(sam_c, 24) CPA(sam_d, 24) CP1(sam_count) CP1(fade_dc27) CP1(fade_dc_insert) CP1(carrier_freq_offset)
     CP1(fm_i_prev) CP1(fm_q_prev) CP1(fm_lpf_prev) CP1(fm_hpf_prev_a) CP1(fm_hpf_prev_b) CP1(fm_sql_avg) CP1(fm_count) CP1(fm_squelched)
+    CPA(fm_gz, 9) CP1(fm_subdet) CP1(fm_gcount) CP1(fm_tdet) CP1(fm_tone_detected)
     if (notch) {
         CPA(notch_coef, NOTCH_TAPS) CPA(notch_x, NOTCH_TAPS) CPA(notch_delay, NOTCH_DELAY)
         CP1(notch_energy) CP1(notch_x0) CP1(notch_head) CP1(notch_inbuf) CP1(notch_outbuf)

@@ -66,6 +66,8 @@ struct ChanParams {
     int sam_c0, sam_c1;    // pool offsets of demod_sam_const.c0/.c1
     // FM
     int fm_sql_threshold;
+    int fm_tone_det;        // ads.fm_conf.subaudible_tone_det_freq != 0
+    float fm_gz_r[3], fm_gz_cos[3], fm_gz_sin[3];   // AudioFilter_CalcGoertzel for 1.04 f, 0.95 f, f over 400 blocks (audio_management.c:311-326)
     float fm_scaling;
     int fm_translate_on;
     // spectral NR
@@ -124,6 +126,8 @@ struct ChanState {
     // FM, audio_driver.c:1516-1531
     float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
     int fm_count, fm_squelched;
+    float fm_gz[9], fm_subdet;               // Goertzel buf[3] of the HIGH / LOW / CTR subtone detectors, smoothed ratio (audio_driver.c:1665-1734)
+    int fm_gcount, fm_tdet, fm_tone_detected;
     // LMS automatic notch: arm_lms_norm_f32 instance (coefficients, the newest 64 inputs as a circular window with
     // notch_head = slot of the oldest, energy, x0) and the decorrelation delay line of AudioDriver_NotchFilter
     float notch_coef[NOTCH_TAPS], notch_x[NOTCH_TAPS], notch_delay[NOTCH_DELAY];
@@ -155,6 +159,8 @@ struct SerState {
     int carrier_freq_offset;
     float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
     int fm_count, fm_squelched;
+    float fm_gz[9], fm_subdet;               // Goertzel buf[3] of the HIGH / LOW / CTR subtone detectors, smoothed ratio (audio_driver.c:1665-1734)
+    int fm_gcount, fm_tdet, fm_tone_detected;
     // LMS automatic notch: arm_lms_norm_f32 instance (coefficients, the newest 64 inputs as a circular window with
     // notch_head = slot of the oldest, energy, x0) and the decorrelation delay line of AudioDriver_NotchFilter
     float notch_coef[NOTCH_TAPS], notch_x[NOTCH_TAPS], notch_delay[NOTCH_DELAY];

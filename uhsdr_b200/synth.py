@@ -53,6 +53,22 @@ def rx_iq(cfg: ChanCfg, channel: int, nsamples: int, seed: int = 0x55485344, sta
     return out
 
 
+def rx_fm_subtone_iq(cfg: ChanCfg, channel: int, nsamples: int, tone_hz: float, tone_dev_hz: float = 300.0,
+                     seed: int = 0x55485344) -> np.ndarray:
+    """FM test signal (1 kHz tone, 2.5 kHz deviation) with a sub-audible (CTCSS) tone of `tone_dev_hz` deviation on top --
+    the input of the Goertzel tone detector (audio_driver.c:1665-1734).  tone_dev_hz = 0: no sub-audible tone."""
+    t = np.arange(nsamples, dtype=np.float64) / FS
+    rng = np.random.default_rng([seed, channel, 0x4354])
+    phase = 2 * np.pi * carrier_offset(cfg) * t + 2.5 * np.sin(2 * np.pi * 1000.0 * t)
+    if tone_dev_hz:
+        phase = phase + (tone_dev_hz / tone_hz) * np.sin(2 * np.pi * tone_hz * t)
+    x = 4000.0 * np.exp(1j * phase) + 30.0 * (rng.standard_normal(nsamples) + 1j * rng.standard_normal(nsamples))
+    out = np.empty((nsamples, 2), dtype=np.int32)
+    out[:, 0] = np.round(x.real * 65536.0)
+    out[:, 1] = np.round(x.imag * 65536.0)
+    return out
+
+
 def add_impulses(iq: np.ndarray, seed: int, count: int, amplitude: float = 25000.0) -> np.ndarray:
     """Copy of `iq` with `count` one-sample impulses (ignition-noise like) on I and Q at seeded random positions --
     the input the LPC noise blanker (alt_noise_blanking, audio_nr.c:2210) is there for."""
