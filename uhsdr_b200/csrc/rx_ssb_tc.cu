@@ -70,7 +70,7 @@ constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilb
 constexpr int MMA_PAUSE = 120;        // cycles between k-steps of the MMA issue (sweep: profiles/r01_tc2_experiments.txt)
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
-constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POST = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;
+constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;   // NWARP_FE + 6: the output warp
 constexpr int NTHREADS = 32 * (NWARP_FE + 9);
 // software pipeline, in steps of 128 input samples.  Step s (virtual steps included) is written into the decimator
 // ring at iteration s, its decimator MMAs are issued at s + 1, the decimator outputs leave TMEM for the Hilbert ring
@@ -159,9 +159,6 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, unsigned &whi, u
     wlo = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
 }
 __device__ __forceinline__ float join_bf16(unsigned hi, unsigned lo) { return __uint_as_float(hi << 16) + __uint_as_float(lo << 16); }
-
-// byte offset of (column group gr, channel-in-group c8, time slot s) inside one ring array with `tgs` time groups
-__device__ __forceinline__ int ring_off(int gr, int c8, int s, int tgs) { return gr * (tgs * 128) + (s >> 3) * 128 + c8 * 16 + (s & 7) * 2; }
 
 struct FirLaneState {
     float te1, te2, te3;     // teta*_old
