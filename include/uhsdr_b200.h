@@ -140,6 +140,9 @@ typedef struct {
      * decorrelation delay are fixed by the firmware (DSP_NOTCH_NUMTAPS_MIN == MAX == 64,
      * DSP_NOTCH_BUFLEN_MIN == MAX == 128, audio_driver.h:486-492); only the convergence rate is a setting. */
     int32_t notch_mu;            /* ts.dsp.notch_mu, 0..40, default 10 (DSP_NOTCH_MU_DEFAULT)       */
+    /* FM transmit tones, tx_processor.c:554-564 (softdds single tones added to the pre-emphasised audio) */
+    float   fm_subaudible_tone_gen_freq; /* ads.fm_conf.subaudible_tone_gen_freq in Hz, 0 = off (default)  */
+    int32_t fm_tone_burst_mode;  /* ts.fm_tone_burst_mode while the burst is keyed: 0 off, 1 = 1750 Hz, 2 = 2135 Hz */
 } uhsdr_chan_cfg_t;
 
 /* Per-channel side outputs (SURVEY.md section 5 "metrics"); none is on the parity-critical path. */

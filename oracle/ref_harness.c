@@ -93,6 +93,10 @@ static void ref_select_path(int path)
     ts.filter_path_mem[fm][0] = (uint8_t)path;
 }
 
+/* FM transmit tones: the UI calls these when the settings change (audio_management.c:301-305, :339-349) and keys
+ * tone_burst_active for the length of the burst; the oracle keeps it keyed while the mode is non-zero. */
+static void ref_apply_fm_tones(const uhsdr_chan_cfg_t *cfg);
+
 /* One-time init for this copy of the library == firmware boot: configuration load
  * (ui_configuration.c defaults, overridden by cfg), AudioDriver_Init (uhsdr_main.c:444), then
  * AudioDriver_SetProcessingChain (audio_driver.c:1093). */
@@ -113,6 +117,7 @@ int ref_init(const uhsdr_chan_cfg_t *cfg)
     AudioDriver_Init();
     nr_params.NR_decimation_enable = cfg->nr_decimation_enable;   /* NR_Init (audio_nr.c:88) forces it to true */
     if (cfg->fm_subaudible_tone_det_freq > 0.0f) AudioManagement_CalcSubaudibleDetFreq(cfg->fm_subaudible_tone_det_freq);
+    ref_apply_fm_tones(cfg);
     ref_select_path(cfg->filter_path);
     AudioDriver_SetProcessingChain(ts.dmod_mode, true);
     if (ts.filter_path != cfg->filter_path) return -3;
@@ -127,6 +132,7 @@ int ref_reconfigure(const uhsdr_chan_cfg_t *cfg)
     g_cfg = *cfg;
     ref_apply_cfg(cfg);
     if (cfg->fm_subaudible_tone_det_freq > 0.0f) AudioManagement_CalcSubaudibleDetFreq(cfg->fm_subaudible_tone_det_freq);
+    ref_apply_fm_tones(cfg);
     ref_select_path(cfg->filter_path);
     AudioDriver_SetProcessingChain(ts.dmod_mode, false);
     return ts.filter_path == cfg->filter_path ? 0 : -3;
@@ -211,3 +217,11 @@ int ref_get_status(uhsdr_chan_status_t *st)
 const float *ref_tap_iq_i(void) { return adb.iq_buf.i_buffer; }
 const float *ref_tap_iq_q(void) { return adb.iq_buf.q_buffer; }
 const float *ref_tap_a0(void) { return adb.a_buffer[0]; }
+
+static void ref_apply_fm_tones(const uhsdr_chan_cfg_t *cfg)
+{
+    AudioManagement_CalcSubaudibleGenFreq(cfg->fm_subaudible_tone_gen_freq > 0.0f ? cfg->fm_subaudible_tone_gen_freq : 0.0f);
+    ts.fm_tone_burst_mode = (uint8_t)cfg->fm_tone_burst_mode;
+    AudioManagement_LoadToneBurstMode();
+    ads.fm_conf.tone_burst_active = cfg->fm_tone_burst_mode != 0;
+}

@@ -589,6 +589,7 @@ struct port_chan {
     float tx_delay[320];
     uint32_t alc_delay_inbuf;
     float tx_fm_hpf_a, tx_fm_hpf_b; uint32_t tx_fm_accum;   /* TxProcessor_FM statics, tx_processor.c:537-538 */
+    uint32_t tx_dds_sub_acc, tx_dds_sub_step, tx_dds_burst_acc, tx_dds_burst_step;   /* soft_dds_t subaudible_tone_dds / tone_burst_dds */
     /* FM subaudible-tone detector, audio_driver.c:1665-1734: Goertzel HIGH / LOW / CTR {r, cos, sin, buf[3]}, smoothed ratio, debounce */
     float gz_r[3], gz_cos[3], gz_sin[3], gz_buf[3][3], fm_subdet; int fm_tdet, fm_tone_detected; unsigned long fm_gcount;
     float tx_postfilt_gain_var;

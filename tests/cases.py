@@ -84,6 +84,9 @@ TX_CASES = [
     ("tx_fm", dict(dmod_mode=DEMOD_FM, filter_path=2), 160),
     ("tx_fm_5k_p6k", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_dev_5khz=1, iq_freq_mode=FREQ_IQ_CONV_P6KHZ, tx_mic_gain=60), 160),
     ("tx_fm_m6k", dict(dmod_mode=DEMOD_FM, filter_path=2, iq_freq_mode=FREQ_IQ_CONV_M6KHZ), 160),
+    # FM transmit tones (tx_processor.c:554-564): sub-audible tone on the modulation; tone burst (which silences the former)
+    ("tx_fm_subtone_88", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_subaudible_tone_gen_freq=88.5), 160),
+    ("tx_fm_burst_1750_5k", dict(dmod_mode=DEMOD_FM, filter_path=2, fm_dev_5khz=1, fm_subaudible_tone_gen_freq=100.0, fm_tone_burst_mode=1), 160),
 ]
 
 # float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these

@@ -44,6 +44,7 @@ class ChanCfg(ctypes.Structure):
         ("tx_power_factor", _f32), ("tx_adj_gain_i", _f32), ("tx_adj_gain_q", _f32),
         ("iq_phase_balance_tx", _f32),
         ("notch_mu", _i32),
+        ("fm_subaudible_tone_gen_freq", _f32), ("fm_tone_burst_mode", _i32),
     ]
 
     def copy(self) -> "ChanCfg":

@@ -83,6 +83,7 @@ __global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *
         // TxProcessor_Set (tx_processor.c:72-119): lattice state and Hilbert histories cleared
         for (int k = 0; k < MAX_LAT; k++) tx[ch].lat_s[k] = 0.0f;
         for (int k = 0; k < H2; k++) tx[ch].hist[k] = 0.0f;
+        tx[ch].fm_dds_sub_acc = 0u; tx[ch].fm_dds_burst_acc = 0u;       // softdds_setFreqDDS, smooth == false (softdds.c:38-45)
     }
 }
 

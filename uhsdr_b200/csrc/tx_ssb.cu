@@ -108,6 +108,15 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
         tp->fm_swap = shift < 0;
         tp->fm_mult = cfg.fm_dev_5khz ? 2 : 1;
         tp->dds_off = t.off(t.ex->dds_table_array);
+        // softdds_setFreqDDS (softdds.c:26-45): step = ((uint64)(freq * 1024) << 22) / 48000
+        static const unsigned burst_freq[3] = { 0, 1750, 2135 };          // fm_tone_burst_freq, audio_management.c:328
+        const int bm = cfg.fm_tone_burst_mode;
+        const float fburst = (uint16_t)((bm >= 0 && bm <= 2) ? burst_freq[bm] : 0);
+        const float fsub = (cfg.fm_subaudible_tone_gen_freq > 0.0f && !bm) ? cfg.fm_subaudible_tone_gen_freq : 0.0f;   // no sub-audible tone during a burst
+        uint64_t f64 = fsub * 1024; f64 <<= 22; tp->fm_sub_step = (uint32_t)(f64 / 48000);
+        f64 = fburst * 1024; f64 <<= 22; tp->fm_burst_step = bm ? (uint32_t)(f64 / 48000) : 0u;
+        tp->fm_sub_scale = 0.00045 * tp->fm_mult;
+        tp->fm_burst_scale = (16 / 4266.0) * tp->fm_mult;
         if (tp->dds_off < 0) { if (err) *err = "DDS sine table missing from the table blob"; return UHSDR_ERR_TABLES; }
     }
     return UHSDR_OK;
@@ -118,11 +127,16 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
 // product), then the 16-bit NCO accumulator `acc += word + a1 * FM_MOD_SCALING * mult; acc %= 65536` -- the += goes through
 // float, and a negative sum wraps the way the x86-64 build of the reference does it (conversion to 64 bits, low word).
 // Returns the index into the 1024-entry sine table.
-__device__ __forceinline__ uint32_t fm_step(float a, float &hpf_a, float &hpf_b, uint32_t &accum, const TxParams &tp)
+__device__ __forceinline__ uint32_t fm_step(float a, float &hpf_a, float &hpf_b, uint32_t &accum, uint32_t &sub_acc, uint32_t &burst_acc,
+                                            const TxParams &tp, const float *__restrict__ pool)
 {
     hpf_b = (float)(0.05 * (double)__fsub_rn(__fadd_rn(hpf_b, a), hpf_a));
     hpf_a = a;
-    const float inc = __fadd_rn((float)(uint32_t)tp.fm_word, __fmul_rn(__fmul_rn(hpf_b, 16.0f), tp.fm_mult));
+    float a1 = hpf_b;
+    // sub-audible tone / tone burst: softdds_addSingleTone (softdds.c:113-119) on the pre-emphasised audio, :554-564
+    if (tp.fm_sub_step) { const uint32_t k = (sub_acc >> 22) & 1023u; sub_acc += tp.fm_sub_step; a1 = __fadd_rn(a1, __fmul_rn(__ldg(pool + tp.dds_off + k), tp.fm_sub_scale)); }
+    if (tp.fm_burst_step) { const uint32_t k = (burst_acc >> 22) & 1023u; burst_acc += tp.fm_burst_step; a1 = __fadd_rn(a1, __fmul_rn(__ldg(pool + tp.dds_off + k), tp.fm_burst_scale)); }
+    const float inc = __fadd_rn((float)(uint32_t)tp.fm_word, __fmul_rn(__fmul_rn(a1, 16.0f), tp.fm_mult));
     accum = (uint32_t)(long long)__float2ll_rz(__fadd_rn((float)accum, inc));
     accum %= 65536u;
     return accum >> 6;
@@ -234,7 +248,7 @@ tx_ssb_kernel(TxArgs a)
                 __syncwarp();
                 w.scr[lane] = v;
                 __syncwarp();
-                if (lane == 0) for (int i = 0; i < BLK; i++) w.scr[i] = (float)fm_step(w.scr[i], st.fm_hpf_a, st.fm_hpf_b, st.fm_accum, tp);
+                if (lane == 0) for (int i = 0; i < BLK; i++) w.scr[i] = (float)fm_step(w.scr[i], st.fm_hpf_a, st.fm_hpf_b, st.fm_accum, st.fm_dds_sub_acc, st.fm_dds_burst_acc, tp, pool);
                 __syncwarp();
                 v = w.scr[lane];
                 __syncwarp();
@@ -339,7 +353,7 @@ tx_serial_kernel(TxArgs a)
     for (int s = 0; s < 3; s++) { bq[s] = g.bq[s]; for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
     float alc_val = g.alc_val, peak_audio = g.peak_audio;
     float fm_hpf_a = g.fm_hpf_a, fm_hpf_b = g.fm_hpf_b;
-    uint32_t fm_accum = g.fm_accum;
+    uint32_t fm_accum = g.fm_accum, sub_acc = g.fm_dds_sub_acc, burst_acc = g.fm_dds_burst_acc;
     uint32_t inbuf = g.alc_delay_inbuf;
     float delay[320];
     for (int i = 0; i < 320; i++) delay[i] = g.delay[i];
@@ -392,11 +406,11 @@ tx_serial_kernel(TxArgs a)
             inbuf = inb;
         }
         if (tp.fm) {
-            for (int i = 0; i < BLK; i++) v[i] = (float)fm_step(v[i], fm_hpf_a, fm_hpf_b, fm_accum, tp);      // table index for the FIR-stage kernel
+            for (int i = 0; i < BLK; i++) v[i] = (float)fm_step(v[i], fm_hpf_a, fm_hpf_b, fm_accum, sub_acc, burst_acc, tp, pool);      // table index for the FIR-stage kernel
         }
         for (int i = 0; i < BLK; i += 4) *reinterpret_cast<float4 *>(out + (size_t)blk * BLK + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
-    g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum;
+    g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum; g.fm_dds_sub_acc = sub_acc; g.fm_dds_burst_acc = burst_acc;
     for (int i = 0; i < MAX_LAT; i++) g.lat_s[i] = lat_s[i];
     for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
     g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;

@@ -190,6 +190,8 @@ struct TxParams {
     int fm_swap;             // translate_freq < 0: I and Q buffers swapped, :572-573
     float fm_mult;           // 2 for 5 kHz deviation, else 1
     int dds_off;             // pool offset of DDS_TABLE (1024 entries)
+    uint32_t fm_sub_step, fm_burst_step;   // softdds steps of the sub-audible tone / the tone burst, 0 = off (tx_processor.c:554-564)
+    float fm_sub_scale, fm_burst_scale;    // FM_SUBAUDIBLE_TONE_AMPLITUDE_SCALING / FM_TONE_BURST_AMPLITUDE_SCALING x deviation factor
     int lsb;                 // dmod_mode == DEMOD_LSB: I/Q filters swapped (tx_processor.c:477-478)
     float gain_calc;         // mic gain / MIC_GAIN_RESCALE * 2^-16 (tx_processor.c:360-381)
     LatticeP lat;            // IIR_TXFilter
@@ -215,6 +217,7 @@ struct TxState {
     long long blocks;
     float fm_hpf_a, fm_hpf_b;   // TxProcessor_FM statics hpf_prev_a / hpf_prev_b / fm_mod_accum (tx_processor.c:537-538)
     uint32_t fm_accum;
+    uint32_t fm_dds_sub_acc, fm_dds_burst_acc;   // soft_dds_t accumulators (reset by every configuration, softdds.c:38-45)
 };
 
 // Coefficients of the fused narrow-SSB kernel, passed by value as a kernel parameter so that
