@@ -147,3 +147,29 @@ def test_tensor_core_kernel_mute_and_float_copy(built):
     mask = np.repeat(mute.astype(bool), 32, axis=1)
     assert np.all(w_m[mask] == 0) and np.all(f_m[mask] == 0.0)
     assert np.array_equal(w_m[~mask], w_plain[~mask])
+
+
+def test_tensor_core_kernel_long_call(built):
+    """One call of 3000 blocks (2 s of signal, 750 pipeline steps: every ring / accumulator / mbarrier phase wraps
+    hundreds of times) against the oracle, and against the same signal in two calls, bit for bit."""
+    cfg_u, cfg_l = default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
+    nch, nb = 6, 3000
+    cfgs = [cfg_u if c % 2 == 0 else cfg_l for c in range(nch)]
+    iq = np.stack([synth.rx_iq(cfgs[c], 700 + c, nb * 32, seed=48) for c in range(nch)])
+    outs = []
+    for cut in (None, 1996):
+        with Engine(nch) as eng:
+            for c in range(nch):
+                eng.configure(cfgs[c], first=c, count=1)
+            if cut is None:
+                outs.append(run_engine_float(eng, iq))
+            else:
+                w1, f1 = run_engine_float(eng, iq[:, : cut * 32])
+                w2, f2 = run_engine_float(eng, iq[:, cut * 32:])
+                outs.append((np.concatenate([w1, w2], axis=1), np.concatenate([f1, f2], axis=1)))
+    (w1, f1), (w2, f2) = outs
+    assert np.array_equal(w1, w2)
+    for c in range(nch):
+        with oracle_channel(cfgs[c]) as o:
+            want_w, want_f = o.rx(iq[c])
+        check_tolerance(f1[c], want_f, w1[c, :, 0], want_w[:, 0], f"long/ch{c}")
