@@ -246,6 +246,17 @@ def gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device visible; the engine has no CPU fallback")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # host buffers of the e2e leg live on the NUMA node next to this rank's GPU: bind the process to the CPUs NVML names
+    # for the device before anything is allocated (first touch places the pinned pages); without it 8 ranks share one node
+    numa = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = sorted(os.sched_getaffinity(0))
+        numa = f"{numa[0]}-{numa[-1]} ({len(numa)} cpus)"
+    except Exception as exc:                                   # affinity is an optimisation, never a requirement
+        numa = f"not set: {exc!r}"
 
     nch, T = args.channels, args.blocks
     ns = T * 32
@@ -393,7 +404,8 @@ def gpu_arm(args):
                                   "note": "direct-form FLOP count of the chain (SURVEY.md 8d) against the FP32 FMA pipe, 148 SM x 128 lanes x 2 x 1.965 GHz; "
                                           "282 of the 346 FLOP (the 83-tap decimator and the 199-tap Hilbert pair) run on the tensor cores as bf16-split Toeplitz GEMMs"}},
             "cpu_baseline": cpu_baseline,
-            "e2e": {"value": e2e_value, "unit": "channel-samples/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "channel-samples/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps,
+                    "host_cpu_affinity_rank0": numa},
             "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
         print(json.dumps(line), flush=True)
