@@ -122,7 +122,7 @@ typedef struct {
     int32_t nr_decimation_enable;/* nr_params.NR_decimation_enable (default 1)                      */
     /* spectrum display, ui_spectrum.c:1350-1390 */
     int32_t spectrum_enable;     /* 0 = no spectrum ring / FFT for this channel                     */
-    int32_t spectrum_magnify;    /* sd.magnify (only 0 implemented)                                 */
+    int32_t spectrum_magnify;    /* sd.magnify 0..5 (1..5 = zoom FFT)                               */
     float   codec_gain_calc;     /* ads.codec_gain_calc (spectrum scaling), default 1               */
     /* TX, tx_processor.c */
     int32_t tx_filter;           /* ts.tx_filter, default SOPRANO                                   */
@@ -174,6 +174,11 @@ const char *uhsdr_last_error(const uhsdr_engine_t *e);
 /* Reference defaults (ui_configuration.c:60-220; USB, path 35, -12 kHz translate, AGC mode 2). */
 int uhsdr_default_chan_cfg(uhsdr_chan_cfg_t *cfg);
 
+/* Checks a table blob (uhsdr_tables.h) without touching a device: magic / version / size, every section and
+ * every cross-index inside the blob.  UHSDR_OK or UHSDR_ERR_TABLES (text in uhsdr_last_error(NULL)).
+ * uhsdr_engine_create runs the same check. */
+int uhsdr_tables_validate(const void *tables, size_t tables_bytes);
+
 /* Engine for num_channels channels on CUDA device `device`.  `tables` is the blob described in
  * uhsdr_tables.h (the reference's FilterPathInfo[] + coefficient arrays); it is copied.
  * Replaces AudioDriver_Init (audio_driver.c:677). */
@@ -221,6 +226,34 @@ void *uhsdr_engine_stream(uhsdr_engine_t *e);
  * spectrum ring, Hann window, 512-point complex FFT, magnitudes.  mags: [count][512] floats (host). */
 int uhsdr_get_spectrum(uhsdr_engine_t *e, int first, int count, float *mags);
 int uhsdr_get_spectrum_device(uhsdr_engine_t *e, int first, int count, float *mags_dev);
+
+/* UiSpectrum_RedrawSpectrum states 0-4 (ui_spectrum.c:1362-1487), the display-side post-processing of the spectrum:
+ * the FFT above, IIR averaging of the bins (:1432-1446), log scaling with the sliding display offset in frequency order
+ * (UiSpectrum_ScaleFFT :1258-1296, :1485), rescaling to the scope width (UiSpectrum_ScaleFFT2SpectrumWidth :1300-1337), and
+ * the S-meter basis UiSpectrum_CalculateDBm (:1990-2122): dBm and dBm/Hz of the signal inside the filter passband.
+ * The settings are the reference's own (ts.spectrum_db_scale / spectrum_agc_rate / spectrum_filter / dbm_constant,
+ * ui_configuration.c:94,137,138,206; slayout.scope.w).  The averaged bins and the display offset persist per channel. */
+typedef struct {
+    int32_t struct_size;
+    int32_t spectrum_db_scale;   /* 1..8 = 5 / 7.5 / 10 / 15 / 20 dB, 1 / 2 / 3 S-units per division; default 3 (DB_DIV_10)   */
+    int32_t spectrum_agc_rate;   /* 1..50, default 25 (SPECTRUM_SCOPE_AGC_DEFAULT)                                            */
+    int32_t spectrum_filter;     /* 1..20, default 4 (SPECTRUM_FILTER_DEFAULT)                                                */
+    int32_t dbm_constant;        /* -100..100, default 0                                                                      */
+    int32_t scope_width;         /* slayout.scope.w: display columns, 1..512 (reference: <= 480, default 480); 512 = one per bin */
+} uhsdr_spectrum_display_cfg_t;
+typedef struct {
+    float dbm;                   /* sm.dbm_cur,   ui_spectrum.c:2114 */
+    float dbmhz;                 /* sm.dbmhz_cur, ui_spectrum.c:2115 */
+    float display_offset;        /* sd.display_offset after the update of :1485 */
+} uhsdr_spectrum_level_t;
+int uhsdr_default_spectrum_display_cfg(uhsdr_spectrum_display_cfg_t *cfg);
+/* disp: [count][scope_width] floats (sd.FFT_Samples after state 4); levels: [count]; avg (optional): [count][512] floats
+ * (sd.FFT_AVGData after state 3).  Host buffers. */
+int uhsdr_spectrum_display(uhsdr_engine_t *e, int first, int count, const uhsdr_spectrum_display_cfg_t *cfg,
+                           float *disp, uhsdr_spectrum_level_t *levels, float *avg);
+/* Same with device buffers, asynchronous on the engine's stream; mags_dev (optional): [count][512] magnitudes of state 2. */
+int uhsdr_spectrum_display_device(uhsdr_engine_t *e, int first, int count, const uhsdr_spectrum_display_cfg_t *cfg,
+                                  float *disp_dev, uhsdr_spectrum_level_t *levels_dev, float *avg_dev, float *mags_dev);
 
 int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_t *status);
 

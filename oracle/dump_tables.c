@@ -4,7 +4,7 @@
  * Walks the reference's FilterInfo[] / FilterPathInfo[] and coefficient arrays (linked from
  * /root/reference at build time) and serialises them into the blob format of
  * include/uhsdr_tables.h.  This is the code a UHSDR maintainer would add on the firmware side
- * (INTEGRATION.md); here it produces tests/golden/uhsdr_tables.bin.
+ * (INTEGRATION.md); here it produces uhsdr_b200/data/uhsdr_tables.bin.
  *
  * audio_driver.c is #included to reach its file-static NR coefficient arrays
  * (audio_driver.c:195,198).

@@ -7,7 +7,7 @@ import subprocess
 
 import numpy as np
 
-from uhsdr_b200.config import ChanCfg, ChanStatus
+from uhsdr_b200.config import ChanCfg, ChanStatus, SpectrumDisplayCfg
 from uhsdr_b200.tables import DEFAULT_BLOB
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +35,7 @@ def lib():
         L.port_rx.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]
         L.port_tx.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p]
         L.port_spectrum.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.port_spectrum_display.argtypes = [ctypes.c_void_p, ctypes.POINTER(SpectrumDisplayCfg)] + [ctypes.c_void_p] * 4
         L.port_get_status.argtypes = [ctypes.c_void_p, ctypes.POINTER(ChanStatus)]
         _lib = L
     return _lib
@@ -113,6 +114,15 @@ class PortChannel:
         if rc != 0:
             raise RuntimeError(f"port_spectrum: {rc}")
         return mags
+
+    def spectrum_display(self, dc: SpectrumDisplayCfg):
+        """UiSpectrum_RedrawSpectrum states 0-4: (mags[512], avg[512], disp[scope_width], (dbm, dbmhz, display_offset))."""
+        mags, avg = np.empty(512, dtype=np.float32), np.empty(512, dtype=np.float32)
+        disp, lvl = np.empty(dc.scope_width, dtype=np.float32), np.empty(3, dtype=np.float32)
+        rc = lib().port_spectrum_display(self._h, ctypes.byref(dc), mags.ctypes.data, avg.ctypes.data, disp.ctypes.data, lvl.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"port_spectrum_display: {rc}")
+        return mags, avg, disp, lvl
 
     def status(self) -> ChanStatus:
         st = ChanStatus()

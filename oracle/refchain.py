@@ -15,7 +15,7 @@ import tempfile
 
 import numpy as np
 
-from uhsdr_b200.config import ChanCfg, ChanStatus
+from uhsdr_b200.config import ChanCfg, ChanStatus, SpectrumDisplayCfg
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libuhsdr_ref.so")
@@ -94,6 +94,24 @@ class RefChannel:
         if rc != 0:
             raise RuntimeError(f"ref_spectrum failed: {rc}")
         return mags
+
+    def spectrum_display_init(self, dc: SpectrumDisplayCfg) -> None:
+        """UiSpectrum_InitSpectrumDisplayData (the reference's own, ui_spectrum.c:955-1083) with the given settings."""
+        self._lib.ref_spectrum_display_init.argtypes = [ctypes.c_int] * 5
+        rc = self._lib.ref_spectrum_display_init(dc.spectrum_db_scale, dc.spectrum_agc_rate, dc.spectrum_filter, dc.dbm_constant, dc.scope_width)
+        if rc != 0:
+            raise RuntimeError(f"ref_spectrum_display_init failed: {rc}")
+        self._scope_w = dc.scope_width
+
+    def spectrum_display(self):
+        """The reference's UiSpectrum_RedrawSpectrum, states 0-4: (mags[512], avg[512], disp[scope_width], (dbm, dbmhz, offset))."""
+        mags, avg = np.empty(512, dtype=np.float32), np.empty(512, dtype=np.float32)
+        disp, lvl = np.empty(self._scope_w, dtype=np.float32), np.empty(3, dtype=np.float32)
+        self._lib.ref_spectrum_redraw.argtypes = [ctypes.c_void_p] * 4
+        rc = self._lib.ref_spectrum_redraw(mags.ctypes.data, avg.ctypes.data, disp.ctypes.data, lvl.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"ref_spectrum_redraw failed: {rc}")
+        return mags, avg, disp, lvl
 
     def status(self) -> ChanStatus:
         st = ChanStatus()

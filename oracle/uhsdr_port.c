@@ -575,6 +575,7 @@ struct port_chan {
     biquad_t zoom_bq_i[4], zoom_bq_q[4];      /* IIR_biquad_Zoom_FFT_I/Q, audio_driver.c:165-192 (state survives a reconfiguration) */
     firdec_t zoom_dec_i, zoom_dec_q;          /* DECIMATE_ZOOM_FFT_I/Q, re-initialised by AudioDriver_Spectrum_Set :1073-1086 */
     uint32_t samp_ptr;
+    float spec_avg[512], spec_display_offset;     /* sd.FFT_AVGData, sd.display_offset (ui_spectrum.c:1432-1446, :1485) */
     /* NR */
     nr_t nr;
     notch_t notch;

@@ -71,6 +71,18 @@ SPECTRUM_CASES = [
     ("spec_zoom32_am", dict(spectrum_enable=1, spectrum_magnify=5, dmod_mode=DEMOD_AM, filter_path=70)),
 ]
 
+# UiSpectrum_RedrawSpectrum states 0-4 (ui_spectrum.c:1362-1487): (label, channel kw, display-settings kw).  Four redraws per
+# case, 24 blocks apart, so that the bin averages and the sliding display offset carry state.
+SPECDISP_CASES = [
+    ("disp_usb", dict(spectrum_enable=1), dict()),
+    ("disp_lsb_w320_5db", dict(spectrum_enable=1, dmod_mode=DEMOD_LSB, filter_path=38), dict(scope_width=320, spectrum_db_scale=1, spectrum_filter=2)),
+    ("disp_am_zoom4", dict(spectrum_enable=1, spectrum_magnify=2, dmod_mode=DEMOD_AM, filter_path=70), dict(spectrum_agc_rate=50, dbm_constant=-7)),
+    ("disp_sam_usb_2s", dict(spectrum_enable=1, dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=2), dict(spectrum_db_scale=7, spectrum_filter=20)),
+    ("disp_fm_p6k_w256", dict(spectrum_enable=1, dmod_mode=DEMOD_FM, filter_path=2, iq_freq_mode=FREQ_IQ_CONV_P6KHZ), dict(scope_width=256, spectrum_filter=1)),
+    ("disp_cw_lsb_notrans", dict(spectrum_enable=1, dmod_mode=DEMOD_CW, filter_path=8, cw_lsb=1, iq_freq_mode=0), dict(scope_width=479, spectrum_agc_rate=1)),
+]
+SPECDISP_REDRAWS, SPECDISP_BLOCKS = 4, 24
+
 TX_CASES = [
     ("tx_usb", dict(), 160),
     ("tx_lsb", dict(dmod_mode=DEMOD_LSB), 160),
@@ -91,3 +103,18 @@ TX_CASES = [
 
 # float-math libm differences (sincosf / atan2f / expf) rule out bit-exactness for these
 LIBM_CASES = {"sam_p72_both", "sam_p72_usb", "sam_p84_lsb", "fm_p2", "fm_p1_sql0_5k"}
+
+
+def check_spectrum_display(g, label, k, mags, avg, disp, lvl, fft_tol):
+    """Redraw k of a SPECDISP case against the reference vectors.  The display values are pixel rows (0 .. ~150): 1e-4 of that
+    range is 1.5e-2; the sliding offset integrates the minimum over the log of the weakest bins, the most rounding-sensitive
+    number of the display, and is held to 2e-3."""
+    import numpy as np
+    wm, wa, wd, wl = g[f"{label}/mags{k}"], g[f"{label}/avg{k}"], g[f"{label}/disp{k}"], g[f"{label}/lvl{k}"]
+    if mags is not None:
+        assert np.max(np.abs(mags - wm)) <= fft_tol * np.max(wm), (label, k)
+    assert np.max(np.abs(avg - wa)) <= fft_tol * np.max(wa), (label, k)
+    assert disp.shape == wd.shape
+    assert np.max(np.abs(disp - wd)) <= 1e-4 * max(float(np.max(np.abs(wd))), 100.0), (label, k, float(np.max(np.abs(disp - wd))))
+    assert abs(lvl[0] - wl[0]) <= 1e-3 and abs(lvl[1] - wl[1]) <= 1e-3, (label, k, lvl, wl)
+    assert abs(lvl[2] - wl[2]) <= 2e-3, (label, k, lvl, wl)

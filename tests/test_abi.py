@@ -55,6 +55,38 @@ def test_bad_tables_rejected_before_any_device_work(built):
     assert lib.uhsdr_strerror(-5).decode() == "configuration not implemented"
 
 
+def test_corrupted_table_blobs_are_rejected_without_a_device(built):
+    """Every section offset / count and every cross-index of the blob is bounds-checked at load time
+    (uhsdr_tables_validate runs the same check as uhsdr_engine_create; no device needed)."""
+    import random
+    import struct
+    from uhsdr_b200.tables import DEFAULT_BLOB
+    lib = load_library()
+    blob = open(DEFAULT_BLOB, "rb").read()
+
+    def check(b):
+        buf = ctypes.create_string_buffer(bytes(b), len(b))
+        return lib.uhsdr_tables_validate(buf, len(b))
+
+    assert check(blob) == 0
+    hdr = struct.unpack("<14I", blob[:56])
+    paths_off = hdr[6]
+    cases = {"arrays_off": (16, len(blob) - 8), "paths_off": (24, len(blob) - 4), "extras_off": (52, len(blob)),
+             "num_arrays": (12, 1 << 28), "path0.id": (paths_off, -3), "path0.fir_i_array": (paths_off + 16, 999),
+             "path0.pre_lattice": (paths_off + 40, 4000)}
+    for name, (off, val) in cases.items():
+        b = bytearray(blob)
+        struct.pack_into("<i" if val < 0 else "<I", b, off, val)
+        assert check(b) == -4, name
+        assert b"table blob" in lib.uhsdr_last_error(None)
+    assert check(blob[:-4]) == -4 and check(blob[:40]) == -4
+    rng = random.Random(7)
+    for _ in range(500):          # random word corruptions in the index sections: rejected or harmless, never a crash
+        b = bytearray(blob)
+        struct.pack_into("<i", b, rng.randrange(0, 9900) // 4 * 4, rng.choice([-1, -2, 0x7fffffff, 1 << 20, rng.randrange(-5, 400)]))
+        assert check(b) in (0, -4)
+
+
 def test_library_does_not_link_the_oracle(built):
     """The product library must not reference the oracle (or any CPU chain)."""
     import subprocess

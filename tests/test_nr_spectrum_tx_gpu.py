@@ -4,11 +4,12 @@ import os
 import numpy as np
 import pytest
 
-from cases import NB_CASES, NB_IMPULSES, NR_CASES, SPECTRUM_CASES, TX_CASES
+from cases import (NB_CASES, NB_IMPULSES, NR_CASES, SPECDISP_BLOCKS, SPECDISP_CASES, SPECDISP_REDRAWS, SPECTRUM_CASES, TX_CASES,
+                   check_spectrum_display)
 from conftest import oracle_channel
 from test_rx_parity_gpu import check_tolerance, run_engine_float
 from uhsdr_b200 import synth
-from uhsdr_b200.config import DEMOD_AM, default_cfg
+from uhsdr_b200.config import DEMOD_AM, default_cfg, default_spectrum_display_cfg
 from uhsdr_b200.engine import Engine, UhsdrError
 
 pytestmark = pytest.mark.gpu
@@ -85,6 +86,32 @@ def test_spectrum_fft(built, label, kw):
         want = g[f"{label}/{key}"]
         assert np.max(np.abs(got - want)) <= 1e-4 * np.max(want), label
         assert int(np.argmax(got)) == int(np.argmax(want))
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,dkw", SPECDISP_CASES, ids=[c[0] for c in SPECDISP_CASES])
+def test_spectrum_display_states_3_4(built, label, kw, dkw, exact):
+    """Bin averaging, dBm / dBm-per-Hz, log scaling, width rescaling and the sliding display offset (ui_spectrum.c:1432-1487,
+    :1990-2122) against vectors from the reference's own ui_spectrum.c; two channels of a batch, a sub-range call in between."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spectrum_display_golden.npz"))
+    cfg, dc = default_cfg(**kw), default_spectrum_display_cfg(**dkw)
+    iq = g[f"{label}/iq"]
+    n = SPECDISP_BLOCKS * (1 << cfg.spectrum_magnify) * 32
+    nch = 3
+    batch = np.stack([iq] * nch)
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        for k in range(SPECDISP_REDRAWS):
+            eng.rx(batch[:, k * n:(k + 1) * n])
+            if k == 2:          # channel 1 alone first, then the other two: per-channel state, any sub-range
+                d1, l1, a1 = eng.spectrum_display(dc, first=1, count=1)
+                d0, l0, a0 = eng.spectrum_display(dc, first=0, count=1)
+                d2, l2, a2 = eng.spectrum_display(dc, first=2, count=1)
+                disp, lvl, avg = np.concatenate([d0, d1, d2]), np.concatenate([l0, l1, l2]), np.concatenate([a0, a1, a2])
+            else:
+                disp, lvl, avg = eng.spectrum_display(dc)
+            for c in range(nch):
+                check_spectrum_display(g, label, k, None, avg[c], disp[c], lvl[c], fft_tol=1e-5)
 
 
 def test_spectrum_requires_enable(built):

@@ -6,11 +6,11 @@ import os
 import numpy as np
 import pytest
 
-from cases import FM_TONE_CASES, NB_CASES, NR_CASES, RX_CASES
+from cases import SPECDISP_BLOCKS, SPECDISP_CASES, SPECDISP_REDRAWS, check_spectrum_display, FM_TONE_CASES, NB_CASES, NR_CASES, RX_CASES
 from oracle import refchain
 from oracle.port import PortChannel
 from uhsdr_b200 import synth
-from uhsdr_b200.config import default_cfg
+from uhsdr_b200.config import default_cfg, default_spectrum_display_cfg
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "rx_golden.npz")
 
@@ -166,6 +166,21 @@ def test_port_spectrum_matches_golden(golden, label, kw):
         want = golden[f"{label}/{key}"]
         assert np.max(np.abs(got - want)) <= 2e-6 * np.max(want)
         assert int(np.argmax(got)) == int(np.argmax(want))
+
+
+@pytest.mark.parametrize("label,kw,dkw", SPECDISP_CASES, ids=[c[0] for c in SPECDISP_CASES])
+def test_port_spectrum_display_matches_golden(label, kw, dkw):
+    """UiSpectrum_RedrawSpectrum states 0-4 of the port against vectors from the reference's own ui_spectrum.c: bin averages
+    to FFT rounding, dBm / dBm-per-Hz to 1e-3 dB, display columns and the sliding offset to 1e-4 of the display range."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spectrum_display_golden.npz"))
+    cfg, dc = default_cfg(**kw), default_spectrum_display_cfg(**dkw)
+    iq = g[f"{label}/iq"]
+    n = SPECDISP_BLOCKS * (1 << cfg.spectrum_magnify) * 32
+    with PortChannel(cfg) as p:
+        for k in range(SPECDISP_REDRAWS):
+            p.rx(iq[k * n:(k + 1) * n])
+            mags, avg, disp, lvl = p.spectrum_display(dc)
+            check_spectrum_display(g, label, k, mags, avg, disp, lvl, fft_tol=2e-6)
 
 
 @pytest.mark.parametrize("label,kw,nblocks", TX_CASES, ids=[c[0] for c in TX_CASES])

@@ -77,6 +77,27 @@ class ChanStatus(ctypes.Structure):
     ]
 
 
+class SpectrumDisplayCfg(ctypes.Structure):
+    """uhsdr_spectrum_display_cfg_t: ts.spectrum_db_scale / spectrum_agc_rate / spectrum_filter / dbm_constant and
+    slayout.scope.w (ui_configuration.c:94,137,138,206)."""
+    _fields_ = [("struct_size", _i32), ("spectrum_db_scale", _i32), ("spectrum_agc_rate", _i32), ("spectrum_filter", _i32),
+                ("dbm_constant", _i32), ("scope_width", _i32)]
+
+
+class SpectrumLevel(ctypes.Structure):
+    _fields_ = [("dbm", _f32), ("dbmhz", _f32), ("display_offset", _f32)]
+
+
+def default_spectrum_display_cfg(**kw) -> SpectrumDisplayCfg:
+    """DB_DIV_10, SPECTRUM_SCOPE_AGC_DEFAULT 25, SPECTRUM_FILTER_DEFAULT 4, 480 display columns (the 480x320 layout)."""
+    c = SpectrumDisplayCfg(ctypes.sizeof(SpectrumDisplayCfg), 3, 25, 4, 0, 480)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
 def default_cfg(**kw) -> ChanCfg:
     """Reference defaults: USB, FilterPathInfo[35] (2.3 kHz LPF), -12 kHz translate, auto IQ
     correction, AGC mode 2 / slope 70 / thresh 20, bass +2 dB (ui_configuration.c:60-220)."""

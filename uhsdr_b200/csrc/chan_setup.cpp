@@ -22,6 +22,17 @@ bool HostTables::load(const void *data, size_t bytes, std::string *err)
         if (err) *err = "table blob: bad magic/version/size";
         return false;
     }
+    // every section must lie inside the blob before anything is dereferenced
+    auto section_ok = [&](uint32_t off, uint64_t count, size_t elem) {
+        return (off % 4) == 0 && (uint64_t)off + count * (uint64_t)elem <= (uint64_t)bytes;
+    };
+    if (!section_ok(hh->arrays_off, hh->num_arrays, sizeof(uhsdr_tbl_array_t)) || !section_ok(hh->paths_off, hh->num_paths, sizeof(uhsdr_tbl_path_t)) ||
+        !section_ok(hh->filters_off, hh->num_filters, sizeof(uhsdr_tbl_filter_t)) || !section_ok(hh->lattices_off, hh->num_lattices, sizeof(uhsdr_tbl_lattice_t)) ||
+        !section_ok(hh->interps_off, hh->num_interps, sizeof(uhsdr_tbl_interp_t)) || !section_ok(hh->extras_off, 1, sizeof(uhsdr_tbl_extras_t)) ||
+        hh->num_arrays > (1u << 20)) {
+        if (err) *err = "table blob: section offset / count out of range";
+        return false;
+    }
     blob.assign(static_cast<const uint8_t *>(data), static_cast<const uint8_t *>(data) + bytes);
     const uint8_t *b = blob.data();
     h = reinterpret_cast<const uhsdr_tbl_header_t *>(b);
@@ -32,10 +43,37 @@ bool HostTables::load(const void *data, size_t bytes, std::string *err)
     interp = reinterpret_cast<const uhsdr_tbl_interp_t *>(b + h->interps_off);
     ex = reinterpret_cast<const uhsdr_tbl_extras_t *>(b + h->extras_off);
     if (h->num_paths != UHSDR_NUM_FILTER_PATHS) { if (err) *err = "table blob: unexpected path count"; return false; }
+    // cross-indices: -1 = NULL where the firmware has a NULL pointer, otherwise inside the table it points into
+    {
+        const int na = (int)h->num_arrays, nl = (int)h->num_lattices, ni = (int)h->num_interps, nf = (int)h->num_filters;
+        auto arr_ok = [&](int a, bool opt) { return (opt && a == -1) || (a >= 0 && a < na); };
+        auto cnt_ok = [&](int a, int need) { return a < 0 || (int64_t)arr[a].count >= (int64_t)need; };
+        bool ok = true;
+        for (uint32_t i = 0; i < h->num_paths && ok; i++) {
+            const uhsdr_tbl_path_t &fp = path[i];
+            ok = fp.id >= 0 && fp.id < nf && arr_ok(fp.fir_i_array, true) && arr_ok(fp.fir_q_array, true) && arr_ok(fp.dec_array, true) &&
+                 (fp.pre_lattice == -1 || (fp.pre_lattice >= 0 && fp.pre_lattice < nl)) && (fp.aa_lattice == -1 || (fp.aa_lattice >= 0 && fp.aa_lattice < nl)) &&
+                 (fp.interpolate == -1 || (fp.interpolate >= 0 && fp.interpolate < ni)) && fp.fir_numtaps >= 0 && fp.dec_numtaps >= 0 &&
+                 cnt_ok(fp.fir_i_array, fp.fir_numtaps) && cnt_ok(fp.fir_q_array, fp.fir_numtaps) && cnt_ok(fp.dec_array, fp.dec_numtaps);
+        }
+        for (int i = 0; i < nl && ok; i++)
+            ok = lat[i].num_stages >= 0 && lat[i].num_stages <= 64 && arr_ok(lat[i].k_array, false) && arr_ok(lat[i].v_array, false) &&
+                 cnt_ok(lat[i].k_array, lat[i].num_stages) && cnt_ok(lat[i].v_array, lat[i].num_stages + 1);
+        for (int i = 0; i < ni && ok; i++)
+            ok = interp[i].L >= 0 && interp[i].num_coeffs >= 0 && arr_ok(interp[i].coeff_array, false) && cnt_ok(interp[i].coeff_array, interp[i].num_coeffs);
+        if (ok) {
+            const int ex_arrays[] = { ex->nr_decimate_array, ex->nr_interpolate_array, ex->sqrt_hann_256_array, ex->spectrum_window_array, ex->sam_c0_array,
+                                      ex->sam_c1_array, ex->tx_hilbert_i_array, ex->tx_hilbert_q_array, ex->dds_table_array, ex->zoom_biquad_array, ex->zoom_decim_array };
+            for (int a : ex_arrays) ok = ok && arr_ok(a, true);
+            const int ex_lats[] = { ex->fm_squelch_lattice, ex->tx_lattice_soprano, ex->tx_lattice_tenor, ex->tx_lattice_bass, ex->tx_lattice_fm };
+            for (int l : ex_lats) ok = ok && (l == -1 || (l >= 0 && l < nl));
+        }
+        if (!ok) { if (err) *err = "table blob: cross-index out of range"; return false; }
+    }
     pool.clear();
     pool_off.assign(h->num_arrays, 0);
     for (uint32_t i = 0; i < h->num_arrays; i++) {
-        if ((size_t)arr[i].offset + (size_t)arr[i].count * 4 > bytes) { if (err) *err = "table blob: array out of range"; return false; }
+        if ((arr[i].offset % 4) != 0 || (uint64_t)arr[i].offset + (uint64_t)arr[i].count * 4 > (uint64_t)bytes) { if (err) *err = "table blob: array out of range"; return false; }
         while (pool.size() % 4) pool.push_back(0.0f);
         pool_off[i] = (int)pool.size();
         const float *src = reinterpret_cast<const float *>(b + arr[i].offset);
@@ -405,6 +443,40 @@ int build_chan_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, ChanPara
         p->zoom_dec_off = zd + (p->zoom_m - 1) * 4;
     }
     p->codec_gain_calc = cfg.codec_gain_calc;
+    {
+        // UiSpectrum_CalculateDBm, ui_spectrum.c:2004-2081, for fft_iq_len = 1024 / spec_len = 512 (480x320 layout)
+        const int buff_len_int = 1024;
+        const float buff_len = buff_len_int;
+        const float bin_BW = 48000.0f * 2.0 / (buff_len * (1 << p->zoom_m));
+        float width = t.filt[fp.id].width;
+        float offset = fp.offset_hz;
+        if (offset == 0) offset = width / 2;
+        const float lf_freq = offset - width / 2;
+        const float uf_freq = offset + width / 2;
+        float bw_LOWER = 0.0, bw_UPPER = 0.0;
+        const bool both = mode == UHSDR_DEMOD_AM || (mode == UHSDR_DEMOD_SAM && cfg.sam_sideband == UHSDR_SAM_SIDEBAND_BOTH) || mode == UHSDR_DEMOD_FM;
+        const bool lsb_active = (mode == UHSDR_DEMOD_SAM) ? (cfg.sam_sideband == UHSDR_SAM_SIDEBAND_LSB) : (p->lsb != 0);
+        if (both) { bw_UPPER = uf_freq; bw_LOWER = -uf_freq; }
+        else if (lsb_active) { bw_UPPER = -lf_freq; bw_LOWER = -uf_freq; }
+        else { bw_UPPER = uf_freq; bw_LOWER = lf_freq; }
+        int translate = 0;                                  // AudioDriver_GetTranslateFreq, audio_driver.c:445-464
+        switch (cfg.iq_freq_mode) {
+        case UHSDR_FREQ_IQ_CONV_P6KHZ: translate = 6000; break;
+        case UHSDR_FREQ_IQ_CONV_M6KHZ: translate = -6000; break;
+        case UHSDR_FREQ_IQ_CONV_P12KHZ: translate = 12000; break;
+        case UHSDR_FREQ_IQ_CONV_M12KHZ: translate = -12000; break;
+        default: break;
+        }
+        const int32_t bin_offset = p->zoom_m != 0 ? 0 : (-(buff_len_int * translate) / (2 * 48000));
+        const int32_t posbin = buff_len_int / 4 + bin_offset;
+        float Lbin = (float)posbin + roundf(bw_LOWER / bin_BW);
+        float Ubin = (float)posbin + roundf(bw_UPPER / bin_BW);
+        if (mode == UHSDR_DEMOD_SAM && cfg.sam_sideband == UHSDR_SAM_SIDEBAND_USB) Lbin = Lbin - 1.0;
+        if (Lbin < 0) Lbin = 0;
+        if (Ubin > (512 - 1)) Ubin = 512 - 1;
+        p->dbm_lbin = (int)Lbin; p->dbm_ubin = (int)Ubin;
+        p->dbm_span_hz = (float)(((int)Ubin - (int)Lbin) * bin_BW);
+    }
     return UHSDR_OK;
 }
 

@@ -34,6 +34,7 @@ struct uhsdr_engine {
     ChanState *d_state = nullptr;
     NrState *d_nr = nullptr;
     float *d_spec = nullptr;
+    float *d_spec_avg = nullptr, *d_spec_off = nullptr;      // sd.FFT_AVGData [nch][512], sd.display_offset [nch]
     TxState *d_tx = nullptr;
     TxParams *d_txp = nullptr;
     std::vector<ChanParams> h_params;
@@ -107,12 +108,20 @@ int uhsdr_default_chan_cfg(uhsdr_chan_cfg_t *cfg)
     return UHSDR_OK;
 }
 
+int uhsdr_tables_validate(const void *tables, size_t tables_bytes)
+{
+    HostTables t;
+    std::string err;
+    if (!t.load(tables, tables_bytes, &err)) { g_create_error = err; return UHSDR_ERR_TABLES; }
+    return UHSDR_OK;
+}
+
 int uhsdr_engine_destroy(uhsdr_engine_t *e)
 {
     if (!e) return UHSDR_ERR_ARG;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec);
+    cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec); cudaFree(e->d_spec_avg); cudaFree(e->d_spec_off);
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
     cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_list_split_nr); cudaFree(e->d_scratch);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
@@ -537,6 +546,81 @@ int uhsdr_get_spectrum(uhsdr_engine_t *e, int first, int count, float *mags)
     rc = uhsdr_get_spectrum_device(e, first, count, (float *)e->d_out);
     if (rc != UHSDR_OK) return rc;
     CK(e, cudaMemcpyAsync(mags, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaStreamSynchronize(e->stream));
+    return UHSDR_OK;
+}
+
+// sd.db_scale / sd.agc_rate / the dBm constant from the reference's settings (UiSpectrum_InitSpectrumDisplayData,
+// ui_spectrum.c:955-1083; dB-per-division factors :193-200, :225-237)
+static bool spec_disp_params(const uhsdr_spectrum_display_cfg_t *c, SpecDisp *d)
+{
+    static const float kDbScaling[9] = { 0, 63.2456, 42.1637, 31.6228, 21.0819, 15.8114, 52.7046, 26.3523, 17.5682 };
+    if (!c || c->scope_width < 1 || c->scope_width > UHSDR_SPECTRUM_FFT_LEN || c->spectrum_filter < 1 || c->spectrum_filter > 255 ||
+        c->spectrum_agc_rate < 0 || c->spectrum_agc_rate > 255) return false;
+    int idx = c->spectrum_db_scale;
+    if (idx < 0 || idx >= 9) idx = 3;                       // DB_DIV_ADJUST_DEFAULT, :1023-1026
+    d->db_scale = kDbScaling[idx];
+    if (c->scope_width != UHSDR_SPECTRUM_FFT_LEN) d->db_scale *= (float)c->scope_width / (float)UHSDR_SPECTRUM_FFT_LEN;
+    d->agc_rate = ((float)c->spectrum_agc_rate) / 25;       // SPECTRUM_AGC_SCALING
+    d->filt_factor = 1 / (float)c->spectrum_filter;
+    d->cons = (float)(c->dbm_constant - 225 - 3);
+    d->scope_w = c->scope_width;
+    return true;
+}
+
+int uhsdr_default_spectrum_display_cfg(uhsdr_spectrum_display_cfg_t *cfg)
+{
+    if (!cfg) return UHSDR_ERR_ARG;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(*cfg);
+    cfg->spectrum_db_scale = 3; cfg->spectrum_agc_rate = 25; cfg->spectrum_filter = 4; cfg->dbm_constant = 0;
+    cfg->scope_width = 480;                                 // slayout.scope.w of the 480x320 layout (SPECTRUM_WIDTH_MAX)
+    return UHSDR_OK;
+}
+
+int uhsdr_spectrum_display_device(uhsdr_engine_t *e, int first, int count, const uhsdr_spectrum_display_cfg_t *cfg, float *disp_dev,
+                                  uhsdr_spectrum_level_t *levels_dev, float *avg_dev, float *mags_dev)
+{
+    SpecDisp dc;
+    if (!e || !disp_dev || !levels_dev || first < 0 || count <= 0 || first + count > e->nch || !spec_disp_params(cfg, &dc)) {
+        if (e) e->last_error = "spectrum_display: bad arguments";
+        return UHSDR_ERR_ARG;
+    }
+    if (!e->d_spec) { e->last_error = "spectrum_display: no channel has spectrum_enable set"; return UHSDR_ERR_STATE; }
+    CK(e, cudaSetDevice(e->device));
+    if (!e->d_spec_avg) {
+        const size_t n = (size_t)e->nch;
+        CK(e, cudaMalloc(&e->d_spec_avg, n * 512 * sizeof(float)));
+        CK(e, cudaMemsetAsync(e->d_spec_avg, 0, n * 512 * sizeof(float), e->stream));
+        CK(e, cudaMalloc(&e->d_spec_off, n * sizeof(float)));
+        CK(e, cudaMemsetAsync(e->d_spec_off, 0, n * sizeof(float), e->stream));
+    }
+    static_assert(sizeof(uhsdr_spectrum_level_t) == 3 * sizeof(float), "levels are three packed floats");
+    CK(e, launch_spectrum_display(e->d_params, e->d_state, e->d_spec, e->d_pool, e->tables.off(e->tables.ex->spectrum_window_array), e->tables.tw512_off,
+                                  first, count, dc, e->d_spec_avg, e->d_spec_off, mags_dev, avg_dev, disp_dev, reinterpret_cast<float *>(levels_dev), e->stream));
+    e->launches++;
+    return UHSDR_OK;
+}
+
+int uhsdr_spectrum_display(uhsdr_engine_t *e, int first, int count, const uhsdr_spectrum_display_cfg_t *cfg, float *disp,
+                           uhsdr_spectrum_level_t *levels, float *avg)
+{
+    if (!e || !disp || !levels || !cfg || count <= 0 || cfg->scope_width < 1 || cfg->scope_width > UHSDR_SPECTRUM_FFT_LEN) {
+        if (e) e->last_error = "spectrum_display: bad arguments";
+        return UHSDR_ERR_ARG;
+    }
+    CK(e, cudaSetDevice(e->device));
+    const size_t nd = (size_t)count * (size_t)cfg->scope_width * sizeof(float), nl = (size_t)count * sizeof(uhsdr_spectrum_level_t);
+    const size_t na = avg ? (size_t)count * 512 * sizeof(float) : 0;
+    const size_t o_l = (nd + 255) / 256 * 256, o_a = o_l + (nl + 255) / 256 * 256;
+    int rc = ensure_staging(e, 0, o_a + na, 0);
+    if (rc != UHSDR_OK) return rc;
+    char *base = (char *)e->d_out;
+    rc = uhsdr_spectrum_display_device(e, first, count, cfg, (float *)base, (uhsdr_spectrum_level_t *)(base + o_l), avg ? (float *)(base + o_a) : nullptr, nullptr);
+    if (rc != UHSDR_OK) return rc;
+    CK(e, cudaMemcpyAsync(disp, base, nd, cudaMemcpyDeviceToHost, e->stream));
+    CK(e, cudaMemcpyAsync(levels, base + o_l, nl, cudaMemcpyDeviceToHost, e->stream));
+    if (avg) CK(e, cudaMemcpyAsync(avg, base + o_a, na, cudaMemcpyDeviceToHost, e->stream));
     CK(e, cudaStreamSynchronize(e->stream));
     return UHSDR_OK;
 }

@@ -70,6 +70,18 @@ cudaError_t launch_nr_boot(NrState *nr, int n, cudaStream_t stream);
 cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, const float *spec_ring, const float *pool,
                             int window_off, int twiddle_off, int first, int count, float *mags, cudaStream_t stream);
 
+// UiSpectrum_RedrawSpectrum states 0-4 (spectrum.cu): display settings derived on the host (engine.cu)
+struct SpecDisp {
+    float filt_factor;     // 1 / ts.spectrum_filter, ui_spectrum.c:1434
+    float db_scale;        // sd.db_scale, :1027-1036
+    float agc_rate;        // sd.agc_rate, :988
+    float cons;            // ts.dbm_constant - 225 - 3, :2004
+    int scope_w;           // slayout.scope.w
+};
+cudaError_t launch_spectrum_display(const ChanParams *params, const ChanState *state, const float *spec_ring, const float *pool,
+                                    int window_off, int twiddle_off, int first, int count, const SpecDisp &dc, float *avg_state,
+                                    float *off_state, float *mags_out, float *avg_out, float *disp_out, float *lvl_out, cudaStream_t stream);
+
 // configure: write params for channels [first, first+count) and apply the reference's state
 // reset rules (reset != 0: boot state; 0: AudioDriver_SetProcessingChain semantics)
 cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, float *spec_ring, TxState *tx,

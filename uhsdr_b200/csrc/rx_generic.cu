@@ -454,13 +454,10 @@ rx_generic_kernel(RxArgs a)
 
 template <bool FRONT> static cudaError_t launch_generic(const RxArgs &a, cudaStream_t stream)
 {
-    static bool attr_set = false;
+    // the attribute is per device: set it on every launch (an engine may live on any GPU of the process)
     const size_t smem = sizeof(WarpWork) * G_WARPS;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rx_generic_kernel<FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(rx_generic_kernel<FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     const int grid = (a.num_items + G_WARPS - 1) / G_WARPS;
     if (grid == 0) return cudaSuccess;
     rx_generic_kernel<FRONT><<<grid, 32 * G_WARPS, smem, stream>>>(a);

@@ -80,6 +80,26 @@ constexpr int NTHREADS = 32 * (NWARP_FE + 9);
 constexpr int IT_LAT = V + 5, IT_AGC = V + 6, IT_GAIN = V + 7, IT_BQ = V + 8, IT_POST = V + 9;
 constexpr int PIPE_DEPTH = IT_POST;
 
+// Per-role timing (tools only, -DUHSDR_TC_PROF: `make prof`, scripts/tc_role_times.py): every warp of CTA 0 adds up the
+// cycles between the top of a pipeline iteration and its arrival at the step barrier, for the iterations in which all
+// roles have work (steady state); [warp][0] = work cycles, [1] = iterations counted, [2] = whole iterations (barrier to barrier).
+#ifdef UHSDR_TC_PROF
+__device__ unsigned long long g_tc_prof[32][4];
+__device__ int g_tc_knock;      // knock-out mask (timing experiments only, results wrong): 1 front end, 2 MMAs, 4 decimator epilogue,
+                                // 8 Hilbert epilogue, 16 gain law, 32 lattice, 64 AGC detector, 128 biquads, 256 output
+#define KNOCK(b) ((knock & (b)) != 0)
+#define PROF_DECL long long prof_t0 = 0, prof_work = 0, prof_tot = 0, prof_last = 0; int prof_n = 0
+#define PROF_TOP(it) do { prof_t0 = clock64(); if ((it) > PIPE_DEPTH + 1 && (it) < nsteps - 1 && prof_last) prof_tot += prof_t0 - prof_last; prof_last = prof_t0; } while (0)
+#define PROF_END(it) do { if ((it) > PIPE_DEPTH && (it) < nsteps - 1) { prof_work += clock64() - prof_t0; prof_n++; } } while (0)
+#define PROF_SAVE() do { if (blockIdx.x == 0 && lane == 0) { g_tc_prof[warp][0] = (unsigned long long)prof_work; g_tc_prof[warp][1] = (unsigned long long)prof_n; g_tc_prof[warp][2] = (unsigned long long)prof_tot; } } while (0)
+#else
+#define KNOCK(b) false
+#define PROF_DECL
+#define PROF_TOP(it)
+#define PROF_END(it)
+#define PROF_SAVE()
+#endif
+
 struct Smem {
     alignas(128) unsigned char xring[2][XR_BYTES];    // [I1 | Q1], [I2 | Q2]: bf16 split of the front-end outputs
     alignas(128) unsigned char hring[4][HR_BYTES];    // I1, I2, Q1, Q2: bf16 split of the decimator outputs
@@ -195,6 +215,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
     const int niter = nsteps + PIPE_DEPTH;
     const int s_end = V + nsteps;                      // one past the last real step
     const float *__restrict__ pool = a.pool;
+#ifdef UHSDR_TC_PROF
+    const int knock = g_tc_knock;
+#endif
 
     // ---- one-time setup by all threads: Toeplitz tables, zeroed rings, barriers, TMEM ----
     for (int i = threadIdx.x; i < 2 * HROWS * 16; i += NTHREADS) {
@@ -271,7 +294,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll
         for (int i = 0; i < 4; i++) { pre[i] = active ? __ldg(src + i) : make_int4(0, 0, 0, 0); pre1[i] = active ? __ldg(src + 32 + i) : make_int4(0, 0, 0, 0); }
 
+        PROF_DECL;
         for (int it = 0; it < niter; it++) {
+            PROF_TOP(it);
             if (it == V - 1 && active) {
                 // decimator history x[-96..-1] (82 used) -> the last 96 slots of virtual step V - 1
                 for (int b = rp; b < 96; b += 8) {
@@ -284,7 +309,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (it >= V && it < s_end) {
+            if (it >= V && it < s_end && !KNOCK(1)) {
                 const int t = it - V;
                 // The MMAs of step it - 2 read the ring buffer written now; they were committed one iteration ago.
                 mbar_wait(&sm.bar_dec[it & 1], (unsigned)(((it - 2) >> 1) & 1));
@@ -408,8 +433,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     }
                 }
             }
+            PROF_END(it);
             __syncthreads();
         }
+        PROF_SAVE();
         // ---- store state: decimator history = the last 96 samples of the last step, IQ-correction state ----
         if (active) {
             const int sl = (s_end - 1) & 1;
@@ -449,7 +476,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // The operand fetch of the MMAs saturates shared memory; issued back to back they starve the LDS of the serial warps for
         // the length of the burst.  A short pause after every k-step leaves gaps for them (the MMAs have the whole iteration).
         auto pause = [&]() { const long long t0 = clock64(); while (clock64() - t0 < MMA_PAUSE) { } };
+        PROF_DECL;
         for (int it = 0; it < niter; it++) {
+            PROF_TOP(it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (elect_one()) {
                 const int sd = it - 1;               // step whose samples were written into the decimator ring in the previous iteration
@@ -461,6 +490,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
 #pragma unroll 1
                         for (int j = 0; j < 8; j++) {
+                            if (KNOCK(2)) continue;
                             umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, 1u);
                             pause();
                         }
@@ -470,6 +500,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
 #pragma unroll 1
                         for (int j = 2; j < 8; j++) {
+                            if (KNOCK(2)) continue;
                             umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, j > 2 ? 1u : 0u);
                             pause();
                         }
@@ -487,7 +518,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
 #pragma unroll 1
                             for (int dd = 0; dd < 3; dd++) {
                                 const int oc = oa + dd;                      // output chunk this slab contributes to
-                                if ((dd < 2 || ob >= 3) && oc >= V / 4 && oc <= oc_last) {
+                                if ((dd < 2 || ob >= 3) && oc >= V / 4 && oc <= oc_last && !KNOCK(2)) {
                                     const int kk = u - 8 * oc + 13;
                                     const unsigned d_tmem = tmem + HIL_COL0 + (unsigned)((oc & 3) * 32);
                                     umma3_bf16(d_tmem, ah[0] - 16 * kk, ah[1] - 16 * kk, bh[0] + boff, bh[1] + boff, idesc_h, kk > 0 ? 1u : 0u);
@@ -501,8 +532,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
             }
             __syncwarp();
+            PROF_END(it);
             __syncthreads();
         }
+        PROF_SAVE();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
         return;
@@ -523,7 +556,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             g_inv_max = ap.inv_max_input; g_slope = ap.slope_constant; g_target = ap.out_target; g_fixed = ap.fixed_gain; g_off = ap.mode == 5;
         }
         const int gcol = lane < n_here ? lane : 0;
+        PROF_DECL;
         for (int it = 0; it < niter; it++) {
+            PROF_TOP(it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int sd = it - 2;
             if (sd >= 1 && sd < s_end && (sd & 3) == qd) {
@@ -559,7 +594,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
                     const bool save = i_new >= 2;
 #pragma unroll 1
-                    for (int gq = 0; gq < FG / 4; gq++) {         // 4 channels per pass (rolled: the instruction cache is the scarce resource)
+                    for (int gq = 0; gq < (KNOCK(4) ? 0 : FG / 4); gq++) {         // 4 channels per pass (rolled: the instruction cache is the scarce resource)
                         unsigned vi[4], vq[4];
                         TMEM_LD_X4(vi, taddr + (unsigned)(4 * gq));
                         TMEM_LD_X4(vq, taddr + (unsigned)(32 + 4 * gq));
@@ -584,7 +619,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
             }
             const int sh = it - 4;
-            if (sh >= V && sh < s_end && (sh & 3) == qd) {
+            if (sh >= V && sh < s_end && (sh & 3) == qd && !KNOCK(8)) {
                 // ---- Hilbert outputs of step sh leave TMEM: lane = decimated sample, column = channel ----
                 mbar_wait(&sm.bar_hil[sh & 1], (unsigned)((sh >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -602,7 +637,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             {
                 const int c = it - IT_GAIN;
                 const int k1 = (qd - it - 1) & 3;                       // 0: first half, 2: second half, 1 / 3: busy with an epilogue
-                if (c >= 0 && c < nsteps && !(k1 & 1)) {
+                if (c >= 0 && c < nsteps && !(k1 & 1) && !KNOCK(16)) {
                     const int i0 = k1 * 8;
                     const float *vin = sm.agc[c & 1] + gcol;
                     float *out = sm.gq[c & 1] + gcol;
@@ -639,8 +674,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            PROF_END(it);
             __syncthreads();
         }
+        PROF_SAVE();
         return;
     }
 
@@ -663,9 +700,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             s[j] = (j >= pad) ? st->pre_s[j - pad] : 0.0f;
         }
         v[10] = (n > 0) ? __ldg(pool + p.pre.v_off + n) : 1.0f;
+        PROF_DECL;
         for (int t = 0; t < niter; t++) {
+            PROF_TOP(t);
             const int c = t - IT_LAT;
-            if (c >= 0 && c < nsteps) {
+            if (c >= 0 && c < nsteps && !KNOCK(32)) {
                 const float *in = sm.aud[c & 1];
                 float *out = sm.lat + (c % 5) * ND * SMS;
                 // Two samples per loop iteration: the loop body (~80 instructions) then stays resident in the 6 KB level-0
@@ -705,8 +744,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     }
                 }
             }
+            PROF_END(t);
             __syncthreads();
         }
+        PROF_SAVE();
         if (active) {
 #pragma unroll
             for (int j = 0; j < 10; j++) if (j >= pad) st->pre_s[j - pad] = s[j];
@@ -749,9 +790,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         }
         __syncwarp();
         const bool any_hang = __any_sync(0xffffffffu, active && (ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0));
+        PROF_DECL;
         for (int t = 0; t < niter; t++) {
+            PROF_TOP(t);
             const int c = t - IT_AGC;
-            if (c >= 0 && c < nsteps && active && ap.mode != 5) {
+            if (c >= 0 && c < nsteps && active && ap.mode != 5 && !KNOCK(64)) {
                 const int row0 = (c % 5) * ND;                  // ring row of the first sample of this step
                 const float *in = latp + row0 * SMS;
                 float *out = sm.agc[c & 1] + g;
@@ -867,8 +910,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     const int tmp = s1; s1 = s2; s2 = tmp;
                 }
             }
+            PROF_END(t);
             __syncthreads();
         }
+        PROF_SAVE();
         if (active && ap.mode != 5) {
             const long long T = (long long)nsteps * ND;
             int new_in = (int)(((long long)st->agc_in_index + T) % AGC_RB);
@@ -937,16 +982,20 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             }
         };
         if (skipmask != 0xbu) skipmask = 0;      // only the default plan (bass shelf alone) has a specialised loop
+        PROF_DECL;
         for (int t = 0; t < niter; t++) {
+            PROF_TOP(t);
             const int c = t - IT_BQ;
-            if (c >= 0 && c < nsteps && active) {
+            if (c >= 0 && c < nsteps && active && !KNOCK(128)) {
                 const float *in = sm.gq[c & 1] + g;
                 float *out = sm.bq[c & 1] + g;
                 if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out);
                 else run_step(std::integral_constant<unsigned, 0u>{}, in, out);
             }
+            PROF_END(t);
             __syncthreads();
         }
+        PROF_SAVE();
         if (active) {
             // a skipped (pass-through) stage saw the output of the nearest computed stage before it
             float s1v = xl1, s2v = xl2;
@@ -1063,9 +1112,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
             }
         };
+        PROF_DECL;
         for (int t = 0; t < niter; t++) {
+            PROF_TOP(t);
             const int c = t - IT_POST;
-            if (c >= 0 && c < nsteps && active) {
+            if (c >= 0 && c < nsteps && active && !KNOCK(256)) {
                 const float *in = sm.bq[c & 1] + g;
 #pragma unroll
                 for (int i = 0; i < 2; i++) { nx[0][i] = in[i * SMS]; nx[1][i] = in[(2 + i) * SMS]; }
@@ -1080,8 +1131,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                     else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
                 }
             }
+            PROF_END(t);
             __syncthreads();
         }
+        PROF_SAVE();
         if (active) {
             for (int q = 0; q < INTERP_HIST - 3; q++) st->interp_hist[q] = 0.0f;
 #pragma unroll
@@ -1113,6 +1166,16 @@ cudaError_t launch_rx_ssb_tc(const RxArgs &a, int dec_c, int hil_ci, int hil_cq,
 bool rx_ssb_tc_available() { return true; }
 
 }  // namespace uhsdr
+
+#ifdef UHSDR_TC_PROF
+// tools only (libuhsdr_b200_prof.so): read the role timers of the last launch, set the knock-out mask of the next ones
+extern "C" int uhsdr_debug_tc_prof(unsigned long long *out, int knock)
+{
+    if (out && cudaMemcpyFromSymbol(out, uhsdr::g_tc_prof, sizeof(unsigned long long) * 32 * 4) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(uhsdr::g_tc_knock, &knock, sizeof(int)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
 
 #else   // UHSDR_EXACT: reference-order arithmetic has no tensor-core form
 

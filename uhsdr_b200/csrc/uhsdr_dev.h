@@ -87,6 +87,10 @@ struct ChanParams {
     int zoom_bq_off;       // pool offset of mag_coeffs[zoom_m] (4 stages x {b0, b1, b2, a1, a2})
     int zoom_dec_off;      // pool offset of FirZoomFFTDecimate[zoom_m].pCoeffs (4 taps)
     float codec_gain_calc;
+    // UiSpectrum_CalculateDBm (ui_spectrum.c:1990-2122): passband bins [dbm_lbin, dbm_ubin] of the frequency-ordered spectrum
+    // and the bandwidth ((int)Ubin - (int)Lbin) * bin_BW the dBm/Hz figure is referred to
+    int dbm_lbin, dbm_ubin;
+    float dbm_span_hz;
     // LMS automatic notch (audio_driver.c:1165-1187, :2443-2456)
     int notch_enable;
     float notch_mu;        // log10f((ts.dsp.notch_mu + 1.0) / 1500.0 + 1.0)

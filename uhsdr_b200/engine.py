@@ -15,7 +15,7 @@ import os
 
 import numpy as np
 
-from .config import BLOCK_SIZE, ChanCfg, ChanStatus
+from .config import BLOCK_SIZE, ChanCfg, ChanStatus, SpectrumDisplayCfg, SpectrumLevel
 from .tables import DEFAULT_BLOB
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -31,6 +31,7 @@ EXPORTS = [
     "uhsdr_configure_channels", "uhsdr_configure_channel", "uhsdr_configure_channels_strided", "uhsdr_rx_process", "uhsdr_rx_process_device",
     "uhsdr_tx_process", "uhsdr_tx_process_device", "uhsdr_engine_sync", "uhsdr_engine_stream",
     "uhsdr_get_spectrum", "uhsdr_get_spectrum_device", "uhsdr_get_status", "uhsdr_engine_launch_count",
+    "uhsdr_tables_validate", "uhsdr_default_spectrum_display_cfg", "uhsdr_spectrum_display", "uhsdr_spectrum_display_device",
 ]
 
 _libs: dict[str, ctypes.CDLL] = {}
@@ -60,6 +61,7 @@ def load_library(exact: bool = False) -> ctypes.CDLL:
     L.uhsdr_default_chan_cfg.argtypes = [ctypes.POINTER(ChanCfg)]
     L.uhsdr_engine_create.argtypes = [ctypes.POINTER(vp), ci, ci, vp, ctypes.c_size_t]
     L.uhsdr_engine_destroy.argtypes = [vp]
+    L.uhsdr_tables_validate.argtypes = [vp, ctypes.c_size_t]
     L.uhsdr_engine_num_channels.argtypes = [vp]
     L.uhsdr_configure_channels.argtypes = [vp, ci, ci, ctypes.POINTER(ChanCfg), ci]
     L.uhsdr_configure_channel.argtypes = [vp, ci, ctypes.POINTER(ChanCfg), ci]
@@ -74,6 +76,9 @@ def load_library(exact: bool = False) -> ctypes.CDLL:
     L.uhsdr_get_spectrum.argtypes = [vp, ci, ci, vp]
     L.uhsdr_get_spectrum_device.argtypes = [vp, ci, ci, vp]
     L.uhsdr_get_status.argtypes = [vp, ci, ci, ctypes.POINTER(ChanStatus)]
+    L.uhsdr_default_spectrum_display_cfg.argtypes = [ctypes.POINTER(SpectrumDisplayCfg)]
+    L.uhsdr_spectrum_display.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp]
+    L.uhsdr_spectrum_display_device.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp, vp]
     L.uhsdr_engine_launch_count.restype = ctypes.c_int64
     L.uhsdr_engine_launch_count.argtypes = [vp]
     _libs[path] = L
@@ -157,6 +162,16 @@ class Engine:
         mags = np.empty((count, 512), dtype=np.float32)
         self._check(self._lib.uhsdr_get_spectrum(self._h, first, count, mags.ctypes.data))
         return mags
+
+    def spectrum_display(self, dc: SpectrumDisplayCfg, first: int = 0, count: int | None = None):
+        """UiSpectrum_RedrawSpectrum states 0-4: (disp [count, scope_width], levels [count, 3] = dBm, dBm/Hz, display offset,
+        avg [count, 512])."""
+        count = self.num_channels - first if count is None else count
+        disp = np.empty((count, dc.scope_width), dtype=np.float32)
+        lvl = np.empty((count, 3), dtype=np.float32)
+        avg = np.empty((count, 512), dtype=np.float32)
+        self._check(self._lib.uhsdr_spectrum_display(self._h, first, count, ctypes.byref(dc), disp.ctypes.data, lvl.ctypes.data, avg.ctypes.data))
+        return disp, lvl, avg
 
     def status(self, first: int = 0, count: int | None = None) -> list[ChanStatus]:
         count = self.num_channels - first if count is None else count

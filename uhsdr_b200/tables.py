@@ -14,8 +14,7 @@ import numpy as np
 
 MAGIC = 0x42545355
 VERSION = 2
-DEFAULT_BLOB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                            "tests", "golden", "uhsdr_tables.bin")
+DEFAULT_BLOB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "uhsdr_tables.bin")
 
 FILTER_MODE_CW, FILTER_MODE_SSB, FILTER_MODE_AM, FILTER_MODE_FM, FILTER_MODE_SAM = range(5)
 
