@@ -18,7 +18,7 @@ import uhsdr_b200.engine as E                                      # noqa: E402
 E.LIB_FAST = os.path.join(ROOT, "uhsdr_b200", "csrc", "libuhsdr_b200_prof.so")
 from uhsdr_b200.config import DEMOD_LSB, default_cfg               # noqa: E402
 
-ROLES = ["fe0", "fe1", "fe2", "fe3", "fe4", "fe5", "fe6", "mma", "epi0", "epi1", "epi2", "epi3", "agc", "post", "lat", "bq"]
+ROLES = ["fe0", "fe1", "fe2", "fe3", "fe4", "fe5", "fe6", "mma", "epi0", "epi1", "epi2", "epi3", "agc", "postB", "lat", "postA", "bq"]
 KNOCKS = {1: "front end", 2: "MMAs", 4: "dec epilogue", 8: "hil epilogue", 16: "gain law", 32: "lattice", 64: "AGC", 128: "biquads", 256: "output"}
 
 
@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--channels", type=int, default=4096)
     ap.add_argument("--blocks", type=int, default=400)
     ap.add_argument("--masks", default="0,1,2,4,8,16,32,64,128,256,3,15,31,479,447,255")
+    ap.add_argument("--pauses", default="-1", help="MMA issue pause overrides (cycles) to sweep, -1 = built-in")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(1)
@@ -39,7 +40,9 @@ def main():
     eng.configure(default_cfg(dmod_mode=DEMOD_LSB, filter_path=38), first=1, stride=2)
     ext = torch.cuda.ExternalStream(eng.stream, device=dev)
     buf = (ctypes.c_ulonglong * 128)()
-    for mask in [int(m) for m in a.masks.split(",")]:
+    runs = [(int(m), int(pz)) for pz in a.pauses.split(",") for m in a.masks.split(",")]
+    for mask, pz in runs:
+        assert lib.uhsdr_debug_tc_pause(pz) == 0
         assert lib.uhsdr_debug_tc_prof(None, mask) == 0
         with torch.cuda.stream(ext):
             for _ in range(2):
@@ -54,10 +57,10 @@ def main():
         ms = e0.elapsed_time(e1) / 3
         assert lib.uhsdr_debug_tc_prof(buf, mask) == 0
         v = np.array(list(buf), dtype=np.float64).reshape(32, 4)
-        per = {ROLES[w]: round(v[w, 0] / max(v[w, 1], 1)) for w in range(16)}
+        per = {ROLES[w]: round(v[w, 0] / max(v[w, 1], 1)) for w in range(len(ROLES))}
         step = round(v[0, 2] / max(v[0, 1] - 1, 1))
         off = [KNOCKS[b] for b in KNOCKS if mask & b]
-        print(json.dumps({"knocked_out": off, "ms": round(ms, 4), "chsamp_per_s": a.channels * a.blocks * 32 / (ms * 1e-3),
+        print(json.dumps({"knocked_out": off, "mma_pause": pz, "ms": round(ms, 4), "chsamp_per_s": a.channels * a.blocks * 32 / (ms * 1e-3),
                           "cycles_per_step": step, "work_cycles_per_step": per}), flush=True)
     eng.close()
 

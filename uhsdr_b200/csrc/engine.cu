@@ -318,7 +318,7 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
         // the tensor-core kernel stores 32-byte vectors; rows are nblocks*256 bytes apart, so only the base matters
-        const bool tc_ok = e->use_tc && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 16 == 0) && (chan_stride % 4 == 0);
+        const bool tc_ok = e->use_tc && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 32 == 0) && (chan_stride % 4 == 0);
         if (nblocks % 4 == 0 && tc_ok) CK(e, launch_rx_ssb_tc(a, e->fused_s1_ci, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
         else if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
         else CK(e, launch_rx_generic(a, stream));

@@ -52,13 +52,13 @@ constexpr int ND = 32;             // decimated samples per step
 constexpr int SMS = 29;            // channel-minor stride of the serial-stage queues (odd: conflict free)
 constexpr int AGC_W = 49;          // attack_buffsize at 12 ksps (audio_agc.c:290)
 constexpr int LR = 5 * ND;          // rows of the lattice-output ring (decimated samples)
-constexpr int AG = 2;              // AGC samples per loop iteration (short body: level-0 instruction cache)              // AGC samples per group (operands loaded together, detector serial, gain law parallel)
+constexpr int AG = 2;              // AGC samples per loop iteration (short body: level-0 instruction cache)
 constexpr int NWARP_FE = FG / 4;
 // tensor-core FIRs
 constexpr int V = 8;               // virtual steps in front of the first real one: they carry the filter histories in
 constexpr int XSLOTS = 2 * CH4;    // decimator input ring: two steps
-constexpr int XLBO = 160;          // byte stride between time groups: 128-byte core matrix + 32 bytes, so that the front-end stores (2 time
-                                   // groups apart between neighbouring lane groups) and the 4 channels of a warp tile one 128-byte bank row
+constexpr int XLBO = 144;          // byte stride between time groups: 128-byte core matrix + 16 bytes, so that the front-end's 8-byte stores of a
+                                   // half-warp (4 channels x two halves of a row, in two time groups 4 apart) tile one 128-byte bank row
 constexpr int XSBO = (XSLOTS / 8) * XLBO;
 constexpr int XR_BYTES = 8 * XSBO;                 // one array: [I groups 0..3 | Q groups 0..3][time/8][channel%8][time%8] bf16
 constexpr int HSLOTS = 2 * ND;     // Hilbert input ring: two steps
@@ -67,11 +67,14 @@ constexpr int HSBO = (HSLOTS / 8) * HLBO;
 constexpr int HR_BYTES = 4 * HSBO;                 // one array: [channel group 0..3][time/8][channel%8][time%8] bf16
 constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
 constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
-constexpr int MMA_PAUSE = 120;        // cycles between k-steps of the MMA issue (sweep: profiles/r01_tc2_experiments.txt)
+constexpr int MMA_PAUSE = 60;         // cycles between k-steps of the MMA issue (sweeps: profiles/r01_tc2_experiments.txt, r02_tc_experiments.txt)
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
-constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_LAT = NWARP_FE + 7, W_BQ = NWARP_FE + 8;   // NWARP_FE + 6: the output warp
-constexpr int NTHREADS = 32 * (NWARP_FE + 9);
+// scheduler 0: front end 0, 4 | epilogue 0 | AGC detector | biquads      1: front end 1, 5 | epilogue 1 | output B
+//           2: front end 2, 6 | epilogue 2 | lattice                     3: front end 3 | MMA issue | epilogue 3 | output A
+constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POSTB = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_POSTA = NWARP_FE + 8,
+              W_BQ = NWARP_FE + 9;
+constexpr int NTHREADS = 32 * (NWARP_FE + 10);
 // software pipeline, in steps of 128 input samples.  Step s (virtual steps included) is written into the decimator
 // ring at iteration s, its decimator MMAs are issued at s + 1, the decimator outputs leave TMEM for the Hilbert ring
 // at s + 2, the Hilbert MMAs are issued at s + 3, the Hilbert outputs leave TMEM at s + 4, then lattice s + 5,
@@ -85,6 +88,7 @@ constexpr int PIPE_DEPTH = IT_POST;
 // roles have work (steady state); [warp][0] = work cycles, [1] = iterations counted, [2] = whole iterations (barrier to barrier).
 #ifdef UHSDR_TC_PROF
 __device__ unsigned long long g_tc_prof[32][4];
+__device__ int g_tc_pause = -1;  // MMA issue pause override (cycles), -1 = MMA_PAUSE
 __device__ int g_tc_knock;      // knock-out mask (timing experiments only, results wrong): 1 front end, 2 MMAs, 4 decimator epilogue,
                                 // 8 Hilbert epilogue, 16 gain law, 32 lattice, 64 AGC detector, 128 biquads, 256 output
 #define KNOCK(b) ((knock & (b)) != 0)
@@ -109,7 +113,7 @@ struct Smem {
     float lat[LR * SMS];              // lattice output, a ring of 5 steps: AGC detector and gain stage read x[n-49] from it
     float agc[2][ND * SMS];           // AGC "volts" per sample (detector -> gain stage)
     float gq[2][ND * SMS];            // delayed sample x gain (gain stage -> biquad cascade)
-    float bq[2][ND * SMS];
+    float bq[2][(3 + ND) * SMS];      // biquad output: rows 0..2 = the last three samples of the previous step (interpolator history), then the step
     float smax[2][ND * SMS];
     int chan[32];                     // channel index of every slot (epilogue warps: state save / restore)
     alignas(8) unsigned long long bar_dec[2], bar_hil[2];
@@ -266,10 +270,13 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // A 128-sample step is done in two passes of 64 samples (two 32-sample blocks); in a pass lane slot r owns the 8
         // consecutive samples 8r .. 8r+7, i.e. a quarter of block r >> 2.  (Two short passes instead of one long one: half the
         // instructions in the loop body -- the instruction cache is the scarce resource of this kernel.)
-        // lane = 4 r' + cl with r = r' with its two low bits swapped: the lanes of a quarter-warp then hold 4 channels x two
-        // time groups 2 apart, which tile one conflict-free 128-byte bank row of the ring (time-group stride 160 B).
+        // A pass is two 32-sample blocks; lane = cl + 4 rp with rp = q_lo + 2 h + 4 q_hi: the lane works on block h and owns its
+        // samples 16 j + 4 q .. + 3 (q = q_lo + 2 q_hi; j = 0, 1: one 32-byte load each).  The 8 lanes of a channel then read 256
+        // contiguous bytes per load instruction (two full 128-byte lines instead of eight quarter-used ones: the load / store
+        // data path is the busiest unit of this kernel), and the 16 lanes of a half-warp (q_hi fixed) store 4 channels x two
+        // row halves in two time groups 4 apart = one conflict-free 128-byte bank row of the ring (time-group stride 144 B).
         const int cl = lane & 3, rp = lane >> 2;
-        const int r = (rp & 4) | ((rp & 1) << 1) | ((rp >> 1) & 1);
+        const int q_lo = rp & 1, hb = (rp >> 1) & 1, q_hi = rp >> 2;
         const int g = warp * 4 + cl;                   // channel slot in the CTA
         const bool active = g < n_here;
         const int ch = active ? a.chan_list[cta_first + g] : a.chan_list[cta_first];
@@ -287,12 +294,21 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const bool fast_fe = __all_sync(0xffffffffu, iq_auto != 0 && shift_kind == 1);
         const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
         const size_t chan_base = (size_t)ch * (size_t)a.chan_stride;
-        const int4 *__restrict__ src = reinterpret_cast<const int4 *>(reinterpret_cast<const int2 *>(a.iq) + chan_base) + 4 * r;
-
-        // input prefetch: 2 x 4 x int4 = the 8 samples of either pass of the next step, straight from global memory into registers
+        // the lane's first sample: block hb of pass 0, sample 4 q of the block
+        const int2 *__restrict__ src = reinterpret_cast<const int2 *>(a.iq) + chan_base + 32 * hb + 4 * (q_lo + 2 * q_hi);
+        auto ld256 = [](int4 &lo, int4 &hi, const int2 *ptr) {
+            asm volatile("ld.global.nc.v8.s32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(ptr));
+        };
+        // input prefetch: 2 x 2 x 32 bytes = the 8 samples of either pass of the next step, straight from global memory into registers
+        // (pre[2 j], pre[2 j + 1] = samples 16 j + 4 q .. + 3 of the block)
         int4 pre[4], pre1[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { pre[i] = active ? __ldg(src + i) : make_int4(0, 0, 0, 0); pre1[i] = active ? __ldg(src + 32 + i) : make_int4(0, 0, 0, 0); }
+        for (int i = 0; i < 4; i++) { pre[i] = make_int4(0, 0, 0, 0); pre1[i] = make_int4(0, 0, 0, 0); }
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) { ld256(pre[2 * j], pre[2 * j + 1], src + 16 * j); ld256(pre1[2 * j], pre1[2 * j + 1], src + 64 + 16 * j); }
+        }
 
         PROF_DECL;
         for (int it = 0; it < niter; it++) {
@@ -343,21 +359,21 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             s1 += __uint_as_float(__float_as_uint(fq[k]) ^ (__float_as_uint(fi[k]) & 0x80000000u));
                             s2 += fabsf(fi[k]); s3 += fabsf(fq[k]);
                         }
-                        // the four lanes of a block: slots r & 3 = lane bits 2, 3
+                        // the four lanes of a block: q_lo, q_hi = lane bits 2, 4
                         s1 += __shfl_xor_sync(0xffffffffu, s1, 4); s2 += __shfl_xor_sync(0xffffffffu, s2, 4); s3 += __shfl_xor_sync(0xffffffffu, s3, 4);
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8); s3 += __shfl_xor_sync(0xffffffffu, s3, 8);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16); s3 += __shfl_xor_sync(0xffffffffu, s3, 16);
                         // first-order low-pass over the two blocks of the pass (:2281-2283), then M_c1 / M_c2 (:2285-2295) of the own block
                         float t1 = ls.te1, t2 = ls.te2, t3 = ls.te3, m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
                         const float kE = 0.003f * 0.03125f * kS;
                         float bs1[2], bs2[2], bs3[2];
 #pragma unroll
                         for (int b = 0; b < 2; b++) {
-                            bs1[b] = __shfl_sync(0xffffffffu, s1, 16 * b + cl); bs2[b] = __shfl_sync(0xffffffffu, s2, 16 * b + cl); bs3[b] = __shfl_sync(0xffffffffu, s3, 16 * b + cl);
+                            bs1[b] = __shfl_sync(0xffffffffu, s1, 8 * b + cl); bs2[b] = __shfl_sync(0xffffffffu, s2, 8 * b + cl); bs3[b] = __shfl_sync(0xffffffffu, s3, 8 * b + cl);
                         }
 #pragma unroll
                         for (int b = 0; b < 2; b++) {
                             t1 = fmaf(0.997f, t1, -kE * bs1[b]); t2 = fmaf(0.997f, t2, kE * bs2[b]); t3 = fmaf(0.997f, t3, kE * bs3[b]);
-                            if ((r >> 2) == b) { m1 = t1; m2 = t2; m3 = t3; }
+                            if (hb == b) { m1 = t1; m2 = t2; m3 = t3; }
                         }
                         const float den = m2 * m2;
                         const float hlp = (den > 0.0f) ? __fdividef(fmaf(m3, m3, -m1 * m1), den) : den;
@@ -365,7 +381,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             ls.te1 = t1; ls.te2 = t2; ls.te3 = t3;
                             c1m = (m2 != 0.0f) ? __fdividef(m1, m2) : 0.0f;
                             c2m = (hlp > 0.0f) ? hlp * rsqrtf(hlp) : 1.0f;
-                            ls.c1 = c1m; ls.c2 = c2m;                            // after the second pass, slots 4..7 hold the block-3 values the state keeps
+                            ls.c1 = c1m; ls.c2 = c2m;                            // after the second pass, the lanes of block 1 hold the block-3 values the state keeps
                         }
                     }
                     if (fast_fe) {
@@ -405,7 +421,8 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             fi[k] = vi; fq[k] = vq;
                         }
                     }
-                    // ---- bf16 split, decimator ring: slots 64 h + 8 r .. +7 of buffer it & 1 = one 16-byte row per array
+                    // ---- bf16 split, decimator ring: samples 16 j + 4 q .. + 3 of block hb of pass h of buffer it & 1 = half a 16-byte
+                    // row (time group 8 h + 4 hb + 2 j + q_hi, bytes 8 q_lo .. + 7) per array and j
                     {
                         unsigned wi1[4], wi2[4], wq1[4], wq2[4];
 #pragma unroll
@@ -413,11 +430,14 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             split_pack2(fi[2 * k], fi[2 * k + 1], wi1[k], wi2[k]);
                             split_pack2(fq[2 * k], fq[2 * k + 1], wq1[k], wq2[k]);
                         }
-                        const int bo = ((it & 1) * (CH4 / 8) + 8 * h + r) * XLBO;
-                        *reinterpret_cast<uint4 *>(xi1 + bo) = make_uint4(wi1[0], wi1[1], wi1[2], wi1[3]);
-                        *reinterpret_cast<uint4 *>(xi2 + bo) = make_uint4(wi2[0], wi2[1], wi2[2], wi2[3]);
-                        *reinterpret_cast<uint4 *>(xq1 + bo) = make_uint4(wq1[0], wq1[1], wq1[2], wq1[3]);
-                        *reinterpret_cast<uint4 *>(xq2 + bo) = make_uint4(wq2[0], wq2[1], wq2[2], wq2[3]);
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const int bo = ((it & 1) * (CH4 / 8) + 8 * h + 4 * hb + 2 * j + q_hi) * XLBO + 8 * q_lo;
+                            *reinterpret_cast<uint2 *>(xi1 + bo) = make_uint2(wi1[2 * j], wi1[2 * j + 1]);
+                            *reinterpret_cast<uint2 *>(xi2 + bo) = make_uint2(wi2[2 * j], wi2[2 * j + 1]);
+                            *reinterpret_cast<uint2 *>(xq1 + bo) = make_uint2(wq1[2 * j], wq1[2 * j + 1]);
+                            *reinterpret_cast<uint2 *>(xq2 + bo) = make_uint2(wq2[2 * j], wq2[2 * j + 1]);
+                        }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // visible to the tensor core after the step barrier
@@ -425,12 +445,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 // consumed after the step barrier, where this warp waits for the slower roles anyway (both passes: a load issued
                 // inside the step does not arrive in time for its second pass)
                 if (t + 1 < nsteps && active) {
-                    const int4 *nx = src + (size_t)(t + 1) * 64;
+                    const int2 *nx = src + (size_t)(t + 1) * CH4;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre[i].x), "=r"(pre[i].y), "=r"(pre[i].z), "=r"(pre[i].w) : "l"(nx + i));
-                        asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(pre1[i].x), "=r"(pre1[i].y), "=r"(pre1[i].z), "=r"(pre1[i].w) : "l"(nx + 32 + i));
-                    }
+                    for (int j = 0; j < 2; j++) { ld256(pre[2 * j], pre[2 * j + 1], nx + 16 * j); ld256(pre1[2 * j], pre1[2 * j + 1], nx + 64 + 16 * j); }
                 }
             }
             PROF_END(it);
@@ -440,7 +457,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // ---- store state: decimator history = the last 96 samples of the last step, IQ-correction state ----
         if (active) {
             const int sl = (s_end - 1) & 1;
-            for (int b = r; b < 96; b += 8) {
+            for (int b = rp; b < 96; b += 8) {
                 const int off = sl * CH4 + 32 + b;
                 const int bo = (off >> 3) * XLBO + (off & 7) * 2;
                 const unsigned i1 = *reinterpret_cast<const unsigned short *>(xi1 + bo), i2 = *reinterpret_cast<const unsigned short *>(xi2 + bo);
@@ -449,7 +466,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 st->s1_hist_q[b] = join_bf16(q1, q2);
             }
             int clip = ls.clip;
-            ls.c1 = __shfl_sync(gmask, ls.c1, 16 + cl); ls.c2 = __shfl_sync(gmask, ls.c2, 16 + cl);
+            ls.c1 = __shfl_sync(gmask, ls.c1, 8 + cl); ls.c2 = __shfl_sync(gmask, ls.c2, 8 + cl);
             clip |= __shfl_xor_sync(gmask, clip, 4); clip |= __shfl_xor_sync(gmask, clip, 8); clip |= __shfl_xor_sync(gmask, clip, 16);
             if (rp == 0) {
                 st->teta1_old = ls.te1; st->teta2_old = ls.te2; st->teta3_old = ls.te3; st->M_c1 = ls.c1; st->M_c2 = ls.c2;
@@ -475,7 +492,12 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         const int oc_last = (s_end - 1) >> 2;
         // The operand fetch of the MMAs saturates shared memory; issued back to back they starve the LDS of the serial warps for
         // the length of the burst.  A short pause after every k-step leaves gaps for them (the MMAs have the whole iteration).
-        auto pause = [&]() { const long long t0 = clock64(); while (clock64() - t0 < MMA_PAUSE) { } };
+#ifdef UHSDR_TC_PROF
+        const int mma_pause = g_tc_pause >= 0 ? g_tc_pause : MMA_PAUSE;
+#else
+        constexpr int mma_pause = MMA_PAUSE;
+#endif
+        auto pause = [&]() { if (mma_pause > 0) { const long long t0 = clock64(); while (clock64() - t0 < mma_pause) { } } };
         PROF_DECL;
         for (int it = 0; it < niter; it++) {
             PROF_TOP(it);
@@ -952,6 +974,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         }
         const float scale_gain = p.scale_gain;
         float xl1 = 0.0f, xl2 = 0.0f;        // the last two cascade inputs (state of skipped leading stages)
+        float yl[3];                         // the last three cascade outputs: the interpolator's history (arm_fir_interpolate_f32 state)
+#pragma unroll
+        for (int q = 0; q < 3; q++) yl[q] = st->interp_hist[INTERP_HIST - 3 + q];
         // one step of 32 samples with the skipped stages known at compile time
         auto run_step = [&](auto maskc, const float *in, float *out) {
             constexpr unsigned MASK = decltype(maskc)::value;
@@ -979,6 +1004,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) out[(i0 + i) * SMS] = xv[i];
+                yl[0] = xv[5]; yl[1] = xv[6]; yl[2] = xv[7];
             }
         };
         if (skipmask != 0xbu) skipmask = 0;      // only the default plan (bass shelf alone) has a specialised loop
@@ -988,7 +1014,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             const int c = t - IT_BQ;
             if (c >= 0 && c < nsteps && active && !KNOCK(128)) {
                 const float *in = sm.gq[c & 1] + g;
-                float *out = sm.bq[c & 1] + g;
+                float *out = sm.bq[c & 1] + 3 * SMS + g;
+#pragma unroll
+                for (int q = 0; q < 3; q++) out[(q - 3) * SMS] = yl[q];
                 if (skipmask == 0xbu) run_step(std::integral_constant<unsigned, 0xbu>{}, in, out);
                 else run_step(std::integral_constant<unsigned, 0u>{}, in, out);
             }
@@ -1009,7 +1037,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         return;
     }
 
-    // warp == W_POST: x4 interpolator (:2560-2577), anti-alias lattice (:2581-2583, 6 stages, some paths), treble biquad
+    // W_POSTA / W_POSTB: x4 interpolator (:2560-2577), anti-alias lattice (:2581-2583, 6 stages, some paths), treble biquad
     // (:2832), x10, output formatting (:2845-2941), straight to global memory: 32 bytes (4 output samples) per channel
     // and decimated sample.
     {
@@ -1055,6 +1083,15 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         float nx[2][2];                       // the inputs of the next two loop iterations, fetched from the queue ahead of their use
         // the lean variant: no anti-alias lattice, unity treble, no mute array, no float copy (same arithmetic, fewer instructions)
         const bool lean = plain && !any_aa && tr_unity;
+        // The lean variant has no recurrence left (the interpolator is a FIR), so its lanes need not be channels.  When every
+        // channel of the CTA also uses the same interpolator (there is one per decimation factor among the paths without an
+        // anti-alias filter), the two output warps turn the step around: LANE = DECIMATED SAMPLE, one channel after the other
+        // (W_POSTA the even slots, W_POSTB the odd ones).  A warp store is then 1 KB of one channel's row -- eight full
+        // 128-byte lines -- instead of 28 separate 32-byte sectors in 28 rows, which is what keeps the load/store data path,
+        // the busiest unit of this kernel, free for the other roles.  Otherwise W_POSTA runs one channel per lane.
+        const bool postB = warp == W_POSTB;
+        const int ic0 = __shfl_sync(0xffffffffu, p.interp_c, 0), P0 = __shfl_sync(0xffffffffu, P, 0);
+        const bool tlean = lean && __all_sync(0xffffffffu, !active || (p.interp_c == ic0 && P == P0));
         auto run_block = [&](auto aac, auto trc, auto plainc, const float *in, int blk, int4 *d4, float4 *df, bool muted) {
             constexpr bool AA = decltype(aac)::value, TR = decltype(trc)::value, PLAIN = decltype(plainc)::value;
             const int mm = (!PLAIN && muted) ? 0 : -1;    // external_mute: zeros out, all state advanced (:2845-2853)
@@ -1116,26 +1153,68 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         for (int t = 0; t < niter; t++) {
             PROF_TOP(t);
             const int c = t - IT_POST;
-            if (c >= 0 && c < nsteps && active && !KNOCK(256)) {
-                const float *in = sm.bq[c & 1] + g;
+            if (c >= 0 && c < nsteps && tlean && !KNOCK(256)) {
+                // lane = decimated sample: rows lane .. lane + 3 of the queue are x[n-3] .. x[n]
+                const float *col = sm.bq[c & 1] + lane * SMS;
+                int2 *const obase = reinterpret_cast<int2 *>(a.audio) + ((size_t)c * CH4 + 4 * lane);
+                const bool last = c == nsteps - 1;
+                // operands of the next two channels are fetched before the current two are computed (shared-memory latency off the path)
+                struct Ops { float x0, x1, x2, x3; int chn; };
+                auto fetch = [&](int gi) {
+                    Ops r;
+                    const int gs = gi < n_here ? gi : 0;
+                    r.x0 = col[gs]; r.x1 = col[SMS + gs]; r.x2 = col[2 * SMS + gs]; r.x3 = col[3 * SMS + gs];
+                    r.chn = sm.chan[gs];
+                    return r;
+                };
+                auto emit = [&](const Ops &v) {
+                    float o[4];
 #pragma unroll
-                for (int i = 0; i < 2; i++) { nx[0][i] = in[i * SMS]; nx[1][i] = in[(2 + i) * SMS]; }
+                    for (int j = 0; j < 4; j++) o[j] = fmaf(v.x3, ic[j][3], fmaf(v.x2, ic[j][2], fmaf(v.x1, ic[j][1], __fmul_rn(v.x0, ic[j][0]))));
+                    const int w0 = format_audio_word(__fmul_rn(o[0], 10.0f)), w1 = format_audio_word(__fmul_rn(o[1], 10.0f));   // LINE_OUT_SCALING_FACTOR (:2860)
+                    const int w2 = format_audio_word(__fmul_rn(o[2], 10.0f)), w3 = format_audio_word(__fmul_rn(o[3], 10.0f));
+                    int2 *d = obase + (size_t)v.chn * (size_t)a.chan_stride;
+                    asm volatile("st.global.v8.b32 [%0], {%1, %1, %2, %2, %3, %3, %4, %4};" ::"l"(d), "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+                    if (last && lane >= ND - 3) {
+                        // end of the launch: interpolator history = the last three samples; the (identity) treble stage's state follows the signal
+                        ChanState *stn = a.state + v.chn;
+                        stn->interp_hist[INTERP_HIST - 3 + (lane - (ND - 3))] = v.x3;
+                        if (lane == ND - 1) {
+                            for (int q = 0; q < INTERP_HIST - 3; q++) stn->interp_hist[q] = 0.0f;
+                            BiquadS tsn; tsn.x1 = o[3]; tsn.y1 = o[3]; tsn.x2 = o[2]; tsn.y2 = o[2];
+                            stn->bq2 = tsn;
+                        }
+                    }
+                };
+                // one channel per iteration (short body: the instruction cache is the scarce resource of this kernel)
+                Ops nx = fetch(postB ? 1 : 0);
 #pragma unroll 1
-                for (int blk = 0; blk < 4; blk++) {
-                    int4 *d4 = dst + (size_t)c * 64 + blk * 16;
-                    if (lean) { run_block(std::false_type{}, std::false_type{}, std::true_type{}, in, blk, d4, nullptr, false); continue; }
-                    const bool muted = mute && mute[c * 4 + blk];
-                    float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
-                    if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
-                    else if (tr_unity) run_block(std::false_type{}, std::false_type{}, std::false_type{}, in, blk, d4, df, muted);
-                    else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
+                for (int gi = postB ? 1 : 0; gi < n_here; gi += 2) {
+                    const Ops v = nx;
+                    nx = fetch(gi + 2);
+                    emit(v);
+                }
+            } else if (c >= 0 && c < nsteps && active && !tlean && !KNOCK(256)) {
+                const float *in = sm.bq[c & 1] + 3 * SMS + g;
+                if (!postB) {
+#pragma unroll
+                    for (int i = 0; i < 2; i++) { nx[0][i] = in[i * SMS]; nx[1][i] = in[(2 + i) * SMS]; }
+#pragma unroll 1
+                    for (int blk = 0; blk < 4; blk++) {
+                        int4 *d4 = dst + (size_t)c * 64 + blk * 16;
+                        const bool muted = mute && mute[c * 4 + blk];
+                        float4 *df = dst_f ? dst_f + (size_t)c * 32 + blk * 8 : nullptr;
+                        if (any_aa) run_block(std::true_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
+                        else if (tr_unity) run_block(std::false_type{}, std::false_type{}, std::false_type{}, in, blk, d4, df, muted);
+                        else run_block(std::false_type{}, std::true_type{}, std::false_type{}, in, blk, d4, df, muted);
+                    }
                 }
             }
             PROF_END(t);
             __syncthreads();
         }
         PROF_SAVE();
-        if (active) {
+        if (active && !tlean && !postB) {             // (the lane-per-sample variant has stored its state with the last step)
             for (int q = 0; q < INTERP_HIST - 3; q++) st->interp_hist[q] = 0.0f;
 #pragma unroll
             for (int q = 0; q < 3; q++) st->interp_hist[INTERP_HIST - 3 + q] = ih[q];
@@ -1169,6 +1248,7 @@ bool rx_ssb_tc_available() { return true; }
 
 #ifdef UHSDR_TC_PROF
 // tools only (libuhsdr_b200_prof.so): read the role timers of the last launch, set the knock-out mask of the next ones
+extern "C" int uhsdr_debug_tc_pause(int cycles) { return cudaMemcpyToSymbol(uhsdr::g_tc_pause, &cycles, sizeof(int)) == cudaSuccess ? 0 : -1; }
 extern "C" int uhsdr_debug_tc_prof(unsigned long long *out, int knock)
 {
     if (out && cudaMemcpyFromSymbol(out, uhsdr::g_tc_prof, sizeof(unsigned long long) * 32 * 4) != cudaSuccess) return -1;

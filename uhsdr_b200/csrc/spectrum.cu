@@ -88,18 +88,24 @@ spectrum_display_kernel(const ChanParams *__restrict__ params, const ChanState *
     // ---- state 3: averaging ----
     float *avg = avg_state + (size_t)ch * 512;
     float *fs = buf;                       // sd.FFT_Samples
-    for (int i = tid; i < 512; i += 128) {
+    float av[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + 128 * k;
         float a = avg[i];
         a = __fsub_rn(a, __fmul_rn(a, dc.filt_factor));
         a = __fadd_rn(__fmul_rn(mag[i], dc.filt_factor), a);
         if (a < 1.0f) a = 1.0f;
         avg[i] = a;
         if (avg_out) avg_out[(size_t)blockIdx.x * 512 + i] = a;
+        av[k] = a;
         // CalculateDBm's frequency-ordered copy of the NEW magnitudes (:2084-2091)
         const int src = i < 256 ? i + 256 : i - 256;
         fs[512 - i - 1] = __fmul_rn(mag[src], 1000.0f);                 // SCOPE_PREAMP_GAIN
-        mag[i] = a;                                                     // averaged data for state 4
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) mag[tid + 128 * k] = av[k];             // averaged data for state 4
     __syncthreads();
     if (tid == 0) {
         float sum_db = 0.0f;
