@@ -62,6 +62,27 @@ def channel_cfg(ch: int):
     return default_cfg(dmod_mode=DEMOD_USB, filter_path=35) if ch % 2 == 0 else default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
 
 
+def plan_groups(name: str):
+    """Channel plans of BASELINE.json's configs: list of (label, cfg, share) -- channels are sorted by kind
+    (8e) and every kind gets `share` of them; "ssb_narrow" alternates instead (configs[1] as written)."""
+    from uhsdr_b200.config import (DEMOD_AM, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, DSP_NR_ENABLE, SAM_SIDEBAND_USB, default_cfg)
+    if name in ("ssb_narrow", "rx_tx"):
+        return [("usb_p35", default_cfg(), 1), ("lsb_p38", default_cfg(dmod_mode=DEMOD_LSB, filter_path=38), 1)]
+    if name == "ssb_wide":
+        return [("usb_p48", default_cfg(filter_path=48), 1), ("usb_p55", default_cfg(filter_path=55), 1)]
+    if name == "mixed_am_sam_fm":
+        return [("am_p70", default_cfg(dmod_mode=DEMOD_AM, filter_path=70), 2), ("sam_p72_both", default_cfg(dmod_mode=DEMOD_SAM, filter_path=72), 1),
+                ("sam_p72_usb", default_cfg(dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=SAM_SIDEBAND_USB), 1),
+                ("fm_p2", default_cfg(dmod_mode=DEMOD_FM, filter_path=2), 2)]
+    if name == "ssb_nr_spectrum":
+        return [("usb_p35_nr_spec", default_cfg(dsp_active=DSP_NR_ENABLE, spectrum_enable=1), 1)]
+    raise KeyError(name)
+
+
+# direct-form FLOP per channel-sample (MAC = 2), SURVEY.md 8a / 8d
+PLAN_FLOP = {"ssb_narrow": 346.0, "ssb_wide": 440.0, "mixed_am_sam_fm": 310.0, "ssb_nr_spectrum": 346.0 + 65.0, "rx_tx": (346.0 + 910.0) / 2}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's own C on the host cores
 # ------------------------------------------------------------------------------------------------
@@ -70,7 +91,7 @@ def _cpu_worker(idx, nblocks, reps, barrier, q):
     from oracle.port import PortChannel
     from uhsdr_b200 import synth
     cfg = channel_cfg(idx)
-    iq = synth.rx_iq(cfg, idx, nblocks * 32)
+    iq = synth.counter_block(np, [synth.kind_of(cfg)], [idx], 0, nblocks * 32)[0]
     ch = refchain.RefChannel(cfg) if refchain.available() else PortChannel(cfg)
     ch.rx(iq[: 32 * 64])    # warm the caches / page in the library
     times = []
@@ -127,43 +148,6 @@ def reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-# ------------------------------------------------------------------------------------------------
-# GPU arm
-# ------------------------------------------------------------------------------------------------
-def gen_iq_device(torch, nch, nsamples, device, ch0=0, seed=0x55485344):
-    """Synthetic multi-tone + interferer + fading + AWGN I/Q generated on the device:
-    int32 [nch, nsamples, 2], value = round(x * 2^16).  Even channels USB, odd channels LSB."""
-    out = torch.empty((nch, nsamples, 2), dtype=torch.int32, device=device)
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
-    t = torch.arange(nsamples, dtype=torch.float64, device=device) / 48000.0
-    two_pi = 2.0 * np.pi
-    B = 64
-    for c0 in range(0, nch, B):
-        n = min(B, nch - c0)
-        ch = torch.arange(ch0 + c0, ch0 + c0 + n, dtype=torch.float64, device=device)[:, None]
-        sgn = torch.where((ch % 2) == 0, 1.0, -1.0)
-        d = 3.0 * (ch % 64)
-        fade = 10.0 ** ((6.0 * torch.sin(two_pi * 0.5 * t[None, :] + 0.1 * ch)) / 20.0)
-        re = torch.zeros((n, nsamples), dtype=torch.float64, device=device)
-        im = torch.zeros_like(re)
-        for fa, amp in ((700.0, 3000.0), (1500.0, 2000.0), (2100.0, 1000.0)):
-            ph = two_pi * ((12000.0 + sgn * (fa + d)) * t[None, :])
-            re += amp * torch.cos(ph)
-            im += amp * torch.sin(ph)
-        re *= fade
-        im *= fade
-        ph = two_pi * ((12000.0 - sgn * 1500.0) * t[None, :])
-        re += 3000.0 * torch.cos(ph)
-        im += 3000.0 * torch.sin(ph)
-        re += 100.0 * torch.randn((n, nsamples), dtype=torch.float64, device=device, generator=g)
-        im += 100.0 * torch.randn((n, nsamples), dtype=torch.float64, device=device, generator=g)
-        out[c0:c0 + n, :, 0] = torch.round(re * 65536.0).to(torch.int32)
-        out[c0:c0 + n, :, 1] = torch.round(im * 65536.0).to(torch.int32)
-        del re, im, fade, ph
-    return out
 
 
 class ClockSampler:
@@ -228,10 +212,205 @@ class ClockSampler:
                 "window": "timed region + untimed continuation of the same launches (>= %.1f s under load)" % self.MIN_LOAD_S}
 
 
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+DTYPE_LABEL = "f32 (I/O, state and accumulation f32; operands of the decimator / Hilbert FIR GEMMs split into 2 bf16 terms)"
+
+
+def local_plan(name: str, nch: int, ch0: int):
+    """Per-rank channel plan: list of (cfg, label) per local channel, channels of one kind contiguous (except the alternating
+    narrow-SSB plan of configs[1]), and the generator kind of each channel."""
+    from uhsdr_b200 import synth
+    groups = plan_groups(name)
+    cfgs, labels = [], []
+    if name in ("ssb_narrow", "rx_tx"):
+        for c in range(nch):
+            lab, cfg, _ = groups[(ch0 + c) % 2]
+            cfgs.append(cfg); labels.append(lab)
+    else:
+        tot = sum(g[2] for g in groups)
+        done = 0
+        for gi, (lab, cfg, share) in enumerate(groups):
+            cnt = nch - done if gi == len(groups) - 1 else (nch * share) // tot
+            cfgs += [cfg] * cnt; labels += [lab] * cnt
+            done += cnt
+    kinds = [synth.kind_of(c) for c in cfgs]
+    return cfgs, labels, kinds
+
+
+def configure_plan(eng, name, cfgs, ch0):
+    if name in ("ssb_narrow", "rx_tx") and len(cfgs) >= 2:
+        first_usb = 0 if ch0 % 2 == 0 else 1
+        eng.configure(cfgs[first_usb], first=first_usb, stride=2)
+        eng.configure(cfgs[1 - first_usb], first=1 - first_usb, stride=2)
+        return
+    c = 0
+    while c < len(cfgs):
+        e = c
+        while e < len(cfgs) and cfgs[e] is cfgs[c]:
+            e += 1
+        eng.configure(cfgs[c], first=c, count=e - c)
+        c = e
+
+
+def gen_device(torch, kinds, ch_global, ns, dev, mic=False, chunk=128):
+    """Counter-based integer generator (uhsdr_b200/synth.py counter_block), evaluated on the device: the same code on numpy
+    regenerates any channel / time slice bit for bit on the host."""
+    from uhsdr_b200 import synth
+    out = torch.empty((len(kinds), ns, 2), dtype=torch.int32, device=dev)
+    for c0 in range(0, len(kinds), chunk):
+        k = [synth.KIND_MIC] * min(chunk, len(kinds) - c0) if mic else kinds[c0:c0 + chunk]
+        out[c0:c0 + len(k)] = synth.counter_block(torch, k, ch_global[c0:c0 + len(k)], 0, ns, device=dev)
+    return out
+
+
+def snr_db(got, ref):
+    e = got.astype(np.float64) - ref.astype(np.float64)
+    return float(10 * np.log10(max(np.mean(ref.astype(np.float64) ** 2), 1e-30) / max(np.mean(e ** 2), 1e-30)))
+
+
+def parity_at_size(torch, eng, name, cfgs, labels, iq, mic, P, nsub, dev, tx, spectrum, ch0):
+    """The first P blocks of the FULL batch from fresh state; a subset of channels that covers every kind is compared with
+    the oracle (the compiled reference where oracle/_ref travelled, else the port) on the float audio before the int32
+    formatting: max |err| / max |ref| (north_star: <= 1e-4) and SNR (>= 90 dB), plus the int32 words (<= 1 LSB of 16 bits)."""
+    from oracle import refchain
+    from oracle.port import PortChannel
+    nch = len(cfgs)
+    configure_plan(eng, name, cfgs, ch0)
+    sub_iq = iq[:, : P * 32].contiguous()
+    out = torch.empty_like(sub_iq)
+    out_f = torch.empty((nch, P * 32), dtype=torch.float32, device=dev)
+    eng.rx_device(sub_iq, out, P, audio_f_dev=out_f)
+    if tx:
+        sub_mic = mic[:, : P * 32].contiguous()
+        txo = torch.empty_like(sub_mic)
+        txo_f = torch.empty((nch, P * 32, 2), dtype=torch.float32, device=dev)
+        eng.tx_device(sub_mic, txo, P, iq_f_dev=txo_f)
+    eng.sync()
+    # subset: evenly spaced, at least 8 of every kind
+    idx = set(np.linspace(0, nch - 1, num=min(nsub, nch), dtype=np.int64).tolist())
+    for lab in dict.fromkeys(labels):
+        members = [i for i, l in enumerate(labels) if l == lab]
+        idx.update(members[:: max(1, len(members) // 8)][:8])
+    idx = sorted(idx)
+    rel, snr, lsb, tx_rel, tx_snr, spec_rel = 0.0, 1e9, 0, 0.0, 1e9, 0.0
+    per_kind = {}
+    mags = eng.spectrum() if spectrum else None
+    for c in idx:
+        x = sub_iq[c].cpu().numpy()
+        ch = refchain.RefChannel(cfgs[c]) if refchain.available() else PortChannel(cfgs[c])
+        want, want_f = ch.rx(x)
+        got_f = out_f[c].cpu().numpy()
+        got_w = out[c, :, 0].cpu().numpy()
+        r = float(np.max(np.abs(got_f - want_f)) / max(float(np.max(np.abs(want_f))), 1e-30))
+        s = snr_db(got_f, want_f)
+        rel, snr = max(rel, r), min(snr, s)
+        lsb = max(lsb, int(np.max(np.abs((got_w.astype(np.int64) >> 16) - (want[:, 0].astype(np.int64) >> 16)))))
+        k = per_kind.setdefault(labels[c], {"channels": 0, "max_rel_err": 0.0, "min_snr_db": 1e9})
+        k["channels"] += 1; k["max_rel_err"] = max(k["max_rel_err"], r); k["min_snr_db"] = min(k["min_snr_db"], s)
+        if spectrum:
+            wm = ch.spectrum()
+            spec_rel = max(spec_rel, float(np.max(np.abs(mags[c] - wm)) / np.max(wm)))
+        if tx:
+            wiq, wiq_f = ch.tx(sub_mic[c].cpu().numpy())
+            g = txo_f[c].cpu().numpy()
+            tx_rel = max(tx_rel, float(np.max(np.abs(g - wiq_f)) / max(float(np.max(np.abs(wiq_f))), 1e-30)))
+            tx_snr = min(tx_snr, snr_db(g, wiq_f))
+        ch.close()
+    res = {"channels_compared": len(idx), "of": nch, "blocks": P, "oracle": cpu_kind(), "max_rel_err": rel, "min_snr_db": snr,
+           "max_word_diff_lsb16": lsb, "per_kind": per_kind,
+           "tolerance": "north_star: |err| <= 1e-4 relative (read as max|err| / max|ref| over the run) and >= 90 dB SNR, on the float audio",
+           "within_tolerance": bool(rel <= 1e-4 and snr >= 90.0)}
+    if tx:
+        res["tx"] = {"max_rel_err": tx_rel, "min_snr_db": tx_snr}
+        res["within_tolerance"] = bool(res["within_tolerance"] and tx_rel <= 1e-4 and tx_snr >= 90.0)
+    if spectrum:
+        res["spectrum_max_rel_err"] = spec_rel
+    return res
+
+
+
+def run_config(torch, dist, args, name, nch, T, rank, local_rank, world, dev, steps, warmup, tx=False, spectrum=False, keep=False):
+    """One BASELINE config on this rank: engine + device-resident synthetic input, W warm-up and K timed steps (CUDA events on
+    the engine's stream, barrier + synchronize on both sides, max over ranks), then the at-size parity check on rank 0."""
+    from uhsdr_b200.engine import Engine
+    from uhsdr_b200.partition import channel_range
+    ns = T * 32
+    ch0, ch1 = channel_range(rank, world, world * nch)
+    cfgs, labels, kinds = local_plan(name, nch, ch0)
+    ch_global = list(range(ch0, ch1))
+    eng = Engine(nch, device=local_rank)
+    configure_plan(eng, name, cfgs, ch0)
+    iq = gen_device(torch, kinds, ch_global, ns, dev)
+    audio = torch.empty_like(iq)
+    mic = iqtx = mags = None
+    if tx:
+        mic = gen_device(torch, kinds, ch_global, ns, dev, mic=True)
+        iqtx = torch.empty_like(mic)
+    if spectrum:
+        mags = torch.empty((nch, 512), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.rx_device(iq, audio, T)
+        if tx:
+            eng.tx_device(mic, iqtx, T)
+        if spectrum:                       # one 512-point spectrum FFT per 512 input samples and channel (SURVEY.md 8d config 4)
+            for _ in range(max(1, ns // 512)):
+                eng._check(eng._lib.uhsdr_get_spectrum_device(eng._h, 0, nch, mags.data_ptr()))
+
+    with torch.cuda.stream(ext):
+        for _ in range(warmup):
+            step()
+        barrier()
+        l0 = eng.launch_count
+        t_begin = time.time()
+        ev0.record(ext)
+        for _ in range(steps):
+            step()
+        ev1.record(ext)
+        barrier()
+        launches = eng.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / steps
+    units_per_gpu = nch * ns * (2 if tx else 1)
+    res = {"name": name, "eng": eng, "iq": iq, "audio": audio, "ext": ext, "ms_per_step": ms_per_step, "launches": launches,
+           "units_per_gpu": units_per_gpu, "value": float(world) * units_per_gpu / (ms_per_step * 1e-3), "t_begin": t_begin,
+           "cfgs": cfgs, "labels": labels, "kinds": kinds, "ch0": ch0, "parity": None}
+    if rank == 0 and args.parity_channels > 0:
+        with torch.cuda.stream(ext):
+            res["parity"] = parity_at_size(torch, eng, name, cfgs, labels, iq, mic, min(T, args.parity_blocks) // 4 * 4, args.parity_channels, dev, tx, spectrum, ch0)
+            configure_plan(eng, name, cfgs, ch0)
+    if not keep:
+        eng.close()
+        res["eng"] = None
+        res["iq"] = res["audio"] = None
+    return res
+
+
+def roofline_of(res, peaks, which, plan):
+    gbs = res["units_per_gpu"] * BYTES_PER_SAMPLE / (res["ms_per_step"] * 1e-3) / 1e9
+    tf = res["units_per_gpu"] * PLAN_FLOP[plan] / (res["ms_per_step"] * 1e-3) / 1e12
+    return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": which, "algorithmic_bytes_per_step": res["units_per_gpu"] * BYTES_PER_SAMPLE,
+            "fp32": {"achieved_tflops": tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL, "frac": tf / FP32_PEAK_TFLOPS_NOMINAL,
+                     "flop_per_unit": PLAN_FLOP[plan]}}
+
+
 def gpu_arm(args):
     import torch
-
-    from uhsdr_b200.engine import Engine
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -260,73 +439,42 @@ def gpu_arm(args):
 
     nch, T = args.channels, args.blocks
     ns = T * 32
-    # host-side partitioning: rank r owns a contiguous range of the world*nch global channels
-    from uhsdr_b200.partition import channel_range
-    ch0, ch1 = channel_range(rank, world, world * nch)
-    assert ch1 - ch0 == nch
-    eng = Engine(nch, device=local_rank)
-    from uhsdr_b200.config import DEMOD_LSB, default_cfg
-    # even/odd channels alternate USB path 35 / LSB path 38
-    cfg_usb, cfg_lsb = default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)
-    if nch >= 2 and not args.uniform:
-        first_usb = 0 if ch0 % 2 == 0 else 1
-        eng.configure(cfg_usb, first=first_usb, stride=2)
-        eng.configure(cfg_lsb, first=1 - first_usb, stride=2)
-    else:
-        eng.configure(cfg_usb)
-    iq = gen_iq_device(torch, nch, ns, dev, ch0=ch0)
-    audio = torch.empty_like(iq)
-    torch.cuda.synchronize()
-
-    ext = torch.cuda.ExternalStream(eng.stream, device=dev)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- headline: BASELINE.json configs[1] -------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    head = run_config(torch, dist, args, "ssb_narrow", nch, T, rank, local_rank, world, dev, args.steps, args.warmup, keep=True)
+    eng, iq, audio, ext = head["eng"], head["iq"], head["audio"], head["ext"]
     with torch.cuda.stream(ext):
-        for _ in range(args.warmup):
-            eng.rx_device(iq, audio, T)
-        barrier()
-        launches0 = eng.launch_count
-        t_begin = time.time()
-        ev0.record(ext)
-        for _ in range(args.steps):
-            eng.rx_device(iq, audio, T)
-        ev1.record(ext)
-        barrier()
-        launches = eng.launch_count - launches0
         # keep the same load running (untimed) until the clock sampler has seen MIN_LOAD_S of it
-        while rank == 0 and time.time() - t_begin < ClockSampler.MIN_LOAD_S:
+        t_load = time.time()
+        while rank == 0 and time.time() - t_load < ClockSampler.MIN_LOAD_S:
             for _ in range(4):
                 eng.rx_device(iq, audio, T)
             torch.cuda.synchronize()
-        clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
+        clocks = sampler.stop(head["t_begin"], time.time()) if rank == 0 else None
         barrier()
-    ms = ev0.elapsed_time(ev1)
-    if dist is not None:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    ms_per_step = ms / args.steps
+    ms_per_step, value, launches = head["ms_per_step"], head["value"], head["launches"]
     total_samples = float(world) * nch * ns
-    value = total_samples / (ms_per_step * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h_iq = torch.empty((nch, ns, 2), dtype=torch.int32, pin_memory=True)
     h_audio = torch.empty((nch, ns, 2), dtype=torch.int32, pin_memory=True)
     h_iq.copy_(iq)
     torch.cuda.synchronize()
     lib, h = eng._lib, eng._h
     with torch.cuda.stream(ext):
-        rc = lib.uhsdr_rx_process(h, h_iq.data_ptr(), h_audio.data_ptr(), T, None)   # warm-up (staging alloc)
-        assert rc == 0, rc
+        for _ in range(3):                                                               # warm-up (staging allocation, first touch)
+            rc = lib.uhsdr_rx_process(h, h_iq.data_ptr(), h_audio.data_ptr(), T, None)
+            assert rc == 0, rc
         barrier()
         ev0.record(ext)
         for _ in range(e2e_steps):
@@ -341,75 +489,84 @@ def gpu_arm(args):
         e2e_ms = float(tms.item())
     e2e_value = total_samples / (e2e_ms / e2e_steps * 1e-3)
     io_bytes = nch * ns * 8
+    # the host-buffer path (sliced, three streams) must deliver what the device path delivers: compare a strided sample of rows
+    e2e_match = None
+    if rank == 0:
+        with torch.cuda.stream(ext):
+            configure_plan(eng, "ssb_narrow", head["cfgs"], head["ch0"])
+            rc = lib.uhsdr_rx_process(h, h_iq.data_ptr(), h_audio.data_ptr(), T, None)
+            assert rc == 0, rc
+            configure_plan(eng, "ssb_narrow", head["cfgs"], head["ch0"])
+            eng.rx_device(iq, audio, T)
+            eng.sync()
+            rows = torch.arange(0, nch, max(1, nch // 64), device=dev)
+            e2e_match = bool(torch.equal(audio[rows].cpu(), h_audio[rows.cpu()]))
+    del h_iq, h_audio
+    eng.close()
+    del iq, audio
+    torch.cuda.empty_cache()
 
-    # ---- parity spot check against the oracle (not timed) -----------------------------------------
-    parity = None
-    if rank == 0 and args.parity_channels > 0:
-        from oracle import refchain
-        from oracle.port import PortChannel
-        pc = min(nch, args.parity_channels)
-        pb = min(T, 256) // 4 * 4
-        sub = iq[:pc, : pb * 32].contiguous()
-        sub_out = torch.empty_like(sub)
-        with Engine(pc, device=local_rank) as peng:
-            for c in range(pc):
-                peng.configure(cfg_usb if (args.uniform or (ch0 + c) % 2 == 0) else cfg_lsb, first=c, count=1)
-            peng.rx_device(sub, sub_out, pb)
-            peng.sync()
-        snrs = []
-        for c in range(pc):
-            cfg = cfg_usb if (args.uniform or (ch0 + c) % 2 == 0) else cfg_lsb
-            x = sub[c].cpu().numpy()
-            chan = refchain.RefChannel(cfg) if refchain.available() else PortChannel(cfg)
-            want, _ = chan.rx(x)
-            chan.close()
-            got = sub_out[c, :, 0].cpu().numpy().astype(np.float64) / 65536.0
-            ref = want[:, 0].astype(np.float64) / 65536.0
-            snrs.append(10 * np.log10(np.mean(ref ** 2) / max(np.mean((got - ref) ** 2), 1e-30)))
-        parity = {"channels": len(snrs), "blocks": pb, "min_snr_db_int16": float(min(snrs)), "oracle": cpu_kind()}
+    # ---- the other BASELINE configs (device-resident, same timing rules, at-size parity) -----------------------------
+    others = []
+    if not args.no_other_configs:
+        osteps, owarm = max(1, min(args.steps, args.other_steps)), 3
+        plans = [("ssb_wide", 4096, args.other_blocks, {}), ("mixed_am_sam_fm", 16384, args.other_blocks, {}),
+                 ("ssb_nr_spectrum", 4096, args.other_blocks, {"spectrum": True}),
+                 ("rx_tx", (65536 // world) if world > 1 else 8192, args.other_blocks, {"tx": True})]
+        for pname, pch, pT, kw in plans:
+            r = run_config(torch, dist, args, pname, pch, pT, rank, local_rank, world, dev, osteps, owarm, **kw)
+            if rank == 0:
+                peaks, which = measured_peaks()
+                cfgdesc = {"ssb_wide": "wide SSB: Hilbert pair at 48 ksps, then the audio decimator (FilterPathInfo[48] / [55])",
+                           "mixed_am_sam_fm": "BASELINE.json configs[2]: 1/3 AM path 70, 1/3 SAM path 72 (sideband BOTH and USB), 1/3 FM path 2, channels sorted by mode",
+                           "ssb_nr_spectrum": "BASELINE.json configs[3]: SSB path 35 + spectral noise reduction + one 512-point spectrum FFT per 512 input samples and channel",
+                           "rx_tx": "BASELINE.json configs[4]: narrow SSB RX chain + SSB TX modulator on every channel" +
+                                    (f", 65536 channels sharded over {world} GPUs (contiguous ranges)" if world > 1 else ", one GPU's share at 8 GPUs (8192 channels)")}[pname]
+                others.append({"name": pname, "workload": cfgdesc, "channels_per_gpu": pch, "channels_total": pch * world, "blocks_per_step": pT,
+                               "unit": "channel-samples/s" + (" (RX + TX samples)" if kw.get("tx") else ""), "value": r["value"],
+                               "ms_per_step": r["ms_per_step"], "steps": osteps, "warmup": owarm, "gpu_launches": r["launches"],
+                               "roofline": roofline_of(r, peaks, which, pname), "parity": r["parity"]})
+            torch.cuda.empty_cache()
 
     # ---- cpu baseline (rank 0, N == 1 only) -------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         reps, nb = 10, 15000
+        one = run_cpu_chain(1, nb, 1 + 3)[1:]                       # B1: one channel on one core (BASELINE.json configs[0])
         per_pass = run_cpu_chain(cores, nb, 1 + reps)[1:]
         cpu_baseline = {"value": cores * nb * 32 * reps / sum(per_pass), "unit": "channel-samples/s", "cores": cores,
-                        "kind": cpu_kind(), "sample": f"{cores} channels x {nb} blocks x {reps} passes, one process per channel"}
+                        "kind": cpu_kind(), "sample": f"{cores} channels x {nb} blocks x {reps} passes, one process per channel",
+                        "single_core": {"value": nb * 32 * 3 / sum(one), "unit": "channel-samples/s", "cores": 1,
+                                        "sample": f"1 channel x {nb} blocks (10 s of signal) x 3 passes: BASELINE.json configs[0]"}}
 
     if rank == 0:
         peaks, which = measured_peaks()
         launch_ms = ms_per_step / max(1, launches / args.steps)
-        per_gpu_samples = nch * ns
-        achieved_gbs = per_gpu_samples * BYTES_PER_SAMPLE / (ms_per_step * 1e-3) / 1e9
-        achieved_tf = per_gpu_samples * FLOP_PER_SAMPLE / (ms_per_step * 1e-3) / 1e12
         tr = measured_traffic()
-        launch_samples = per_gpu_samples / max(1, launches / args.steps)
-        traffic = tr["dram_bytes_per_channel_sample"] * launch_samples if tr else None
+        launch_samples = nch * ns / max(1, launches / args.steps)
+        roof = roofline_of(head, peaks, which, "ssb_narrow")
+        roof.update({"traffic": tr["dram_bytes_per_channel_sample"] * launch_samples if tr else None,
+                     "traffic_source": ("profiled constant, not measured in this run: " + tr["source"]) if tr else None,
+                     "kernel": "rx_ssb_tc_kernel", "kernel_ms_per_launch": launch_ms, "algorithmic_bytes_per_launch": launch_samples * BYTES_PER_SAMPLE})
+        roof["fp32"]["note"] = ("direct-form FLOP count of the chain (SURVEY.md 8d) against the FP32 FMA pipe, 148 SM x 128 lanes x 2 x 1.965 GHz; "
+                                "282 of the 346 FLOP (the 83-tap decimator and the 199-tap Hilbert pair) run on the tensor cores as bf16-split Toeplitz GEMMs")
         line = {
             "metric": "channel-samples/s, full SSB RX chain", "value": value, "unit": "channel-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_LABEL, "data": "synthetic",
             "config": {"workload": f"{nch}-channel batched SSB (alternating USB path 35 / LSB path 38) RX chain per GPU, "
                                    f"{T} blocks (x32 samples) per channel per step (BASELINE.json configs[1])",
                        "channels_per_gpu": nch, "blocks_per_step": T, "parallelism": f"channels sharded over {world} GPU(s), no collective",
-                       "l2": f"inputs larger than L2 ({2 * io_bytes / 2**20:.0f} MiB streamed per step)"},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_source": which,
-                         "kernel": "rx_ssb_tc_kernel", "kernel_ms_per_launch": launch_ms,
-                         "algorithmic_bytes_per_launch": launch_samples * BYTES_PER_SAMPLE,
-                         "traffic_source": tr["source"] if tr else None,
-                         "fp32": {"achieved_tflops": achieved_tf, "peak_tflops_nominal": FP32_PEAK_TFLOPS_NOMINAL,
-                                  "frac": achieved_tf / FP32_PEAK_TFLOPS_NOMINAL, "flop_per_channel_sample": FLOP_PER_SAMPLE,
-                                  "note": "direct-form FLOP count of the chain (SURVEY.md 8d) against the FP32 FMA pipe, 148 SM x 128 lanes x 2 x 1.965 GHz; "
-                                          "282 of the 346 FLOP (the 83-tap decimator and the 199-tap Hilbert pair) run on the tensor cores as bf16-split Toeplitz GEMMs"}},
+                       "l2": f"inputs larger than L2 ({2 * io_bytes / 2**20:.0f} MiB streamed per step)",
+                       "generator": "uhsdr_b200/synth.py counter_block: integer counter-based, bit-identical on host (numpy) and device (torch)"},
+            "roofline": roof,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": "channel-samples/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": e2e_steps,
-                    "host_cpu_affinity_rank0": numa},
-            "gpu_launches": launches, "clocks": clocks, "parity": parity,
+                    "host_cpu_affinity_rank0": numa, "matches_device_path": e2e_match},
+            "gpu_launches": launches, "clocks": clocks, "parity": head["parity"], "other_configs": others,
         }
         print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -420,11 +577,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--channels", type=int, default=4096, help="channels per GPU")
-    ap.add_argument("--blocks", type=int, default=1500, help="32-sample blocks per channel per step")
+    ap.add_argument("--channels", type=int, default=4096, help="channels per GPU (headline)")
+    ap.add_argument("--blocks", type=int, default=1500, help="32-sample blocks per channel per step (headline)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--parity-channels", type=int, default=4)
-    ap.add_argument("--uniform", action="store_true", help="all channels USB path 35")
+    ap.add_argument("--parity-channels", type=int, default=64, help="channels of every config compared with the oracle (0 = skip)")
+    ap.add_argument("--parity-blocks", type=int, default=256)
+    ap.add_argument("--other-blocks", type=int, default=400, help="blocks per step of the other BASELINE configs")
+    ap.add_argument("--other-steps", type=int, default=3)
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

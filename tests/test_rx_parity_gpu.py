@@ -54,7 +54,19 @@ def check_tolerance(got_f, want_f, got_w, want_w, label):
     same_trunc = np.trunc(got_f) == np.trunc(want_f)
     assert np.all(diff[same_trunc] == 0), label
     assert np.all((got_w & 0xFFFF) == 0), label      # << 16 formatting
+    _record_margin(label, rel, snr)
     return rel, snr
+
+
+def _record_margin(label, rel, snr):
+    """Achieved margins of every tolerance-checked case, one JSON line each, for profiles/rNN_parity_margins.json
+    (UHSDR_MARGINS_FILE names the file; scripts/collect_margins.py folds the lines into worst-case per label)."""
+    path = os.environ.get("UHSDR_MARGINS_FILE")
+    if path:
+        import json
+        test = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": test, "label": label, "max_rel_err": float(rel), "snr_db": float(snr)}) + "\n")
 
 
 @pytest.mark.parametrize("label,kw,nblocks", RX_CASES, ids=[c[0] for c in RX_CASES])
