@@ -18,7 +18,7 @@ import uhsdr_b200.engine as E                                      # noqa: E402
 E.LIB_FAST = os.path.join(ROOT, "uhsdr_b200", "csrc", "libuhsdr_b200_prof.so")
 from uhsdr_b200.config import DEMOD_LSB, default_cfg               # noqa: E402
 
-ROLES = ["fe0", "fe1", "fe2", "fe3", "fe4", "fe5", "fe6", "mma", "epi0", "epi1", "epi2", "epi3", "agc", "postB", "lat", "postA", "bq"]
+ROLES = ["fe0", "fe1", "fe2", "fe3", "fe4", "fe5", "fe6", "postA", "epi0", "epi1", "epi2", "epi3", "bq", "postB", "lat", "agc", "mma"]
 KNOCKS = {1: "front end", 2: "MMAs", 4: "dec epilogue", 8: "hil epilogue", 16: "gain law", 32: "lattice", 64: "AGC", 128: "biquads", 256: "output"}
 
 

@@ -70,10 +70,11 @@ constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilb
 constexpr int MMA_PAUSE = 60;         // cycles between k-steps of the MMA issue (sweeps: profiles/r01_tc2_experiments.txt, r02_tc_experiments.txt)
 constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
-// scheduler 0: front end 0, 4 | epilogue 0 | AGC detector | biquads      1: front end 1, 5 | epilogue 1 | output B
-//           2: front end 2, 6 | epilogue 2 | lattice                     3: front end 3 | MMA issue | epilogue 3 | output A
-constexpr int W_MMA = NWARP_FE, W_EPI = NWARP_FE + 1, W_AGC = NWARP_FE + 5, W_POSTB = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_POSTA = NWARP_FE + 8,
-              W_BQ = NWARP_FE + 9;
+// scheduler 0: front end 0, 4 | epilogue 0 | biquads (+ AGC helper) | MMA issue     1: front end 1, 5 | epilogue 1 | output B
+//           2: front end 2, 6 | epilogue 2 | lattice                                 3: front end 3 | output A | epilogue 3 | AGC detector
+// (17 warps: scheduler 0 has five; it gets the two lightest roles, and the AGC detector -- the longest recurrence -- the emptiest one)
+constexpr int W_POSTA = NWARP_FE, W_EPI = NWARP_FE + 1, W_BQ = NWARP_FE + 5, W_POSTB = NWARP_FE + 6, W_LAT = NWARP_FE + 7, W_AGC = NWARP_FE + 8,
+              W_MMA = NWARP_FE + 9;
 constexpr int NTHREADS = 32 * (NWARP_FE + 10);
 // software pipeline, in steps of 128 input samples.  Step s (virtual steps included) is written into the decimator
 // ring at iteration s, its decimator MMAs are issued at s + 1, the decimator outputs leave TMEM for the Hilbert ring
@@ -114,7 +115,7 @@ struct Smem {
     float agc[2][ND * SMS];           // AGC "volts" per sample (detector -> gain stage)
     float gq[2][ND * SMS];            // delayed sample x gain (gain stage -> biquad cascade)
     float bq[2][(3 + ND) * SMS];      // biquad output: rows 0..2 = the last three samples of the previous step (interpolator history), then the step
-    float smax[2][ND * SMS];
+    float smax[3][ND * SMS];          // suffix maxima of |x| per step (van Herk / Gil-Werman), step c in buffer c % 3
     int chan[32];                     // channel index of every slot (epilogue warps: state save / restore)
     alignas(8) unsigned long long bar_dec[2], bar_hil[2];
     unsigned tmem_base;
@@ -797,17 +798,19 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         }
         // Sliding maximum of |x| over the newest 49 samples (audio_agc.c:409-429 rescans on demand): van Herk /
         // Gil-Werman decomposition with blocks = steps of 32, see rx_ssb_fused.cu.
-        int s1 = 0, s2 = 1;
+        // The suffix maxima of step c live in buffer c % 3; the biquad warp, which has time to spare, computes them (and, when no
+        // channel uses the hang AGC, the hang back-average, which then feeds nothing but the status word) while this warp works
+        // on step c with the buffers of steps c - 1 and c - 2.  Steps -1 and -2 (the history) are prepared here.
         if (active) {
             float m = 0.0f;
             for (int o = ND - 1; o >= 0; o--) {
                 m = fmaxf(m, fabsf(latp[(LR - ND + o) * SMS]));
-                sm.smax[s1][o * SMS + g] = m;
+                sm.smax[2][o * SMS + g] = m;
             }
             m = 0.0f;
             for (int o = ND - 1; o >= 16; o--) {
                 m = fmaxf(m, fabsf(latp[(LR - 2 * ND + o) * SMS]));
-                sm.smax[s2][o * SMS + g] = m;
+                sm.smax[1][o * SMS + g] = m;
             }
         }
         __syncwarp();
@@ -820,7 +823,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 const int row0 = (c % 5) * ND;                  // ring row of the first sample of this step
                 const float *in = latp + row0 * SMS;
                 float *out = sm.agc[c & 1] + g;
-                const float *S1 = sm.smax[s1] + g, *S2 = sm.smax[s2] + g;
+                const float *S1 = sm.smax[(c + 2) % 3] + g, *S2 = sm.smax[(c + 1) % 3] + g;      // steps c - 1, c - 2
                 const float mprev = S1[0];
                 float pmax = 0.0f;
                 auto detect = [&](auto hangc) {
@@ -864,7 +867,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                         const float abs_out = fabsf(dly[j]), abs_in = fabsf(x[j]);
                         pmax = fmaxf(pmax, abs_in);
                         ar.fast_backaverage = fmaf(ap.fast_backmult, abs_out, __fmul_rn(ap.onemfast_backmult, ar.fast_backaverage));
-                        ar.hang_backaverage = fmaf(ap.hang_backmult, abs_out, __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
+                        if constexpr (HANG) ar.hang_backaverage = fmaf(ap.hang_backmult, abs_out, __fmul_rn(ap.onemhang_backmult, ar.hang_backaverage));
                         ar.ring_max = fmaxf(pmax, cmx[j]);
                         const float dv = __fsub_rn(ar.ring_max, ar.volts);
                         const bool attack = ar.ring_max >= ar.volts;
@@ -916,21 +919,6 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
                 };
                 if (any_hang) detect(std::true_type{}); else detect(std::false_type{});
-                ar.hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
-                {
-                    // suffix maxima of this step replace those of the step before the previous one; roles rotate
-                    float *Sn = sm.smax[s2] + g;
-                    float m = 0.0f;
-#pragma unroll 1
-                    for (int o8 = ND - 8; o8 >= 0; o8 -= 8) {
-                        float rv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) rv[j] = in[(o8 + j) * SMS];
-#pragma unroll
-                        for (int j = 7; j >= 0; j--) { m = fmaxf(m, fabsf(rv[j])); Sn[(o8 + j) * SMS] = m; }
-                    }
-                    const int tmp = s1; s1 = s2; s2 = tmp;
-                }
             }
             PROF_END(t);
             __syncthreads();
@@ -949,9 +937,13 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             }
             st->agc_in_index = new_in; st->agc_out_index = new_out;
             st->agc_ring_max = ar.ring_max; st->agc_volts = ar.volts; st->agc_save_volts = ar.save_volts;
-            st->agc_fast_backaverage = ar.fast_backaverage; st->agc_hang_backaverage = ar.hang_backaverage;
+            st->agc_fast_backaverage = ar.fast_backaverage;
             st->agc_hang_counter = ar.hang_counter; st->agc_decay_type = ar.decay_type; st->agc_state = ar.state;
-            st->agc_action = ar.action; st->agc_hang_action = ar.hang_action;
+            st->agc_action = ar.action;
+            if (any_hang) {          // otherwise the biquad warp keeps the hang back-average
+                st->agc_hang_backaverage = ar.hang_backaverage;
+                st->agc_hang_action = (ar.hang_backaverage > ap.hang_level) ? 1 : 0;
+            }
         }
         return;
     }
@@ -1008,9 +1000,44 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             }
         };
         if (skipmask != 0xbu) skipmask = 0;      // only the default plan (bass shelf alone) has a specialised loop
+        // Helper for the AGC detector (the longest of the serial roles; this warp is the shortest): while W_AGC works on step c,
+        // this warp computes the suffix maxima of |x| of step c (needed from step c + 1 on) and, when no channel of the CTA
+        // uses the hang AGC, the hang back-average over x[n - 49] (audio_agc.c:400-407).
+        const AgcP &hp = p.agc;
+        const bool agc_on = active && hp.mode != 5;
+        const bool any_hang = __any_sync(0xffffffffu, active && (hp.hang_enable || st->agc_state == 2 || st->agc_state == 4 || st->agc_decay_type != 0 ||
+                                                                  st->agc_hang_counter > 0));
+        const float hbm = hp.hang_backmult, ohbm = hp.onemhang_backmult;
+        float hba = st->agc_hang_backaverage;
         PROF_DECL;
         for (int t = 0; t < niter; t++) {
             PROF_TOP(t);
+            const int ca = t - IT_AGC;
+            if (ca >= 0 && ca < nsteps && agc_on && !KNOCK(64)) {
+                const float *latp = sm.lat + g;
+                const float *in = latp + (ca % 5) * ND * SMS;
+                float *Sn = sm.smax[ca % 3] + g;
+                int ra = (ca % 5) * ND - AGC_W; if (ra < 0) ra += LR;
+                float m = 0.0f;
+#pragma unroll 1
+                for (int o8 = ND - 8; o8 >= 0; o8 -= 8) {
+                    float rv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) rv[j] = in[(o8 + j) * SMS];
+#pragma unroll
+                    for (int j = 7; j >= 0; j--) { m = fmaxf(m, fabsf(rv[j])); Sn[(o8 + j) * SMS] = m; }
+                }
+                if (!any_hang) {
+#pragma unroll 1
+                    for (int o8 = 0; o8 < ND; o8 += 8) {
+                        float dl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { int rr = ra + o8 + j; if (rr >= LR) rr -= LR; dl[j] = latp[rr * SMS]; }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) hba = fmaf(hbm, fabsf(dl[j]), __fmul_rn(ohbm, hba));
+                    }
+                }
+            }
             const int c = t - IT_BQ;
             if (c >= 0 && c < nsteps && active && !KNOCK(128)) {
                 const float *in = sm.gq[c & 1] + g;
@@ -1032,6 +1059,10 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 if (skipmask & (1u << s)) { bs[s].x1 = s1v; bs[s].x2 = s2v; bs[s].y1 = s1v; bs[s].y2 = s2v; }
                 else { s1v = bs[s].y1; s2v = bs[s].y2; }
                 st->bq1[s] = bs[s];
+            }
+            if (agc_on && !any_hang) {
+                st->agc_hang_backaverage = hba;
+                st->agc_hang_action = (hba > hp.hang_level) ? 1 : 0;
             }
         }
         return;
