@@ -47,6 +47,8 @@ struct uhsdr_engine {
     float *d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
     int use_split = 1;       // general path as front (FIR) kernel + thread-per-channel serial kernel
+    int use_front2 = 1;      // register-blocked front kernel (rx_front2.cu) where every split channel's chain fits it
+    bool front2_ok = false;
     FusedCoefs fused_coefs;
     bool fused_coefs_valid = false;
     int fused_s1_ci = -1, fused_s2_ci = -1, fused_s2_cq = -1;
@@ -161,6 +163,8 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (nf && nf[0] == '1') e->use_fused = 0;
     const char *ns = getenv("UHSDR_B200_NO_SPLIT");
     if (ns && ns[0] == '1') e->use_split = 0;
+    const char *nf2 = getenv("UHSDR_B200_NO_FRONT2");
+    if (nf2 && nf2[0] == '1') e->use_front2 = 0;
     const char *nt = getenv("UHSDR_B200_NO_TC");
     if ((nt && nt[0] == '1') || !rx_ssb_tc_available()) e->use_tc = 0;
     auto fail = [&](const char *what, cudaError_t er) {
@@ -271,6 +275,7 @@ static int rebuild_lists(uhsdr_engine *e)
     e->h_list_fused.clear(); e->h_list_generic.clear(); e->h_list_split.clear(); e->h_list_split_nr.clear();
     e->fused_s1_ci = -1;
     e->split_floats_per_block = 0;
+    e->front2_ok = e->use_front2 != 0;
     for (int c = 0; c < e->nch; c++) {
         const ChanParams &p = e->h_params[c];
         if (!p.configured) { e->last_error = "rx/tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
@@ -283,6 +288,7 @@ static int rebuild_lists(uhsdr_engine *e)
         else if (e->use_split && rx_split_floats_per_block(p) > 0) {
             // channels with the spectral noise reduction take two serial phases around the warp-cooperative NR kernel
             (p.nr_enable ? e->h_list_split_nr : e->h_list_split).push_back(c);
+            if (!rx_front2_eligible(p)) e->front2_ok = false;
             e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));
         } else {
             if (p.notch_enable) { e->last_error = "rx: the LMS auto-notch runs on the split path only (UHSDR_B200_NO_SPLIT is set, or the chain is not split-eligible)"; return UHSDR_ERR_UNSUPPORTED; }
@@ -362,7 +368,8 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
                 s.chan_list = with_nr ? e->d_list_split_nr : e->d_list_split; s.num_items = (int)lst.size();
                 s.scratch = sc;
                 sc += (size_t)s.num_items * (size_t)s.scratch_stride;
-                CK(e, launch_rx_front(s, stream));
+                if (e->front2_ok) CK(e, launch_rx_front2(s, stream));
+                else CK(e, launch_rx_front(s, stream));
                 cudaEvent_t ev = e->ev_split[2 * si + with_nr];
                 CK(e, cudaEventRecord(ev, stream));
                 CK(e, cudaStreamWaitEvent(e->aux_stream, ev, 0));

@@ -30,6 +30,9 @@ cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);
 // split general path: time-parallel front end + FIR stages (one warp per channel, rx_generic.cu) into
 // a.scratch, then the sample-serial stages with one channel per thread (rx_serial.cu)
 cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream);
+// second-generation front kernel (rx_front2.cu): register-blocked FIRs, 512-sample chunks; same contract as launch_rx_front
+bool rx_front2_eligible(const ChanParams &p);
+cudaError_t launch_rx_front2(const RxArgs &a, cudaStream_t stream);
 cudaError_t launch_rx_serial(const RxArgs &a, int phase, cudaStream_t stream);   // phase: see rx_serial.cu
 cudaError_t launch_rx_nr(const RxArgs &a, cudaStream_t stream);                   // spectral NR on a.scratch, in place
 int rx_split_floats_per_block(const ChanParams &p);     // scratch floats per 32-sample block and channel

@@ -7,7 +7,7 @@
 //   IqFinalProcessing (:282-330) x power factor x IQ gain x 1.133 x 65536, phase mix, float -> int32
 // One warp per channel: the recurrences (lattice, biquads, ALC) run on lane 0, the two 201-tap
 // FIRs, translation and output formatting on all 32 lanes.
-#include "dsp_device.cuh"
+#include "fir_device.cuh"
 #include "host_tables.h"
 #include "kernels.h"
 
@@ -417,8 +417,154 @@ tx_serial_kernel(TxArgs a)
     for (int i = 0; i < 320; i++) g.delay[i] = delay[i];
 }
 
+// Second-generation FIR stage of the split modulator (no mute array): 512-sample chunks, the 201-tap Hilbert pair register-blocked
+// (fir_device.cuh fir4_m1_dual: both tap sets on one window, four outputs per lane, taps staged in shared memory), one 32-byte
+// store of four {I, Q} samples per lane.  Same arithmetic order as tx_ssb_kernel<true> (taps ascending), so the exact build
+// stays bit-identical.
+namespace {
+constexpr int TX2_CS = 512, TX2_TAPS = 208;
+struct Tx2Work {
+    alignas(16) float a[H2 + TX2_CS + 8];
+    alignas(16) float ti[TX2_TAPS], tq[TX2_TAPS];
+    float osc[2 * TX2_CS];
+};
+}  // namespace
+
+__global__ void __launch_bounds__(32 * TX_WARPS)
+tx_fir2_kernel(TxArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x * TX_WARPS + warp;
+    if (ch >= a.num_items) return;
+    Tx2Work &w = reinterpret_cast<Tx2Work *>(smem_raw)[warp];
+    const TxParams &tp = a.txp[ch];
+    ChanState *rst = a.state + ch;
+    TxState *tst = a.tx + ch;
+    const float *__restrict__ pool = a.pool;
+    const int N = tp.hil_ntaps;
+    for (int i = lane; i < H2; i += 32) w.a[i] = tst->hist[i];
+    for (int i = lane; i < TX2_CS + 8; i += 32) w.a[H2 + i] = 0.0f;
+    fir_stage_taps(w.ti, pool + (tp.lsb ? tp.hil_cq : tp.hil_ci), N, lane);      // I/Q filters swapped for LSB (tx_processor.c:477-478)
+    fir_stage_taps(w.tq, pool + (tp.lsb ? tp.hil_ci : tp.hil_cq), N, lane);
+    const int groups = fir_padded_len(N) / 4, off = N - 1 + fir_pad_front(N);
+    float osc_q = rst->osc_vect_q, osc_i = rst->osc_vect_i;
+    int conv = rst->conversion_freq;
+    if (tp.shift_kind != 0 && conv != tp.shift_freq) { conv = tp.shift_freq; osc_i = 0.0f; osc_q = 1.0f; }   // freq_shift.c:289-305
+    __syncwarp();
+    const size_t base = (size_t)ch * (size_t)a.chan_stride;
+    int2 *__restrict__ iq = reinterpret_cast<int2 *>(a.iq) + base;
+    float2 *__restrict__ iq_f = a.iq_f ? reinterpret_cast<float2 *>(a.iq_f) + base : nullptr;
+    const float *__restrict__ src = a.scratch + (size_t)ch * (size_t)a.nblocks * BLK;
+
+    for (int s0 = 0; s0 < a.nblocks * BLK; s0 += TX2_CS) {
+        const int ns = min(TX2_CS, a.nblocks * BLK - s0);
+        if (tp.enabled && !tp.fm) {
+            for (int i = lane; i < ns; i += 32) w.a[H2 + i] = src[s0 + i];
+            if (tp.shift_kind == 2) {
+                // FreqShift_Approx (freq_shift.c:57-108): recursive oscillator, renormalised after every 32-sample block
+                if (lane == 0) {
+                    float q0 = osc_q, i0 = osc_i;
+                    for (int n = 0; n < ns; n++) {
+                        const float oq = __fsub_rn(__fmul_rn(q0, tp.osc_cos), __fmul_rn(i0, tp.osc_sin));
+                        const float oi = __fadd_rn(__fmul_rn(i0, tp.osc_cos), __fmul_rn(q0, tp.osc_sin));
+                        w.osc[n] = oq; w.osc[TX2_CS + n] = oi; q0 = oq; i0 = oi;
+                        if ((n & (BLK - 1)) == BLK - 1) {
+                            const float g = __fdiv_rn(__fsub_rn(3.0f, __fadd_rn(__fmul_rn(q0, q0), __fmul_rn(i0, i0))), 2.0f);
+                            q0 = __fmul_rn(g, q0); i0 = __fmul_rn(g, i0);
+                        }
+                    }
+                    osc_q = q0; osc_i = i0;
+                }
+                osc_q = __shfl_sync(0xffffffffu, osc_q, 0); osc_i = __shfl_sync(0xffffffffu, osc_i, 0);
+            }
+            __syncwarp();
+        }
+        for (int sub = 0; sub < ns; sub += 128) {
+            const int n0 = sub + 4 * lane;                 // first of this lane's four samples within the chunk
+            float vi[4] = { 0.0f, 0.0f, 0.0f, 0.0f }, vq[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+            if (tp.enabled && n0 < ns) {
+                if (tp.fm) {
+                    // TxProcessor_FM, tx_processor.c:575-585: I = sine table at the accumulator, Q a quarter turn behind
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const uint32_t idx = (uint32_t)src[s0 + n0 + r];
+                        const float t0 = __ldg(pool + tp.dds_off + idx), t1 = __ldg(pool + tp.dds_off + ((idx + 768u) & 1023u));
+                        vi[r] = tp.fm_swap ? t1 : t0; vq[r] = tp.fm_swap ? t0 : t1;
+                    }
+                } else {
+                    float yi[4], yq[4];
+                    fir4_m1_dual<false>(w.a + H2 + n0 - off, w.ti, w.tq, groups, yi, yq);
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        float i_ = yi[r], q_ = yq[r];
+                        if (tp.am) {                         // both AM sidebands and the carrier, tx_processor.c:783-790
+                            i_ = __fadd_rn(__fsub_rn(yi[r], yq[r]), 10200.0f);
+                            q_ = __fsub_rn(__fsub_rn(yq[r], yi[r]), 10200.0f);
+                        }
+                        if (tp.shift_kind == 1) {            // FreqShift_QuarterFs: the phase is the sample index in the block, = r
+                            float ib = tp.shift_down ? q_ : i_, qb = tp.shift_down ? i_ : q_;
+                            float ni = ib, nq = qb;
+                            if (r == 1) { ni = qb; nq = -ib; } else if (r == 2) { ni = -ib; nq = -qb; } else if (r == 3) { ni = -qb; nq = ib; }
+                            if (tp.shift_down) { q_ = ni; i_ = nq; } else { i_ = ni; q_ = nq; }
+                        } else if (tp.shift_kind == 2) {
+                            const float oq = w.osc[n0 + r], oi = w.osc[TX2_CS + n0 + r];
+                            float ib = tp.shift_down ? q_ : i_, qb = tp.shift_down ? i_ : q_;
+                            const float nq = __fsub_rn(__fmul_rn(qb, oq), __fmul_rn(ib, oi));
+                            const float ni = __fadd_rn(__fmul_rn(ib, oq), __fmul_rn(qb, oi));
+                            if (tp.shift_down) { q_ = ni; i_ = nq; } else { i_ = ni; q_ = nq; }
+                        }
+                        vi[r] = i_; vq[r] = q_;
+                    }
+                }
+            }
+            if (n0 < ns) {
+                int wi[4], wq[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {                // IqFinalProcessing, tx_processor.c:282-330
+                    float i_ = __fmul_rn(vi[r], tp.final_gain_i), q_ = __fmul_rn(vq[r], tp.final_gain_q);
+                    if (tp.phase_bal < 0.0f) q_ = __fadd_rn(q_, __fmul_rn(i_, tp.phase_bal));
+                    else if (tp.phase_bal > 0.0f) i_ = __fadd_rn(i_, __fmul_rn(q_, tp.phase_bal));
+                    wi[r] = __float2int_rz(i_); wq[r] = __float2int_rz(q_);
+                    if (iq_f) iq_f[s0 + n0 + r] = make_float2(i_, q_);
+                }
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(iq + s0 + n0), "r"(wi[0]), "r"(wq[0]), "r"(wi[1]), "r"(wq[1]),
+                             "r"(wi[2]), "r"(wq[2]), "r"(wi[3]), "r"(wq[3]) : "memory");
+            }
+        }
+        __syncwarp();
+        if (tp.enabled && !tp.fm) {
+            // keep the newest H2 samples
+            float keep[(H2 + 31) / 32];
+            int cnt = 0;
+            for (int i = lane; i < H2; i += 32) keep[cnt++] = w.a[ns + i];
+            __syncwarp();
+            cnt = 0;
+            for (int i = lane; i < H2; i += 32) w.a[i] = keep[cnt++];
+            __syncwarp();
+        }
+    }
+    for (int i = lane; i < H2; i += 32) tst->hist[i] = w.a[i];
+    if (lane == 0) { tst->blocks += a.nblocks; rst->osc_vect_q = osc_q; rst->osc_vect_i = osc_i; rst->conversion_freq = conv; }
+}
+
+static bool tx_fir2_ok(const TxArgs &a)
+{
+    static const bool off = [] { const char *v = getenv("UHSDR_B200_NO_FRONT2"); return v && v[0] == '1'; }();
+    return !off && a.scratch != nullptr && a.mute == nullptr && ((uintptr_t)a.iq % 32 == 0) && (a.chan_stride % 4 == 0) && (a.nblocks * BLK) % 4 == 0;
+}
+
 cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
 {
+    if (tx_fir2_ok(a)) {
+        const size_t smem2 = sizeof(Tx2Work) * TX_WARPS;
+        const int grid2 = (a.num_items + TX_WARPS - 1) / TX_WARPS;
+        if (grid2 == 0) return cudaSuccess;
+        cudaError_t e2 = cudaFuncSetAttribute(tx_fir2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e2 != cudaSuccess) return e2;
+        tx_fir2_kernel<<<grid2, 32 * TX_WARPS, smem2, stream>>>(a);
+        return cudaGetLastError();
+    }
     const size_t smem = sizeof(TxWork) * TX_WARPS;
     const int grid = (a.num_items + TX_WARPS - 1) / TX_WARPS;
     if (grid == 0) return cudaSuccess;
