@@ -160,7 +160,15 @@ typedef struct {
     float   tx_peak_audio;       /* ads.peak_audio, tx_processor.c:403                              */
     float   tx_alc_val;          /* ads.alc_val                                                     */
     int64_t blocks_processed;
+    /* "twin peaks" detector of the automatic IQ correction (AudioDriver_RxHandleTwinpeaks, audio_driver.c:2173-2248):
+     * ts.twinpeaks_tested -- 2 = waiting for the channel to settle (1000 blocks), 0 = sampling the I/Q phase error (50 blocks),
+     * 1 = done, phase error below 22.5 degrees, 4 = codec restart requested (phase error above), 3 = uncorrectable (4th request).
+     * The firmware's main loop answers 4 by restarting the codec and re-arming the detector (ui_driver.c:7422-7425):
+     * uhsdr_twinpeaks_rearm is that re-arm. */
+    int32_t twinpeaks_state;
+    int32_t twinpeaks_restarts;  /* codec_restarts, audio_driver.c:2186 */
 } uhsdr_chan_status_t;
+enum { UHSDR_TWINPEAKS_SAMPLING = 0, UHSDR_TWINPEAKS_DONE = 1, UHSDR_TWINPEAKS_WAIT = 2, UHSDR_TWINPEAKS_UNCORRECTABLE = 3, UHSDR_TWINPEAKS_CODEC_RESTART = 4 };
 
 typedef struct uhsdr_engine uhsdr_engine_t;
 
@@ -256,6 +264,8 @@ int uhsdr_spectrum_display_device(uhsdr_engine_t *e, int first, int count, const
                                   float *disp_dev, uhsdr_spectrum_level_t *levels_dev, float *avg_dev, float *mags_dev);
 
 int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_t *status);
+/* ts.twinpeaks_tested = TWINPEAKS_WAIT for channels [first, first+count) (after the host has "restarted the codec"). */
+int uhsdr_twinpeaks_rearm(uhsdr_engine_t *e, int first, int count);
 
 /* Number of kernel launches issued by this engine so far (bench.py "gpu_launches"). */
 int64_t uhsdr_engine_launch_count(const uhsdr_engine_t *e);

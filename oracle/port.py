@@ -124,6 +124,10 @@ class PortChannel:
             raise RuntimeError(f"port_spectrum_display: {rc}")
         return mags, avg, disp, lvl
 
+    def twinpeaks_rearm(self) -> None:
+        lib().port_twinpeaks_rearm.argtypes = [ctypes.c_void_p]
+        lib().port_twinpeaks_rearm(self._h)
+
     def status(self) -> ChanStatus:
         st = ChanStatus()
         lib().port_get_status(self._h, ctypes.byref(st))

@@ -113,6 +113,7 @@ int ref_init(const uhsdr_chan_cfg_t *cfg)
     ts.rx_gain[RX_AUDIO_SPKR].value = 10;
     ts.rx_gain[RX_AUDIO_DIG].value = 31;
     ts.beep_frequency = DEFAULT_BEEP_FREQUENCY;
+    ts.twinpeaks_tested = TWINPEAKS_WAIT;                         /* uhsdr_main.c:339 */
     ref_apply_cfg(cfg);
     AudioDriver_Init();
     nr_params.NR_decimation_enable = cfg->nr_decimation_enable;   /* NR_Init (audio_nr.c:88) forces it to true */
@@ -210,6 +211,7 @@ int ref_get_status(uhsdr_chan_status_t *st)
     st->sam_carrier_freq_offset = ads.carrier_freq_offset;
     st->iq_corr_c1 = adb.iq_corr.M_c1; st->iq_corr_c2 = adb.iq_corr.M_c2;
     st->tx_peak_audio = ads.peak_audio; st->tx_alc_val = ads.alc_val;
+    st->twinpeaks_state = ts.twinpeaks_tested;                    /* codec_restarts is a function-local static: not reachable */
     return 0;
 }
 
@@ -225,3 +227,6 @@ static void ref_apply_fm_tones(const uhsdr_chan_cfg_t *cfg)
     AudioManagement_LoadToneBurstMode();
     ads.fm_conf.tone_burst_active = cfg->fm_tone_burst_mode != 0;
 }
+
+/* what the firmware's main loop does after TWINPEAKS_CODEC_RESTART (ui_driver.c:7422-7425), minus the codec */
+int ref_twinpeaks_rearm(void) { ts.twinpeaks_tested = TWINPEAKS_WAIT; return 0; }

@@ -113,6 +113,9 @@ class RefChannel:
             raise RuntimeError(f"ref_spectrum_redraw failed: {rc}")
         return mags, avg, disp, lvl
 
+    def twinpeaks_rearm(self) -> None:
+        self._lib.ref_twinpeaks_rearm()
+
     def status(self) -> ChanStatus:
         st = ChanStatus()
         self._lib.ref_get_status(ctypes.byref(st))

@@ -547,6 +547,7 @@ struct port_chan {
     int use_decimated_iq;
     /* IQ correction, audio_driver.h:125-135 */
     float teta1, teta2, teta3, teta1_old, teta2_old, teta3_old, M_c1, M_c2;
+    int tw_state; uint32_t tw_counter, tw_runs, tw_restarts; float tw_phase;   /* ts.twinpeaks_tested + statics of AudioDriver_RxHandleTwinpeaks */
     /* FreqShift_Approx NCO, freq_shift.c:20-47 */
     int conversion_freq;
     float osc_cos, osc_sin, osc_vect_q, osc_vect_i;
@@ -743,6 +744,7 @@ port_chan_t *port_chan_create(const port_tables_t *t, const uhsdr_chan_cfg_t *cf
     for (int s = 0; s < 3; s++) memcpy(c->tx_bq[s].c, BQ_PASS, sizeof(BQ_PASS));
     c->fm_squelched = 1;                      /* audio_driver.c:475 */
     c->alc_val = 1;                           /* tx_processor.c:137 */
+    c->tw_state = UHSDR_TWINPEAKS_WAIT;       /* uhsdr_main.c:339 */
     c->sam_c0 = tbl_array(t, t->ex->sam_c0_array, NULL);
     c->sam_c1 = tbl_array(t, t->ex->sam_c1_array, NULL);
     lattice_from_table(t, t->ex->fm_squelch_lattice, &c->sql_hpf);   /* audio_driver.c:481-485 */
@@ -759,6 +761,26 @@ void port_chan_free(port_chan_t *c) { free(c); }
 /* ------------------------------------------------------------------------------------------ */
 
 /* AudioDriver_RxHandleIqCorrection, audio_driver.c:2254-2316 */
+/* AudioDriver_RxHandleTwinpeaks, audio_driver.c:2173-2248 (ts.twinpeaks_tested and the function's statics per channel) */
+static void rx_twinpeaks(port_chan_t *c)
+{
+    if (c->tw_state == UHSDR_TWINPEAKS_WAIT) c->tw_counter++;
+    if (c->tw_counter > 1000) { c->tw_state = UHSDR_TWINPEAKS_SAMPLING; c->tw_counter = 0; c->tw_phase = 0.0; c->tw_runs = 0; }
+    if (c->teta3 != 0.0 && c->tw_state == UHSDR_TWINPEAKS_SAMPLING) {
+        float phase_IQ_cur = asinf(c->teta1 / c->teta3);
+        if (c->tw_runs == 0) c->tw_phase = phase_IQ_cur;
+        else c->tw_phase = 0.05 * phase_IQ_cur + 0.95 * c->tw_phase;
+        c->tw_runs++;
+        if (c->tw_runs == 50) {
+            if (fabsf(c->tw_phase) > (M_PI / 8.0)) {
+                c->tw_state = UHSDR_TWINPEAKS_CODEC_RESTART;
+                c->tw_restarts++;
+                if (c->tw_restarts >= 4) { c->tw_state = UHSDR_TWINPEAKS_UNCORRECTABLE; c->tw_restarts = 0; }
+            } else { c->tw_state = UHSDR_TWINPEAKS_DONE; c->tw_restarts = 0; }
+        }
+    }
+}
+
 static void rx_iq_correction(port_chan_t *c, float *ib, float *qb)
 {
     if (!c->cfg.iq_auto_correction) {
@@ -782,6 +804,7 @@ static void rx_iq_correction(port_chan_t *c, float *ib, float *qb)
     float help = (c->teta2 * c->teta2);
     if (help > 0.0) help = (c->teta3 * c->teta3 - c->teta1 * c->teta1) / help;
     c->M_c2 = (help > 0.0) ? sqrtf(help) : 1.0;
+    rx_twinpeaks(c);
     c->teta1_old = c->teta1; c->teta2_old = c->teta2; c->teta3_old = c->teta3;
     c->teta1 = 0.0; c->teta2 = 0.0; c->teta3 = 0.0;
     for (int i = 0; i < BLK; i++) qb[i] += c->M_c1 * ib[i];
@@ -1103,6 +1126,8 @@ int port_rx(port_chan_t *c, const int32_t *iq, int32_t *audio, float *audio_f, i
     return UHSDR_OK;
 }
 
+int port_twinpeaks_rearm(port_chan_t *c) { if (!c) return UHSDR_ERR_ARG; c->tw_state = UHSDR_TWINPEAKS_WAIT; return UHSDR_OK; }
+
 int port_get_status(const port_chan_t *c, uhsdr_chan_status_t *st)
 {
     memset(st, 0, sizeof(*st));
@@ -1113,6 +1138,7 @@ int port_get_status(const port_chan_t *c, uhsdr_chan_status_t *st)
     st->iq_corr_c1 = c->M_c1; st->iq_corr_c2 = c->M_c2;
     st->tx_peak_audio = c->peak_audio; st->tx_alc_val = c->alc_val;
     st->blocks_processed = c->blocks;
+    st->twinpeaks_state = c->tw_state; st->twinpeaks_restarts = (int32_t)c->tw_restarts;
     return UHSDR_OK;
 }
 

@@ -40,6 +40,7 @@ int port_tx(port_chan_t *c, const int32_t *mic, int32_t *iq, float *iq_f, int nb
 int port_spectrum(port_chan_t *c, float *mags);
 /* UiSpectrum_RedrawSpectrum states 0-4: mags_out / avg_out optional [512]; disp [scope_width]; lvl [3] = dBm, dBm/Hz, display offset. */
 int port_spectrum_display(port_chan_t *c, const uhsdr_spectrum_display_cfg_t *dc, float *mags_out, float *avg_out, float *disp, float *lvl);
+int port_twinpeaks_rearm(port_chan_t *c);
 int port_get_status(const port_chan_t *c, uhsdr_chan_status_t *st);
 
 #ifdef __cplusplus

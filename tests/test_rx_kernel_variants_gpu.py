@@ -173,3 +173,105 @@ def test_tensor_core_kernel_long_call(built):
         with oracle_channel(cfgs[c]) as o:
             want_w, want_f = o.rx(iq[c])
         check_tolerance(f1[c], want_f, w1[c, :, 0], want_w[:, 0], f"long/ch{c}")
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("path_kw", [dict(), dict(filter_path=48), dict(dmod_mode=3, filter_path=70)], ids=["narrow_fused", "wide_split", "am_split"])
+def test_twinpeaks_detector_state(built, exact, path_kw):
+    """AudioDriver_RxHandleTwinpeaks (audio_driver.c:2173-2248) as a host-visible flag: a healthy I/Q pair ends in DONE after
+    1050 blocks, a pair without mirror rejection (Q = I: phase error 90 degrees) requests a codec restart; re-arming starts over;
+    the fourth request in a row reads UNCORRECTABLE.  Same state sequence as the oracle, on the fused and on the split path."""
+    from uhsdr_b200.config import TWINPEAKS_CODEC_RESTART, TWINPEAKS_DONE, TWINPEAKS_UNCORRECTABLE, TWINPEAKS_WAIT
+    cfg = default_cfg(**path_kw)
+    nb = 1100
+    good = synth.counter_block(np, [synth.kind_of(cfg)], [3], 0, nb * 32)[0]
+    twin = good.copy()
+    twin[:, 1] = twin[:, 0]
+    iq = np.stack([good, twin, good])
+    with oracle_channel(cfg) as og, oracle_channel(cfg) as ot, Engine(3, exact=exact) as eng:
+        eng.configure(cfg)
+        seq, want = [], []
+        for k in range(0, nb, 100):
+            eng.rx(iq[:, k * 32:(k + 100) * 32])
+            og.rx(good[k * 32:(k + 100) * 32]); ot.rx(twin[k * 32:(k + 100) * 32])
+            st = eng.status()
+            seq.append((st[0].twinpeaks_state, st[1].twinpeaks_state, st[2].twinpeaks_state))
+            want.append((og.status().twinpeaks_state, ot.status().twinpeaks_state, og.status().twinpeaks_state))
+        assert seq == want
+        assert seq[0] == (TWINPEAKS_WAIT,) * 3 and seq[-1] == (TWINPEAKS_DONE, TWINPEAKS_CODEC_RESTART, TWINPEAKS_DONE)
+        assert eng.status()[1].twinpeaks_restarts == 1
+        for rep in range(3):                      # three more failed attempts: the fourth in a row is final
+            eng.twinpeaks_rearm(first=1, count=1)
+            ot.twinpeaks_rearm()
+            assert eng.status()[1].twinpeaks_state == TWINPEAKS_WAIT
+            for k in range(0, nb, 100):
+                eng.rx(iq[:, k * 32:(k + 100) * 32])
+                ot.rx(twin[k * 32:(k + 100) * 32])
+            assert eng.status()[1].twinpeaks_state == ot.status().twinpeaks_state
+        assert eng.status()[1].twinpeaks_state == TWINPEAKS_UNCORRECTABLE
+        assert eng.status()[0].twinpeaks_state == TWINPEAKS_DONE
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_clip_flags_with_clipping_input(built, exact):
+    """ads.adc_quarter_clip / adc_half_clip / adc_clip (audio_driver.c:2662-2675) against the oracle, fused and split path:
+    one channel per threshold region (below a quarter, above a quarter, above half, full scale)."""
+    for kw in (dict(), dict(filter_path=48)):
+        cfg = default_cfg(**kw)
+        base = synth.counter_block(np, [synth.kind_of(cfg)], [5], 0, 64 * 32)[0].astype(np.int64)
+        chans = []
+        for peak in (900, 1500, 3000, 6000):                     # thresholds are 1024 / 2048 / 4096 in 16-bit units
+            x = (base.astype(np.float64) / np.max(np.abs(base[:, 0])) * (peak * 65536.0)).astype(np.int64)
+            chans.append(np.clip(x, -2**31, 2**31 - 1).astype(np.int32))
+        iq = np.stack(chans)
+        with Engine(4, exact=exact) as eng:
+            eng.configure(cfg)
+            eng.rx(iq)
+            got = [(s.adc_quarter_clip, s.adc_half_clip, s.adc_clip) for s in eng.status()]
+        want = []
+        for c in range(4):
+            with oracle_channel(cfg) as o:
+                o.rx(iq[c])
+                s = o.status()
+                want.append((s.adc_quarter_clip, s.adc_half_clip, s.adc_clip))
+        assert got == want
+        assert want == [(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)]
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+def test_host_path_time_slices_match_one_device_call(built, monkeypatch, exact):
+    """uhsdr_rx_process cuts a large host call into time slices on three streams (H2D | kernels | D2H).  Forced here with
+    UHSDR_B200_SLICES on a call whose block count is not a multiple of the slice size (the last slice takes the general kernel),
+    with a mute array: the exact build is bit-equal to a single device-resident call (which, 282 blocks not being a multiple
+    of 4, runs on the general kernel throughout); the shipping build, whose fused and general kernels differ by rounding, within
+    one 16-bit LSB."""
+    import torch
+    monkeypatch.setenv("UHSDR_B200_SLICES", "5")
+    nch, nb = 12, 70 * 4 + 2
+    cfgs = [default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38), default_cfg(filter_path=48)]
+    iq = np.concatenate([synth.counter_block(np, [synth.kind_of(cfgs[c % 3])], [c], 0, nb * 32) for c in range(nch)])
+    big = np.tile(iq, (128, 1, 1))[: 128 * nch]                     # >= 32 MB so that the slicing engages
+    n = big.shape[0]
+    mute = np.zeros((n, nb), dtype=np.uint8)
+    mute[:, 33:41] = 1
+    mute[::3, 200:203] = 1
+    outs = []
+    for host in (True, False):
+        with Engine(n, exact=exact) as eng:
+            for k in range(3):
+                eng.configure(cfgs[k], first=k, stride=3)
+            if host:
+                outs.append(eng.rx(big, mute))
+            else:
+                dev = torch.device("cuda", 0)
+                d_iq, d_m = torch.from_numpy(big).to(dev), torch.from_numpy(mute).to(dev)
+                d_out = torch.empty_like(d_iq)
+                eng.rx_device(d_iq, d_out, nb, mute_dev=d_m)
+                eng.sync()
+                outs.append(d_out.cpu().numpy())
+    if exact:
+        assert np.array_equal(outs[0], outs[1])
+    else:
+        d = (outs[0].astype(np.int64) >> 16) - (outs[1].astype(np.int64) >> 16)
+        assert int(np.max(np.abs(d))) <= 1
+    assert np.all(outs[0][:, 33 * 32:41 * 32] == 0)

@@ -15,6 +15,8 @@ DSP_NR_ENABLE, DSP_NR_POSTAGC_ENABLE, DSP_NOTCH_ENABLE, DSP_NB_ENABLE, DSP_MNOTC
     0x01, 0x02, 0x04, 0x08, 0x10, 0x20)
 TX_FILTER_SOPRANO, TX_FILTER_TENOR, TX_FILTER_BASS = 1, 2, 3
 
+TWINPEAKS_SAMPLING, TWINPEAKS_DONE, TWINPEAKS_WAIT, TWINPEAKS_UNCORRECTABLE, TWINPEAKS_CODEC_RESTART = range(5)
+
 BLOCK_SIZE = 32
 SAMPLE_RATE = 48000
 
@@ -74,6 +76,7 @@ class ChanStatus(ctypes.Structure):
         ("iq_corr_c1", _f32), ("iq_corr_c2", _f32),
         ("tx_peak_audio", _f32), ("tx_alc_val", _f32),
         ("blocks_processed", ctypes.c_int64),
+        ("twinpeaks_state", _i32), ("twinpeaks_restarts", _i32),
     ]
 
 

@@ -7,6 +7,7 @@
 //                are cleared; the AGC ring is re-initialised only when the decimated rate changed
 //                (audio_agc.c:138-142) and in_index is re-derived from out_index (:292-293);
 //                biquad, SAM, FM, fade-leveler and NR state are kept.
+#include "dsp_device.cuh"
 #include "kernels.h"
 
 namespace uhsdr {
@@ -46,6 +47,7 @@ __global__ void configure_kernel(ChanParams *params, ChanState *state, NrState *
         s.fm_squelched = 1;             // audio_driver.c:475
         s.agc_out_index = -1;           // audio_agc.c:190
         s.agc_sample_rate = 0.0f;
+        s.tw_state = 2;                 // ts.twinpeaks_tested = TWINPEAKS_WAIT, uhsdr_main.c:339
         if (nr) {
             uint32_t *wn = reinterpret_cast<uint32_t *>(&nr[ch]);
             for (int k = 0; k < (int)(sizeof(NrState) / 4); k++) wn[k] = 0u;
@@ -94,6 +96,59 @@ cudaError_t launch_configure(ChanParams *params, ChanState *state, NrState *nr, 
     const int threads = 64;
     configure_kernel<<<(count + threads - 1) / threads, threads, 0, stream>>>(params, state, nr, spec_ring, tx, txparams,
                                                                                newp, newtx, first, count, stride, reset);
+    return cudaGetLastError();
+}
+
+__global__ void twinpeaks_rearm_kernel(ChanState *state, int first, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) state[first + i].tw_state = 2;       // ui_driver.c:7425; the detector's own statics keep their values
+}
+
+// AudioDriver_RxHandleTwinpeaks as its own small kernel, launched in front of the receiver kernels while a channel's detector can
+// still be active (the 1050 blocks after a reset or a re-arm): one warp per channel walks through the call's blocks, forms the
+// block statistics of the automatic IQ correction from the raw input (audio_driver.c:2274-2283, reference summation order, EMA
+// in double), and feeds teta1 / teta3 of every block to the detector.  It reads the correction averages the receiver kernel will
+// start from and writes nothing but the detector's own state -- so none of the hot kernels carries the detector.
+__global__ void __launch_bounds__(128)
+twinpeaks_kernel(const ChanParams *__restrict__ params, ChanState *state, const void *iq, int nch, int nblocks, long long chan_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ch >= nch) return;
+    const ChanParams &p = params[ch];
+    ChanState *st = state + ch;
+    TwinPeaks tw = twinpeaks_load(st);
+    if (!p.configured || !p.iq_auto || !twinpeaks_active(tw)) return;
+    const int2 *__restrict__ src = reinterpret_cast<const int2 *>(iq) + (size_t)ch * (size_t)chan_stride;
+    float te1 = st->teta1_old, te2 = st->teta2_old, te3 = st->teta3_old;
+    for (int b = 0; b < nblocks && twinpeaks_active(tw); b++) {
+        const int2 s = src[(size_t)b * BLK + lane];
+        const float fi = __fmul_rn((float)s.x, 0.0000152587890625f), fq = __fmul_rn((float)s.y, 0.0000152587890625f);
+        const float t1 = __fmul_rn(sign_new(fi), fq), t2 = __fmul_rn(sign_new(fi), fi), t3 = __fmul_rn(sign_new(fq), fq);
+        float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        for (int j = 0; j < 32; j++) {
+            s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, t1, j));
+            s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, t2, j));
+            s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, t3, j));
+        }
+        te1 = (float)(-0.003 * (double)__fdiv_rn(s1, 32.0f) + 0.997 * (double)te1);
+        te2 = (float)(0.003 * (double)__fdiv_rn(s2, 32.0f) + 0.997 * (double)te2);
+        te3 = (float)(0.003 * (double)__fdiv_rn(s3, 32.0f) + 0.997 * (double)te3);
+        tw = twinpeaks_block(tw, te1, te3);
+    }
+    if (lane == 0) twinpeaks_store(st, tw);
+}
+
+cudaError_t launch_twinpeaks(const ChanParams *params, ChanState *state, const void *iq, int nch, int nblocks, long long chan_stride, cudaStream_t stream)
+{
+    twinpeaks_kernel<<<(nch + 3) / 4, 128, 0, stream>>>(params, state, iq, nch, nblocks, chan_stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_twinpeaks_rearm(ChanState *state, int first, int count, cudaStream_t stream)
+{
+    twinpeaks_rearm_kernel<<<(count + 127) / 128, 128, 0, stream>>>(state, first, count);
     return cudaGetLastError();
 }
 

@@ -182,6 +182,35 @@ __device__ __forceinline__ float agc_step(float x, const AgcP &a, AgcRun &r, flo
     return __fmul_rn(out_sample, mult);
 }
 
+// AudioDriver_RxHandleTwinpeaks (audio_driver.c:2173-2248), one block: called after the block's IQ-correction averages teta1 /
+// teta3 have been updated (automatic IQ correction only).  Used by twinpeaks_kernel (configure.cu), not by the receiver kernels.
+struct TwinPeaks { int state, counter, runs, restarts; float phase; };
+__device__ __forceinline__ bool twinpeaks_active(const TwinPeaks &t) { return t.state == 2 || t.state == 0; }
+__device__ __forceinline__ TwinPeaks twinpeaks_block(TwinPeaks t, float teta1, float teta3)
+{
+    if (t.state == 2) t.counter++;
+    if (t.counter > 1000) { t.state = 0; t.counter = 0; t.phase = 0.0f; t.runs = 0; }
+    if (teta3 != 0.0f && t.state == 0) {
+        const float cur = asinf(__fdiv_rn(teta1, teta3));
+        if (t.runs == 0) t.phase = cur;
+        else t.phase = (float)(0.05 * (double)cur + 0.95 * (double)t.phase);
+        t.runs++;
+        if (t.runs == 50) {
+            if ((double)fabsf(t.phase) > (3.14159265358979323846 / 8.0)) {
+                t.state = 4;
+                t.restarts++;
+                if (t.restarts >= 4) { t.state = 3; t.restarts = 0; }
+            } else { t.state = 1; t.restarts = 0; }
+        }
+    }
+    return t;
+}
+__device__ __forceinline__ TwinPeaks twinpeaks_load(const ChanState *st) { TwinPeaks t = { st->tw_state, st->tw_counter, st->tw_runs, st->tw_restarts, st->tw_phase }; return t; }
+__device__ __forceinline__ void twinpeaks_store(ChanState *st, const TwinPeaks &t)
+{
+    st->tw_state = t.state; st->tw_counter = t.counter; st->tw_runs = t.runs; st->tw_restarts = t.restarts; st->tw_phase = t.phase;
+}
+
 // float -> int32 -> << 16 output formatting, audio_driver.c:2911-2922.  In range this is C
 // truncation toward zero; out-of-range values (undefined behaviour in the reference) saturate.
 __device__ __forceinline__ int32_t format_audio_word(float a)

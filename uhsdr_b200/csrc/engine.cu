@@ -49,6 +49,7 @@ struct uhsdr_engine {
     int use_split = 1;       // general path as front (FIR) kernel + thread-per-channel serial kernel
     int use_front2 = 1;      // register-blocked front kernel (rx_front2.cu) where every split channel's chain fits it
     bool front2_ok = false;
+    long long tw_blocks_left = 0;    // > 0: some channel's twin-peaks detector may still be active (1050 blocks after a reset / re-arm)
     FusedCoefs fused_coefs;
     bool fused_coefs_valid = false;
     int fused_s1_ci = -1, fused_s2_ci = -1, fused_s2_cq = -1;
@@ -260,6 +261,7 @@ int uhsdr_configure_channels_strided(uhsdr_engine_t *e, int first, int count, in
     e->launches++;
     for (int i = 0; i < count; i++) { const int c = first + i * stride; e->h_params[c] = p; e->h_tx_enabled[c] = tp.enabled; }
     e->lists_dirty = true;
+    if (reset) e->tw_blocks_left = 1056;      // 1001 blocks of settling + 50 of sampling (audio_driver.c:2194-2225), rounded up
     return UHSDR_OK;
 }
 
@@ -320,6 +322,11 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
     a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
     a.chan_stride = chan_stride; a.mute_stride = mute_stride; a.scratch = nullptr; a.scratch_stride = 0;
+    if (e->tw_blocks_left > 0) {
+        CK(e, launch_twinpeaks(e->d_params, e->d_state, iq_dev, e->nch, nblocks, chan_stride, stream));
+        e->launches++;
+        e->tw_blocks_left -= nblocks;
+    }
     if (!e->h_list_fused.empty()) {
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
@@ -654,8 +661,19 @@ int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_
         o.sam_carrier_freq_offset = s.carrier_freq_offset;
         o.iq_corr_c1 = s.M_c1; o.iq_corr_c2 = s.M_c2;
         o.blocks_processed = s.blocks;
+        o.twinpeaks_state = s.tw_state; o.twinpeaks_restarts = s.tw_restarts;
         if (!ht.empty()) { o.tx_peak_audio = ht[i].peak_audio; o.tx_alc_val = ht[i].alc_val; }
     }
+    return UHSDR_OK;
+}
+
+int uhsdr_twinpeaks_rearm(uhsdr_engine_t *e, int first, int count)
+{
+    if (!e || first < 0 || count <= 0 || first + count > e->nch) { if (e) e->last_error = "twinpeaks_rearm: bad arguments"; return UHSDR_ERR_ARG; }
+    CK(e, cudaSetDevice(e->device));
+    CK(e, launch_twinpeaks_rearm(e->d_state, first, count, e->stream));
+    e->launches++;
+    e->tw_blocks_left = 1056;
     return UHSDR_OK;
 }
 

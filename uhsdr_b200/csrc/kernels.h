@@ -68,6 +68,9 @@ cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream);
 cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream);
 cudaError_t launch_tx_boot(TxState *tx, int n, cudaStream_t stream);
 cudaError_t launch_nr_boot(NrState *nr, int n, cudaStream_t stream);
+cudaError_t launch_twinpeaks_rearm(ChanState *state, int first, int count, cudaStream_t stream);
+// the twin-peaks detector over the blocks of one call, before the receiver kernels (configure.cu)
+cudaError_t launch_twinpeaks(const ChanParams *params, ChanState *state, const void *iq, int nch, int nblocks, long long chan_stride, cudaStream_t stream);
 
 // UiSpectrum_RedrawSpectrum states 0-2
 cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, const float *spec_ring, const float *pool,

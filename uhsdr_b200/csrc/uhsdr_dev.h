@@ -143,6 +143,9 @@ struct ChanState {
     float zoom_hist_i[4], zoom_hist_q[4]; // DECIMATE_ZOOM_FFT_I/Q state (3 used; zeroed by AudioDriver_Spectrum_Set)
     int adc_clip, adc_half_clip, adc_quarter_clip;
     long long blocks;
+    // AudioDriver_RxHandleTwinpeaks statics (audio_driver.c:2183-2187) and ts.twinpeaks_tested
+    int tw_state, tw_counter, tw_runs, tw_restarts;
+    float tw_phase;
 };
 
 // The sample-serial part of ChanState (same member names), the per-thread working copy of rx_serial.cu.

@@ -31,7 +31,7 @@ EXPORTS = [
     "uhsdr_configure_channels", "uhsdr_configure_channel", "uhsdr_configure_channels_strided", "uhsdr_rx_process", "uhsdr_rx_process_device",
     "uhsdr_tx_process", "uhsdr_tx_process_device", "uhsdr_engine_sync", "uhsdr_engine_stream",
     "uhsdr_get_spectrum", "uhsdr_get_spectrum_device", "uhsdr_get_status", "uhsdr_engine_launch_count",
-    "uhsdr_tables_validate", "uhsdr_default_spectrum_display_cfg", "uhsdr_spectrum_display", "uhsdr_spectrum_display_device",
+    "uhsdr_twinpeaks_rearm", "uhsdr_tables_validate", "uhsdr_default_spectrum_display_cfg", "uhsdr_spectrum_display", "uhsdr_spectrum_display_device",
 ]
 
 _libs: dict[str, ctypes.CDLL] = {}
@@ -76,6 +76,7 @@ def load_library(exact: bool = False) -> ctypes.CDLL:
     L.uhsdr_get_spectrum.argtypes = [vp, ci, ci, vp]
     L.uhsdr_get_spectrum_device.argtypes = [vp, ci, ci, vp]
     L.uhsdr_get_status.argtypes = [vp, ci, ci, ctypes.POINTER(ChanStatus)]
+    L.uhsdr_twinpeaks_rearm.argtypes = [vp, ci, ci]
     L.uhsdr_default_spectrum_display_cfg.argtypes = [ctypes.POINTER(SpectrumDisplayCfg)]
     L.uhsdr_spectrum_display.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp]
     L.uhsdr_spectrum_display_device.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp, vp]
@@ -178,6 +179,10 @@ class Engine:
         arr = (ChanStatus * count)()
         self._check(self._lib.uhsdr_get_status(self._h, first, count, arr))
         return list(arr)
+
+    def twinpeaks_rearm(self, first: int = 0, count: int | None = None) -> None:
+        count = self.num_channels - first if count is None else count
+        self._check(self._lib.uhsdr_twinpeaks_rearm(self._h, first, count))
 
     def sync(self) -> None:
         self._check(self._lib.uhsdr_engine_sync(self._h))
