@@ -173,7 +173,7 @@ enum { UHSDR_TWINPEAKS_SAMPLING = 0, UHSDR_TWINPEAKS_DONE = 1, UHSDR_TWINPEAKS_W
 typedef struct uhsdr_engine uhsdr_engine_t;
 
 /* Library identity.  uhsdr_b200_backend() returns "cuda-sm100a". */
-int         uhsdr_b200_abi_version(void);
+int         uhsdr_b200_abi_version(void);   /* 2: + tables_validate, spectrum_display, twinpeaks, multi */
 const char *uhsdr_b200_backend(void);
 const char *uhsdr_strerror(int code);
 /* Text of the last CUDA failure on this engine (or of engine creation when e == NULL). */
@@ -266,6 +266,31 @@ int uhsdr_spectrum_display_device(uhsdr_engine_t *e, int first, int count, const
 int uhsdr_get_status(uhsdr_engine_t *e, int first, int count, uhsdr_chan_status_t *status);
 /* ts.twinpeaks_tested = TWINPEAKS_WAIT for channels [first, first+count) (after the host has "restarted the codec"). */
 int uhsdr_twinpeaks_rearm(uhsdr_engine_t *e, int first, int count);
+
+/* ---- several GPUs of one box behind one handle -------------------------------------------------------
+ * Channels are independent, so global channel c lives on exactly one device: device g of G owns the contiguous range
+ * uhsdr_channel_range(g, G, num_channels).  There is no collective and no peer traffic; a call is forwarded to the per-device
+ * engines from one host thread per device.  Buffers are host memory, channel-major over ALL channels. */
+typedef struct uhsdr_multi uhsdr_multi_t;
+/* [first, first+count) of `total` channels owned by `rank` of `world`; sizes differ by at most one. */
+int uhsdr_channel_range(int rank, int world, int total, int *first, int *count);
+int uhsdr_multi_create(uhsdr_multi_t **out, int num_channels, const int *devices, int num_devices,
+                       const void *tables, size_t tables_bytes);
+int uhsdr_multi_destroy(uhsdr_multi_t *m);
+int uhsdr_multi_num_devices(const uhsdr_multi_t *m);
+int uhsdr_multi_num_channels(const uhsdr_multi_t *m);
+const char *uhsdr_multi_last_error(const uhsdr_multi_t *m);
+/* The engine of device slot `index` and the global channel range it owns (for the device-pointer entry points). */
+uhsdr_engine_t *uhsdr_multi_engine(uhsdr_multi_t *m, int index, int *first, int *count);
+/* Global channel numbers; forwarded to the owning engines. */
+int uhsdr_multi_configure_channels(uhsdr_multi_t *m, int first, int count, const uhsdr_chan_cfg_t *cfg, int reset);
+int uhsdr_multi_configure_channels_strided(uhsdr_multi_t *m, int first, int count, int stride,
+                                           const uhsdr_chan_cfg_t *cfg, int reset);
+int uhsdr_multi_rx_process(uhsdr_multi_t *m, const uhsdr_iq_sample_t *iq, uhsdr_audio_sample_t *audio,
+                           int nblocks, const uint8_t *mute);
+int uhsdr_multi_tx_process(uhsdr_multi_t *m, const uhsdr_audio_sample_t *audio, uhsdr_iq_sample_t *iq,
+                           int nblocks, const uint8_t *mute);
+int uhsdr_multi_get_status(uhsdr_multi_t *m, int first, int count, uhsdr_chan_status_t *status);
 
 /* Number of kernel launches issued by this engine so far (bench.py "gpu_launches"). */
 int64_t uhsdr_engine_launch_count(const uhsdr_engine_t *e);

@@ -26,8 +26,33 @@ def test_library_exports_every_declared_symbol(built, exact):
     for n in names:
         assert hasattr(lib, n), n
     assert set(EXPORTS) == set(names)
-    assert lib.uhsdr_b200_abi_version() == 1
+    assert lib.uhsdr_b200_abi_version() == 2
     assert lib.uhsdr_b200_backend().decode().startswith("cuda-sm100a")
+
+
+def test_channel_range_in_c_matches_the_python_partition(built):
+    from uhsdr_b200.partition import channel_range
+    lib = load_library()
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                f, c = ctypes.c_int(), ctypes.c_int()
+                assert lib.uhsdr_channel_range(rank, world, total, ctypes.byref(f), ctypes.byref(c)) == 0
+                lo, hi = channel_range(rank, world, total)
+                assert (f.value, c.value) == (lo, hi - lo)
+    assert lib.uhsdr_channel_range(2, 2, 10, ctypes.byref(f), ctypes.byref(c)) == -1
+
+
+def test_c_host_example_is_built_against_the_abi(built):
+    """examples/host.c is compiled by a plain C compiler against include/uhsdr_b200.h and linked to the shipping library
+    (the GPU test runs it); without a GPU it must fail loudly at engine creation, not fall back."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "host")
+    assert os.path.exists(exe)
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, os.path.join(ROOT, "uhsdr_b200", "data", "uhsdr_tables.bin"), "8", "4", "0"], capture_output=True, text=True)
+        assert r.returncode == 1 and "uhsdr_multi_create" in r.stderr
 
 
 def test_default_cfg_matches_python_mirror(built):

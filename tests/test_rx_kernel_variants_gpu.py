@@ -275,3 +275,45 @@ def test_host_path_time_slices_match_one_device_call(built, monkeypatch, exact):
         d = (outs[0].astype(np.int64) >> 16) - (outs[1].astype(np.int64) >> 16)
         assert int(np.max(np.abs(d))) <= 1
     assert np.all(outs[0][:, 33 * 32:41 * 32] == 0)
+
+
+def test_c_host_program_multi_handle(built):
+    """examples/host.c (plain C, uhsdr_multi_* over the device list) against the Python binding on the same input: the multi
+    handle over one device -- or over two slots of the same device, which exercises the per-device ranges and host threads --
+    returns what one engine returns."""
+    import ctypes
+    import os
+    import subprocess
+    import torch
+    from uhsdr_b200.engine import load_library
+    from uhsdr_b200.tables import DEFAULT_BLOB
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "host")
+    outs = []
+    devs = ["0", "1"] if torch.cuda.device_count() > 1 else ["0", "0"]
+    for dl in (["0"], devs):
+        r = subprocess.run([exe, DEFAULT_BLOB, "37", "24"] + dl, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.splitlines()[1])
+        assert "abi=2" in r.stdout and "ch0_blocks=24" in r.stdout
+    assert outs[0] == outs[1]
+    # the same through ctypes: multi handle with ragged ranges (37 channels over 3 slots) == single engine
+    lib = load_library()
+    blob = open(DEFAULT_BLOB, "rb").read()
+    buf = ctypes.create_string_buffer(blob, len(blob))
+    nch, nb = 37, 24
+    cfgs = [default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)]
+    iq = np.concatenate([synth.counter_block(np, [synth.kind_of(cfgs[c % 2])], [c], 0, nb * 32) for c in range(nch)])
+    with Engine(nch) as eng:
+        eng.configure(cfgs[0], first=0, stride=2)
+        eng.configure(cfgs[1], first=1, stride=2)
+        want = eng.rx(iq)
+    m = ctypes.c_void_p()
+    dl = (ctypes.c_int * 3)(0, 0, 0)
+    assert lib.uhsdr_multi_create(ctypes.byref(m), nch, dl, 3, buf, len(blob)) == 0
+    assert lib.uhsdr_multi_configure_channels_strided(m, 0, 19, 2, ctypes.byref(cfgs[0]), 1) == 0
+    assert lib.uhsdr_multi_configure_channels_strided(m, 1, 18, 2, ctypes.byref(cfgs[1]), 1) == 0
+    got = np.empty_like(iq)
+    assert lib.uhsdr_multi_rx_process(m, iq.ctypes.data, got.ctypes.data, nb, None) == 0
+    lib.uhsdr_multi_destroy(m)
+    assert np.array_equal(got, want)

@@ -77,7 +77,7 @@ static std::string g_create_error;
 
 extern "C" {
 
-int uhsdr_b200_abi_version(void) { return 1; }
+int uhsdr_b200_abi_version(void) { return 2; }
 
 const char *uhsdr_b200_backend(void)
 {

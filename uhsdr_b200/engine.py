@@ -31,6 +31,9 @@ EXPORTS = [
     "uhsdr_configure_channels", "uhsdr_configure_channel", "uhsdr_configure_channels_strided", "uhsdr_rx_process", "uhsdr_rx_process_device",
     "uhsdr_tx_process", "uhsdr_tx_process_device", "uhsdr_engine_sync", "uhsdr_engine_stream",
     "uhsdr_get_spectrum", "uhsdr_get_spectrum_device", "uhsdr_get_status", "uhsdr_engine_launch_count",
+    "uhsdr_channel_range", "uhsdr_multi_create", "uhsdr_multi_destroy", "uhsdr_multi_num_devices", "uhsdr_multi_num_channels",
+    "uhsdr_multi_last_error", "uhsdr_multi_engine", "uhsdr_multi_configure_channels", "uhsdr_multi_configure_channels_strided",
+    "uhsdr_multi_rx_process", "uhsdr_multi_tx_process", "uhsdr_multi_get_status",
     "uhsdr_twinpeaks_rearm", "uhsdr_tables_validate", "uhsdr_default_spectrum_display_cfg", "uhsdr_spectrum_display", "uhsdr_spectrum_display_device",
 ]
 
@@ -77,6 +80,20 @@ def load_library(exact: bool = False) -> ctypes.CDLL:
     L.uhsdr_get_spectrum_device.argtypes = [vp, ci, ci, vp]
     L.uhsdr_get_status.argtypes = [vp, ci, ci, ctypes.POINTER(ChanStatus)]
     L.uhsdr_twinpeaks_rearm.argtypes = [vp, ci, ci]
+    L.uhsdr_channel_range.argtypes = [ci, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.uhsdr_multi_create.argtypes = [ctypes.POINTER(vp), ci, ctypes.POINTER(ci), ci, vp, ctypes.c_size_t]
+    L.uhsdr_multi_destroy.argtypes = [vp]
+    L.uhsdr_multi_num_devices.argtypes = [vp]
+    L.uhsdr_multi_num_channels.argtypes = [vp]
+    L.uhsdr_multi_last_error.restype = ctypes.c_char_p
+    L.uhsdr_multi_last_error.argtypes = [vp]
+    L.uhsdr_multi_engine.restype = vp
+    L.uhsdr_multi_engine.argtypes = [vp, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.uhsdr_multi_configure_channels.argtypes = [vp, ci, ci, ctypes.POINTER(ChanCfg), ci]
+    L.uhsdr_multi_configure_channels_strided.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ChanCfg), ci]
+    L.uhsdr_multi_rx_process.argtypes = [vp, vp, vp, ci, vp]
+    L.uhsdr_multi_tx_process.argtypes = [vp, vp, vp, ci, vp]
+    L.uhsdr_multi_get_status.argtypes = [vp, ci, ci, ctypes.POINTER(ChanStatus)]
     L.uhsdr_default_spectrum_display_cfg.argtypes = [ctypes.POINTER(SpectrumDisplayCfg)]
     L.uhsdr_spectrum_display.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp]
     L.uhsdr_spectrum_display_device.argtypes = [vp, ci, ci, ctypes.POINTER(SpectrumDisplayCfg), vp, vp, vp, vp]
