@@ -16,17 +16,31 @@ sys.path.insert(0, ROOT)
 from uhsdr_b200.config import (DEMOD_AM, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, SAM_SIDEBAND_USB, ChanCfg, default_cfg)   # noqa: E402
 from uhsdr_b200.tables import DEFAULT_BLOB   # noqa: E402
 
+def _rep(c):
+    return [c, c, c, c]
+
+
 PLANS = {
     "narrow": [default_cfg(), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38)],
-    "wide": [default_cfg(filter_path=48), default_cfg(filter_path=55)],
+    "wide": [default_cfg(filter_path=48), default_cfg(filter_path=48), default_cfg(filter_path=55), default_cfg(filter_path=55)],
     "mixed": [default_cfg(dmod_mode=DEMOD_AM, filter_path=70), default_cfg(dmod_mode=DEMOD_SAM, filter_path=72),
               default_cfg(dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=SAM_SIDEBAND_USB), default_cfg(dmod_mode=DEMOD_FM, filter_path=2)],
+    "am": _rep(default_cfg(dmod_mode=DEMOD_AM, filter_path=70)), "sam": _rep(default_cfg(dmod_mode=DEMOD_SAM, filter_path=72)),
+    "samu": _rep(default_cfg(dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=SAM_SIDEBAND_USB)), "fm": _rep(default_cfg(dmod_mode=DEMOD_FM, filter_path=2)),
+    "w48": _rep(default_cfg(filter_path=48)), "w55": _rep(default_cfg(filter_path=55)),
 }
 
 
 class Lib:
     def __init__(self, path, nch, cfgs):
-        self.L = L = ctypes.CDLL(path)
+        # "lib.so::NAME=VALUE,NAME2=VALUE2": environment switches read at engine creation (UHSDR_B200_NO_SERIAL2=1 ...)
+        path, _, envs = path.partition("::")
+        saved = {}
+        for kv in filter(None, envs.split(",")):
+            k, _, v = kv.partition("=")
+            saved[k] = os.environ.get(k)
+            os.environ[k] = v
+        self.L = L = ctypes.CDLL(os.path.abspath(path))
         vp, ci = ctypes.c_void_p, ctypes.c_int
         L.uhsdr_engine_create.argtypes = [ctypes.POINTER(vp), ci, ci, vp, ctypes.c_size_t]
         L.uhsdr_configure_channels_strided.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ChanCfg), ci]
@@ -41,9 +55,18 @@ class Lib:
         assert L.uhsdr_engine_create(ctypes.byref(self.h), nch, 0, buf, len(blob)) == 0
         k = len(cfgs)
         for i, c in enumerate(cfgs):
-            cnt = (nch - i + k - 1) // k
-            assert L.uhsdr_configure_channels_strided(self.h, i, cnt, k, ctypes.byref(c), 1) == 0
+            if k == 2:      # alternating plan (BASELINE configs[1])
+                cnt = (nch - i + k - 1) // k
+                assert L.uhsdr_configure_channels_strided(self.h, i, cnt, k, ctypes.byref(c), 1) == 0
+            else:           # channels sorted by kind
+                lo, hi = i * nch // k, (i + 1) * nch // k
+                assert L.uhsdr_configure_channels_strided(self.h, lo, hi - lo, 1, ctypes.byref(c), 1) == 0
         self.stream = torch.cuda.ExternalStream(L.uhsdr_engine_stream(self.h), device=torch.device("cuda", 0))
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
 
     def run(self, iq, out, nb, reps):
         L = self.L
@@ -72,15 +95,15 @@ def main():
     g = torch.Generator(device=dev); g.manual_seed(1)
     iq = (torch.randn((a.channels, a.blocks * 32, 2), device=dev, generator=g) * 3000.0 * 65536.0).to(torch.int32)
     out = torch.empty_like(iq)
-    libs = [Lib(os.path.abspath(p), a.channels, PLANS[a.plan]) for p in a.libs]
+    libs = [Lib(p, a.channels, PLANS[a.plan]) for p in a.libs]
     ms = [[] for _ in libs]
     for _ in range(a.rounds):
         for i, lb in enumerate(libs):
             ms[i].append(lb.run(iq, out, a.blocks, a.reps))
     best = [min(m) for m in ms]
     print(json.dumps({"plan": a.plan, "channels": a.channels, "blocks": a.blocks,
-                      "ms": {os.path.basename(p): [round(x, 4) for x in m] for p, m in zip(a.libs, ms)},
-                      "chsamp_per_s": {os.path.basename(p): a.channels * a.blocks * 32 / (b * 1e-3) for p, b in zip(a.libs, best)},
+                      "ms": {os.path.basename(p) + f"#{i}": [round(x, 4) for x in m] for i, (p, m) in enumerate(zip(a.libs, ms))},
+                      "chsamp_per_s": {os.path.basename(p) + f"#{i}": a.channels * a.blocks * 32 / (b * 1e-3) for i, (p, b) in enumerate(zip(a.libs, best))},
                       "speedup_vs_first": [round(best[0] / b, 4) for b in best]}), flush=True)
 
 

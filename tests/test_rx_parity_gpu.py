@@ -205,6 +205,7 @@ def test_full_size_properties_4096_channels(built):
                 a = d_iq[:, : h * 32].contiguous(); b = d_iq[:, h * 32:].contiguous()
                 oa, ob = torch.empty_like(a), torch.empty_like(b)
                 eng.rx_device(a, oa, h); eng.rx_device(b, ob, h)
+                eng.sync()                       # the engine runs on its own non-blocking stream: finish before torch reads
                 d_out = torch.cat([oa, ob], dim=1)
             eng.sync()
             outs.append(d_out.cpu().numpy())

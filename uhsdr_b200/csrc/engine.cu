@@ -49,6 +49,8 @@ struct uhsdr_engine {
     int use_split = 1;       // general path as front (FIR) kernel + thread-per-channel serial kernel
     int use_front2 = 1;      // register-blocked front kernel (rx_front2.cu) where every split channel's chain fits it
     bool front2_ok = false;
+    int use_serial2 = 1;     // FMA / shared-memory-AGC serial kernel (rx_serial2.cu, shipping build) where every split channel's chain fits it
+    bool serial2_ok = false;
     long long tw_blocks_left = 0;    // > 0: some channel's twin-peaks detector may still be active (1050 blocks after a reset / re-arm)
     FusedCoefs fused_coefs;
     bool fused_coefs_valid = false;
@@ -166,6 +168,8 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (ns && ns[0] == '1') e->use_split = 0;
     const char *nf2 = getenv("UHSDR_B200_NO_FRONT2");
     if (nf2 && nf2[0] == '1') e->use_front2 = 0;
+    const char *ns2 = getenv("UHSDR_B200_NO_SERIAL2");
+    if (ns2 && ns2[0] == '1') e->use_serial2 = 0;
     const char *nt = getenv("UHSDR_B200_NO_TC");
     if ((nt && nt[0] == '1') || !rx_ssb_tc_available()) e->use_tc = 0;
     auto fail = [&](const char *what, cudaError_t er) {
@@ -278,6 +282,7 @@ static int rebuild_lists(uhsdr_engine *e)
     e->fused_s1_ci = -1;
     e->split_floats_per_block = 0;
     e->front2_ok = e->use_front2 != 0;
+    e->serial2_ok = e->use_serial2 != 0;
     for (int c = 0; c < e->nch; c++) {
         const ChanParams &p = e->h_params[c];
         if (!p.configured) { e->last_error = "rx/tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
@@ -291,6 +296,7 @@ static int rebuild_lists(uhsdr_engine *e)
             // channels with the spectral noise reduction take two serial phases around the warp-cooperative NR kernel
             (p.nr_enable ? e->h_list_split_nr : e->h_list_split).push_back(c);
             if (!rx_front2_eligible(p)) e->front2_ok = false;
+            if (!rx_serial2_eligible(p)) e->serial2_ok = false;
             e->split_floats_per_block = std::max(e->split_floats_per_block, rx_split_floats_per_block(p));
         } else {
             if (p.notch_enable) { e->last_error = "rx: the LMS auto-notch runs on the split path only (UHSDR_B200_NO_SPLIT is set, or the chain is not split-eligible)"; return UHSDR_ERR_UNSUPPORTED; }
@@ -380,13 +386,16 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
                 cudaEvent_t ev = e->ev_split[2 * si + with_nr];
                 CK(e, cudaEventRecord(ev, stream));
                 CK(e, cudaStreamWaitEvent(e->aux_stream, ev, 0));
+                // the second-generation serial kernel stores 32-byte / 16-byte vectors
+                const bool s2 = e->serial2_ok && ((uintptr_t)audio_dev % 32 == 0) && (chan_stride % 4 == 0) && ((uintptr_t)audio_f_dev % 16 == 0);
+                auto serial = [&](int phase) { return s2 ? launch_rx_serial2(s, phase, e->aux_stream) : launch_rx_serial(s, phase, e->aux_stream); };
                 if (!with_nr) {
-                    CK(e, launch_rx_serial(s, 0, e->aux_stream));
+                    CK(e, serial(0));
                     e->launches += 2;
                 } else {
-                    CK(e, launch_rx_serial(s, 1, e->aux_stream));
+                    CK(e, serial(1));
                     CK(e, launch_rx_nr(s, e->aux_stream));
-                    CK(e, launch_rx_serial(s, 2, e->aux_stream));
+                    CK(e, serial(2));
                     e->launches += 4;
                 }
             }

@@ -34,6 +34,9 @@ cudaError_t launch_rx_front(const RxArgs &a, cudaStream_t stream);
 bool rx_front2_eligible(const ChanParams &p);
 cudaError_t launch_rx_front2(const RxArgs &a, cudaStream_t stream);
 cudaError_t launch_rx_serial(const RxArgs &a, int phase, cudaStream_t stream);   // phase: see rx_serial.cu
+// second-generation serial kernel (rx_serial2.cu, shipping build): same contract and phases
+bool rx_serial2_eligible(const ChanParams &p);
+cudaError_t launch_rx_serial2(const RxArgs &a, int phase, cudaStream_t stream);
 cudaError_t launch_rx_nr(const RxArgs &a, cudaStream_t stream);                   // spectral NR on a.scratch, in place
 int rx_split_floats_per_block(const ChanParams &p);     // scratch floats per 32-sample block and channel
 
