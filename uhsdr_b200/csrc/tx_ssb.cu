@@ -62,7 +62,7 @@ int build_tx_params(const HostTables &t, const uhsdr_chan_cfg_t &cfg, TxParams *
     if (cfg.tx_filter == UHSDR_TX_FILTER_BASS) li = t.ex->tx_lattice_bass;
     else if (cfg.tx_filter == UHSDR_TX_FILTER_TENOR) li = t.ex->tx_lattice_tenor;
     if (mode == UHSDR_DEMOD_FM) li = t.ex->tx_lattice_fm;             // IIR_TX_2k7_FM, tx_processor.c:104-107
-    if (li < 0 || li >= (int)t.h->num_lattices || t.lat[li].num_stages > MAX_LAT) { if (err) *err = "TX lattice missing from the table blob"; return UHSDR_ERR_TABLES; }
+    if (li < 0 || li >= (int)t.h->num_lattices || t.lat[li].num_stages > 10) { if (err) *err = "TX lattice missing from the table blob (or longer than the 10 stages the modulator kernels keep in registers)"; return UHSDR_ERR_TABLES; }
     tp->lat.n = t.lat[li].num_stages; tp->lat.k_off = t.off(t.lat[li].k_array); tp->lat.v_off = t.off(t.lat[li].v_array);
     shelf(tp->bq[0], true, 1700, 0.9, cfg.tx_treble_gain, 48000);
     shelf(tp->bq[1], false, 300, 0.7, cfg.tx_bass_gain, 48000);
@@ -580,10 +580,140 @@ cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// Second generation of the serial stages: the same operations in the same order (bit-identical results in both builds), but the
+// per-sample loop is rolled and touches registers and shared memory only -- lattice and biquad coefficients and states in
+// registers (the lattice front-padded to 10 stages: k = v = 0 stages pass the sample through exactly), the block's samples and the
+// 320-sample look-ahead delay line of the compressor in shared memory [slot][lane] (the first version kept them in per-thread
+// local memory and fetched the lattice coefficients from global memory for every stage of every sample).
+namespace {
+constexpr int TXS2_DELAY = 320;
+}
+
+__global__ void __launch_bounds__(TXS_THREADS)
+tx_serial2_kernel(TxArgs a)
+{
+    extern __shared__ __align__(16) float txs2_smem[];
+    const int ch = blockIdx.x * TXS_THREADS + threadIdx.x;
+    if (ch >= a.num_items) return;
+    const TxParams &tp = a.txp[ch];
+    if (!tp.enabled) return;
+    const float *__restrict__ pool = a.pool;
+    TxState &g = a.tx[ch];
+    float *dl = txs2_smem + threadIdx.x;                            // delay line [320][32]
+    float *sv = dl + TXS2_DELAY * TXS_THREADS;                       // block samples [32][32]
+    float *sa = sv + BLK * TXS_THREADS;                              // ALC gains of the block [32][32]
+    float lk[10], lv[11], ls[10];
+    const int ln = tp.lat.n, lpad = 10 - ln;
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        lk[j] = (j >= lpad) ? __ldg(pool + tp.lat.k_off + (j - lpad)) : 0.0f;
+        lv[j] = (j >= lpad) ? __ldg(pool + tp.lat.v_off + (j - lpad)) : 0.0f;
+        ls[j] = (j >= lpad) ? g.lat_s[j - lpad] : 0.0f;
+    }
+    lv[10] = __ldg(pool + tp.lat.v_off + ln);
+    BiquadS bq[3];
+    float bc[3][5];
+#pragma unroll
+    for (int s = 0; s < 3; s++) { bq[s] = g.bq[s];
+#pragma unroll
+        for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
+    float alc_val = g.alc_val, peak_audio = g.peak_audio;
+    float fm_hpf_a = g.fm_hpf_a, fm_hpf_b = g.fm_hpf_b;
+    uint32_t fm_accum = g.fm_accum, sub_acc = g.fm_dds_sub_acc, burst_acc = g.fm_dds_burst_acc;
+    uint32_t inbuf = g.alc_delay_inbuf;
+    for (int i = 0; i < TXS2_DELAY; i++) dl[i * TXS_THREADS] = g.delay[i];
+    const float gain_calc = tp.gain_calc, postfilt_gain = tp.postfilt_gain, alc_decay = tp.alc_decay, alc_scale = tp.alc_gain_scaling;
+    const bool gain_on = (double)gain_calc != 1.0, comp = tp.comp_enabled != 0, fm = tp.fm != 0;
+    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + (size_t)ch * (size_t)a.chan_stride;
+    float *__restrict__ out = a.scratch + (size_t)ch * (size_t)a.nblocks * BLK;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
+
+    for (int blk = 0; blk < a.nblocks; blk++) {
+        if (mute && mute[blk]) continue;
+        // AudioBufferFill (tx_processor.c:339-405)
+        float mx = 0.0f, mn = 0.0f;
+#pragma unroll
+        for (int i = 0; i < BLK; i += 2) {
+            const int4 s_ = *reinterpret_cast<const int4 *>(mic + (size_t)blk * BLK + i);
+            float x0 = (float)s_.x, x1 = (float)s_.z;
+            if (gain_on) { x0 = __fmul_rn(x0, gain_calc); x1 = __fmul_rn(x1, gain_calc); }
+            if (i == 0) { mx = x0; mn = x0; }
+            mx = fmaxf(mx, fmaxf(x0, x1)); mn = fminf(mn, fminf(x0, x1));
+            sv[i * TXS_THREADS] = x0; sv[(i + 1) * TXS_THREADS] = x1;
+        }
+        peak_audio = (-mn > mx) ? -mn : mx;
+        // FilterAudio (:416-429): lattice + 3 biquads, then the compressor's detector (:173-242), sample by sample
+#pragma unroll 1
+        for (int i = 0; i < BLK; i++) {
+            float f = sv[i * TXS_THREADS], acc = 0.0f, fn = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 10; j++) {
+                const float gg = ls[j];
+                fn = __fsub_rn(f, __fmul_rn(lk[j], gg));
+                const float gn = __fadd_rn(__fmul_rn(fn, lk[j]), gg);
+                acc = __fadd_rn(acc, __fmul_rn(gn, lv[j]));
+                if (j > 0) ls[j - 1] = gn;
+                f = fn;
+            }
+            float x = __fadd_rn(acc, __fmul_rn(fn, lv[10]));
+            ls[9] = fn;
+#pragma unroll
+            for (int s = 0; s < 3; s++) x = biquad_step(x, bc[s], bq[s]);
+            if (comp) {
+                x = __fmul_rn(x, postfilt_gain);
+                // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
+                const float alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(x, alc_val)), 30000.0f) - 1.0);
+                if (alc_var < 0.0f) {
+                    alc_val = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
+                } else {
+                    alc_val = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
+                    if ((double)alc_val < 0.001) alc_val = (float)0.001;
+                }
+                if (alc_val > 1.0f) alc_val = 1.0f;
+                sa[i * TXS_THREADS] = __fmul_rn(alc_val, alc_scale);
+            }
+            sv[i * TXS_THREADS] = x;
+        }
+        if (comp) {
+            inbuf += BLK;
+            // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
+            const uint32_t inb = inbuf % 320u, outb = (inbuf + BLK) % 320u;
+#pragma unroll 4
+            for (int i = 0; i < BLK; i++) dl[(inb + i) * TXS_THREADS] = sv[i * TXS_THREADS];
+#pragma unroll 4
+            for (int i = 0; i < BLK; i++) sv[i * TXS_THREADS] = __fmul_rn(dl[(outb + i) * TXS_THREADS], sa[i * TXS_THREADS]);
+            inbuf = inb;
+        }
+        if (fm) {
+#pragma unroll 1
+            for (int i = 0; i < BLK; i++)
+                sv[i * TXS_THREADS] = (float)fm_step(sv[i * TXS_THREADS], fm_hpf_a, fm_hpf_b, fm_accum, sub_acc, burst_acc, tp, pool);      // table index for the FIR-stage kernel
+        }
+#pragma unroll
+        for (int i = 0; i < BLK; i += 4)
+            *reinterpret_cast<float4 *>(out + (size_t)blk * BLK + i) = make_float4(sv[i * TXS_THREADS], sv[(i + 1) * TXS_THREADS], sv[(i + 2) * TXS_THREADS], sv[(i + 3) * TXS_THREADS]);
+    }
+    g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum; g.fm_dds_sub_acc = sub_acc; g.fm_dds_burst_acc = burst_acc;
+#pragma unroll
+    for (int j = 0; j < 10; j++) if (j >= lpad) g.lat_s[j - lpad] = ls[j];
+#pragma unroll
+    for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
+    g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;
+    for (int i = 0; i < TXS2_DELAY; i++) g.delay[i] = dl[i * TXS_THREADS];
+}
+
 cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream)
 {
     if (a.num_items <= 0) return cudaSuccess;
     if (a.scratch == nullptr) return cudaErrorInvalidValue;
+    static const bool no2 = [] { const char *v = getenv("UHSDR_B200_NO_SERIAL2"); return v && v[0] == '1'; }();
+    if (!no2 && ((uintptr_t)a.audio % 16 == 0) && (a.chan_stride % 2 == 0)) {
+        const size_t smem = (size_t)(TXS2_DELAY + 2 * BLK) * TXS_THREADS * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(tx_serial2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tx_serial2_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, smem, stream>>>(a);
+        return cudaGetLastError();
+    }
     tx_serial_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, 0, stream>>>(a);
     return cudaGetLastError();
 }
