@@ -127,11 +127,20 @@ twinpeaks_kernel(const ChanParams *__restrict__ params, ChanState *state, const 
         const float fi = __fmul_rn((float)s.x, 0.0000152587890625f), fq = __fmul_rn((float)s.y, 0.0000152587890625f);
         const float t1 = __fmul_rn(sign_new(fi), fq), t2 = __fmul_rn(sign_new(fi), fi), t3 = __fmul_rn(sign_new(fq), fq);
         float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-        for (int j = 0; j < 32; j++) {
+#if UHSDR_EXACT
+        for (int j = 0; j < 32; j++) {                       // the reference's summation order
             s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, t1, j));
             s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, t2, j));
             s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, t3, j));
         }
+#else
+        s1 = t1; s2 = t2; s3 = t3;                           // butterfly: the detector's 22.5 degree threshold does not see the rounding
+        for (int d = 16; d > 0; d >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, d);
+        }
+#endif
         te1 = (float)(-0.003 * (double)__fdiv_rn(s1, 32.0f) + 0.997 * (double)te1);
         te2 = (float)(0.003 * (double)__fdiv_rn(s2, 32.0f) + 0.997 * (double)te2);
         te3 = (float)(0.003 * (double)__fdiv_rn(s3, 32.0f) + 0.997 * (double)te3);
