@@ -49,7 +49,7 @@ def measured_peaks():
 
 def measured_traffic():
     """DRAM bytes per channel-sample of the dominant kernel from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(path) as f:
             return json.load(f)

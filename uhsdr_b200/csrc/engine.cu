@@ -23,8 +23,9 @@ struct uhsdr_engine {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream[2] = { nullptr, nullptr };
     cudaStream_t aux_stream = nullptr;          // split paths: serial kernels of slice s run beside the FIR kernel of slice s+1
-    static constexpr int kSplitSlices = 4;
-    cudaEvent_t ev_split[2 * kSplitSlices] = {}, ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux2_stream = nullptr;         // serial kernels in two phases: phase 2 of slice s beside phase 1 of slice s+1
+    static constexpr int kSplitSlices = 4, kSplitSlicesMax = 8;
+    cudaEvent_t ev_split[2 * kSplitSlicesMax] = {}, ev_phase[2 * kSplitSlicesMax] = {}, ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     static constexpr int kMaxSlices = 40;
     cudaEvent_t ev_in[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
     cudaEvent_t ev_done = nullptr;
@@ -49,6 +50,8 @@ struct uhsdr_engine {
     int use_split = 1;       // general path as front (FIR) kernel + thread-per-channel serial kernel
     int use_front2 = 1;      // register-blocked front kernel (rx_front2.cu) where every split channel's chain fits it
     bool front2_ok = false;
+    int use_pipe2 = 1;       // second-generation serial kernel in two phases on two streams (phase 2 of slice s beside phase 1 of slice s+1)
+    int split_slices = 0;    // > 0: forces the number of time slices of the split path (experiments)
     int use_serial2 = 1;     // FMA / shared-memory-AGC serial kernel (rx_serial2.cu, shipping build) where every split channel's chain fits it
     bool serial2_ok = false;
     long long tw_blocks_left = 0;    // > 0: some channel's twin-peaks detector may still be active (1050 blocks after a reset / re-arm)
@@ -131,7 +134,10 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_list_split_nr); cudaFree(e->d_scratch);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->aux2_stream) cudaStreamDestroy(e->aux2_stream);
     for (auto &v : e->ev_split) if (v) cudaEventDestroy(v);
+    for (auto &v : e->ev_phase) if (v) cudaEventDestroy(v);
+    if (e->ev_join2) cudaEventDestroy(e->ev_join2);
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     for (auto &v : e->ev_in) if (v) cudaEventDestroy(v);
@@ -170,6 +176,10 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (nf2 && nf2[0] == '1') e->use_front2 = 0;
     const char *ns2 = getenv("UHSDR_B200_NO_SERIAL2");
     if (ns2 && ns2[0] == '1') e->use_serial2 = 0;
+    const char *np2 = getenv("UHSDR_B200_NO_PIPE2");
+    if (np2 && np2[0] == '1') e->use_pipe2 = 0;
+    const char *nss = getenv("UHSDR_B200_SPLIT_SLICES");
+    if (nss && atoi(nss) > 0) e->split_slices = std::min(atoi(nss), (int)uhsdr_engine::kSplitSlicesMax);
     const char *nt = getenv("UHSDR_B200_NO_TC");
     if ((nt && nt[0] == '1') || !rx_ssb_tc_available()) e->use_tc = 0;
     auto fail = [&](const char *what, cudaError_t er) {
@@ -190,8 +200,11 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if ((er = cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", er);
+        if ((er = cudaStreamCreateWithPriority(&e->aux2_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail("cudaStreamCreate", er);
     }
     for (auto &v : e->ev_split) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    for (auto &v : e->ev_phase) if ((er = cudaEventCreateWithFlags(&v, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
+    if ((er = cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     if ((er = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     if ((er = cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", er);
     const size_t n = (size_t)num_channels;
@@ -351,19 +364,28 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     // Split general path.  The call is cut into time slices: the FIR front kernel of slice s+1 (this stream) runs
     // beside the sample-serial kernels of slice s (aux stream); neither fills the GPU on its own.
     if (!e->h_list_split.empty() || !e->h_list_split_nr.empty()) {
-        const int nsl = (nblocks >= 64) ? uhsdr_engine::kSplitSlices : 1;
+        // the second-generation serial kernel stores 32-byte / 16-byte vectors
+        const bool s2 = e->serial2_ok && ((uintptr_t)audio_dev % 32 == 0) && (chan_stride % 4 == 0) && ((uintptr_t)audio_f_dev % 16 == 0);
+        // Its chain is cut once more at the AGC output (the hand-off point of the spectral NR): phase 1 (demodulator, lattice, AGC) of
+        // slice s+1 runs beside phase 2 (NR frames, biquads, interpolator, output stage) of slice s.  One warp carries 32 channels
+        // through a dependent chain, so a serial kernel's time is the chain latency however few SMs it occupies.
+        const bool pipe2 = s2 && e->use_pipe2 && nblocks >= 64;
+        const int nsl = e->split_slices > 0 ? std::min(e->split_slices, std::max(1, nblocks / 4))
+                        : (nblocks >= 64) ? ((pipe2 && nblocks >= 256) ? uhsdr_engine::kSplitSlicesMax : uhsdr_engine::kSplitSlices) : 1;
         const int per = ((nblocks + nsl - 1) / nsl + 3) / 4 * 4;
         const size_t n_all = e->h_list_split.size() + e->h_list_split_nr.size();
         const size_t need = n_all * (size_t)nblocks * (size_t)e->split_floats_per_block * sizeof(float) + 64 * n_all * nsl;
         if (need > e->d_scratch_bytes) {
             CK(e, cudaStreamSynchronize(stream));
             CK(e, cudaStreamSynchronize(e->aux_stream));
+            CK(e, cudaStreamSynchronize(e->aux2_stream));
             cudaFree(e->d_scratch); e->d_scratch = nullptr; e->d_scratch_bytes = 0;
             CK(e, cudaMalloc(&e->d_scratch, need));
             e->d_scratch_bytes = need;
         }
         CK(e, cudaEventRecord(e->ev_fork, stream));
         CK(e, cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        if (pipe2) CK(e, cudaStreamWaitEvent(e->aux2_stream, e->ev_fork, 0));
         float *sc = e->d_scratch;
         int si = 0;
         for (int b0 = 0; b0 < nblocks; b0 += per, si++) {
@@ -386,19 +408,29 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
                 cudaEvent_t ev = e->ev_split[2 * si + with_nr];
                 CK(e, cudaEventRecord(ev, stream));
                 CK(e, cudaStreamWaitEvent(e->aux_stream, ev, 0));
-                // the second-generation serial kernel stores 32-byte / 16-byte vectors
-                const bool s2 = e->serial2_ok && ((uintptr_t)audio_dev % 32 == 0) && (chan_stride % 4 == 0) && ((uintptr_t)audio_f_dev % 16 == 0);
-                auto serial = [&](int phase) { return s2 ? launch_rx_serial2(s, phase, e->aux_stream) : launch_rx_serial(s, phase, e->aux_stream); };
-                if (!with_nr) {
-                    CK(e, serial(0));
+                auto serial = [&](int phase, cudaStream_t st) { return s2 ? launch_rx_serial2(s, phase, st) : launch_rx_serial(s, phase, st); };
+                if (pipe2) {
+                    CK(e, serial(1, e->aux_stream));
+                    cudaEvent_t evp = e->ev_phase[2 * si + with_nr];
+                    CK(e, cudaEventRecord(evp, e->aux_stream));
+                    CK(e, cudaStreamWaitEvent(e->aux2_stream, evp, 0));
+                    if (with_nr) CK(e, launch_rx_nr(s, e->aux2_stream));
+                    CK(e, serial(2, e->aux2_stream));
+                    e->launches += with_nr ? 4 : 3;
+                } else if (!with_nr) {
+                    CK(e, serial(0, e->aux_stream));
                     e->launches += 2;
                 } else {
-                    CK(e, serial(1));
+                    CK(e, serial(1, e->aux_stream));
                     CK(e, launch_rx_nr(s, e->aux_stream));
-                    CK(e, serial(2));
+                    CK(e, serial(2, e->aux_stream));
                     e->launches += 4;
                 }
             }
+        }
+        if (pipe2) {
+            CK(e, cudaEventRecord(e->ev_join2, e->aux2_stream));
+            CK(e, cudaStreamWaitEvent(stream, e->ev_join2, 0));
         }
         CK(e, cudaEventRecord(e->ev_join, e->aux_stream));
         CK(e, cudaStreamWaitEvent(stream, e->ev_join, 0));

@@ -21,9 +21,18 @@ __host__ __device__ constexpr int fir_padded_len(int ntaps) { return (ntaps + fi
 __device__ __forceinline__ void fir_stage_taps(float *dst, const float *__restrict__ c, int ntaps, int lane)
 {
     const int pf = fir_pad_front(ntaps), np = fir_padded_len(ntaps);
-    for (int i = lane; i < np; i += 32) {
-        const int k = i - pf;
-        dst[i] = (k >= 0 && k < ntaps) ? __ldg(c + k) : 0.0f;
+    for (int i0 = 0; i0 < np; i0 += 128) {               // four loads in flight per lane
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i0 + 32 * u + lane - pf;
+            v[u] = (k >= 0 && k < ntaps) ? __ldg(c + k) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + 32 * u + lane;
+            if (i < np) dst[i] = v[u];
+        }
     }
 }
 

@@ -24,7 +24,8 @@ constexpr int T1MAX = 96, T2MAX = 208; // padded tap counts (stage 1 <= 89 + pad
 
 struct Front2Work {
     alignas(16) float xi[H1 + CS + 8], xq[H1 + CS + 8];   // stage-1 input @48k: [history | new | finite slack for the padded tap tail]
-    alignas(16) float bi[H2 + CS + 8], bq[H2 + CS + 8];   // stage-2 input:      [history | new | slack]
+    alignas(16) float bi[H2 + CS + 16], bq[H2 + CS + 16]; // stage-2 input:      [history | new | slack]; the "new" part doubles as the
+                                                          // front end's [block][33] staging (16 x 33 = 528 floats)
     alignas(16) float t1i[T1MAX], t1q[T1MAX], t2i[T2MAX], t2q[T2MAX];
     float scr[2 * BLK];
 };
@@ -58,9 +59,26 @@ rx_front2_kernel(RxArgs a)
     const float *__restrict__ pool = a.pool;
 
     // ---- state and taps -> shared memory -------------------------------------------------------
-    for (int i = lane; i < H1; i += 32) { w.xi[i] = gst->s1_hist_i[i]; w.xq[i] = gst->s1_hist_q[i]; }
-    for (int i = lane; i < H2; i += 32) { w.bi[i] = gst->s2_hist_i[i]; w.bq[i] = gst->s2_hist_q[i]; }
-    for (int i = lane; i < CS + 8; i += 32) { w.xi[H1 + i] = 0.0f; w.xq[H1 + i] = 0.0f; w.bi[H2 + i] = 0.0f; w.bq[H2 + i] = 0.0f; }
+    // (all loads of a group first, then the stores: a launch covers only a few chunks, so the prologue's load latencies count)
+    {
+        float h1i[H1 / 32], h1q[H1 / 32], h2i[(H2 + 31) / 32], h2q[(H2 + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < H1 / 32; k++) { h1i[k] = gst->s1_hist_i[lane + 32 * k]; h1q[k] = gst->s1_hist_q[lane + 32 * k]; }
+#pragma unroll
+        for (int k = 0; k < (H2 + 31) / 32; k++) {
+            const int i = lane + 32 * k;
+            h2i[k] = (i < H2) ? gst->s2_hist_i[i] : 0.0f; h2q[k] = (i < H2) ? gst->s2_hist_q[i] : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < H1 / 32; k++) { w.xi[lane + 32 * k] = h1i[k]; w.xq[lane + 32 * k] = h1q[k]; }
+#pragma unroll
+        for (int k = 0; k < (H2 + 31) / 32; k++) {
+            const int i = lane + 32 * k;
+            if (i < H2) { w.bi[i] = h2i[k]; w.bq[i] = h2q[k]; }
+        }
+    }
+    for (int i = lane; i < CS + 8; i += 32) { w.xi[H1 + i] = 0.0f; w.xq[H1 + i] = 0.0f; }
+    for (int i = lane; i < CS + 16; i += 32) { w.bi[H2 + i] = 0.0f; w.bq[H2 + i] = 0.0f; }
     const int N1 = p.s1_ntaps, M1 = p.s1_M, N2 = p.s2_ntaps, M2 = p.s2_M, topo = p.topo;
     fir_stage_taps(w.t1i, pool + p.s1_ci, N1, lane);
     fir_stage_taps(w.t1q, pool + p.s1_cq, N1, lane);
@@ -89,40 +107,60 @@ rx_front2_kernel(RxArgs a)
         const int ns = nb * BLK;
         const int ndec = nb * ndec_blk;
 
-        // ---- front end: format, IQ correction, spectrum tap, frequency translation (block by block, lane = sample) ----
-        for (int b = 0; b < nb; b++) {
-            const int2 s = iq[(size_t)(blk0 + b) * BLK + lane];
-            const int level = abs(s.x) >> 16;                                    // audio_driver.c:2660-2685
-            clip_q |= (level > 4096 / 4); clip_h |= (level > 4096 / 2); clip_f |= (level > 4096);
-            float fi = __fmul_rn((float)s.x, 0.0000152587890625f);
-            float fq = __fmul_rn((float)s.y, 0.0000152587890625f);
-            if (p.iq_auto) {
-                // audio_driver.c:2274-2313 (Moseley & Slump): block statistics, EMA in double
-                float t1 = __fmul_rn(sign_new(fi), fq), t2 = __fmul_rn(sign_new(fi), fi), t3 = __fmul_rn(sign_new(fq), fq);
-                float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-                if (UHSDR_EXACT || topo == TOPO_AM_SAM) {
-                    for (int j = 0; j < 32; j++) {
-                        s1 = __fadd_rn(s1, __shfl_sync(0xffffffffu, t1, j));
-                        s2 = __fadd_rn(s2, __shfl_sync(0xffffffffu, t2, j));
-                        s3 = __fadd_rn(s3, __shfl_sync(0xffffffffu, t3, j));
-                    }
-                } else {
-                    s1 = t1; s2 = t2; s3 = t3;
-                    for (int d = 16; d > 0; d >>= 1) {
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
-                        s3 += __shfl_xor_sync(0xffffffffu, s3, d);
-                    }
+        // ---- front end: format, IQ correction, spectrum tap, frequency translation ----
+        // The reference walks block by block (statistics of the block -> low-pass -> M_c1 / M_c2 -> correction of the same block);
+        // done that way on the GPU every block pays a global-load latency and a chain of three IEEE divisions and a square root.
+        // Here the chunk's blocks are (1) loaded and converted together, (2) summed with lane b on block b in sample order (the
+        // reference's order, so both builds keep its sums), (3) low-passed block after block (the only sequential part: three
+        // double multiply-adds), (4) turned into M_c1 / M_c2 with lane b on block b, (5) corrected block by block.
+        float *ti = w.bi + H2, *tq = w.bq + H2;          // staging [block][33]: free until the FIR stages write their outputs there
+        {
+            int2 raw[CB];
+#pragma unroll
+            for (int b = 0; b < CB; b++) raw[b] = (b < nb) ? iq[(size_t)(blk0 + b) * BLK + lane] : make_int2(0, 0);
+#pragma unroll
+            for (int b = 0; b < CB; b++) {
+                const int level = abs(raw[b].x) >> 16;                            // audio_driver.c:2660-2685
+                clip_q |= (level > 4096 / 4); clip_h |= (level > 4096 / 2); clip_f |= (level > 4096);
+                ti[b * 33 + lane] = __fmul_rn((float)raw[b].x, 0.0000152587890625f);
+                tq[b * 33 + lane] = __fmul_rn((float)raw[b].y, 0.0000152587890625f);
+            }
+        }
+        __syncwarp();
+        float mc1 = M_c1, mc2 = M_c2;                    // lane b: the factors of block b
+        if (p.iq_auto) {
+            // audio_driver.c:2274-2313 (Moseley & Slump): block statistics, EMA in double
+            float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            if (lane < nb) {
+                const float *ri = ti + lane * 33, *rq = tq + lane * 33;
+#pragma unroll 8
+                for (int j = 0; j < BLK; j++) {
+                    const float vi = ri[j], vq = rq[j];
+                    s1 = __fadd_rn(s1, __fmul_rn(sign_new(vi), vq));
+                    s2 = __fadd_rn(s2, __fmul_rn(sign_new(vi), vi));
+                    s3 = __fadd_rn(s3, __fmul_rn(sign_new(vq), vq));
                 }
-                teta1 = (float)(-0.003 * (double)__fdiv_rn(s1, 32.0f) + 0.997 * (double)teta1);
-                teta2 = (float)(0.003 * (double)__fdiv_rn(s2, 32.0f) + 0.997 * (double)teta2);
-                teta3 = (float)(0.003 * (double)__fdiv_rn(s3, 32.0f) + 0.997 * (double)teta3);
-                M_c1 = (teta2 != 0.0f) ? __fdiv_rn(teta1, teta2) : 0.0f;
-                float help = __fmul_rn(teta2, teta2);
-                if (help > 0.0f) help = __fdiv_rn(__fsub_rn(__fmul_rn(teta3, teta3), __fmul_rn(teta1, teta1)), help);
-                M_c2 = (help > 0.0f) ? __fsqrt_rn(help) : 1.0f;
-                fq = __fadd_rn(fq, __fmul_rn(M_c1, fi));
-                fi = __fmul_rn(fi, M_c2);
+            }
+            float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+            for (int b = 0; b < nb; b++) {
+                const float b1 = __shfl_sync(0xffffffffu, s1, b), b2 = __shfl_sync(0xffffffffu, s2, b), b3 = __shfl_sync(0xffffffffu, s3, b);
+                teta1 = (float)(-0.003 * (double)__fdiv_rn(b1, 32.0f) + 0.997 * (double)teta1);
+                teta2 = (float)(0.003 * (double)__fdiv_rn(b2, 32.0f) + 0.997 * (double)teta2);
+                teta3 = (float)(0.003 * (double)__fdiv_rn(b3, 32.0f) + 0.997 * (double)teta3);
+                if (lane == b) { m1 = teta1; m2 = teta2; m3 = teta3; }
+            }
+            mc1 = (m2 != 0.0f) ? __fdiv_rn(m1, m2) : 0.0f;
+            float help = __fmul_rn(m2, m2);
+            if (help > 0.0f) help = __fdiv_rn(__fsub_rn(__fmul_rn(m3, m3), __fmul_rn(m1, m1)), help);
+            mc2 = (help > 0.0f) ? __fsqrt_rn(help) : 1.0f;
+            M_c1 = __shfl_sync(0xffffffffu, mc1, nb - 1); M_c2 = __shfl_sync(0xffffffffu, mc2, nb - 1);
+        }
+        for (int b = 0; b < nb; b++) {
+            float fi = ti[b * 33 + lane], fq = tq[b * 33 + lane];
+            if (p.iq_auto) {
+                const float c1 = __shfl_sync(0xffffffffu, mc1, b), c2 = __shfl_sync(0xffffffffu, mc2, b);
+                fq = __fadd_rn(fq, __fmul_rn(c1, fi));
+                fi = __fmul_rn(fi, c2);
             } else {
                 fi = __fmul_rn(fi, p.adj_i);                                     // manual gain + phase, audio_driver.c:2259-2267
                 fq = __fmul_rn(fq, p.adj_q);

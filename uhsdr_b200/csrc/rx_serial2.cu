@@ -246,7 +246,8 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
         }
         for (int b = 1; b < NSUF; b++) m5 = fmaxf(m5, suf[(b * ND) * S2_THREADS]);
     }
-    const bool any_hang = __any_sync(__activemask(), ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0);
+    // (phase 2 does not run the AGC and must not look at its state: phase 1 of the next time slice may be writing it)
+    const bool any_hang = phase != 2 && __any_sync(__activemask(), ap.hang_enable || ar.state == 2 || ar.state == 4 || ar.decay_type != 0 || ar.hang_counter > 0);
     // biquad cascade: t-form (see rx_ssb_tc.cu), identity stages skipped per thread
     float bc[4][5], tq[4];
     BiquadS bs[4];
@@ -660,7 +661,7 @@ rx_serial2_kernel(RxArgs a, int phase)
     const int ch = a.chan_list[slot];
     const ChanParams &p = a.params[ch];
     const bool ex = p.topo == TOPO_AM_SAM;
-    if (p.topo == TOPO_FM) serial2_fm(a, slot, ch, s2_smem);
+    if (p.topo == TOPO_FM) { if (phase != 2) serial2_fm(a, slot, ch, s2_smem); }      // FM has no AGC hand-off: the whole chain is "phase 1"
     else if (p.M == 4) { if (ex) serial2_dec<8, true>(a, phase, slot, ch, s2_smem); else serial2_dec<8, false>(a, phase, slot, ch, s2_smem); }
     else { if (ex) serial2_dec<16, true>(a, phase, slot, ch, s2_smem); else serial2_dec<16, false>(a, phase, slot, ch, s2_smem); }
 }
