@@ -64,6 +64,29 @@ __device__ __forceinline__ void fir4_m1(const float *__restrict__ x, const float
     }
 }
 
+// Two independent filters side by side (I with its taps, Q with its taps): eight accumulator chains and four loads in flight
+// per group instead of four and two -- these loops wait on shared-memory latency at the occupancy the staging buffers allow.
+template <bool EXACTSUM>
+__device__ __forceinline__ void fir4_m1_pair(const float *__restrict__ xa, const float *__restrict__ ta, const float *__restrict__ xb,
+                                             const float *__restrict__ tb, int groups, float (&ya)[4], float (&yb)[4])
+{
+    float4 wa = *reinterpret_cast<const float4 *>(xa), wb = *reinterpret_cast<const float4 *>(xb);
+#pragma unroll
+    for (int r = 0; r < 4; r++) { ya[r] = 0.0f; yb[r] = 0.0f; }
+#pragma unroll 2
+    for (int g = 0; g < groups; g++) {
+        const float4 na = *reinterpret_cast<const float4 *>(xa + 4 * g + 4), nb = *reinterpret_cast<const float4 *>(xb + 4 * g + 4);
+        const float4 ca = *reinterpret_cast<const float4 *>(ta + 4 * g), cb = *reinterpret_cast<const float4 *>(tb + 4 * g);
+        const float va[8] = { wa.x, wa.y, wa.z, wa.w, na.x, na.y, na.z, na.w }, vb[8] = { wb.x, wb.y, wb.z, wb.w, nb.x, nb.y, nb.z, nb.w };
+        const float ka[4] = { ca.x, ca.y, ca.z, ca.w }, kb[4] = { cb.x, cb.y, cb.z, cb.w };
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) { ya[r] = fir_mac<EXACTSUM>(va[r + j], ka[j], ya[r]); yb[r] = fir_mac<EXACTSUM>(vb[r + j], kb[j], yb[r]); }
+        wa = na; wb = nb;
+    }
+}
+
 // Same with two tap sets on one input (TX Hilbert pair: one microphone signal, I and Q filters).
 template <bool EXACTSUM>
 __device__ __forceinline__ void fir4_m1_dual(const float *__restrict__ x, const float *__restrict__ ta, const float *__restrict__ tb, int groups,

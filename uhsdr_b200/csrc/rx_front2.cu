@@ -279,8 +279,7 @@ rx_front2_kernel(RxArgs a)
             } else {
                 // stage 2: Hilbert pair at the decimated rate, USB = I + Q / LSB = I - Q (:2751-2790); four outputs per lane
                 float yi[4], yq[4];
-                fir4_m1<false>(w.bi + H2 + 4 * lane - off2, w.t2i, g2, yi);
-                fir4_m1<false>(w.bq + H2 + 4 * lane - off2, w.t2q, g2, yq);
+                fir4_m1_pair<false>(w.bi + H2 + 4 * lane - off2, w.t2i, w.bq + H2 + 4 * lane - off2, w.t2q, g2, yi, yq);
                 const size_t o = (size_t)blk0 * ndec_blk;
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
@@ -296,8 +295,7 @@ rx_front2_kernel(RxArgs a)
             const size_t half = (size_t)a.nblocks * BLK, o = (size_t)blk0 * BLK;
             for (int sub = 0; sub < ns; sub += 128) {
                 float yi[4], yq[4];
-                fir4_m1<false>(w.xi + H1 + sub + 4 * lane - off1, w.t1i, g1, yi);
-                fir4_m1<false>(w.xq + H1 + sub + 4 * lane - off1, w.t1q, g1, yq);
+                fir4_m1_pair<false>(w.xi + H1 + sub + 4 * lane - off1, w.t1i, w.xq + H1 + sub + 4 * lane - off1, w.t1q, g1, yi, yq);
                 if (topo == TOPO_FM) {
                     if (sub + 4 * lane < ns) {
                         *reinterpret_cast<float4 *>(sc + o + sub + 4 * lane) = make_float4(yi[0], yi[1], yi[2], yi[3]);

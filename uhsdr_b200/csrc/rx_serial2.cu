@@ -26,40 +26,140 @@ namespace {
 constexpr int S2_THREADS = 32;
 constexpr int NSUF = 6;                 // blocks whose suffix maxima are kept: attack_buffsize - 1 = 6 ND
 
-// the demodulators' state (member names as in ChanState: demod_device.cuh is a template over the state type)
-struct DemodState {
-    float sam_fil_out, sam_lowpass, sam_omega2, sam_phs, sam_dsI, sam_dsQ;
-    float sam_a[24], sam_b[24], sam_c[24], sam_d[24];
-    int sam_count;
-    float fade_dc27, fade_dc_insert;
-    int carrier_freq_offset;
-    float fm_i_prev, fm_q_prev, fm_lpf_prev, fm_hpf_prev_a, fm_hpf_prev_b, fm_sql_avg;
-    int fm_count, fm_squelched;
-    float fm_gz[9], fm_subdet;
-    int fm_gcount, fm_tdet, fm_tone_detected;
-    float sql_s[MAX_LAT];
+// AM / SAM demodulator (AudioDriver_DemodSAM, audio_driver.c:1990-2166; demod_am_sam in demod_device.cuh is the operation-for-
+// operation form the other kernels run): constants and the PLL / fade-leveler state in registers, the four 7-stage all-pass chains of
+// the sideband selector in shared memory.  The reference keeps each chain as a 24-element array shifted by one per sample
+// (a[3 s], a[3 s + 1], a[3 s + 2] = signal s now, one and two samples ago; signal 0 = the chain's input, signal s = the output of
+// section s; a[3 s + 3] = k (a[3 s] - a[3 s + 5]) + a[3 s + 2]): that is a cascade of second-order all-pass sections whose state is
+// the last two values of its eight signals.  Here: AP[chain][signal][slot][lane], slot = sample parity, the value of two samples
+// ago is read and then overwritten by the new one.  Same operations in the same order as the reference, so the same bits.
+struct Demod2 {
+    bool am, sel, lsb, fade;
+    float mtauR, onem_mtauR, mtauI, onem_mtauI, g1, g2, omin, omax, rate;
+    float k0[7], k1[7];
+    // state
+    float fil_out, lowpass, omega2, phs, dsI, dsQ, dc27, dc_insert;
+    int count, carrier, par;
 };
+constexpr int AP_FLOATS = 4 * 8 * 2 * S2_THREADS;       // all-pass state per CTA
 
-#define DS_SCALARS(X) X(sam_fil_out) X(sam_lowpass) X(sam_omega2) X(sam_phs) X(sam_dsI) X(sam_dsQ) X(sam_count) X(fade_dc27) X(fade_dc_insert) \
-    X(carrier_freq_offset) X(fm_i_prev) X(fm_q_prev) X(fm_lpf_prev) X(fm_hpf_prev_a) X(fm_hpf_prev_b) X(fm_sql_avg) X(fm_count) X(fm_squelched)   \
-    X(fm_subdet) X(fm_gcount) X(fm_tdet) X(fm_tone_detected)
-
-__device__ __forceinline__ void demod_load(DemodState &d, const ChanState &g, bool sam, bool fm)
+__device__ __forceinline__ void demod2_load(Demod2 &d, const ChanParams &p, const ChanState &g, const float *__restrict__ pool, float *ap)
 {
-#define X(f) d.f = g.f;
-    DS_SCALARS(X)
-#undef X
-    if (sam) for (int i = 0; i < 24; i++) { d.sam_a[i] = g.sam_a[i]; d.sam_b[i] = g.sam_b[i]; d.sam_c[i] = g.sam_c[i]; d.sam_d[i] = g.sam_d[i]; }
-    if (fm) { for (int i = 0; i < 9; i++) d.fm_gz[i] = g.fm_gz[i]; for (int i = 0; i < MAX_LAT; i++) d.sql_s[i] = g.sql_s[i]; }
+    d.am = p.mode == UHSDR_DEMOD_AM; d.sel = !d.am && p.sam_sideband != UHSDR_SAM_SIDEBAND_BOTH; d.lsb = p.sam_sideband == UHSDR_SAM_SIDEBAND_LSB;
+    d.fade = p.fade_leveler != 0;
+    d.mtauR = p.sam_mtauR; d.onem_mtauR = p.sam_onem_mtauR; d.mtauI = p.sam_mtauI; d.onem_mtauI = p.sam_onem_mtauI;
+    d.g1 = p.sam_g1; d.g2 = p.sam_g2; d.omin = p.sam_omega_min; d.omax = p.sam_omega_max; d.rate = (float)p.decimated_freq;
+#pragma unroll
+    for (int j = 0; j < 7; j++) { d.k0[j] = d.am ? 0.0f : __ldg(pool + p.sam_c0 + j); d.k1[j] = d.am ? 0.0f : __ldg(pool + p.sam_c1 + j); }
+    d.fil_out = g.sam_fil_out; d.lowpass = g.sam_lowpass; d.omega2 = g.sam_omega2; d.phs = g.sam_phs; d.dsI = g.sam_dsI; d.dsQ = g.sam_dsQ;
+    d.dc27 = g.fade_dc27; d.dc_insert = g.fade_dc_insert; d.count = g.sam_count; d.carrier = g.carrier_freq_offset; d.par = 0;
+    if (d.sel) {
+        for (int sg = 0; sg < 8; sg++) {
+            // slot 0 = two samples ago (a[3 s + 2]), slot 1 = one sample ago (a[3 s + 1])
+            ap[((0 * 8 + sg) * 2 + 0) * S2_THREADS] = g.sam_a[3 * sg + 2]; ap[((0 * 8 + sg) * 2 + 1) * S2_THREADS] = g.sam_a[3 * sg + 1];
+            ap[((1 * 8 + sg) * 2 + 0) * S2_THREADS] = g.sam_b[3 * sg + 2]; ap[((1 * 8 + sg) * 2 + 1) * S2_THREADS] = g.sam_b[3 * sg + 1];
+            ap[((2 * 8 + sg) * 2 + 0) * S2_THREADS] = g.sam_c[3 * sg + 2]; ap[((2 * 8 + sg) * 2 + 1) * S2_THREADS] = g.sam_c[3 * sg + 1];
+            ap[((3 * 8 + sg) * 2 + 0) * S2_THREADS] = g.sam_d[3 * sg + 2]; ap[((3 * 8 + sg) * 2 + 1) * S2_THREADS] = g.sam_d[3 * sg + 1];
+        }
+    }
 }
 
-__device__ __forceinline__ void demod_store(ChanState &g, const DemodState &d, bool sam, bool fm)
+__device__ __forceinline__ void demod2_store(ChanState &g, const Demod2 &d, const float *ap)
 {
-#define X(f) g.f = d.f;
-    DS_SCALARS(X)
-#undef X
-    if (sam) for (int i = 0; i < 24; i++) { g.sam_a[i] = d.sam_a[i]; g.sam_b[i] = d.sam_b[i]; g.sam_c[i] = d.sam_c[i]; g.sam_d[i] = d.sam_d[i]; }
-    if (fm) { for (int i = 0; i < 9; i++) g.fm_gz[i] = d.fm_gz[i]; for (int i = 0; i < MAX_LAT; i++) g.sql_s[i] = d.sql_s[i]; }
+    g.sam_fil_out = d.fil_out; g.sam_lowpass = d.lowpass; g.sam_omega2 = d.omega2; g.sam_phs = d.phs; g.sam_dsI = d.dsI; g.sam_dsQ = d.dsQ;
+    g.fade_dc27 = d.dc27; g.fade_dc_insert = d.dc_insert; g.sam_count = d.count; g.carrier_freq_offset = d.carrier;
+    if (d.sel) {
+        // slot par = two samples before the next one = a[3 s + 2] after the reference's shift; the other slot = a[3 s + 1]; a[3 s]
+        // is written before it is read (a[0] from dsI / the input, a[3 s] by section s - 1) and carries no state
+        const int o = d.par, n = d.par ^ 1;
+        for (int sg = 0; sg < 8; sg++) {
+            g.sam_a[3 * sg + 2] = ap[((0 * 8 + sg) * 2 + o) * S2_THREADS]; g.sam_a[3 * sg + 1] = ap[((0 * 8 + sg) * 2 + n) * S2_THREADS];
+            g.sam_b[3 * sg + 2] = ap[((1 * 8 + sg) * 2 + o) * S2_THREADS]; g.sam_b[3 * sg + 1] = ap[((1 * 8 + sg) * 2 + n) * S2_THREADS];
+            g.sam_c[3 * sg + 2] = ap[((2 * 8 + sg) * 2 + o) * S2_THREADS]; g.sam_c[3 * sg + 1] = ap[((2 * 8 + sg) * 2 + n) * S2_THREADS];
+            g.sam_d[3 * sg + 2] = ap[((3 * 8 + sg) * 2 + o) * S2_THREADS]; g.sam_d[3 * sg + 1] = ap[((3 * 8 + sg) * 2 + n) * S2_THREADS];
+            g.sam_a[3 * sg] = sg ? g.sam_a[3 * sg - 1] : 0.0f; g.sam_b[3 * sg] = sg ? g.sam_b[3 * sg - 1] : 0.0f;
+            g.sam_c[3 * sg] = sg ? g.sam_c[3 * sg - 1] : 0.0f; g.sam_d[3 * sg] = sg ? g.sam_d[3 * sg - 1] : 0.0f;
+        }
+    }
+}
+
+// one all-pass chain, one sample: x = the chain's input now; returns the output of section 7 (the reference's a[21])
+__device__ __forceinline__ float allpass7(float *chain, int par, const float (&k)[7], float x)
+{
+    float m2[8];
+#pragma unroll
+    for (int sg = 0; sg < 8; sg++) m2[sg] = chain[(sg * 2 + par) * S2_THREADS];       // every signal two samples ago
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        chain[(j * 2 + par) * S2_THREADS] = x;
+        x = __fadd_rn(__fmul_rn(k[j], __fsub_rn(x, m2[j + 1])), m2[j]);
+    }
+    chain[(7 * 2 + par) * S2_THREADS] = x;
+    return x;
+}
+
+// AudioDriver_FadeLeveler, audio_driver.c:1911-1923
+__device__ __forceinline__ float fade2(Demod2 &d, float audio, float corr)
+{
+    d.dc27 = __fadd_rn(__fmul_rn(d.mtauR, d.dc27), __fmul_rn(d.onem_mtauR, audio));
+    d.dc_insert = __fadd_rn(__fmul_rn(d.mtauI, d.dc_insert), __fmul_rn(d.onem_mtauI, corr));
+    return __fsub_rn(__fadd_rn(audio, d.dc_insert), d.dc27);
+}
+
+template <int ND>
+__device__ __forceinline__ void demod2_block(Demod2 &d, float *ap, const float (&ib)[ND], const float (&qb)[ND], float (&a)[ND])
+{
+    if (d.am) {
+#pragma unroll
+        for (int i = 0; i < ND; i++) {
+            float audio = __fsqrt_rn(__fadd_rn(__fmul_rn(ib[i], ib[i]), __fmul_rn(qb[i], qb[i])));
+            if (d.fade) audio = fade2(d, audio, 0.0f);
+            a[i] = audio;
+        }
+        return;
+    }
+    const double two_pi = 2.0 * (double)3.14159265358979f;
+#pragma unroll 1
+    for (int i = 0; i < ND; i++) {
+        float Sin, Cos;
+        sincosf(d.phs, &Sin, &Cos);
+        const float ai = __fmul_rn(Cos, ib[i]), bi = __fmul_rn(Sin, ib[i]);
+        const float aq = __fmul_rn(Cos, qb[i]), bq = __fmul_rn(Sin, qb[i]);
+        const float corr0 = __fadd_rn(ai, bq), corr1 = __fadd_rn(-bi, aq);
+        float audio = corr0;
+        if (d.sel) {
+            const float ai_ps = allpass7(ap + 0 * 16 * S2_THREADS, d.par, d.k0, d.dsI);
+            const float bi_ps = allpass7(ap + 1 * 16 * S2_THREADS, d.par, d.k1, bi);
+            const float bq_ps = allpass7(ap + 2 * 16 * S2_THREADS, d.par, d.k0, d.dsQ);
+            const float aq_ps = allpass7(ap + 3 * 16 * S2_THREADS, d.par, d.k1, aq);
+            d.dsI = ai; d.dsQ = bq;
+            d.par ^= 1;
+            if (d.lsb) audio = __fsub_rn(__fadd_rn(ai_ps, bi_ps), __fsub_rn(aq_ps, bq_ps));
+            else audio = __fadd_rn(__fsub_rn(ai_ps, bi_ps), __fadd_rn(aq_ps, bq_ps));
+        }
+        if (d.fade) audio = fade2(d, audio, corr0);
+        a[i] = audio;
+        const float phzerror = atan2f(corr1, corr0);
+        const float del_out = d.fil_out;
+        d.omega2 = __fadd_rn(d.omega2, __fmul_rn(d.g2, phzerror));
+        if (d.omega2 < d.omin) d.omega2 = d.omin;
+        else if (d.omega2 > d.omax) d.omega2 = d.omax;
+        d.fil_out = __fadd_rn(__fmul_rn(d.g1, phzerror), d.omega2);
+        float phs = __fadd_rn(d.phs, del_out);
+        // wrap to [0, 2 pi): the comparisons and corrections are double expressions (:2146-2147)
+        while ((double)phs >= two_pi) phs = (float)((double)phs - two_pi);
+        while (phs < 0.0f) phs = (float)((double)phs + two_pi);
+        d.phs = phs;
+    }
+    // carrier-offset display value, once per call of the reference function (:2150-2162)
+    d.count++;
+    if (d.count > 50) {
+        float carrier = (float)(0.1 * (double)__fmul_rn(d.omega2, d.rate) / two_pi);
+        carrier = (float)((double)carrier + 0.9 * (double)d.lowpass);
+        d.carrier = (int)carrier;
+        d.count = 0;
+        d.lowpass = carrier;
+    }
 }
 
 // arm_fir_interpolate_f32 (:2560-2577) for one block: output n = i L + j uses taps c[(L-1-j) + k L] on ip[INTERP_HIST - (P-1) + i + k]
@@ -200,7 +300,7 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
     const ChanParams &p = a.params[ch];
     ChanState &st = a.state[ch];
     const float *__restrict__ pool = a.pool;
-    const bool amsam = p.topo == TOPO_AM_SAM, sam = amsam && p.mode != UHSDR_DEMOD_AM;
+    const bool amsam = p.topo == TOPO_AM_SAM;
     const bool notch = p.notch_enable != 0;
     float *ring = smem + lane;                                   // AGC sample ring [AGC_RB][32]
     float *suf = smem + AGC_RB * S2_THREADS + lane;              // suffix maxima [NSUF][ND][32]
@@ -211,8 +311,9 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
     float *__restrict__ audio_f = a.audio_f ? a.audio_f + chan_base : nullptr;
     const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
-    DemodState ds;
-    if (amsam && phase != 2) demod_load(ds, st, sam, false);
+    Demod2 ds;
+    float *apc = smem + (AGC_RB + NSUF * 16) * S2_THREADS + lane;  // all-pass chains of the SAM sideband selector
+    if (amsam && phase != 2) demod2_load(ds, p, st, pool, apc);
     // lattice pre-filter, front-padded to 10 stages (k = v = 0 stages pass the sample through)
     float pk[10], pv[11], ps[10];
     const int pn = p.pre.n, ppad = 10 - pn;
@@ -305,7 +406,7 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
                 float bi[ND];
 #pragma unroll
                 for (int i = 0; i < ND; i++) bi[i] = ad[i];
-                demod_am_sam(p, ds, pool, bi, bq_, ad, 1, ND);
+                demod2_block<ND>(ds, apc, bi, bq_, ad);
             }
             if (notch) notch_block2<ND>(st, ad, notch_mu);
             // lattice pre-filter (the per-sample loops are unrolled: rolled, the per-block arrays go to local memory and the kernel
@@ -498,7 +599,7 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
 
     // ---- state ----
     if (phase != 2) {
-        if (amsam) demod_store(st, ds, sam, false);
+        if (amsam) demod2_store(st, ds, apc);
 #pragma unroll
         for (int j = 0; j < 10; j++) if (j >= ppad) st.pre_s[j - ppad] = ps[j];
         if (!agc_off) {
@@ -683,7 +784,8 @@ cudaError_t launch_rx_serial2(const RxArgs &a, int phase, cudaStream_t stream)
 {
     if (a.num_items <= 0) return cudaSuccess;
     if (a.scratch == nullptr || a.chan_list == nullptr) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)(AGC_RB + NSUF * 16) * S2_THREADS * sizeof(float);
+    // AGC ring + suffix maxima + SAM all-pass chains; phase 2 (behind the AGC) uses none of them
+    const size_t smem = phase == 2 ? 0 : (size_t)((AGC_RB + NSUF * 16) * S2_THREADS + AP_FLOATS) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(rx_serial2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (a.num_items + S2_THREADS - 1) / S2_THREADS;
