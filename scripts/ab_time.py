@@ -13,7 +13,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from uhsdr_b200.config import (DEMOD_AM, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, SAM_SIDEBAND_USB, ChanCfg, default_cfg)   # noqa: E402
+from uhsdr_b200.config import (DEMOD_AM, DEMOD_FM, DEMOD_LSB, DEMOD_SAM, DSP_NR_ENABLE, SAM_SIDEBAND_USB, ChanCfg, default_cfg)   # noqa: E402
 from uhsdr_b200.tables import DEFAULT_BLOB   # noqa: E402
 
 def _rep(c):
@@ -28,6 +28,7 @@ PLANS = {
     "am": _rep(default_cfg(dmod_mode=DEMOD_AM, filter_path=70)), "sam": _rep(default_cfg(dmod_mode=DEMOD_SAM, filter_path=72)),
     "samu": _rep(default_cfg(dmod_mode=DEMOD_SAM, filter_path=72, sam_sideband=SAM_SIDEBAND_USB)), "fm": _rep(default_cfg(dmod_mode=DEMOD_FM, filter_path=2)),
     "w48": _rep(default_cfg(filter_path=48)), "w55": _rep(default_cfg(filter_path=55)),
+    "nr": _rep(default_cfg(dsp_active=DSP_NR_ENABLE)),
 }
 
 

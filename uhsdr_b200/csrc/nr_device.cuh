@@ -292,4 +292,137 @@ __device__ inline void nr_block(const ChanParams &p, NrState &nr, const float *_
     }
 }
 
+// The same walk for a whole time slice with the warp's lanes over samples (rx_nr_kernel): nr_block above does the interface work --
+// 4-tap decimation by 2, packing into the frame buffers, FIFO bookkeeping, unpacking, 40-tap interpolation by 2 -- on lane 0 with the
+// bookkeeping in global memory, which costs more than the FFT frames themselves.  Here the bookkeeping scalars live in registers
+// (uniform across the warp) for the launch, the two small FIRs run with one output per lane (taps in registers, every sum in the
+// reference's order: same bits as nr_block), and the copies are coalesced.  `hs`: 64 floats of shared memory of this warp.
+struct NrRun {
+    int trans_count_in, outbuff_count, fill_in_pt, out_buffer, in_head, in_tail, out_head, out_tail, current_buffer_idx, was_here;
+    int in_fifo[NR_FIFO], out_fifo[NR_FIFO];
+};
+__device__ __forceinline__ int fifo_get(const int (&f)[NR_FIFO], int i)
+{
+    int v = f[0];
+#pragma unroll
+    for (int q = 1; q < NR_FIFO; q++) v = (i == q) ? f[q] : v;
+    return v;
+}
+__device__ __forceinline__ void fifo_set(int (&f)[NR_FIFO], int i, int v)
+{
+#pragma unroll
+    for (int q = 0; q < NR_FIFO; q++) f[q] = (i == q) ? v : f[q];
+}
+
+__device__ inline void nr_slice(const ChanParams &p, NrState &nr, const float *__restrict__ pool, float *sc, int nblocks, int n, float *fft,
+                                float *hs, int lane)
+{
+    NrRun r;
+    r.trans_count_in = nr.trans_count_in; r.outbuff_count = nr.outbuff_count; r.fill_in_pt = nr.fill_in_pt; r.out_buffer = nr.out_buffer;
+    r.in_head = nr.in_head; r.in_tail = nr.in_tail; r.out_head = nr.out_head; r.out_tail = nr.out_tail;
+    r.current_buffer_idx = nr.current_buffer_idx; r.was_here = nr.was_here;
+#pragma unroll
+    for (int q = 0; q < NR_FIFO; q++) { r.in_fifo[q] = nr.in_fifo[q]; r.out_fifo[q] = nr.out_fifo[q]; }
+    const bool decim = p.nr_decim != 0;
+    const int no_dec = decim ? n / 2 : n;
+    // shared staging: sd = [3 history | n new] of the decimator, si = [19 history | no_dec new] of the interpolator
+    float *sd = hs, *si = hs + 3 + BLK;
+    float cd[4], ci[20];
+#pragma unroll
+    for (int k = 0; k < 4; k++) cd[k] = decim ? __ldg(pool + p.nr_dec_c + k) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 20; k++) ci[k] = decim ? __ldg(pool + p.nr_int_c + (1 - (lane & 1)) + 2 * k) : 0.0f;
+    if (decim) {
+        if (lane < 3) sd[lane] = nr.dec_hist[lane];
+        if (lane < 19) si[lane] = nr.int_hist[lane];
+    }
+    __syncwarp();
+    for (int blk = 0; blk < nblocks; blk++) {
+        float *buf = sc + (size_t)blk * n;
+        float x = (lane < n) ? buf[lane] : 0.0f;
+        if (decim) {
+            // DECIMATE_NR: 4 taps, M = 2 (audio_driver.c:195, :649): y[m] = sum_k c[k] s[2m - 3 + k]
+            if (lane < n) sd[3 + lane] = x;
+            __syncwarp();
+            float acc = 0.0f;
+            if (lane < no_dec) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) acc = __fadd_rn(acc, __fmul_rn(sd[2 * lane + k], cd[k]));
+            }
+            const float h = (lane < 3) ? sd[n + lane] : 0.0f;
+            __syncwarp();
+            if (lane < 3) sd[lane] = h;
+            x = acc;
+        }
+        if (lane < no_dec) nr.bufs[r.fill_in_pt][2 * r.trans_count_in + lane] = x;
+        r.trans_count_in += no_dec / 2;
+        if (r.trans_count_in >= 64) {
+            const int next = (r.in_head + 1) % NR_FIFO;
+            if (next != r.in_tail) { fifo_set(r.in_fifo, r.in_head, r.fill_in_pt); r.in_head = next; }
+            r.trans_count_in = 0;
+            r.fill_in_pt = (r.fill_in_pt + 1) % 4;
+        }
+        if (r.out_buffer < 0 && nr_fifo_count(r.out_head, r.out_tail) > 1) r.out_buffer = fifo_get(r.out_fifo, r.out_tail);
+        float d = 0.0f;
+        if (r.out_buffer >= 0) {
+            if (lane < no_dec) d = nr.bufs[r.out_buffer][128 + 2 * r.outbuff_count + lane];
+            r.outbuff_count += no_dec / 2;
+            if (r.outbuff_count >= 64) {
+                r.outbuff_count = 0;
+                if (r.out_head != r.out_tail) r.out_tail = (r.out_tail + 1) % NR_FIFO;
+                r.out_buffer = (r.out_head != r.out_tail) ? fifo_get(r.out_fifo, r.out_tail) : -1;
+            }
+        }
+        if (decim) {
+            // INTERPOLATE_NR: L = 2, 40 taps -> phase length 20 (audio_driver.c:198, :653), then x2.0; lane = output 2 i + j
+            if (lane < no_dec) si[19 + lane] = d;
+            __syncwarp();
+            if (lane < 2 * no_dec) {
+                const int i = lane >> 1;
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 20; k++) sum = __fadd_rn(sum, __fmul_rn(si[i + k], ci[k]));
+                buf[lane] = __fmul_rn(sum, 2.0f);
+            }
+            const float h = (lane < 19) ? si[no_dec + lane] : 0.0f;
+            __syncwarp();
+            if (lane < 19) si[lane] = h;
+        } else if (lane < n) {
+            buf[lane] = d;
+        }
+        // deferred task bookkeeping (AudioNr_HandleNoiseReduction)
+        if (!r.was_here) { r.was_here = 1; r.current_buffer_idx = 0; r.in_tail = r.in_head; r.out_tail = r.out_head; }
+        const int pending = nr_fifo_count(r.in_head, r.in_tail) && (NR_FIFO - 1 - nr_fifo_count(r.out_head, r.out_tail));
+        if (pending) {
+            const int cur = r.current_buffer_idx % 4;
+            const int k = fifo_get(r.in_fifo, r.in_tail);
+            __threadfence_block();
+            __syncwarp();
+            if (p.nb_enable) { nb_frame(p, nr, nr.bufs[k], fft, lane); __threadfence_block(); __syncwarp(); }   // AudioNr_RunNoiseReduction, audio_nr.c:362-365
+            if (p.nr_spectral) nr_spectral(p, nr, pool, nr.bufs[k], fft, lane);
+            __threadfence_block();
+            __syncwarp();
+            for (int i = lane; i < 128; i += 32) nr.bufs[cur][128 + i] = nr.bufs[k][i];
+            r.in_tail = (r.in_tail + 1) % NR_FIFO;
+            const int next = (r.out_head + 1) % NR_FIFO;
+            if (next != r.out_tail) { fifo_set(r.out_fifo, r.out_head, cur); r.out_head = next; }
+            r.current_buffer_idx = cur + 1;
+            __threadfence_block();
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (decim) {
+        if (lane < 3) nr.dec_hist[lane] = sd[lane];
+        if (lane < 19) nr.int_hist[lane] = si[lane];
+    }
+    if (lane == 0) {
+        nr.trans_count_in = r.trans_count_in; nr.outbuff_count = r.outbuff_count; nr.fill_in_pt = r.fill_in_pt; nr.out_buffer = r.out_buffer;
+        nr.in_head = r.in_head; nr.in_tail = r.in_tail; nr.out_head = r.out_head; nr.out_tail = r.out_tail;
+        nr.current_buffer_idx = r.current_buffer_idx; nr.was_here = r.was_here;
+#pragma unroll
+        for (int q = 0; q < NR_FIFO; q++) { nr.in_fifo[q] = r.in_fifo[q]; nr.out_fifo[q] = r.out_fifo[q]; }
+    }
+}
+
 }  // namespace uhsdr

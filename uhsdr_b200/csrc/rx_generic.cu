@@ -479,6 +479,7 @@ __global__ void __launch_bounds__(32 * G_WARPS)
 rx_nr_kernel(RxArgs a)
 {
     __shared__ __align__(16) float fft[G_WARPS][512];
+    __shared__ float hs[G_WARPS][3 + BLK + 19 + BLK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot = blockIdx.x * G_WARPS + warp;
     if (slot >= a.num_items) return;
@@ -487,7 +488,7 @@ rx_nr_kernel(RxArgs a)
     if (!p.nr_enable || !a.nr) return;
     const int nd = BLK / p.M;
     float *sc = a.scratch + (size_t)slot * (size_t)a.scratch_stride;
-    for (int blk = 0; blk < a.nblocks; blk++) nr_block(p, a.nr[ch], a.pool, sc + (size_t)blk * nd, nd, fft[warp], lane);
+    nr_slice(p, a.nr[ch], a.pool, sc, a.nblocks, nd, fft[warp], hs[warp], lane);
 }
 
 cudaError_t launch_rx_nr(const RxArgs &a, cudaStream_t stream)
