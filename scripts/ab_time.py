@@ -46,6 +46,7 @@ class Lib:
         L.uhsdr_engine_create.argtypes = [ctypes.POINTER(vp), ci, ci, vp, ctypes.c_size_t]
         L.uhsdr_configure_channels_strided.argtypes = [vp, ci, ci, ci, ctypes.POINTER(ChanCfg), ci]
         L.uhsdr_rx_process_device.argtypes = [vp, vp, vp, vp, ci, vp]
+        L.uhsdr_tx_process_device.argtypes = [vp, vp, vp, vp, ci, vp]
         L.uhsdr_engine_stream.restype = vp
         L.uhsdr_engine_stream.argtypes = [vp]
         L.uhsdr_engine_sync.argtypes = [vp]
@@ -69,8 +70,20 @@ class Lib:
             else:
                 os.environ[k] = v
 
-    def run(self, iq, out, nb, reps):
+    def run(self, iq, out, nb, reps, tx=False):
         L = self.L
+        if tx:      # the modulator alone (TxProcessor_Run): iq = microphone words, out = I/Q words
+            call = lambda: L.uhsdr_tx_process_device(self.h, iq.data_ptr(), out.data_ptr(), None, nb, None)
+            with torch.cuda.stream(self.stream):
+                assert call() == 0
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(self.stream)
+                for _ in range(reps):
+                    assert call() == 0
+                e1.record(self.stream)
+                torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
         with torch.cuda.stream(self.stream):
             assert L.uhsdr_rx_process_device(self.h, iq.data_ptr(), out.data_ptr(), None, nb, None) == 0
             torch.cuda.synchronize()
@@ -91,16 +104,19 @@ def main():
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--plan", default="narrow")
+    ap.add_argument("--tx", action="store_true", help="time uhsdr_tx_process_device instead of the receiver")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(1)
     iq = (torch.randn((a.channels, a.blocks * 32, 2), device=dev, generator=g) * 3000.0 * 65536.0).to(torch.int32)
+    if a.tx:
+        iq[:, :, 1] = iq[:, :, 0]
     out = torch.empty_like(iq)
     libs = [Lib(p, a.channels, PLANS[a.plan]) for p in a.libs]
     ms = [[] for _ in libs]
     for _ in range(a.rounds):
         for i, lb in enumerate(libs):
-            ms[i].append(lb.run(iq, out, a.blocks, a.reps))
+            ms[i].append(lb.run(iq, out, a.blocks, a.reps, a.tx))
     best = [min(m) for m in ms]
     print(json.dumps({"plan": a.plan, "channels": a.channels, "blocks": a.blocks,
                       "ms": {os.path.basename(p) + f"#{i}": [round(x, 4) for x in m] for i, (p, m) in enumerate(zip(a.libs, ms))},

@@ -628,7 +628,7 @@ __device__ void serial2_fm(const RxArgs &a, int slot, int ch, float *smem)
 {
     // block staging in shared memory, [sample][lane]: the per-sample loop stays rolled (a few hundred instructions), its inputs and
     // outputs are indexed at run time, and register arrays indexed at run time would live in local memory
-    float *s_i = smem + threadIdx.x, *s_q = s_i + BLK * S2_THREADS, *s_a = s_q + BLK * S2_THREADS;
+    float *s_i = smem + threadIdx.x, *s_q = s_i + BLK * S2_THREADS, *s_a = s_q + BLK * S2_THREADS, *s_g = s_a + BLK * S2_THREADS;
     const ChanParams &p = a.params[ch];
     ChanState &st = a.state[ch];
     const float *__restrict__ pool = a.pool;
@@ -667,12 +667,19 @@ __device__ void serial2_fm(const RxArgs &a, int slot, int ch, float *smem)
         if (blk + 1 < a.nblocks) fetch(blk + 1);
         if (translate_on) {
             float first_hp = 0.0f;
-#pragma unroll 1
+            // the discriminator itself is feed-forward: four samples side by side, ahead of the recurrences
+#pragma unroll 4
             for (int n = 0; n < BLK; n++) {
                 const float bin = s_i[n * S2_THREADS], bqn = s_q[n * S2_THREADS];
-                const float y = __fsub_rn(__fmul_rn(i_prev, bqn), __fmul_rn(bin, q_prev));
-                const float x = __fadd_rn(__fmul_rn(i_prev, bin), __fmul_rn(bqn, q_prev));
-                const float angle = atan2f(y, x);
+                const float ip = n ? s_i[(n - 1) * S2_THREADS] : i_prev, qp = n ? s_q[(n - 1) * S2_THREADS] : q_prev;
+                const float y = __fsub_rn(__fmul_rn(ip, bqn), __fmul_rn(bin, qp));
+                const float x = __fadd_rn(__fmul_rn(ip, bin), __fmul_rn(bqn, qp));
+                s_g[n * S2_THREADS] = atan2f(y, x);
+            }
+            i_prev = s_i[(BLK - 1) * S2_THREADS]; q_prev = s_q[(BLK - 1) * S2_THREADS];
+#pragma unroll 1
+            for (int n = 0; n < BLK; n++) {
+                const float angle = s_g[n * S2_THREADS];
                 // squelch noise high-pass (6-stage lattice, arm_iir_lattice_f32) on the raw angle (:1594)
                 float f = angle, acc = 0.0f, fn = 0.0f;
 #pragma unroll
@@ -701,7 +708,6 @@ __device__ void serial2_fm(const RxArgs &a, int slot, int ch, float *smem)
                     hpf_a = av; hpf_b = hb;
                     s_a[n * S2_THREADS] = hb;
                 }
-                q_prev = bqn; i_prev = bin;
             }
             sql_avg = (float)(((double)(1 - 0.005) * (double)sql_avg) + (0.005 * (double)__fsqrt_rn(fabsf(first_hp))));
             count = (count + 1) % 200;

@@ -7,6 +7,8 @@
 //   IqFinalProcessing (:282-330) x power factor x IQ gain x 1.133 x 65536, phase mix, float -> int32
 // One warp per channel: the recurrences (lattice, biquads, ALC) run on lane 0, the two 201-tap
 // FIRs, translation and output formatting on all 32 lanes.
+#include <type_traits>
+
 #include "fir_device.cuh"
 #include "host_tables.h"
 #include "kernels.h"
@@ -628,52 +630,104 @@ tx_serial2_kernel(TxArgs a)
     float *__restrict__ out = a.scratch + (size_t)ch * (size_t)a.nblocks * BLK;
     const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
 
+    // microphone words of the next block, fetched one block ahead (the .l words of 32 AudioSample_t = every other int32)
+    int4 nxt[BLK / 2];
+    auto fetch = [&](int blk) {
+#pragma unroll
+        for (int i = 0; i < BLK / 2; i++)       // volatile: the compiler must not sink the loads to their first use one block later
+            asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt[i].x), "=r"(nxt[i].y), "=r"(nxt[i].z), "=r"(nxt[i].w)
+                         : "l"(mic + (size_t)blk * BLK + 2 * i));
+    };
+    if (a.nblocks > 0) fetch(0);
     for (int blk = 0; blk < a.nblocks; blk++) {
+        int mw[BLK];
+#pragma unroll
+        for (int i = 0; i < BLK / 2; i++) { mw[2 * i] = nxt[i].x; mw[2 * i + 1] = nxt[i].z; }
+        if (blk + 1 < a.nblocks) fetch(blk + 1);
         if (mute && mute[blk]) continue;
         // AudioBufferFill (tx_processor.c:339-405)
         float mx = 0.0f, mn = 0.0f;
 #pragma unroll
         for (int i = 0; i < BLK; i += 2) {
-            const int4 s_ = *reinterpret_cast<const int4 *>(mic + (size_t)blk * BLK + i);
-            float x0 = (float)s_.x, x1 = (float)s_.z;
+            float x0 = (float)mw[i], x1 = (float)mw[i + 1];
             if (gain_on) { x0 = __fmul_rn(x0, gain_calc); x1 = __fmul_rn(x1, gain_calc); }
             if (i == 0) { mx = x0; mn = x0; }
             mx = fmaxf(mx, fmaxf(x0, x1)); mn = fminf(mn, fminf(x0, x1));
             sv[i * TXS_THREADS] = x0; sv[(i + 1) * TXS_THREADS] = x1;
         }
         peak_audio = (-mn > mx) ? -mn : mx;
-        // FilterAudio (:416-429): lattice + 3 biquads, then the compressor's detector (:173-242), sample by sample
-#pragma unroll 1
-        for (int i = 0; i < BLK; i++) {
+        // FilterAudio (:416-429): lattice + 3 biquads, then the compressor's detector (:173-242), sample by sample.  Both are
+        // recurrences with nothing to overlap inside; the detector runs one sample behind the filters, so that an iteration holds
+        // two independent chains (filters of sample i, detector of sample i - 1).
+        // Shipping build: fused multiply-adds, biquads with the new sample entering last (one multiply-add on the sample-to-sample
+        // path per stage), the detector in float with a reciprocal knee -- the dependent chain of a sample is what this kernel's time
+        // is made of (one warp per 32 channels, nothing else to issue).  Exact build: the reference's operations one by one.
+        auto run_filters = [&](auto exm) {
+        constexpr bool EXM = decltype(exm)::value;
+        auto filters = [&](int i) {
             float f = sv[i * TXS_THREADS], acc = 0.0f, fn = 0.0f;
 #pragma unroll
             for (int j = 0; j < 10; j++) {
                 const float gg = ls[j];
+                float gn;
+                if constexpr (EXM) {
                 fn = __fsub_rn(f, __fmul_rn(lk[j], gg));
-                const float gn = __fadd_rn(__fmul_rn(fn, lk[j]), gg);
+                gn = __fadd_rn(__fmul_rn(fn, lk[j]), gg);
                 acc = __fadd_rn(acc, __fmul_rn(gn, lv[j]));
+                } else {
+                fn = fmaf(-lk[j], gg, f);
+                gn = fmaf(fn, lk[j], gg);
+                acc = fmaf(gn, lv[j], acc);
+                }
                 if (j > 0) ls[j - 1] = gn;
                 f = fn;
             }
-            float x = __fadd_rn(acc, __fmul_rn(fn, lv[10]));
+            float x = EXM ? __fadd_rn(acc, __fmul_rn(fn, lv[10])) : fmaf(fn, lv[10], acc);
             ls[9] = fn;
 #pragma unroll
-            for (int s = 0; s < 3; s++) x = biquad_step(x, bc[s], bq[s]);
-            if (comp) {
-                x = __fmul_rn(x, postfilt_gain);
-                // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
-                const float alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(x, alc_val)), 30000.0f) - 1.0);
-                if (alc_var < 0.0f) {
-                    alc_val = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
-                } else {
-                    alc_val = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
-                    if ((double)alc_val < 0.001) alc_val = (float)0.001;
-                }
-                if (alc_val > 1.0f) alc_val = 1.0f;
-                sa[i * TXS_THREADS] = __fmul_rn(alc_val, alc_scale);
+            for (int s = 0; s < 3; s++) {
+                if constexpr (EXM) { x = biquad_step(x, bc[s], bq[s]); continue; }
+                const float t = fmaf(bc[s][1], bq[s].x1, fmaf(bc[s][2], bq[s].x2, fmaf(bc[s][3], bq[s].y1, __fmul_rn(bc[s][4], bq[s].y2))));
+                const float y = fmaf(bc[s][0], x, t);
+                bq[s].x2 = bq[s].x1; bq[s].x1 = x; bq[s].y2 = bq[s].y1; bq[s].y1 = y;
+                x = y;
             }
-            sv[i * TXS_THREADS] = x;
+            return x;
+        };
+        auto detector = [&](float xp, int i) {
+            float alc_var, dn, up;
+            if constexpr (EXM) {
+                // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
+                alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(xp, alc_val)), 30000.0f) - 1.0);
+                dn = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
+                up = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
+                if ((double)up < 0.001) up = (float)0.001;
+            } else {
+                alc_var = fmaf(fabsf(__fmul_rn(xp, alc_val)), 1.0f / 30000.0f, -1.0f);
+                dn = fmaf(-__fmul_rn(alc_val, alc_decay), alc_var, alc_val);
+                up = fmaxf(fmaf(-__fmul_rn(alc_val, 0.1f), alc_var, alc_val), 0.001f);
+            }
+            alc_val = (alc_var < 0.0f) ? dn : up;
+            if (alc_val > 1.0f) alc_val = 1.0f;
+            sa[i * TXS_THREADS] = __fmul_rn(alc_val, alc_scale);
+        };
+        if (comp) {
+            float xp = __fmul_rn(filters(0), postfilt_gain);
+            sv[0] = xp;
+#pragma unroll 1
+            for (int i = 1; i < BLK; i++) {            // one basic block: filters of sample i beside the detector of sample i - 1
+                const float x = __fmul_rn(filters(i), postfilt_gain);
+                sv[i * TXS_THREADS] = x;
+                detector(xp, i - 1);
+                xp = x;
+            }
+            detector(xp, BLK - 1);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < BLK; i++) sv[i * TXS_THREADS] = filters(i);
         }
+        };
+        if (UHSDR_EXACT || fm) run_filters(std::true_type{}); else run_filters(std::false_type{});
         if (comp) {
             inbuf += BLK;
             // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
