@@ -591,46 +591,112 @@ namespace {
 constexpr int TXS2_DELAY = 320;
 }
 
-__global__ void __launch_bounds__(TXS_THREADS)
+__global__ void __launch_bounds__(2 * TXS_THREADS)
 tx_serial2_kernel(TxArgs a)
 {
+    // Two warps per 32 channels, one iteration and one __syncthreads per block.  Warp 0 (FILTERS) runs the lattice and the biquads
+    // of block t; warp 1 (REST) converts the microphone words of block t + 1, and runs the compressor's detector, the delay line,
+    // the FM accumulator and the store of block t - 1.  Each is a dependent chain with nothing else to issue, so splitting the
+    // chain over two warps nearly halves the time per block; the buffers between them are double-buffered in shared memory.
     extern __shared__ __align__(16) float txs2_smem[];
-    const int ch = blockIdx.x * TXS_THREADS + threadIdx.x;
-    if (ch >= a.num_items) return;
-    const TxParams &tp = a.txp[ch];
-    if (!tp.enabled) return;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int ch = blockIdx.x * TXS_THREADS + lane;
+    const bool valid = ch < a.num_items && a.txp[ch < a.num_items ? ch : 0].enabled;
+    const TxParams &tp = a.txp[valid ? ch : 0];
     const float *__restrict__ pool = a.pool;
-    TxState &g = a.tx[ch];
-    float *dl = txs2_smem + threadIdx.x;                            // delay line [320][32]
-    float *sv = dl + TXS2_DELAY * TXS_THREADS;                       // block samples [32][32]
-    float *sa = sv + BLK * TXS_THREADS;                              // ALC gains of the block [32][32]
-    float lk[10], lv[11], ls[10];
-    const int ln = tp.lat.n, lpad = 10 - ln;
+    TxState &g = a.tx[valid ? ch : 0];
+    float *dl = txs2_smem + lane;                                    // delay line [320][32]
+    float *xin = dl + TXS2_DELAY * TXS_THREADS;                      // converted microphone samples [2][32][32]
+    float *xb = xin + 2 * BLK * TXS_THREADS;                         // filter outputs [2][32][32]
+    float *sa = xb + 2 * BLK * TXS_THREADS;                          // ALC gains of the block [32][32]
+    const float gain_calc = tp.gain_calc, postfilt_gain = tp.postfilt_gain, alc_decay = tp.alc_decay, alc_scale = tp.alc_gain_scaling;
+    const bool gain_on = (double)gain_calc != 1.0, comp = tp.comp_enabled != 0, fm = tp.fm != 0;
+    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + (size_t)(valid ? ch : 0) * (size_t)a.chan_stride;
+    float *__restrict__ out = a.scratch + (size_t)(valid ? ch : 0) * (size_t)a.nblocks * BLK;
+    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)(valid ? ch : 0) * (size_t)a.mute_stride : nullptr;
+    const int nblocks = a.nblocks;
+    // one arithmetic per warp (the loops below hold the CTA's barriers: no lane may take another path): the reference's operation
+    // order if any channel of the warp is an FM modulator
+    const bool exm = UHSDR_EXACT || __any_sync(0xffffffffu, valid && fm);
+
+    if (role == 0) {
+        // ======================= FILTERS: lattice + 3 biquads (FilterAudio, tx_processor.c:416-429) =======================
+        float lk[10], lv[11], ls[10];
+        const int ln = tp.lat.n, lpad = 10 - ln;
 #pragma unroll
-    for (int j = 0; j < 10; j++) {
-        lk[j] = (j >= lpad) ? __ldg(pool + tp.lat.k_off + (j - lpad)) : 0.0f;
-        lv[j] = (j >= lpad) ? __ldg(pool + tp.lat.v_off + (j - lpad)) : 0.0f;
-        ls[j] = (j >= lpad) ? g.lat_s[j - lpad] : 0.0f;
+        for (int j = 0; j < 10; j++) {
+            lk[j] = (j >= lpad) ? __ldg(pool + tp.lat.k_off + (j - lpad)) : 0.0f;
+            lv[j] = (j >= lpad) ? __ldg(pool + tp.lat.v_off + (j - lpad)) : 0.0f;
+            ls[j] = (j >= lpad) ? g.lat_s[j - lpad] : 0.0f;
+        }
+        lv[10] = __ldg(pool + tp.lat.v_off + ln);
+        BiquadS bq[3];
+        float bc[3][5];
+#pragma unroll
+        for (int s = 0; s < 3; s++) { bq[s] = g.bq[s];
+#pragma unroll
+            for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
+        // Shipping build: fused multiply-adds, biquads with the new sample entering last (one multiply-add on the sample-to-sample
+        // path per stage).  Exact build, and the FM modulator in both builds (its audio drives an integer phase accumulator:
+        // rounding differences would add up): the reference's operations one by one.
+        auto run = [&](auto exm) {
+            constexpr bool EXM = decltype(exm)::value;
+            for (int t = -1; t <= nblocks; t++) {
+                if (valid && t >= 0 && t < nblocks && !(mute && mute[t])) {
+                    const float *src = xin + (t & 1) * BLK * TXS_THREADS;
+                    float *dst = xb + (t & 1) * BLK * TXS_THREADS;
+#pragma unroll 1
+                    for (int i = 0; i < BLK; i++) {
+                        float f = src[i * TXS_THREADS], acc = 0.0f, fn = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 10; j++) {
+                            const float gg = ls[j];
+                            float gn;
+                            if constexpr (EXM) {
+                                fn = __fsub_rn(f, __fmul_rn(lk[j], gg));
+                                gn = __fadd_rn(__fmul_rn(fn, lk[j]), gg);
+                                acc = __fadd_rn(acc, __fmul_rn(gn, lv[j]));
+                            } else {
+                                fn = fmaf(-lk[j], gg, f);
+                                gn = fmaf(fn, lk[j], gg);
+                                acc = fmaf(gn, lv[j], acc);
+                            }
+                            if (j > 0) ls[j - 1] = gn;
+                            f = fn;
+                        }
+                        float x = EXM ? __fadd_rn(acc, __fmul_rn(fn, lv[10])) : fmaf(fn, lv[10], acc);
+                        ls[9] = fn;
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            if constexpr (EXM) { x = biquad_step(x, bc[s], bq[s]); continue; }
+                            const float tt = fmaf(bc[s][1], bq[s].x1, fmaf(bc[s][2], bq[s].x2, fmaf(bc[s][3], bq[s].y1, __fmul_rn(bc[s][4], bq[s].y2))));
+                            const float y = fmaf(bc[s][0], x, tt);
+                            bq[s].x2 = bq[s].x1; bq[s].x1 = x; bq[s].y2 = bq[s].y1; bq[s].y1 = y;
+                            x = y;
+                        }
+                        dst[i * TXS_THREADS] = comp ? __fmul_rn(x, postfilt_gain) : x;
+                    }
+                }
+                __syncthreads();
+            }
+        };
+        if (exm) run(std::true_type{}); else run(std::false_type{});
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 10; j++) if (j >= lpad) g.lat_s[j - lpad] = ls[j];
+#pragma unroll
+            for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
+        }
+        return;
     }
-    lv[10] = __ldg(pool + tp.lat.v_off + ln);
-    BiquadS bq[3];
-    float bc[3][5];
-#pragma unroll
-    for (int s = 0; s < 3; s++) { bq[s] = g.bq[s];
-#pragma unroll
-        for (int q = 0; q < 5; q++) bc[s][q] = tp.bq[s][q]; }
+
+    // ======================= REST: AudioBufferFill of block t + 1; compressor, delay line, FM accumulator, store of block t - 1 ====
     float alc_val = g.alc_val, peak_audio = g.peak_audio;
     float fm_hpf_a = g.fm_hpf_a, fm_hpf_b = g.fm_hpf_b;
     uint32_t fm_accum = g.fm_accum, sub_acc = g.fm_dds_sub_acc, burst_acc = g.fm_dds_burst_acc;
     uint32_t inbuf = g.alc_delay_inbuf;
-    for (int i = 0; i < TXS2_DELAY; i++) dl[i * TXS_THREADS] = g.delay[i];
-    const float gain_calc = tp.gain_calc, postfilt_gain = tp.postfilt_gain, alc_decay = tp.alc_decay, alc_scale = tp.alc_gain_scaling;
-    const bool gain_on = (double)gain_calc != 1.0, comp = tp.comp_enabled != 0, fm = tp.fm != 0;
-    const int2 *__restrict__ mic = reinterpret_cast<const int2 *>(a.audio) + (size_t)ch * (size_t)a.chan_stride;
-    float *__restrict__ out = a.scratch + (size_t)ch * (size_t)a.nblocks * BLK;
-    const uint8_t *__restrict__ mute = a.mute ? a.mute + (size_t)ch * (size_t)a.mute_stride : nullptr;
-
-    // microphone words of the next block, fetched one block ahead (the .l words of 32 AudioSample_t = every other int32)
+    if (valid) for (int i = 0; i < TXS2_DELAY; i++) dl[i * TXS_THREADS] = g.delay[i];
+    // microphone words (the .l words of 32 AudioSample_t = every other int32), fetched one block ahead of their conversion
     int4 nxt[BLK / 2];
     auto fetch = [&](int blk) {
 #pragma unroll
@@ -638,122 +704,74 @@ tx_serial2_kernel(TxArgs a)
             asm volatile("ld.global.nc.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(nxt[i].x), "=r"(nxt[i].y), "=r"(nxt[i].z), "=r"(nxt[i].w)
                          : "l"(mic + (size_t)blk * BLK + 2 * i));
     };
-    if (a.nblocks > 0) fetch(0);
-    for (int blk = 0; blk < a.nblocks; blk++) {
-        int mw[BLK];
+    if (valid && nblocks > 0) fetch(0);
+    for (int t = -1; t <= nblocks; t++) {
+        if (valid && t + 1 < nblocks) {
+            // AudioBufferFill (tx_processor.c:339-405) of block t + 1
+            const int b1 = t + 1;
+            float *dst = xin + (b1 & 1) * BLK * TXS_THREADS;
+            float mx = 0.0f, mn = 0.0f;
+            const bool muted = mute && mute[b1];
 #pragma unroll
-        for (int i = 0; i < BLK / 2; i++) { mw[2 * i] = nxt[i].x; mw[2 * i + 1] = nxt[i].z; }
-        if (blk + 1 < a.nblocks) fetch(blk + 1);
-        if (mute && mute[blk]) continue;
-        // AudioBufferFill (tx_processor.c:339-405)
-        float mx = 0.0f, mn = 0.0f;
-#pragma unroll
-        for (int i = 0; i < BLK; i += 2) {
-            float x0 = (float)mw[i], x1 = (float)mw[i + 1];
-            if (gain_on) { x0 = __fmul_rn(x0, gain_calc); x1 = __fmul_rn(x1, gain_calc); }
-            if (i == 0) { mx = x0; mn = x0; }
-            mx = fmaxf(mx, fmaxf(x0, x1)); mn = fminf(mn, fminf(x0, x1));
-            sv[i * TXS_THREADS] = x0; sv[(i + 1) * TXS_THREADS] = x1;
+            for (int i = 0; i < BLK; i += 2) {
+                float x0 = (float)nxt[i / 2].x, x1 = (float)nxt[i / 2].z;
+                if (gain_on) { x0 = __fmul_rn(x0, gain_calc); x1 = __fmul_rn(x1, gain_calc); }
+                if (i == 0) { mx = x0; mn = x0; }
+                mx = fmaxf(mx, fmaxf(x0, x1)); mn = fminf(mn, fminf(x0, x1));
+                dst[i * TXS_THREADS] = x0; dst[(i + 1) * TXS_THREADS] = x1;
+            }
+            if (!muted) peak_audio = (-mn > mx) ? -mn : mx;
+            if (b1 + 1 < nblocks) fetch(b1 + 1);
         }
-        peak_audio = (-mn > mx) ? -mn : mx;
-        // FilterAudio (:416-429): lattice + 3 biquads, then the compressor's detector (:173-242), sample by sample.  Both are
-        // recurrences with nothing to overlap inside; the detector runs one sample behind the filters, so that an iteration holds
-        // two independent chains (filters of sample i, detector of sample i - 1).
-        // Shipping build: fused multiply-adds, biquads with the new sample entering last (one multiply-add on the sample-to-sample
-        // path per stage), the detector in float with a reciprocal knee -- the dependent chain of a sample is what this kernel's time
-        // is made of (one warp per 32 channels, nothing else to issue).  Exact build: the reference's operations one by one.
-        auto run_filters = [&](auto exm) {
-        constexpr bool EXM = decltype(exm)::value;
-        auto filters = [&](int i) {
-            float f = sv[i * TXS_THREADS], acc = 0.0f, fn = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 10; j++) {
-                const float gg = ls[j];
-                float gn;
-                if constexpr (EXM) {
-                fn = __fsub_rn(f, __fmul_rn(lk[j], gg));
-                gn = __fadd_rn(__fmul_rn(fn, lk[j]), gg);
-                acc = __fadd_rn(acc, __fmul_rn(gn, lv[j]));
-                } else {
-                fn = fmaf(-lk[j], gg, f);
-                gn = fmaf(fn, lk[j], gg);
-                acc = fmaf(gn, lv[j], acc);
+        if (valid && t >= 1 && !(mute && mute[t - 1])) {
+            const int b0 = t - 1;
+            float *sv = xb + (b0 & 1) * BLK * TXS_THREADS;
+            if (comp) {
+                // the compressor's detector (:173-242), sample by sample
+#pragma unroll 1
+                for (int i = 0; i < BLK; i++) {
+                    const float xp = sv[i * TXS_THREADS];
+                    float alc_var, dn, up;
+                    if (exm) {
+                        // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
+                        alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(xp, alc_val)), 30000.0f) - 1.0);
+                        dn = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
+                        up = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
+                        if ((double)up < 0.001) up = (float)0.001;
+                    } else {
+                        alc_var = fmaf(fabsf(__fmul_rn(xp, alc_val)), 1.0f / 30000.0f, -1.0f);
+                        dn = fmaf(-__fmul_rn(alc_val, alc_decay), alc_var, alc_val);
+                        up = fmaxf(fmaf(-__fmul_rn(alc_val, 0.1f), alc_var, alc_val), 0.001f);
+                    }
+                    alc_val = (alc_var < 0.0f) ? dn : up;
+                    if (alc_val > 1.0f) alc_val = 1.0f;
+                    sa[i * TXS_THREADS] = __fmul_rn(alc_val, alc_scale);
                 }
-                if (j > 0) ls[j - 1] = gn;
-                f = fn;
-            }
-            float x = EXM ? __fadd_rn(acc, __fmul_rn(fn, lv[10])) : fmaf(fn, lv[10], acc);
-            ls[9] = fn;
-#pragma unroll
-            for (int s = 0; s < 3; s++) {
-                if constexpr (EXM) { x = biquad_step(x, bc[s], bq[s]); continue; }
-                const float t = fmaf(bc[s][1], bq[s].x1, fmaf(bc[s][2], bq[s].x2, fmaf(bc[s][3], bq[s].y1, __fmul_rn(bc[s][4], bq[s].y2))));
-                const float y = fmaf(bc[s][0], x, t);
-                bq[s].x2 = bq[s].x1; bq[s].x1 = x; bq[s].y2 = bq[s].y1; bq[s].y1 = y;
-                x = y;
-            }
-            return x;
-        };
-        auto detector = [&](float xp, int i) {
-            float alc_var, dn, up;
-            if constexpr (EXM) {
-                // alc_var = fabsf(a*alc_val)/ALC_KNEE - 1.0 (double), tx_processor.c:202
-                alc_var = (float)((double)__fdiv_rn(fabsf(__fmul_rn(xp, alc_val)), 30000.0f) - 1.0);
-                dn = __fsub_rn(alc_val, __fmul_rn(__fmul_rn(alc_val, alc_decay), alc_var));
-                up = (float)((double)alc_val - (double)alc_val * 0.1 * (double)alc_var);
-                if ((double)up < 0.001) up = (float)0.001;
-            } else {
-                alc_var = fmaf(fabsf(__fmul_rn(xp, alc_val)), 1.0f / 30000.0f, -1.0f);
-                dn = fmaf(-__fmul_rn(alc_val, alc_decay), alc_var, alc_val);
-                up = fmaxf(fmaf(-__fmul_rn(alc_val, 0.1f), alc_var, alc_val), 0.001f);
-            }
-            alc_val = (alc_var < 0.0f) ? dn : up;
-            if (alc_val > 1.0f) alc_val = 1.0f;
-            sa[i * TXS_THREADS] = __fmul_rn(alc_val, alc_scale);
-        };
-        if (comp) {
-            float xp = __fmul_rn(filters(0), postfilt_gain);
-            sv[0] = xp;
-#pragma unroll 1
-            for (int i = 1; i < BLK; i++) {            // one basic block: filters of sample i beside the detector of sample i - 1
-                const float x = __fmul_rn(filters(i), postfilt_gain);
-                sv[i * TXS_THREADS] = x;
-                detector(xp, i - 1);
-                xp = x;
-            }
-            detector(xp, BLK - 1);
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < BLK; i++) sv[i * TXS_THREADS] = filters(i);
-        }
-        };
-        if (UHSDR_EXACT || fm) run_filters(std::true_type{}); else run_filters(std::false_type{});
-        if (comp) {
-            inbuf += BLK;
-            // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
-            const uint32_t inb = inbuf % 320u, outb = (inbuf + BLK) % 320u;
+                inbuf += BLK;
+                // 320-sample delay line: write at inbuf, read at inbuf + 32 (:231-238)
+                const uint32_t inb = inbuf % 320u, outb = (inbuf + BLK) % 320u;
 #pragma unroll 4
-            for (int i = 0; i < BLK; i++) dl[(inb + i) * TXS_THREADS] = sv[i * TXS_THREADS];
+                for (int i = 0; i < BLK; i++) dl[(inb + i) * TXS_THREADS] = sv[i * TXS_THREADS];
 #pragma unroll 4
-            for (int i = 0; i < BLK; i++) sv[i * TXS_THREADS] = __fmul_rn(dl[(outb + i) * TXS_THREADS], sa[i * TXS_THREADS]);
-            inbuf = inb;
-        }
-        if (fm) {
+                for (int i = 0; i < BLK; i++) sv[i * TXS_THREADS] = __fmul_rn(dl[(outb + i) * TXS_THREADS], sa[i * TXS_THREADS]);
+                inbuf = inb;
+            }
+            if (fm) {
 #pragma unroll 1
-            for (int i = 0; i < BLK; i++)
-                sv[i * TXS_THREADS] = (float)fm_step(sv[i * TXS_THREADS], fm_hpf_a, fm_hpf_b, fm_accum, sub_acc, burst_acc, tp, pool);      // table index for the FIR-stage kernel
-        }
+                for (int i = 0; i < BLK; i++)
+                    sv[i * TXS_THREADS] = (float)fm_step(sv[i * TXS_THREADS], fm_hpf_a, fm_hpf_b, fm_accum, sub_acc, burst_acc, tp, pool);      // table index for the FIR-stage kernel
+            }
 #pragma unroll
-        for (int i = 0; i < BLK; i += 4)
-            *reinterpret_cast<float4 *>(out + (size_t)blk * BLK + i) = make_float4(sv[i * TXS_THREADS], sv[(i + 1) * TXS_THREADS], sv[(i + 2) * TXS_THREADS], sv[(i + 3) * TXS_THREADS]);
+            for (int i = 0; i < BLK; i += 4)
+                *reinterpret_cast<float4 *>(out + (size_t)b0 * BLK + i) = make_float4(sv[i * TXS_THREADS], sv[(i + 1) * TXS_THREADS], sv[(i + 2) * TXS_THREADS], sv[(i + 3) * TXS_THREADS]);
+        }
+        __syncthreads();
     }
-    g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum; g.fm_dds_sub_acc = sub_acc; g.fm_dds_burst_acc = burst_acc;
-#pragma unroll
-    for (int j = 0; j < 10; j++) if (j >= lpad) g.lat_s[j - lpad] = ls[j];
-#pragma unroll
-    for (int s = 0; s < 3; s++) g.bq[s] = bq[s];
-    g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;
-    for (int i = 0; i < TXS2_DELAY; i++) g.delay[i] = dl[i * TXS_THREADS];
+    if (valid) {
+        g.fm_hpf_a = fm_hpf_a; g.fm_hpf_b = fm_hpf_b; g.fm_accum = fm_accum; g.fm_dds_sub_acc = sub_acc; g.fm_dds_burst_acc = burst_acc;
+        g.alc_val = alc_val; g.peak_audio = peak_audio; g.alc_delay_inbuf = inbuf;
+        for (int i = 0; i < TXS2_DELAY; i++) g.delay[i] = dl[i * TXS_THREADS];
+    }
 }
 
 cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream)
@@ -762,10 +780,10 @@ cudaError_t launch_tx_serial(const TxArgs &a, cudaStream_t stream)
     if (a.scratch == nullptr) return cudaErrorInvalidValue;
     static const bool no2 = [] { const char *v = getenv("UHSDR_B200_NO_SERIAL2"); return v && v[0] == '1'; }();
     if (!no2 && ((uintptr_t)a.audio % 16 == 0) && (a.chan_stride % 2 == 0)) {
-        const size_t smem = (size_t)(TXS2_DELAY + 2 * BLK) * TXS_THREADS * sizeof(float);
+        const size_t smem = (size_t)(TXS2_DELAY + 5 * BLK) * TXS_THREADS * sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(tx_serial2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tx_serial2_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, smem, stream>>>(a);
+        tx_serial2_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, 2 * TXS_THREADS, smem, stream>>>(a);
         return cudaGetLastError();
     }
     tx_serial_kernel<<<(a.num_items + TXS_THREADS - 1) / TXS_THREADS, TXS_THREADS, 0, stream>>>(a);
