@@ -1,5 +1,5 @@
-// fft_device.cuh -- warp-cooperative in-place complex FFT in shared memory (radix-2, decimation in
-// time).  Stands in for CMSIS arm_cfft_f32 (TransformFunctions/arm_cfft_f32.c:574-630): forward
+// fft_device.cuh -- warp-cooperative in-place complex FFT in shared memory (decimation in time, two radix-2
+// stages per pass).  Stands in for CMSIS arm_cfft_f32 (TransformFunctions/arm_cfft_f32.c:574-630): forward
 // = plain DFT; inverse = conjugate, forward transform, conjugate, scale by 1/N (:616-627).
 // Twiddles e^{-2 pi i k / N} (k < N/2, interleaved cos, sin) come from the coefficient pool, where
 // the host computed them in double precision.  Results agree with the reference's radix-8 kernel
@@ -24,21 +24,45 @@ __device__ __forceinline__ void fft_inplace(float *buf /* [2N] re,im */, const f
         }
     }
     if (NTHR > 32) __syncthreads(); else __syncwarp();
-#pragma unroll 1
-    for (int s = 1; s <= LOG2N; s++) {
-        const int half = 1 << (s - 1);
+    // Two radix-2 stages per pass (radix-2^2, in registers): half the passes, barriers and twiddle loads of a plain radix-2 walk.
+    // Stage s (span h = 2^(s-1)) pairs (a, b) and (c, d) with W^(k N / 2h); stage s + 1 pairs (a', c') with w2 = W^(k N / 4h) and
+    // (b', d') with W^((k + h) N / 4h) = -i w2.
+    int s = 1;
+    if (LOG2N & 1) {
+        // odd number of stages: the first one alone (twiddle 1)
         for (int b = tid; b < N / 2; b += NTHR) {
-            const int k = b & (half - 1);
-            const int i = ((b >> (s - 1)) << s) + k;
-            const int j = i + half;
-            const int tidx = k << (LOG2N - s);            // twiddle index: k * N / len
-            const float wr = __ldg(tw + 2 * tidx), wi = __ldg(tw + 2 * tidx + 1);
-            const float xr = buf[2 * j], xi = buf[2 * j + 1];
-            const float tr = __fsub_rn(__fmul_rn(xr, wr), __fmul_rn(xi, wi));
-            const float ti = __fadd_rn(__fmul_rn(xr, wi), __fmul_rn(xi, wr));
-            const float ur = buf[2 * i], ui = buf[2 * i + 1];
-            buf[2 * j] = __fsub_rn(ur, tr); buf[2 * j + 1] = __fsub_rn(ui, ti);
-            buf[2 * i] = __fadd_rn(ur, tr); buf[2 * i + 1] = __fadd_rn(ui, ti);
+            const int i = 2 * b, j = i + 1;
+            const float ur = buf[2 * i], ui = buf[2 * i + 1], xr = buf[2 * j], xi = buf[2 * j + 1];
+            buf[2 * j] = __fsub_rn(ur, xr); buf[2 * j + 1] = __fsub_rn(ui, xi);
+            buf[2 * i] = __fadd_rn(ur, xr); buf[2 * i + 1] = __fadd_rn(ui, xi);
+        }
+        if (NTHR > 32) __syncthreads(); else __syncwarp();
+        s = 2;
+    }
+#pragma unroll 1
+    for (; s < LOG2N; s += 2) {
+        const int h = 1 << (s - 1);
+        for (int q = tid; q < N / 4; q += NTHR) {
+            const int k = q & (h - 1);
+            const int i0 = ((q >> (s - 1)) << (s + 1)) + k;
+            const float w1r = __ldg(tw + 2 * (k << (LOG2N - s))), w1i = __ldg(tw + 2 * (k << (LOG2N - s)) + 1);
+            const float w2r = __ldg(tw + 2 * (k << (LOG2N - s - 1))), w2i = __ldg(tw + 2 * (k << (LOG2N - s - 1)) + 1);
+            float2 va = *reinterpret_cast<float2 *>(buf + 2 * i0), vb = *reinterpret_cast<float2 *>(buf + 2 * (i0 + h));
+            float2 vc = *reinterpret_cast<float2 *>(buf + 2 * (i0 + 2 * h)), vd = *reinterpret_cast<float2 *>(buf + 2 * (i0 + 3 * h));
+            // stage s
+            float tr = __fsub_rn(__fmul_rn(vb.x, w1r), __fmul_rn(vb.y, w1i)), ti = __fadd_rn(__fmul_rn(vb.x, w1i), __fmul_rn(vb.y, w1r));
+            const float ar = __fadd_rn(va.x, tr), ai = __fadd_rn(va.y, ti), br = __fsub_rn(va.x, tr), bi = __fsub_rn(va.y, ti);
+            tr = __fsub_rn(__fmul_rn(vd.x, w1r), __fmul_rn(vd.y, w1i)); ti = __fadd_rn(__fmul_rn(vd.x, w1i), __fmul_rn(vd.y, w1r));
+            const float cr = __fadd_rn(vc.x, tr), ci = __fadd_rn(vc.y, ti), dr = __fsub_rn(vc.x, tr), di = __fsub_rn(vc.y, ti);
+            // stage s + 1
+            tr = __fsub_rn(__fmul_rn(cr, w2r), __fmul_rn(ci, w2i)); ti = __fadd_rn(__fmul_rn(cr, w2i), __fmul_rn(ci, w2r));
+            va.x = __fadd_rn(ar, tr); va.y = __fadd_rn(ai, ti); vc.x = __fsub_rn(ar, tr); vc.y = __fsub_rn(ai, ti);
+            // (-i w2) d' = (w2i dr' ... ): -i (x + i y) = y - i x
+            const float er = __fsub_rn(__fmul_rn(dr, w2r), __fmul_rn(di, w2i)), ei = __fadd_rn(__fmul_rn(dr, w2i), __fmul_rn(di, w2r));
+            tr = ei; ti = -er;
+            vb.x = __fadd_rn(br, tr); vb.y = __fadd_rn(bi, ti); vd.x = __fsub_rn(br, tr); vd.y = __fsub_rn(bi, ti);
+            *reinterpret_cast<float2 *>(buf + 2 * i0) = va; *reinterpret_cast<float2 *>(buf + 2 * (i0 + h)) = vb;
+            *reinterpret_cast<float2 *>(buf + 2 * (i0 + 2 * h)) = vc; *reinterpret_cast<float2 *>(buf + 2 * (i0 + 3 * h)) = vd;
         }
         if (NTHR > 32) __syncthreads(); else __syncwarp();
     }
