@@ -215,7 +215,10 @@ int uhsdr_rx_process(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq, uhsdr_audio
                      int nblocks, const uint8_t *mute);
 /* Same with DEVICE pointers on the engine's device; asynchronous on the engine's stream
  * (uhsdr_engine_sync to wait).  audio_f (optional, device) receives the float audio before the
- * int32 formatting, [num_channels][nblocks*32] floats (adb.a_buffer[1], audio_driver.c:2911). */
+ * int32 formatting, [num_channels][nblocks*32] floats (adb.a_buffer[1], audio_driver.c:2911).
+ * Alignment: any 8-byte aligned iq_dev / audio_dev and 4-byte aligned audio_f_dev are accepted; the fast kernels need
+ * iq_dev and audio_dev 32-byte aligned and audio_f_dev 16-byte aligned (cudaMalloc gives 256), other alignments take
+ * the slower general kernels with identical results within the build's tolerance. */
 int uhsdr_rx_process_device(uhsdr_engine_t *e, const uhsdr_iq_sample_t *iq_dev,
                             uhsdr_audio_sample_t *audio_dev, float *audio_f_dev,
                             int nblocks, const uint8_t *mute_dev);

@@ -98,6 +98,36 @@ def test_unaligned_output_buffer_takes_the_cuda_core_kernel(built):
         assert np.array_equal(got[c, :, 0], got[c, :, 1])
 
 
+def test_unaligned_float_copy_buffer(built):
+    """The optional float copy is stored as 16-byte vectors by the tensor-core kernel (8-byte by the CUDA-core fused kernel): a
+    buffer that is only 4-byte aligned must take a kernel that stores it word by word, with the same result."""
+    _unaligned_float_copy(default_cfg())
+    _unaligned_float_copy(default_cfg(filter_path=48))      # split general path
+
+
+def _unaligned_float_copy(cfg):
+    import torch
+    nch, nb = 2, 64
+    iq = np.stack([synth.rx_iq(cfg, 410 + c, nb * 32, seed=47) for c in range(nch)])
+    dev = torch.device("cuda", 0)
+    d_iq = torch.from_numpy(iq).to(dev)
+    res = []
+    for off in (0, 1, 2):
+        raw = torch.full((nch * nb * 32 + 4,), float("nan"), dtype=torch.float32, device=dev)
+        d_f = raw[off:off + nch * nb * 32].view(nch, nb * 32)
+        assert d_f.data_ptr() % 16 == 4 * off
+        d_out = torch.empty_like(d_iq)
+        with Engine(nch) as eng:
+            eng.configure(cfg)
+            eng.rx_device(d_iq, d_out, nb, audio_f_dev=d_f)
+            eng.sync()
+        assert bool(raw[:off].isnan().all()) and bool(raw[off + nch * nb * 32:].isnan().all())
+        res.append((d_out.cpu().numpy(), d_f.cpu().numpy()))
+    for w, f in res[1:]:
+        assert np.max(np.abs((w[:, :, 0].astype(np.int64) >> 16) - (res[0][0][:, :, 0].astype(np.int64) >> 16))) <= 1
+        assert np.max(np.abs(f - res[0][1])) <= 1e-4 * np.max(np.abs(res[0][1]))
+
+
 def test_tensor_core_kernel_short_calls_carry_both_filter_histories(built):
     """The tensor-core kernel feeds the decimator / Hilbert histories through virtual steps and, for calls shorter than
     the 198-sample Hilbert history (fewer than 7 steps of 4 blocks), moves the part of the old history that survives.

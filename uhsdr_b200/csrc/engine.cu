@@ -350,9 +350,13 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         a.chan_list = e->d_list_fused; a.num_items = (int)e->h_list_fused.size();
         // the fused kernel advances in chunks of 4 blocks; other call sizes take the general kernel
         // the tensor-core kernel stores 32-byte vectors; rows are nblocks*256 bytes apart, so only the base matters
-        const bool tc_ok = e->use_tc && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 32 == 0) && (chan_stride % 4 == 0);
+        // (and the float copy as 16-byte vectors; the CUDA-core fused kernel as 8-byte ones; the general kernel word by word)
+        const bool tc_ok = e->use_tc && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 32 == 0) && (chan_stride % 4 == 0) &&
+                           ((uintptr_t)audio_f_dev % 16 == 0);
+        const bool fused_ok = ((uintptr_t)audio_f_dev % 8 == 0) && (chan_stride % 2 == 0) && ((uintptr_t)iq_dev % 16 == 0) &&
+                              ((uintptr_t)audio_dev % 16 == 0);
         if (nblocks % 4 == 0 && tc_ok) CK(e, launch_rx_ssb_tc(a, e->fused_s1_ci, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
-        else if (nblocks % 4 == 0) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
+        else if (nblocks % 4 == 0 && fused_ok) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
         else CK(e, launch_rx_generic(a, stream));
         e->launches++;
     }
@@ -363,7 +367,17 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     }
     // Split general path.  The call is cut into time slices: the FIR front kernel of slice s+1 (this stream) runs
     // beside the sample-serial kernels of slice s (aux stream); neither fills the GPU on its own.
-    if (!e->h_list_split.empty() || !e->h_list_split_nr.empty()) {
+    // (the serial kernels store 16-byte words and 8-byte float pairs: buffers aligned to less take the one-kernel general path)
+    const bool split_ok = ((uintptr_t)audio_dev % 16 == 0) && ((uintptr_t)audio_f_dev % 8 == 0) && (chan_stride % 2 == 0);
+    if (!split_ok) {
+        for (int with_nr = 0; with_nr < 2; with_nr++) {
+            const std::vector<int> &lst = with_nr ? e->h_list_split_nr : e->h_list_split;
+            if (lst.empty()) continue;
+            a.chan_list = with_nr ? e->d_list_split_nr : e->d_list_split; a.num_items = (int)lst.size();
+            CK(e, launch_rx_generic(a, stream));
+            e->launches++;
+        }
+    } else if (!e->h_list_split.empty() || !e->h_list_split_nr.empty()) {
         // the second-generation serial kernel stores 32-byte / 16-byte vectors
         const bool s2 = e->serial2_ok && ((uintptr_t)audio_dev % 32 == 0) && (chan_stride % 4 == 0) && ((uintptr_t)audio_f_dev % 16 == 0);
         // Its chain is cut once more at the AGC output (the hand-off point of the spectral NR): phase 1 (demodulator, lattice, AGC) of
