@@ -73,7 +73,7 @@ __device__ __forceinline__ void fir4_m1_pair(const float *__restrict__ xa, const
     float4 wa = *reinterpret_cast<const float4 *>(xa), wb = *reinterpret_cast<const float4 *>(xb);
 #pragma unroll
     for (int r = 0; r < 4; r++) { ya[r] = 0.0f; yb[r] = 0.0f; }
-#pragma unroll 2
+#pragma unroll 4
     for (int g = 0; g < groups; g++) {
         const float4 na = *reinterpret_cast<const float4 *>(xa + 4 * g + 4), nb = *reinterpret_cast<const float4 *>(xb + 4 * g + 4);
         const float4 ca = *reinterpret_cast<const float4 *>(ta + 4 * g), cb = *reinterpret_cast<const float4 *>(tb + 4 * g);

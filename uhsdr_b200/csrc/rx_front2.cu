@@ -44,7 +44,7 @@ __device__ __forceinline__ void shift_hist(float *buf, int H, int nnew, int lane
 
 }  // namespace
 
-__global__ void __launch_bounds__(32 * F2_WARPS)
+__global__ void __launch_bounds__(32 * F2_WARPS, 4)      // 4 CTAs per SM is what the staging buffers allow: keep the registers there too
 rx_front2_kernel(RxArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -94,6 +94,10 @@ rx_front2_kernel(RxArgs a)
     if (p.shift_kind != 0 && conv != p.shift_freq) { conv = p.shift_freq; osc_i = 0.0f; osc_q = 1.0f; }   // FreqShift re-prepares the NCO, freq_shift.c:289-305
     __syncwarp();
 
+    // per-channel constants the block loops use, in registers (the loops store to global memory, so the compiler would re-read
+    // them from the parameter block every iteration: a global-load latency per block)
+    const int k_iq_auto = p.iq_auto, k_zoom_m = p.zoom_m, k_shift_kind = p.shift_kind, k_shift_down = p.shift_down, k_lsb = p.lsb;
+    const float k_adj_i = p.adj_i, k_adj_q = p.adj_q, k_phase_bal = p.phase_bal, k_osc_cos = p.osc_cos, k_osc_sin = p.osc_sin;
     const int M = p.M;
     const int ndec_blk = BLK / M;
     float *spec_ring = (p.spectrum_enable && a.spec_ring) ? (a.spec_ring + (size_t)ch * 1024) : nullptr;
@@ -128,7 +132,7 @@ rx_front2_kernel(RxArgs a)
         }
         __syncwarp();
         float mc1 = M_c1, mc2 = M_c2;                    // lane b: the factors of block b
-        if (p.iq_auto) {
+        if (k_iq_auto) {
             // audio_driver.c:2274-2313 (Moseley & Slump): block statistics, EMA in double
             float s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
             if (lane < nb) {
@@ -157,36 +161,36 @@ rx_front2_kernel(RxArgs a)
         }
         for (int b = 0; b < nb; b++) {
             float fi = ti[b * 33 + lane], fq = tq[b * 33 + lane];
-            if (p.iq_auto) {
+            if (k_iq_auto) {
                 const float c1 = __shfl_sync(0xffffffffu, mc1, b), c2 = __shfl_sync(0xffffffffu, mc2, b);
                 fq = __fadd_rn(fq, __fmul_rn(c1, fi));
                 fi = __fmul_rn(fi, c2);
             } else {
-                fi = __fmul_rn(fi, p.adj_i);                                     // manual gain + phase, audio_driver.c:2259-2267
-                fq = __fmul_rn(fq, p.adj_q);
-                if (p.phase_bal < 0.0f) fq = __fadd_rn(fq, __fmul_rn(fi, p.phase_bal));
-                else if (p.phase_bal > 0.0f) fi = __fadd_rn(fi, __fmul_rn(fq, p.phase_bal));
+                fi = __fmul_rn(fi, k_adj_i);                                     // manual gain + phase, audio_driver.c:2259-2267
+                fq = __fmul_rn(fq, k_adj_q);
+                if (k_phase_bal < 0.0f) fq = __fadd_rn(fq, __fmul_rn(fi, k_phase_bal));
+                else if (k_phase_bal > 0.0f) fi = __fadd_rn(fi, __fmul_rn(fq, k_phase_bal));
             }
-            if (spec_ring && p.zoom_m == 0) {                                    // AudioDriver_SpectrumNoZoomProcessSamples, :1811-1849
+            if (spec_ring && k_zoom_m == 0) {                                    // AudioDriver_SpectrumNoZoomProcessSamples, :1811-1849
                 uint32_t ptr = samp_ptr + 2u * (uint32_t)lane;
                 if (ptr >= 1024u) ptr -= 1024u;
                 spec_ring[ptr] = fq; spec_ring[ptr + 1] = fi;
                 samp_ptr += 64u; if (samp_ptr >= 1024u) samp_ptr -= 1024u;
             }
-            if (p.shift_kind == 1) {                                             // FreqShift_QuarterFs, freq_shift.c:219-262
-                float ib = p.shift_down ? fq : fi, qb = p.shift_down ? fi : fq;
+            if (k_shift_kind == 1) {                                             // FreqShift_QuarterFs, freq_shift.c:219-262
+                float ib = k_shift_down ? fq : fi, qb = k_shift_down ? fi : fq;
                 const int ph = lane & 3;
                 float ni = ib, nq = qb;
                 if (ph == 1) { ni = qb; nq = -ib; }
                 else if (ph == 2) { ni = -ib; nq = -qb; }
                 else if (ph == 3) { ni = -qb; nq = ib; }
-                if (p.shift_down) { fq = ni; fi = nq; } else { fi = ni; fq = nq; }
-            } else if (p.shift_kind == 2) {                                      // FreqShift_Approx, freq_shift.c:57-108
+                if (k_shift_down) { fq = ni; fi = nq; } else { fi = ni; fq = nq; }
+            } else if (k_shift_kind == 2) {                                      // FreqShift_Approx, freq_shift.c:57-108
                 if (lane == 0) {
                     float vq = osc_q, vi = osc_i;
                     for (int n = 0; n < BLK; n++) {
-                        const float oq = __fsub_rn(__fmul_rn(vq, p.osc_cos), __fmul_rn(vi, p.osc_sin));
-                        const float oi = __fadd_rn(__fmul_rn(vi, p.osc_cos), __fmul_rn(vq, p.osc_sin));
+                        const float oq = __fsub_rn(__fmul_rn(vq, k_osc_cos), __fmul_rn(vi, k_osc_sin));
+                        const float oi = __fadd_rn(__fmul_rn(vi, k_osc_cos), __fmul_rn(vq, k_osc_sin));
                         w.scr[n] = oq; w.scr[BLK + n] = oi;
                         vq = oq; vi = oi;
                     }
@@ -196,19 +200,19 @@ rx_front2_kernel(RxArgs a)
                 osc_q = __shfl_sync(0xffffffffu, osc_q, 0); osc_i = __shfl_sync(0xffffffffu, osc_i, 0);
                 __syncwarp();
                 const float oq = w.scr[lane], oi = w.scr[BLK + lane];
-                float ib = p.shift_down ? fq : fi, qb = p.shift_down ? fi : fq;
+                float ib = k_shift_down ? fq : fi, qb = k_shift_down ? fi : fq;
                 const float nq = __fsub_rn(__fmul_rn(qb, oq), __fmul_rn(ib, oi));
                 const float ni = __fadd_rn(__fmul_rn(ib, oq), __fmul_rn(qb, oi));
-                if (p.shift_down) { fq = ni; fi = nq; } else { fi = ni; fq = nq; }
+                if (k_shift_down) { fq = ni; fi = nq; } else { fi = ni; fq = nq; }
                 __syncwarp();
             }
-            if (spec_ring && p.zoom_m != 0) {
+            if (spec_ring && k_zoom_m != 0) {
                 // AudioDriver_SpectrumZoomProcessSamples, :1860-1909: 4-stage DF1 low-pass on I and on Q (lane 0 / lane 1), 4-tap
                 // decimation by 2^magnify, 32 >> magnify (Q, I) pairs into the ring; reference operation order
                 __syncwarp();
                 w.scr[lane] = fi; w.scr[BLK + lane] = fq;
                 __syncwarp();
-                const int nout = BLK >> p.zoom_m, MZ = 1 << p.zoom_m;
+                const int nout = BLK >> k_zoom_m, MZ = 1 << k_zoom_m;
                 if (lane < 2) {
                     float *buf = w.scr + lane * BLK;
                     BiquadS *bs = lane ? gst->zoom_bq_q : gst->zoom_bq_i;
@@ -284,7 +288,7 @@ rx_front2_kernel(RxArgs a)
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const int m = 4 * lane + r;
-                    if (m < ndec) sc[o + m] = p.lsb ? __fsub_rn(yi[r], yq[r]) : __fadd_rn(yi[r], yq[r]);
+                    if (m < ndec) sc[o + m] = k_lsb ? __fsub_rn(yi[r], yq[r]) : __fadd_rn(yi[r], yq[r]);
                 }
                 __syncwarp();
                 shift_hist(w.bi, H2, ndec, lane);
@@ -304,7 +308,7 @@ rx_front2_kernel(RxArgs a)
                 } else {
                     float au[4];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) au[r] = p.lsb ? __fsub_rn(yi[r], yq[r]) : __fadd_rn(yi[r], yq[r]);      // combine at 48k (:2781-2803)
+                    for (int r = 0; r < 4; r++) au[r] = k_lsb ? __fsub_rn(yi[r], yq[r]) : __fadd_rn(yi[r], yq[r]);      // combine at 48k (:2781-2803)
                     *reinterpret_cast<float4 *>(w.bi + H2 + sub + 4 * lane) = make_float4(au[0], au[1], au[2], au[3]);
                 }
             }
