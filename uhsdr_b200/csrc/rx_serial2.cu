@@ -408,7 +408,16 @@ __device__ void serial2_dec(const RxArgs &a, int phase, int slot, int ch, float 
                 for (int i = 0; i < ND; i++) bi[i] = ad[i];
                 demod2_block<ND>(ds, apc, bi, bq_, ad);
             }
-            if (notch) notch_block2<ND>(st, ad, notch_mu);
+            if (notch) {
+                // (the LMS routine is a real call taking the block by reference: give it a copy, so that `ad` itself never has its
+                // address taken and stays in registers on the common path)
+                float nb_[ND];
+#pragma unroll
+                for (int i = 0; i < ND; i++) nb_[i] = ad[i];
+                notch_block2<ND>(st, nb_, notch_mu);
+#pragma unroll
+                for (int i = 0; i < ND; i++) ad[i] = nb_[i];
+            }
             // lattice pre-filter (the per-sample loops are unrolled: rolled, the per-block arrays go to local memory and the kernel
             // runs twice as long)
 #pragma unroll
