@@ -325,72 +325,87 @@ __device__ inline void nr_slice(const ChanParams &p, NrState &nr, const float *_
     for (int q = 0; q < NR_FIFO; q++) { r.in_fifo[q] = nr.in_fifo[q]; r.out_fifo[q] = nr.out_fifo[q]; }
     const bool decim = p.nr_decim != 0;
     const int no_dec = decim ? n / 2 : n;
-    // shared staging: sd = [3 history | n new] of the decimator, si = [19 history | no_dec new] of the interpolator
-    float *sd = hs, *si = hs + 3 + BLK;
+    const int per = no_dec / 2;                      // sample pairs a block moves in and out of the frame buffers
+    // Between two FIFO events (input frame full, output frame used up, a frame processed) the interface is plain streaming: RUNS of
+    // up to 32 blocks are decimated, packed, unpacked and interpolated together, lanes over the samples of the run; the events are
+    // handled at the last block of a run exactly as the block-by-block walk of nr_block does.
+    // staging in the FFT buffer (free between frames): sd = [3 history | run input], si = [19 history | run output frames];
+    // the histories themselves live in hs across frames.
+    float *sd = fft, *si = fft + 272;
+    float *hd = hs, *hi = hs + 4;
     float cd[4], ci[20];
 #pragma unroll
     for (int k = 0; k < 4; k++) cd[k] = decim ? __ldg(pool + p.nr_dec_c + k) : 0.0f;
 #pragma unroll
     for (int k = 0; k < 20; k++) ci[k] = decim ? __ldg(pool + p.nr_int_c + (1 - (lane & 1)) + 2 * k) : 0.0f;
     if (decim) {
-        if (lane < 3) sd[lane] = nr.dec_hist[lane];
-        if (lane < 19) si[lane] = nr.int_hist[lane];
+        if (lane < 3) hd[lane] = nr.dec_hist[lane];
+        if (lane < 19) hi[lane] = nr.int_hist[lane];
     }
     __syncwarp();
-    for (int blk = 0; blk < nblocks; blk++) {
+    int blk = 0;
+    while (blk < nblocks) {
+        // ---- length of the run: up to and including the block of the next event ----
+        if (r.out_buffer < 0 && nr_fifo_count(r.out_head, r.out_tail) > 1) r.out_buffer = fifo_get(r.out_fifo, r.out_tail);
+        int R = min(nblocks - blk, 32);
+        R = min(R, (64 - r.trans_count_in + per - 1) / per);
+        if (r.out_buffer >= 0) R = min(R, (64 - r.outbuff_count + per - 1) / per);
+        const bool pend_now = nr_fifo_count(r.in_head, r.in_tail) && (NR_FIFO - 1 - nr_fifo_count(r.out_head, r.out_tail));
+        if (pend_now || !r.was_here) R = 1;          // a waiting frame is processed after every block; the first block ever resets the FIFOs
+        const int n_in = R * n, n_dec = R * no_dec;
         float *buf = sc + (size_t)blk * n;
-        float x = (lane < n) ? buf[lane] : 0.0f;
+        // ---- input side: (decimate,) pack ----
+        float *inb = nr.bufs[r.fill_in_pt] + 2 * r.trans_count_in;
         if (decim) {
             // DECIMATE_NR: 4 taps, M = 2 (audio_driver.c:195, :649): y[m] = sum_k c[k] s[2m - 3 + k]
-            if (lane < n) sd[3 + lane] = x;
+            if (lane < 3) sd[lane] = hd[lane];
+            for (int i = lane; i < n_in; i += 32) sd[3 + i] = buf[i];
             __syncwarp();
-            float acc = 0.0f;
-            if (lane < no_dec) {
+            for (int m = lane; m < n_dec; m += 32) {
+                float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; k++) acc = __fadd_rn(acc, __fmul_rn(sd[2 * lane + k], cd[k]));
+                for (int k = 0; k < 4; k++) acc = __fadd_rn(acc, __fmul_rn(sd[2 * m + k], cd[k]));
+                inb[m] = acc;
             }
-            const float h = (lane < 3) ? sd[n + lane] : 0.0f;
-            __syncwarp();
-            if (lane < 3) sd[lane] = h;
-            x = acc;
+            if (lane < 3) hd[lane] = sd[n_in + lane];
+        } else {
+            for (int i = lane; i < n_in; i += 32) inb[i] = buf[i];
         }
-        if (lane < no_dec) nr.bufs[r.fill_in_pt][2 * r.trans_count_in + lane] = x;
-        r.trans_count_in += no_dec / 2;
+        r.trans_count_in += R * per;
         if (r.trans_count_in >= 64) {
             const int next = (r.in_head + 1) % NR_FIFO;
             if (next != r.in_tail) { fifo_set(r.in_fifo, r.in_head, r.fill_in_pt); r.in_head = next; }
             r.trans_count_in = 0;
             r.fill_in_pt = (r.fill_in_pt + 1) % 4;
         }
-        if (r.out_buffer < 0 && nr_fifo_count(r.out_head, r.out_tail) > 1) r.out_buffer = fifo_get(r.out_fifo, r.out_tail);
-        float d = 0.0f;
+        // ---- output side: unpack, (interpolate) ----
+        const float *ob = (r.out_buffer >= 0) ? nr.bufs[r.out_buffer] + 128 + 2 * r.outbuff_count : nullptr;
+        if (decim) {
+            // INTERPOLATE_NR: L = 2, 40 taps -> phase length 20 (audio_driver.c:198, :653), then x2.0; output o = 2 i + j
+            if (lane < 19) si[lane] = hi[lane];
+            for (int j = lane; j < n_dec; j += 32) si[19 + j] = ob ? ob[j] : 0.0f;
+            __syncwarp();
+            for (int o = lane; o < n_in; o += 32) {
+                const int i = o >> 1;
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 20; k++) sum = __fadd_rn(sum, __fmul_rn(si[i + k], ci[k]));
+                buf[o] = __fmul_rn(sum, 2.0f);
+            }
+            if (lane < 19) hi[lane] = si[n_dec + lane];
+        } else {
+            for (int i = lane; i < n_in; i += 32) buf[i] = ob ? ob[i] : 0.0f;
+        }
         if (r.out_buffer >= 0) {
-            if (lane < no_dec) d = nr.bufs[r.out_buffer][128 + 2 * r.outbuff_count + lane];
-            r.outbuff_count += no_dec / 2;
+            r.outbuff_count += R * per;
             if (r.outbuff_count >= 64) {
                 r.outbuff_count = 0;
                 if (r.out_head != r.out_tail) r.out_tail = (r.out_tail + 1) % NR_FIFO;
                 r.out_buffer = (r.out_head != r.out_tail) ? fifo_get(r.out_fifo, r.out_tail) : -1;
             }
         }
-        if (decim) {
-            // INTERPOLATE_NR: L = 2, 40 taps -> phase length 20 (audio_driver.c:198, :653), then x2.0; lane = output 2 i + j
-            if (lane < no_dec) si[19 + lane] = d;
-            __syncwarp();
-            if (lane < 2 * no_dec) {
-                const int i = lane >> 1;
-                float sum = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 20; k++) sum = __fadd_rn(sum, __fmul_rn(si[i + k], ci[k]));
-                buf[lane] = __fmul_rn(sum, 2.0f);
-            }
-            const float h = (lane < 19) ? si[no_dec + lane] : 0.0f;
-            __syncwarp();
-            if (lane < 19) si[lane] = h;
-        } else if (lane < n) {
-            buf[lane] = d;
-        }
-        // deferred task bookkeeping (AudioNr_HandleNoiseReduction)
+        __syncwarp();
+        // ---- deferred task (AudioNr_HandleNoiseReduction) after the last block of the run ----
         if (!r.was_here) { r.was_here = 1; r.current_buffer_idx = 0; r.in_tail = r.in_head; r.out_tail = r.out_head; }
         const int pending = nr_fifo_count(r.in_head, r.in_tail) && (NR_FIFO - 1 - nr_fifo_count(r.out_head, r.out_tail));
         if (pending) {
@@ -410,11 +425,12 @@ __device__ inline void nr_slice(const ChanParams &p, NrState &nr, const float *_
             __threadfence_block();
             __syncwarp();
         }
+        blk += R;
     }
     __syncwarp();
     if (decim) {
-        if (lane < 3) nr.dec_hist[lane] = sd[lane];
-        if (lane < 19) nr.int_hist[lane] = si[lane];
+        if (lane < 3) nr.dec_hist[lane] = hd[lane];
+        if (lane < 19) nr.int_hist[lane] = hi[lane];
     }
     if (lane == 0) {
         nr.trans_count_in = r.trans_count_in; nr.outbuff_count = r.outbuff_count; nr.fill_in_pt = r.fill_in_pt; nr.out_buffer = r.out_buffer;
