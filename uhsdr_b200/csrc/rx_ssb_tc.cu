@@ -68,7 +68,10 @@ constexpr int HR_BYTES = 4 * HSBO;                 // one array: [channel group 
 constexpr int DROWS = 276, DR0 = 148, DC0 = 578, DPLANE = DROWS * 16;    // decimator Toeplitz table (see above)
 constexpr int HROWS = 448, HR0 = 320, HC0 = 310, HPLANE = HROWS * 16;    // Hilbert Toeplitz table
 constexpr int MMA_PAUSE = 60;         // cycles between k-steps of the MMA issue (sweeps: profiles/r01_tc2_experiments.txt, r02_tc_experiments.txt)
-constexpr int DEC_COL0 = 0, HIL_COL0 = 128, TMEM_COLS = 256;   // 2 decimator accumulators (128 x 64), 4 Hilbert accumulators (128 x 32)
+// 2 decimator accumulators of 128 columns (c1 x1 + c2 x1 for I | Q in 0..63, c1 x2 in 64..127), 4 Hilbert accumulators of 64
+// (c1 x1 + c2 x1 in 0..31, c1 x2 in 32..63): the c1 products of both halves of the split come from ONE MMA with twice the columns,
+// so the Toeplitz slab -- 4 KB of the 5-6 KB an MMA fetches from shared memory -- is read twice per k-step instead of three times
+constexpr int DEC_COL0 = 0, DEC_COLS = 128, HIL_COL0 = 256, HIL_COLS = 64, TMEM_COLS = 512;
 // warp roles (warp id % 4 is the scheduler and the TMEM lane quadrant)
 // scheduler 0: front end 0, 4 | epilogue 0 | biquads (+ AGC helper) | MMA issue     1: front end 1, 5 | epilogue 1 | output B
 //           2: front end 2, 6 | epilogue 2 | lattice                                 3: front end 3 | output A | epilogue 3 | AGC detector
@@ -150,15 +153,15 @@ __device__ __forceinline__ unsigned long long umma_desc(unsigned addr, unsigned 
            ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-// the three products of one k-step: D (+)= A1 B1; D += A2 B1; D += A1 B2
-__device__ __forceinline__ void umma3_bf16(unsigned tmem_d, unsigned long long a1, unsigned long long a2, unsigned long long b1,
-                                           unsigned long long b2, unsigned idesc, unsigned accumulate)
+// the three products of one k-step in two MMAs: D[0 .. 2N) (+)= A1 [B1 | B2] (the lo half B2 of the sample split lies right behind
+// the hi half B1 in shared memory: one descriptor, idesc2 = twice the columns); D[0 .. N) += A2 B1.  The epilogue adds the halves.
+__device__ __forceinline__ void umma2_bf16(unsigned tmem_d, unsigned long long a1, unsigned long long a2, unsigned long long b1,
+                                           unsigned idesc2, unsigned idesc, unsigned accumulate)
 {
     asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %6, 0;\n\tsetp.eq.b32 q, 0, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %4, %5, q;\n\t}"
-                 ::"r"(tmem_d), "l"(a1), "l"(a2), "l"(b1), "l"(b2), "r"(idesc), "r"(accumulate) : "memory");
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %4, p;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %3, %5, q;\n\t}"
+                 ::"r"(tmem_d), "l"(a1), "l"(a2), "l"(b1), "r"(idesc2), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 __device__ __forceinline__ void umma_commit(unsigned long long *bar)
@@ -201,6 +204,11 @@ struct FirLaneState {
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
                  : "r"(taddr))
 
+#define TMEM_LD_X16(v, taddr)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"        \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                                        \
+                 : "r"(taddr))
 #define TMEM_LD_X4(v, taddr) \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr))
 
@@ -485,8 +493,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
         // ======================= MMA issue: one elected lane ====================================
         const unsigned idesc_d = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(64 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
         const unsigned idesc_h = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(32 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        const unsigned idesc_d2 = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(128 >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+        const unsigned idesc_h2 = idesc_d;
         const unsigned long long ad1 = umma_desc(smem_u32(sm.gd[0]) + DR0 * 16, DPLANE, 128), ad2 = umma_desc(smem_u32(sm.gd[1]) + DR0 * 16, DPLANE, 128);
-        const unsigned long long bx1 = umma_desc(smem_u32(sm.xring[0]), XLBO, XSBO), bx2 = umma_desc(smem_u32(sm.xring[1]), XLBO, XSBO);
+        static_assert(sizeof(sm.xring[0]) == 8 * XSBO && sizeof(sm.hring[0]) == 4 * HSBO, "the lo half of a ring is the next column groups of the hi half");
+        const unsigned long long bx1 = umma_desc(smem_u32(sm.xring[0]), XLBO, XSBO);
         unsigned long long ah[4], bh[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) { ah[i] = umma_desc(smem_u32(sm.gh[i]) + HR0 * 16, HPLANE, 128); bh[i] = umma_desc(smem_u32(sm.hring[i]), HLBO, HSBO); }
@@ -506,25 +517,25 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             if (elect_one()) {
                 const int sd = it - 1;               // step whose samples were written into the decimator ring in the previous iteration
                 if (sd >= 0) {
-                    const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16)), b2 = bx2 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16));
+                    const unsigned long long b1 = bx1 + (unsigned)((sd & 1) * (CH4 / 8) * (XLBO / 16));
                     if (sd >= V && sd < s_end) {
                         // the 8 k-steps of this step into its own chunk: kk = 6 + 8 (sd & 3) + j
-                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64);
+                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * DEC_COLS);
                         const unsigned arow = (unsigned)(4 * (6 + 8 * (sd & 3)));
 #pragma unroll 1
                         for (int j = 0; j < 8; j++) {
                             if (KNOCK(2)) continue;
-                            umma3_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, 1u);
+                            umma2_bf16(d_tmem, ad1 - arow - 4 * j, ad2 - arow - 4 * j, b1 + (2 * XLBO / 16) * j, idesc_d2, idesc_d, 1u);
                             pause();
                         }
                     }
                     if ((sd & 3) == 3 && sd >= V - 1 && sd + 1 < s_end) {
                         // the last 96 samples of the step are the history of the next chunk: kk = 0 .. 5, first write of its accumulator
-                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * 64);
+                        const unsigned d_tmem = tmem + DEC_COL0 + (unsigned)((((sd >> 2) + 1) & 1) * DEC_COLS);
 #pragma unroll 1
                         for (int j = 2; j < 8; j++) {
                             if (KNOCK(2)) continue;
-                            umma3_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + (2 * XLBO / 16) * j, b2 + (2 * XLBO / 16) * j, idesc_d, j > 2 ? 1u : 0u);
+                            umma2_bf16(d_tmem, ad1 - 4 * (j - 2), ad2 - 4 * (j - 2), b1 + (2 * XLBO / 16) * j, idesc_d2, idesc_d, j > 2 ? 1u : 0u);
                             pause();
                         }
                     }
@@ -543,9 +554,9 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                                 const int oc = oa + dd;                      // output chunk this slab contributes to
                                 if ((dd < 2 || ob >= 3) && oc >= V / 4 && oc <= oc_last && !KNOCK(2)) {
                                     const int kk = u - 8 * oc + 13;
-                                    const unsigned d_tmem = tmem + HIL_COL0 + (unsigned)((oc & 3) * 32);
-                                    umma3_bf16(d_tmem, ah[0] - 16 * kk, ah[1] - 16 * kk, bh[0] + boff, bh[1] + boff, idesc_h, kk > 0 ? 1u : 0u);
-                                    umma3_bf16(d_tmem, ah[2] - 16 * kk, ah[3] - 16 * kk, bh[2] + boff, bh[3] + boff, idesc_h, 1u);
+                                    const unsigned d_tmem = tmem + HIL_COL0 + (unsigned)((oc & 3) * HIL_COLS);
+                                    umma2_bf16(d_tmem, ah[0] - 16 * kk, ah[1] - 16 * kk, bh[0] + boff, idesc_h2, idesc_h, kk > 0 ? 1u : 0u);     // [I1 | I2]
+                                    umma2_bf16(d_tmem, ah[2] - 16 * kk, ah[3] - 16 * kk, bh[2] + boff, idesc_h2, idesc_h, 1u);                    // [Q1 | Q2]
                                     pause();
                                 }
                             }
@@ -612,16 +623,23 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 } else {
                     mbar_wait(&sm.bar_dec[sd & 1], (unsigned)((sd >> 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned taddr = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * 64) + lane_base;
+                    const unsigned taddr = tmem + DEC_COL0 + (unsigned)(((sd >> 2) & 1) * DEC_COLS) + lane_base;
                     // the Hilbert MMAs of step sd - 2 read this ring buffer; they were committed one iteration ago
                     mbar_wait(&sm.bar_hil[sd & 1], (unsigned)(((sd - 2) >> 1) & 1));
                     const bool save = i_new >= 2;
 #pragma unroll 1
                     for (int gq = 0; gq < (KNOCK(4) ? 0 : FG / 4); gq++) {         // 4 channels per pass (rolled: the instruction cache is the scarce resource)
-                        unsigned vi[4], vq[4];
+                        unsigned vi[4], vq[4], wi[4], wq[4];
                         TMEM_LD_X4(vi, taddr + (unsigned)(4 * gq));
                         TMEM_LD_X4(vq, taddr + (unsigned)(32 + 4 * gq));
+                        TMEM_LD_X4(wi, taddr + (unsigned)(64 + 4 * gq));            // the c1 x2 halves
+                        TMEM_LD_X4(wq, taddr + (unsigned)(96 + 4 * gq));
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int n8 = 0; n8 < 4; n8++) {
+                            vi[n8] = __float_as_uint(__fadd_rn(__uint_as_float(vi[n8]), __uint_as_float(wi[n8])));
+                            vq[n8] = __float_as_uint(__fadd_rn(__uint_as_float(vq[n8]), __uint_as_float(wq[n8])));
+                        }
                         const unsigned lm = lsbmask >> (4 * gq);
                         const int cbase = (gq >> 1) * HSBO + (gq & 1) * 64;
 #pragma unroll
@@ -646,13 +664,18 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 // ---- Hilbert outputs of step sh leave TMEM: lane = decimated sample, column = channel ----
                 mbar_wait(&sm.bar_hil[sh & 1], (unsigned)((sh >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                unsigned v[32];
-                const unsigned taddr = tmem + HIL_COL0 + (unsigned)(((sh >> 2) & 3) * 32) + lane_base;
-                TMEM_LD_X32(v, taddr);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const unsigned taddr = tmem + HIL_COL0 + (unsigned)(((sh >> 2) & 3) * HIL_COLS) + lane_base;
                 float *aud = sm.aud[sh & 1] + lane * SMS;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 32; c0 += 16) {                                 // two halves of 16 channels: c1 x1 + c2 x1 | c1 x2
+                    unsigned v[16], w[16];
+                    TMEM_LD_X16(v, taddr + (unsigned)c0);
+                    TMEM_LD_X16(w, taddr + (unsigned)(32 + c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int c = 0; c < FG; c++) aud[c] = __uint_as_float(v[c]);
+                    for (int c = 0; c < 16; c++)
+                        if (c0 + c < FG) aud[c0 + c] = __fadd_rn(__uint_as_float(v[c]), __uint_as_float(w[c]));
+                }
             }
             // ---- AGC gain law (audio_agc.c:563-570; mode 5 = fixed gain :354-365) for the step the detector finished in the previous
             // iteration: elementwise, lane = channel, on the two warps that have no epilogue in this iteration (16 samples each).
