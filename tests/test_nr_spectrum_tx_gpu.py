@@ -41,6 +41,46 @@ def test_spectral_nr_within_tolerance(built, label, kw, nblocks, exact):
 
 
 @pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
+@pytest.mark.parametrize("label,kw,nblocks", NR_CASES[:2], ids=[c[0] for c in NR_CASES[:2]])
+def test_nr_call_size_invariance(built, label, kw, nblocks, exact):
+    """The NR kernel walks the frame interface in runs of blocks between FIFO events (input frame full, output frame used up, a
+    frame processed).  Where a call ends must not matter: one call of N blocks and the same signal cut into calls of irregular sizes
+    (1, 3, 7, 33, 64 ... blocks: runs cut short at every position relative to the events, kernels of different generations for the
+    small calls) give the same bits."""
+    cfg = default_cfg(**kw)
+    nb = 480
+    nch = 2
+    iq = np.stack([synth.rx_iq(cfg, 60 + c, nb * 32, seed=23) for c in range(nch)])
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        w_one, f_one = run_engine_float(eng, iq)
+    sizes, left = [], nb
+    for sz in [1, 3, 7, 33, 64, 5, 96, 2, 31, 128, 17]:
+        if left <= 0:
+            break
+        sizes.append(min(sz, left)); left -= sizes[-1]
+    if left > 0:
+        sizes.append(left)
+    with Engine(nch, exact=exact) as eng:
+        eng.configure(cfg)
+        parts, pos = [], 0
+        for sz in sizes:
+            parts.append(run_engine_float(eng, iq[:, pos * 32:(pos + sz) * 32]))
+            pos += sz
+    w_cut = np.concatenate([p[0] for p in parts], axis=1)
+    f_cut = np.concatenate([p[1] for p in parts], axis=1)
+    if exact:
+        assert np.array_equal(f_cut.view(np.uint32), f_one.view(np.uint32)), label
+        assert np.array_equal(w_cut, w_one), label
+    else:
+        # small calls take the general kernels (other FIR summation order): float tolerance, same latency
+        assert np.max(np.abs(f_cut - f_one)) <= 1e-4 * np.max(np.abs(f_one)), label
+        thr = 1e-3 * np.max(np.abs(f_one))
+        for c in range(nch):
+            assert np.flatnonzero(np.abs(f_cut[c]) > thr)[0] == np.flatnonzero(np.abs(f_one[c]) > thr)[0], label
+
+
+@pytest.mark.parametrize("exact", [True, False], ids=["exact", "fast"])
 @pytest.mark.parametrize("label,kw,nblocks", NB_CASES, ids=[c[0] for c in NB_CASES])
 def test_lpc_noise_blanker(built, label, kw, nblocks, exact):
     """alt_noise_blanking (audio_nr.c:2210-2539) on inputs with impulses, settings at which the repair path fires on most
