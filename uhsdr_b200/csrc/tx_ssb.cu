@@ -582,7 +582,8 @@ cudaError_t launch_tx_ssb(const TxArgs &a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-// Second generation of the serial stages: the same operations in the same order (bit-identical results in both builds), but the
+// Second generation of the serial stages: the same operations in the same order in the exact build and for FM modulators (bit-
+// identical results), fused forms otherwise (float tolerance); the
 // per-sample loop is rolled and touches registers and shared memory only -- lattice and biquad coefficients and states in
 // registers (the lattice front-padded to 10 stages: k = v = 0 stages pass the sample through exactly), the block's samples and the
 // 320-sample look-ahead delay line of the compressor in shared memory [slot][lane] (the first version kept them in per-thread
