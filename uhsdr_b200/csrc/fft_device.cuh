@@ -73,4 +73,52 @@ __device__ __forceinline__ void fft_inplace(float *buf /* [2N] re,im */, const f
     }
 }
 
+// One warp, data in registers: lane L holds the E = N / 32 consecutive elements E L .. E L + E - 1 of the bit-reversed sequence
+// (decimation in time).  The first log2(E) stages pair elements of one lane; the five last stages pair lane L with lane L ^ 2^j on
+// the same register, so they are shuffles -- no shared-memory pass, no bank conflicts, no barrier.  Same twiddle table and the same
+// butterflies as fft_inplace.  xr / xi: in = element brev(E L + r) of the signal (see fft_warp_load), out = bin E L + r.
+template <int N, int LOG2N>
+__device__ __forceinline__ void fft_warp(float (&xr)[N / 32], float (&xi)[N / 32], const float *__restrict__ tw, int lane)
+{
+    constexpr int E = N / 32, LE = LOG2N - 5;
+#pragma unroll
+    for (int s = 1; s <= LE; s++) {
+        const int h = 1 << (s - 1);
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            if (r & h) continue;
+            const int k = r & (h - 1);
+            const float wr = __ldg(tw + 2 * (k << (LOG2N - s))), wi = __ldg(tw + 2 * (k << (LOG2N - s)) + 1);
+            const float tr = __fsub_rn(__fmul_rn(xr[r + h], wr), __fmul_rn(xi[r + h], wi));
+            const float ti = __fadd_rn(__fmul_rn(xr[r + h], wi), __fmul_rn(xi[r + h], wr));
+            xr[r + h] = __fsub_rn(xr[r], tr); xi[r + h] = __fsub_rn(xi[r], ti);
+            xr[r] = __fadd_rn(xr[r], tr); xi[r] = __fadd_rn(xi[r], ti);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const int s = LE + 1 + j;
+        const bool upper = (lane >> j) & 1;
+        const int kl = E * (lane & ((1 << j) - 1));
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+            const int tidx = (kl + r) << (LOG2N - s);
+            const float wr = __ldg(tw + 2 * tidx), wi = __ldg(tw + 2 * tidx + 1);
+            const float pr = __shfl_xor_sync(0xffffffffu, xr[r], 1 << j), pi = __shfl_xor_sync(0xffffffffu, xi[r], 1 << j);
+            const float br = upper ? xr[r] : pr, bi = upper ? xi[r] : pi;          // the element of the upper half of the pair
+            const float ar = upper ? pr : xr[r], ai = upper ? pi : xi[r];
+            const float tr = __fsub_rn(__fmul_rn(br, wr), __fmul_rn(bi, wi));
+            const float ti = __fadd_rn(__fmul_rn(br, wi), __fmul_rn(bi, wr));
+            xr[r] = upper ? __fsub_rn(ar, tr) : __fadd_rn(ar, tr);
+            xi[r] = upper ? __fsub_rn(ai, ti) : __fadd_rn(ai, ti);
+        }
+    }
+}
+
+// index into the signal of register r of lane `lane` (bit reversal of E lane + r over LOG2N bits)
+template <int N, int LOG2N> __device__ __forceinline__ int fft_warp_src(int lane, int r)
+{
+    return (int)(__brev((unsigned)((N / 32) * lane + r)) >> (32 - LOG2N));
+}
+
 }  // namespace uhsdr

@@ -12,29 +12,40 @@ namespace uhsdr {
 
 __global__ void __launch_bounds__(128)
 spectrum_kernel(const ChanParams *__restrict__ params, const ChanState *__restrict__ state, const float *__restrict__ spec_ring,
-                const float *__restrict__ pool, int window_off, int twiddle_off, int first, float *__restrict__ mags)
+                const float *__restrict__ pool, int window_off, int twiddle_off, int first, int count, float *__restrict__ mags)
 {
-    __shared__ __align__(16) float buf[1024];
-    const int ch = first + blockIdx.x;
-    const int tid = threadIdx.x;
+    // one warp per channel, the whole transform in registers (fft_warp: 16 elements per lane, the last five stages by shuffle)
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot >= count) return;
+    const int ch = first + slot;
     const ChanParams &p = params[ch];
-    float *out = mags + (size_t)blockIdx.x * 512;
+    float *out = mags + (size_t)slot * 512;
     if (!p.configured || !p.spectrum_enable) {
-        for (int i = tid; i < 512; i += 128) out[i] = 0.0f;
+        for (int i = lane; i < 512; i += 32) out[i] = 0.0f;
         return;
     }
     const uint32_t sp = state[ch].samp_ptr;
     const float *ring = spec_ring + (size_t)ch * 1024;
+    const float *win = pool + window_off;
     const float gcalc = (float)(1.0 / (double)p.codec_gain_calc);
-    for (int i = tid; i < 1024; i += 128) {
-        const float v = ring[(sp + (uint32_t)i) & 1023u];
-        buf[i] = __fmul_rn(__fmul_rn(v, __ldg(pool + window_off + i)), gcalc);
+    float xr[16], xi[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        // element n of the 512 complex samples = floats 2n, 2n + 1 of the snapshot; the window runs over the interleaved array
+        const int n = fft_warp_src<512, 9>(lane, r);
+        xr[r] = __fmul_rn(__fmul_rn(ring[(sp + 2u * (uint32_t)n) & 1023u], __ldg(win + 2 * n)), gcalc);
+        xi[r] = __fmul_rn(__fmul_rn(ring[(sp + 2u * (uint32_t)n + 1u) & 1023u], __ldg(win + 2 * n + 1)), gcalc);
     }
-    __syncthreads();
-    fft_inplace<512, 9, 128>(buf, pool + twiddle_off, false, tid);
-    for (int i = tid; i < 512; i += 128) {
-        const float re = buf[2 * i], im = buf[2 * i + 1];
-        out[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+    fft_warp<512, 9>(xr, xi, pool + twiddle_off, lane);
+    float4 *o4 = reinterpret_cast<float4 *>(out + 16 * lane);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float m[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) m[e] = __fsqrt_rn(__fadd_rn(__fmul_rn(xr[4 * q + e], xr[4 * q + e]), __fmul_rn(xi[4 * q + e], xi[4 * q + e])));
+        if (((uintptr_t)out & 15) == 0) o4[q] = make_float4(m[0], m[1], m[2], m[3]);
+        else { for (int e = 0; e < 4; e++) out[16 * lane + 4 * q + e] = m[e]; }
     }
 }
 
@@ -168,7 +179,7 @@ cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, co
                             int window_off, int twiddle_off, int first, int count, float *mags, cudaStream_t stream)
 {
     if (window_off < 0 || twiddle_off < 0) return cudaErrorInvalidValue;
-    spectrum_kernel<<<count, 128, 0, stream>>>(params, state, spec_ring, pool, window_off, twiddle_off, first, mags);
+    spectrum_kernel<<<(count + 3) / 4, 128, 0, stream>>>(params, state, spec_ring, pool, window_off, twiddle_off, first, count, mags);
     return cudaGetLastError();
 }
 
