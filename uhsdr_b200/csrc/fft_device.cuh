@@ -121,4 +121,28 @@ template <int N, int LOG2N> __device__ __forceinline__ int fft_warp_src(int lane
     return (int)(__brev((unsigned)((N / 32) * lane + r)) >> (32 - LOG2N));
 }
 
+// fft_inplace's contract (interleaved re, im in shared memory, one warp) on the register transform: one bit-reversed load and one
+// store pass instead of a pass per stage pair.
+template <int N, int LOG2N>
+__device__ __forceinline__ void fft_warp_smem(float *buf /* [2N] re,im */, const float *__restrict__ tw, bool inverse, int lane)
+{
+    constexpr int E = N / 32;
+    float xr[E], xi[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const float2 v = *reinterpret_cast<const float2 *>(buf + 2 * fft_warp_src<N, LOG2N>(lane, r));
+        xr[r] = v.x; xi[r] = inverse ? -v.y : v.y;
+    }
+    __syncwarp();
+    fft_warp<N, LOG2N>(xr, xi, tw, lane);
+    const float sc = 1.0f / (float)N;
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        float2 v = make_float2(xr[r], xi[r]);
+        if (inverse) { v.x = __fmul_rn(v.x, sc); v.y = __fmul_rn(-v.y, sc); }
+        *reinterpret_cast<float2 *>(buf + 2 * (E * lane + r)) = v;
+    }
+    __syncwarp();
+}
+
 }  // namespace uhsdr

@@ -132,7 +132,7 @@ __device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float
         nr.last_sample[i] = cur;
     }
     __syncwarp();
-    fft_inplace<256, 8, 32>(fft, pool + p.tw256_off, false, lane);
+    fft_warp_smem<256, 8>(fft, pool + p.tw256_off, false, lane);
 
     // audio_nr.c:1989-2003: the 20th averaging frame switches first_time to 3 and the tracker
     // below already runs on that same frame (two consecutive ifs in the reference)
@@ -186,7 +186,7 @@ __device__ inline void nr_spectral(const ChanParams &p, NrState &nr, const float
         fft[512 - 2 * b - 2] = __fmul_rn(fft[512 - 2 * b - 2], hk); fft[512 - 2 * b - 1] = __fmul_rn(fft[512 - 2 * b - 1], hk);
     }
     __syncwarp();
-    fft_inplace<256, 8, 32>(fft, pool + p.tw256_off, true, lane);
+    fft_warp_smem<256, 8>(fft, pool + p.tw256_off, true, lane);
     // window on exit + overlap-add (:2165-2189)
     for (int i = lane; i < 128; i += 32) {
         const float a = __fmul_rn(fft[2 * i], __ldg(win + i));
