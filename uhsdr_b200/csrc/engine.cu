@@ -44,6 +44,14 @@ struct uhsdr_engine {
     bool lists_dirty = true;
     std::vector<int> h_list_fused, h_list_generic, h_list_split, h_list_split_nr;
     int *d_list_fused = nullptr, *d_list_generic = nullptr, *d_list_split = nullptr, *d_list_split_nr = nullptr;
+    // narrow SSB / CW channels with a deferred consumer -- the spectrum ring (h_list_tc_sp) or the spectral NR (h_list_tc_nr, with or
+    // without the ring): tensor-core kernel + spectrum tap kernel (+ NR kernel + serial phase 2)
+    std::vector<int> h_list_tc_sp, h_list_tc_nr;
+    int *d_list_tc_sp = nullptr, *d_list_tc_nr = nullptr;
+    float2 *d_iqc = nullptr;             // [2][nch][16] IQ-correction factors of the last 16 blocks, logged by the tensor-core kernel
+    float *d_scratch_nr = nullptr;       // AGC output of the h_list_tc_nr channels, [n][nblocks * 8]
+    size_t d_scratch_nr_bytes = 0;
+    int use_tcx = 1;
     int split_floats_per_block = 0;      // scratch floats per block and channel of the split path
     float *d_scratch = nullptr;
     size_t d_scratch_bytes = 0;
@@ -132,6 +140,7 @@ int uhsdr_engine_destroy(uhsdr_engine_t *e)
     cudaFree(e->d_pool); cudaFree(e->d_params); cudaFree(e->d_state); cudaFree(e->d_nr); cudaFree(e->d_spec); cudaFree(e->d_spec_avg); cudaFree(e->d_spec_off);
     cudaFree(e->d_tx); cudaFree(e->d_txp); cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_mute);
     cudaFree(e->d_list_fused); cudaFree(e->d_list_generic); cudaFree(e->d_list_split); cudaFree(e->d_list_split_nr); cudaFree(e->d_scratch);
+    cudaFree(e->d_list_tc_sp); cudaFree(e->d_list_tc_nr); cudaFree(e->d_iqc); cudaFree(e->d_scratch_nr);
     for (auto &s : e->copy_stream) if (s) cudaStreamDestroy(s);
     if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
     if (e->aux2_stream) cudaStreamDestroy(e->aux2_stream);
@@ -176,6 +185,8 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if (nf2 && nf2[0] == '1') e->use_front2 = 0;
     const char *ns2 = getenv("UHSDR_B200_NO_SERIAL2");
     if (ns2 && ns2[0] == '1') e->use_serial2 = 0;
+    const char *ntx = getenv("UHSDR_B200_NO_TCX");
+    if (ntx && ntx[0] == '1') e->use_tcx = 0;
     const char *np2 = getenv("UHSDR_B200_NO_PIPE2");
     if (np2 && np2[0] == '1') e->use_pipe2 = 0;
     const char *nss = getenv("UHSDR_B200_SPLIT_SLICES");
@@ -215,6 +226,9 @@ int uhsdr_engine_create(uhsdr_engine_t **out, int num_channels, int device, cons
     if ((er = cudaMalloc(&e->d_state, n * sizeof(ChanState))) != cudaSuccess) return fail("cudaMalloc state", er);
     if ((er = cudaMemset(e->d_state, 0, n * sizeof(ChanState))) != cudaSuccess) return fail("cudaMemset state", er);
     if ((er = cudaMalloc(&e->d_list_fused, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_list_tc_sp, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_list_tc_nr, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
+    if ((er = cudaMalloc(&e->d_iqc, 2 * n * 16 * sizeof(float2))) != cudaSuccess) return fail("cudaMalloc iqc", er);
     if ((er = cudaMalloc(&e->d_list_generic, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_split, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
     if ((er = cudaMalloc(&e->d_list_split_nr, n * sizeof(int))) != cudaSuccess) return fail("cudaMalloc list", er);
@@ -292,6 +306,7 @@ int uhsdr_configure_channel(uhsdr_engine_t *e, int channel, const uhsdr_chan_cfg
 static int rebuild_lists(uhsdr_engine *e)
 {
     e->h_list_fused.clear(); e->h_list_generic.clear(); e->h_list_split.clear(); e->h_list_split_nr.clear();
+    e->h_list_tc_sp.clear(); e->h_list_tc_nr.clear();
     e->fused_s1_ci = -1;
     e->split_floats_per_block = 0;
     e->front2_ok = e->use_front2 != 0;
@@ -300,11 +315,13 @@ static int rebuild_lists(uhsdr_engine *e)
         const ChanParams &p = e->h_params[c];
         if (!p.configured) { e->last_error = "rx/tx: channel " + std::to_string(c) + " is not configured"; return UHSDR_ERR_STATE; }
         bool fused = e->use_fused && fused_eligible(p);
-        if (fused) {
+        bool tcx = !fused && e->use_fused && e->use_tc && e->use_tcx && e->use_serial2 && (p.nr_enable || p.spectrum_enable) && fused_eligible_ext(p);
+        if (fused || tcx) {
             if (e->fused_s1_ci < 0) { e->fused_s1_ci = p.s1_ci; e->fused_s2_ci = p.s2_ci; e->fused_s2_cq = p.s2_cq; }
-            else if (p.s1_ci != e->fused_s1_ci || p.s2_ci != e->fused_s2_ci || p.s2_cq != e->fused_s2_cq) fused = false;
+            else if (p.s1_ci != e->fused_s1_ci || p.s2_ci != e->fused_s2_ci || p.s2_cq != e->fused_s2_cq) fused = tcx = false;
         }
         if (fused) e->h_list_fused.push_back(c);
+        else if (tcx) (p.nr_enable ? e->h_list_tc_nr : e->h_list_tc_sp).push_back(c);
         else if (e->use_split && rx_split_floats_per_block(p) > 0) {
             // channels with the spectral noise reduction take two serial phases around the warp-cooperative NR kernel
             (p.nr_enable ? e->h_list_split_nr : e->h_list_split).push_back(c);
@@ -320,8 +337,13 @@ static int rebuild_lists(uhsdr_engine *e)
         CK(e, cudaMemcpyAsync(e->d_list_split, e->h_list_split.data(), e->h_list_split.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
     if (!e->h_list_split_nr.empty())
         CK(e, cudaMemcpyAsync(e->d_list_split_nr, e->h_list_split_nr.data(), e->h_list_split_nr.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    if (!e->h_list_fused.empty()) {
+    if (!e->h_list_fused.empty())
         CK(e, cudaMemcpyAsync(e->d_list_fused, e->h_list_fused.data(), e->h_list_fused.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if (!e->h_list_tc_sp.empty())
+        CK(e, cudaMemcpyAsync(e->d_list_tc_sp, e->h_list_tc_sp.data(), e->h_list_tc_sp.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if (!e->h_list_tc_nr.empty())
+        CK(e, cudaMemcpyAsync(e->d_list_tc_nr, e->h_list_tc_nr.data(), e->h_list_tc_nr.size() * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    if (e->fused_s1_ci >= 0) {
         const float *pool = e->tables.pool.data();
         fill_fused_coefs(&e->fused_coefs, pool + e->fused_s1_ci, pool + e->fused_s2_ci, pool + e->fused_s2_cq);
     }
@@ -341,6 +363,7 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
     a.params = e->d_params; a.state = e->d_state; a.nr = e->d_nr; a.spec_ring = e->d_spec; a.pool = e->d_pool;
     a.iq = iq_dev; a.audio = audio_dev; a.audio_f = audio_f_dev; a.mute = mute_dev; a.nblocks = nblocks;
     a.chan_stride = chan_stride; a.mute_stride = mute_stride; a.scratch = nullptr; a.scratch_stride = 0;
+    a.iqc_log = nullptr; a.nr_handoff = 0;
     if (e->tw_blocks_left > 0) {
         CK(e, launch_twinpeaks(e->d_params, e->d_state, iq_dev, e->nch, nblocks, chan_stride, stream));
         e->launches++;
@@ -359,6 +382,37 @@ static int rx_launch(uhsdr_engine *e, const uhsdr_iq_sample_t *iq_dev, uhsdr_aud
         else if (nblocks % 4 == 0 && fused_ok) CK(e, launch_rx_ssb_fused(a, e->fused_coefs, e->sm_count, stream));
         else CK(e, launch_rx_generic(a, stream));
         e->launches++;
+    }
+    // Narrow SSB / CW with the spectrum ring and / or the spectral NR: the tensor-core kernel up to the output stage (or, with the NR,
+    // up to the AGC output), the ring from a tap kernel over the call's last 16 blocks, then the NR frames and the serial kernel's
+    // phase 2.  Call sizes / alignments the tensor-core kernel does not take go through the one-kernel general path.
+    for (int which = 0; which < 2; which++) {
+        const std::vector<int> &lst = which ? e->h_list_tc_nr : e->h_list_tc_sp;
+        if (lst.empty()) continue;
+        RxArgs x = a;
+        x.chan_list = which ? e->d_list_tc_nr : e->d_list_tc_sp; x.num_items = (int)lst.size();
+        const bool ok = e->use_tc && nblocks % 4 == 0 && ((uintptr_t)audio_dev % 32 == 0) && ((uintptr_t)iq_dev % 32 == 0) && (chan_stride % 4 == 0) &&
+                        ((uintptr_t)audio_f_dev % 16 == 0);
+        if (!ok) { CK(e, launch_rx_generic(x, stream)); e->launches++; continue; }
+        x.iqc_log = e->d_iqc + (size_t)which * (size_t)e->nch * 16;
+        if (which) {
+            const size_t need = lst.size() * (size_t)nblocks * 8 * sizeof(float);
+            if (need > e->d_scratch_nr_bytes) {
+                CK(e, cudaStreamSynchronize(stream));
+                cudaFree(e->d_scratch_nr); e->d_scratch_nr = nullptr; e->d_scratch_nr_bytes = 0;
+                CK(e, cudaMalloc(&e->d_scratch_nr, need));
+                e->d_scratch_nr_bytes = need;
+            }
+            x.nr_handoff = 1; x.scratch = e->d_scratch_nr; x.scratch_stride = (long long)nblocks * 8;
+        }
+        CK(e, launch_rx_ssb_tc(x, e->fused_s1_ci, e->fused_s2_ci, e->fused_s2_cq, e->sm_count, stream));
+        CK(e, launch_spectrum_tap(x, stream));
+        e->launches += 2;
+        if (which) {
+            CK(e, launch_rx_nr(x, stream));
+            CK(e, launch_rx_serial2(x, 2, stream));
+            e->launches += 2;
+        }
     }
     if (!e->h_list_generic.empty()) {
         a.chan_list = e->d_list_generic; a.num_items = (int)e->h_list_generic.size();

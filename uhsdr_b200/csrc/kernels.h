@@ -24,6 +24,9 @@ struct RxArgs {
     long long mute_stride;      // bytes between consecutive channels in mute (>= nblocks)
     float *scratch;             // split path: FIR-stage outputs, [num_items][scratch_stride] floats
     long long scratch_stride;
+    // tensor-core kernel only:
+    float2 *iqc_log;            // optional [num_items][16]: (M_c1, M_c2) of the last min(16, nblocks) blocks, for the spectrum tap kernel
+    int nr_handoff;             // 1: stop at the AGC output and write it to scratch [num_items][nblocks*8] (spectral NR + serial phase 2 follow)
 };
 
 cudaError_t launch_rx_generic(const RxArgs &a, cudaStream_t stream);
@@ -75,6 +78,11 @@ cudaError_t launch_twinpeaks_rearm(ChanState *state, int first, int count, cudaS
 // the twin-peaks detector over the blocks of one call, before the receiver kernels (configure.cu)
 cudaError_t launch_twinpeaks(const ChanParams *params, ChanState *state, const void *iq, int nch, int nblocks, long long chan_stride, cudaStream_t stream);
 
+// spectrum ring of channels that ran on the tensor-core kernel (last 16 blocks of the call, factors from a.iqc_log)
+cudaError_t launch_spectrum_tap(const RxArgs &a, cudaStream_t stream);
+// the fused chain but for its deferred consumers: spectral NR hand-off and / or the (unzoomed) spectrum ring, both served around the
+// tensor-core kernel
+bool fused_eligible_ext(const ChanParams &p);
 // UiSpectrum_RedrawSpectrum states 0-2
 cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, const float *spec_ring, const float *pool,
                             int window_off, int twiddle_off, int first, int count, float *mags, cudaStream_t stream);

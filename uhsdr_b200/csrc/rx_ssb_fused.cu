@@ -824,6 +824,15 @@ bool fused_eligible(const ChanParams &p)
            p.interp_L == 4 && p.interp_plen >= 1 && p.interp_plen <= 4 && p.agc.attack_buffsize == AGC_W;
 }
 
+bool fused_eligible_ext(const ChanParams &p)
+{
+    return p.configured && p.topo == TOPO_SSB_DEC_FIRST && p.M == 4 && p.s1_ntaps == 83 && p.s2_ntaps == 199 &&
+           p.shift_kind != 2 && !p.notch_enable && (!p.spectrum_enable || p.zoom_m == 0) && p.pre.n <= 10 && (p.aa.n == 0 || p.aa.n == 6) &&
+           p.interp_L == 4 && p.interp_plen >= 1 && p.interp_plen <= 4 && p.agc.attack_buffsize == AGC_W &&
+           (!p.nr_enable || rx_serial2_eligible(p)) &&
+           !p.nb_enable;     // the LPC noise blanker is a chain of threshold decisions: it keeps the FP32 FIRs of the split path in front of it
+}
+
 void fill_fused_coefs(FusedCoefs *fc, const float *dec83, const float *hil_i199, const float *hil_q199)
 {
     memset(fc, 0, sizeof(*fc));

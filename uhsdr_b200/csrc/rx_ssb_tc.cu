@@ -393,6 +393,11 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                             ls.c1 = c1m; ls.c2 = c2m;                            // after the second pass, the lanes of block 1 hold the block-3 values the state keeps
                         }
                     }
+                    if (a.iqc_log != nullptr && q_lo + q_hi == 0 && active) {
+                        // the spectrum tap kernel re-applies the correction to the last 16 blocks of the call: log their factors
+                        const int j = 4 * t + 2 * h + hb - (a.nblocks - min(16, a.nblocks));
+                        if (j >= 0) a.iqc_log[(size_t)(cta_first + g) * 16 + j] = make_float2(c1m, c2m);
+                    }
                     if (fast_fe) {
                         // every channel of the warp: automatic IQ correction + Fs/4 translation (the default).
                         //   i' = c2 i, q' = q + c1 i;  phase 0: (i', q')  1: (q', -i')  2: (-i', -q')  3: (-q', i'), (x sgd when translating down)
@@ -1062,7 +1067,18 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 }
             }
             const int c = t - IT_BQ;
-            if (c >= 0 && c < nsteps && active && !KNOCK(128)) {
+            if (c >= 0 && c < nsteps && active && a.nr_handoff) {
+                // spectral NR follows: the AGC output of this step leaves for the scratch row of the channel (8 floats per block)
+                const float *in = sm.gq[c & 1] + g;
+                float4 *dst = reinterpret_cast<float4 *>(a.scratch + (size_t)(cta_first + g) * (size_t)a.scratch_stride + (size_t)c * ND);
+#pragma unroll 1
+                for (int i0 = 0; i0 < ND; i0 += 8) {
+                    float xv[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) xv[i] = in[(i0 + i) * SMS];
+                    dst[i0 / 4] = make_float4(xv[0], xv[1], xv[2], xv[3]); dst[i0 / 4 + 1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
+                }
+            } else if (c >= 0 && c < nsteps && active && !KNOCK(128)) {
                 const float *in = sm.gq[c & 1] + g;
                 float *out = sm.bq[c & 1] + 3 * SMS + g;
 #pragma unroll
@@ -1074,7 +1090,7 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
             __syncthreads();
         }
         PROF_SAVE();
-        if (active) {
+        if (active && !a.nr_handoff) {
             // a skipped (pass-through) stage saw the output of the nearest computed stage before it
             float s1v = xl1, s2v = xl2;
 #pragma unroll
@@ -1083,11 +1099,16 @@ rx_ssb_tc_kernel(const __grid_constant__ RxArgs a, int chans_per_cta, int dec_c,
                 else { s1v = bs[s].y1; s2v = bs[s].y2; }
                 st->bq1[s] = bs[s];
             }
-            if (agc_on && !any_hang) {
-                st->agc_hang_backaverage = hba;
-                st->agc_hang_action = (hba > hp.hang_level) ? 1 : 0;
-            }
         }
+        if (active && agc_on && !any_hang) {
+            st->agc_hang_backaverage = hba;
+            st->agc_hang_action = (hba > hp.hang_level) ? 1 : 0;
+        }
+        return;
+    }
+    if (a.nr_handoff) {
+        // output warps: nothing to do (the serial kernel's phase 2 owns the stages behind the NR); keep the step barriers
+        for (int t = 0; t < niter; t++) __syncthreads();
         return;
     }
 

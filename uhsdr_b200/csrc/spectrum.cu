@@ -183,4 +183,53 @@ cudaError_t launch_spectrum(const ChanParams *params, const ChanState *state, co
     return cudaGetLastError();
 }
 
+// Spectrum sample tap for channels that ran on the tensor-core kernel (whose front end keeps no copy of the corrected samples):
+// AudioDriver_SpectrumNoZoomProcessSamples (audio_driver.c:1811-1849) writes every block's corrected, not yet translated (Q, I) pairs
+// into the 1024-float ring, so after a call only its last 16 blocks are in it.  One warp per channel re-applies the IQ correction to
+// those blocks (factors logged by the tensor-core kernel's front end, a.iqc_log) and advances samp_ptr by the whole call.
+__global__ void __launch_bounds__(128)
+spectrum_tap_kernel(RxArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot >= a.num_items) return;
+    const int ch = a.chan_list ? a.chan_list[slot] : slot;
+    const ChanParams &p = a.params[ch];
+    if (!p.spectrum_enable || !a.spec_ring || p.zoom_m != 0) return;
+    ChanState &st = a.state[ch];
+    const int ntap = min(16, a.nblocks);
+    const uint32_t sp0 = st.samp_ptr;
+    uint32_t sp = (sp0 + 64u * (uint32_t)(a.nblocks - ntap)) & 1023u;
+    const int2 *iq = reinterpret_cast<const int2 *>(a.iq) + (size_t)ch * (size_t)a.chan_stride + (size_t)(a.nblocks - ntap) * BLK;
+    float *ring = a.spec_ring + (size_t)ch * 1024;
+    const int iq_auto = p.iq_auto;
+    const float adj_i = p.adj_i, adj_q = p.adj_q, phase_bal = p.phase_bal;
+    for (int j = 0; j < ntap; j++) {
+        const int2 s = iq[(size_t)j * BLK + lane];
+        float fi = __fmul_rn((float)s.x, 0.0000152587890625f), fq = __fmul_rn((float)s.y, 0.0000152587890625f);
+        if (iq_auto) {
+            const float2 c = a.iqc_log[(size_t)slot * 16 + j];
+            fq = __fadd_rn(fq, __fmul_rn(c.x, fi));
+            fi = __fmul_rn(fi, c.y);
+        } else {
+            fi = __fmul_rn(fi, adj_i); fq = __fmul_rn(fq, adj_q);
+            if (phase_bal < 0.0f) fq = __fadd_rn(fq, __fmul_rn(fi, phase_bal));
+            else if (phase_bal > 0.0f) fi = __fadd_rn(fi, __fmul_rn(fq, phase_bal));
+        }
+        uint32_t ptr = sp + 2u * (uint32_t)lane;
+        if (ptr >= 1024u) ptr -= 1024u;
+        ring[ptr] = fq; ring[ptr + 1] = fi;
+        sp = (sp + 64u) & 1023u;
+    }
+    if (lane == 0) st.samp_ptr = (sp0 + 64u * (uint32_t)a.nblocks) & 1023u;
+}
+
+cudaError_t launch_spectrum_tap(const RxArgs &a, cudaStream_t stream)
+{
+    if (a.num_items <= 0 || a.nblocks <= 0) return cudaSuccess;
+    if (a.iqc_log == nullptr) return cudaErrorInvalidValue;
+    spectrum_tap_kernel<<<(a.num_items + 3) / 4, 128, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace uhsdr
