@@ -98,6 +98,50 @@ def test_unaligned_output_buffer_takes_the_cuda_core_kernel(built):
         assert np.array_equal(got[c, :, 0], got[c, :, 1])
 
 
+def test_tensor_core_path_with_spectrum_ring_and_nr_matches_the_split_path(built, monkeypatch):
+    """Narrow SSB channels with the spectrum ring and / or the spectral NR run on the tensor-core kernel plus a spectrum tap kernel
+    (+ NR kernel + serial phase 2).  Against the split general path (UHSDR_B200_NO_TCX=1) on the same inputs: audio within the float
+    tolerance, identical NR latency, the spectrum of the last 512 samples equal to FFT rounding, same ring position; 30 channels
+    (ragged CTA), a mute array, two calls (the second shorter than the 16-block ring)."""
+    import torch
+    from uhsdr_b200.config import DEMOD_LSB, DSP_NR_ENABLE
+    cfgs = [default_cfg(spectrum_enable=1), default_cfg(dmod_mode=DEMOD_LSB, filter_path=38, dsp_active=DSP_NR_ENABLE, spectrum_enable=1),
+            default_cfg(dsp_active=DSP_NR_ENABLE)]
+    nch, calls = 30, (96, 12)
+    nb = sum(calls)
+    iq = np.stack([synth.rx_iq(cfgs[c % 3], 500 + c, nb * 32, seed=51) for c in range(nch)])
+    mute = np.zeros((nch, nb), dtype=np.uint8)
+    mute[:, 40:44] = 1
+    res = {}
+    for no_tcx in ("1", "0"):
+        monkeypatch.setenv("UHSDR_B200_NO_TCX", no_tcx)
+        with Engine(nch) as eng:
+            for c in range(nch):
+                eng.configure(cfgs[c % 3], first=c, count=1)
+            parts, pos = [], 0
+            for n in calls:
+                parts.append(run_engine_float(eng, iq[:, pos * 32:(pos + n) * 32], mute[:, pos:pos + n]))
+                pos += n
+            f = np.concatenate([p_[1] for p_ in parts], axis=1)
+            mags = eng.spectrum()
+            st = eng.status()
+            res[no_tcx] = (f, mags, [s_.blocks_processed for s_ in st], eng.launch_count)
+    f0, m0, b0, l0 = res["1"]
+    f1, m1, b1, l1 = res["0"]
+    assert b0 == b1 == [nb] * nch
+    assert l1 != l0                                   # different kernels did run
+    for c in range(nch):
+        scale = np.max(np.abs(f0[c]))
+        assert np.max(np.abs(f1[c] - f0[c])) <= 1e-4 * scale, c
+        assert np.all(f1[c][40 * 32:44 * 32] == 0)
+        if c % 3 != 2:                                 # channels with the spectrum ring
+            assert np.max(np.abs(m1[c] - m0[c])) <= 1e-4 * np.max(m0[c]), c
+            assert np.max(m0[c]) > 0
+        if c % 3 != 0:                                 # NR: same latency
+            thr = 1e-3 * scale
+            assert np.flatnonzero(np.abs(f1[c]) > thr)[0] == np.flatnonzero(np.abs(f0[c]) > thr)[0], c
+
+
 def test_unaligned_float_copy_buffer(built):
     """The optional float copy is stored as 16-byte vectors by the tensor-core kernel (8-byte by the CUDA-core fused kernel): a
     buffer that is only 4-byte aligned must take a kernel that stores it word by word, with the same result."""
