@@ -88,7 +88,8 @@ __device__ __forceinline__ void fft_warp(float (&xr)[N / 32], float (&xi)[N / 32
         for (int r = 0; r < E; r++) {
             if (r & h) continue;
             const int k = r & (h - 1);
-            const float wr = __ldg(tw + 2 * (k << (LOG2N - s))), wi = __ldg(tw + 2 * (k << (LOG2N - s)) + 1);
+            const float2 w_ = *reinterpret_cast<const float2 *>(tw + 2 * (k << (LOG2N - s)));
+            const float wr = w_.x, wi = w_.y;
             const float tr = __fsub_rn(__fmul_rn(xr[r + h], wr), __fmul_rn(xi[r + h], wi));
             const float ti = __fadd_rn(__fmul_rn(xr[r + h], wi), __fmul_rn(xi[r + h], wr));
             xr[r + h] = __fsub_rn(xr[r], tr); xi[r + h] = __fsub_rn(xi[r], ti);
@@ -103,7 +104,8 @@ __device__ __forceinline__ void fft_warp(float (&xr)[N / 32], float (&xi)[N / 32
 #pragma unroll
         for (int r = 0; r < E; r++) {
             const int tidx = (kl + r) << (LOG2N - s);
-            const float wr = __ldg(tw + 2 * tidx), wi = __ldg(tw + 2 * tidx + 1);
+            const float2 w_ = *reinterpret_cast<const float2 *>(tw + 2 * tidx);        // tw: global or shared memory
+            const float wr = w_.x, wi = w_.y;
             const float pr = __shfl_xor_sync(0xffffffffu, xr[r], 1 << j), pi = __shfl_xor_sync(0xffffffffu, xi[r], 1 << j);
             const float br = upper ? xr[r] : pr, bi = upper ? xi[r] : pi;          // the element of the upper half of the pair
             const float ar = upper ? pr : xr[r], ai = upper ? pi : xi[r];

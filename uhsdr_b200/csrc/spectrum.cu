@@ -14,7 +14,11 @@ __global__ void __launch_bounds__(128)
 spectrum_kernel(const ChanParams *__restrict__ params, const ChanState *__restrict__ state, const float *__restrict__ spec_ring,
                 const float *__restrict__ pool, int window_off, int twiddle_off, int first, int count, float *__restrict__ mags)
 {
-    // one warp per channel, the whole transform in registers (fft_warp: 16 elements per lane, the last five stages by shuffle)
+    // one warp per channel, the whole transform in registers (fft_warp: 16 elements per lane, the last five stages by shuffle);
+    // the twiddle table (256 complex) staged once per CTA in shared memory
+    __shared__ __align__(16) float tws[512];
+    for (int i = threadIdx.x; i < 512; i += 128) tws[i] = __ldg(pool + twiddle_off + i);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (slot >= count) return;
@@ -37,7 +41,7 @@ spectrum_kernel(const ChanParams *__restrict__ params, const ChanState *__restri
         xr[r] = __fmul_rn(__fmul_rn(ring[(sp + 2u * (uint32_t)n) & 1023u], __ldg(win + 2 * n)), gcalc);
         xi[r] = __fmul_rn(__fmul_rn(ring[(sp + 2u * (uint32_t)n + 1u) & 1023u], __ldg(win + 2 * n + 1)), gcalc);
     }
-    fft_warp<512, 9>(xr, xi, pool + twiddle_off, lane);
+    fft_warp<512, 9>(xr, xi, tws, lane);
     float4 *o4 = reinterpret_cast<float4 *>(out + 16 * lane);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
