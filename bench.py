@@ -370,6 +370,14 @@ def run_config(torch, dist, args, name, nch, T, rank, local_rank, world, dev, st
     with torch.cuda.stream(ext):
         for _ in range(warmup):
             step()
+        # untimed spin-up of the same launches (bounded): a process that starts on an idle GPU reaches its sustained clock / power
+        # state only after some tenths of a second under load; the W warm-up steps alone are a few milliseconds
+        t_spin = time.time()
+        for _ in range(400):
+            if time.time() - t_spin >= args.spinup_s:
+                break
+            step()
+            torch.cuda.synchronize()
         barrier()
         l0 = eng.launch_count
         t_begin = time.time()
@@ -559,6 +567,7 @@ def gpu_arm(args):
                                    f"{T} blocks (x32 samples) per channel per step (BASELINE.json configs[1])",
                        "channels_per_gpu": nch, "blocks_per_step": T, "parallelism": f"channels sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2 ({2 * io_bytes / 2**20:.0f} MiB streamed per step)",
+                       "warmup_note": f"{args.warmup} warm-up steps + {args.spinup_s} s of untimed launches of the same step before the timed region (sustained clocks)",
                        "generator": "uhsdr_b200/synth.py counter_block: integer counter-based, bit-identical on host (numpy) and device (torch)"},
             "roofline": roof,
             "cpu_baseline": cpu_baseline,
@@ -576,6 +585,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--spinup-s", type=float, default=0.25, help="untimed spin-up under load after the warm-up steps, seconds")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--channels", type=int, default=4096, help="channels per GPU (headline)")
     ap.add_argument("--blocks", type=int, default=1500, help="32-sample blocks per channel per step (headline)")
