@@ -124,3 +124,38 @@ def test_bench_reference_arm_exits_cleanly_on_nonzero_rank():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_plans_shard_like_the_reference_configs():
+    """bench.py's per-rank channel plans (the N > 1 legs of the other configurations): the alternating USB / LSB plan continues
+    across rank boundaries as one global sequence (configs[1], configs[4] at 65536 channels over 8 ranks), mixed plans give every
+    rank the same share of every kind with the kinds contiguous, and every local channel has a generator kind."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from uhsdr_b200.config import DEMOD_LSB
+    world, total = 8, 65536
+    seq = []
+    for r in range(world):
+        per = total // world
+        cfgs, labels, kinds = bench.local_plan("rx_tx", per, r * per)
+        assert len(cfgs) == len(labels) == len(kinds) == per
+        seq += [c.dmod_mode == DEMOD_LSB for c in cfgs]
+    assert seq == [bool(i % 2) for i in range(total)]
+    # an odd first channel starts with the LSB kind
+    cfgs, _, _ = bench.local_plan("ssb_narrow", 5, 3)
+    assert [c.dmod_mode == DEMOD_LSB for c in cfgs] == [True, False, True, False, True]
+    for name in ("ssb_wide", "mixed_am_sam_fm", "ssb_nr_spectrum"):
+        groups = bench.plan_groups(name)
+        tot = sum(g[2] for g in groups)
+        cfgs, labels, kinds = bench.local_plan(name, 4096, 0)
+        assert len(cfgs) == 4096 and len(set(kinds)) >= 1
+        # kinds contiguous, shares as declared
+        runs = [labels[0]]
+        for lab in labels[1:]:
+            if lab != runs[-1]:
+                runs.append(lab)
+        assert runs == [g[0] for g in groups]
+        for lab, _, share in groups[:-1]:
+            assert labels.count(lab) == 4096 * share // tot
